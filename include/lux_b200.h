@@ -1,0 +1,184 @@
+/*
+ * lux_b200.h -- C ABI of the B200-native batched Lux AI 2021 turn engine.
+ *
+ * The reference (glmcdona/LuxPythonEnvGym) has no FFI layer: the per-turn path is the pure
+ * Python call `Game.run_turn_with_actions(actions)` (luxai2021/game/game.py:390-535).  The
+ * entry points below are what a binding for that path would call; each one names the
+ * reference interface it replaces.  Plain pointers and sizes only, no torch types; every
+ * function returns 0 on success or a negative LUX_E_* code, never throws.
+ *
+ * All state pointers are DEVICE pointers unless the function name ends in `_host`.
+ * A batch is `n_matches` independent matches of one map side `size`, stored as six
+ * sections with a leading match dimension (see luxpythonenvgym_b200/state.py):
+ *
+ *   hdr    [n][128]            LuxHeader
+ *   cells  [n][size*size]      LuxCell   (8 B)
+ *   units  [n][u_cap]          LuxUnit   (16 B) team-A units in dict order, then team B
+ *   cities [n][c_cap]          LuxCity   (16 B) Game.cities dict order
+ *   tiles  [n][t_cap]          uint16    cell index of each city tile, cities x city_cells order
+ *   res    [n][r_cap]          uint16    cell index of each resource cell, GameMap.resources order
+ */
+#ifndef LUX_B200_H
+#define LUX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LUX_HDR_BYTES 128
+
+/* resource codes, LuxCell.flags[1:0] */
+enum { LUX_RES_NONE = 0, LUX_RES_WOOD = 1, LUX_RES_COAL = 2, LUX_RES_URANIUM = 3 };
+/* unit action word, bits [2:0] (luxai2021/game/actions.py:44-438 action classes) */
+enum { LUX_UA_NONE = 0, LUX_UA_MOVE = 1, LUX_UA_BCITY = 2, LUX_UA_PILLAGE = 3, LUX_UA_TRANSFER = 4 };
+/* move direction, bits [5:3] of a move word (position.py:36-46) */
+enum { LUX_DIR_CENTER = 0, LUX_DIR_NORTH = 1, LUX_DIR_EAST = 2, LUX_DIR_SOUTH = 3, LUX_DIR_WEST = 4 };
+/* transfer word: [4:3] resource-1, [16:6] amount (0..2047), [31:17] destination unit id */
+/* city-tile action byte */
+enum { LUX_TA_NONE = 0, LUX_TA_BUILD_WORKER = 1, LUX_TA_BUILD_CART = 2, LUX_TA_RESEARCH = 3 };
+/* LuxHeader.status bits */
+enum { LUX_ST_UNIT_OVERFLOW = 1, LUX_ST_CITY_OVERFLOW = 2, LUX_ST_TILE_OVERFLOW = 4, LUX_ST_BAD_STATE = 8 };
+/* LuxHeader.winner */
+enum { LUX_WIN_A = 0, LUX_WIN_B = 1, LUX_WIN_TIE = 2, LUX_WIN_NONE = 255 };
+/* error codes */
+enum { LUX_OK = 0, LUX_E_ARG = -1, LUX_E_CAPACITY = -2, LUX_E_CUDA = -3, LUX_E_NO_DEVICE = -4 };
+
+#pragma pack(push, 1)
+typedef struct LuxHeader {            /* game.py:85-147 */
+    int32_t  turn;
+    int32_t  unit_id_count;            /* Game.global_unit_id_count */
+    int32_t  city_id_count;            /* Game.global_city_id_count */
+    uint16_t n_units, n_cities, n_tiles, n_res;
+    uint16_t n_team_units[2];
+    uint8_t  done;                     /* run_turn_with_actions returned True */
+    uint8_t  winner;                   /* LUX_WIN_* once done */
+    uint8_t  status;                   /* LUX_ST_* */
+    uint8_t  size;                     /* map side */
+    int32_t  research[2];              /* teamStates[t].researchPoints */
+    int32_t  fuel_generated[2];        /* stats.teamStats[t].fuelGenerated */
+    int32_t  collected[2][3];          /* resourcesCollected wood/coal/uranium */
+    int32_t  workers_built[2];
+    int32_t  carts_built[2];
+    int32_t  roads_built_q[2];         /* roadsBuilt * 4 */
+    int32_t  city_tiles_built[2];
+    uint8_t  pad[28];
+} LuxHeader;
+
+typedef struct LuxCell {              /* cell.py:20-33, city.py:53-66 */
+    uint16_t amount;                   /* Resource.amount, 0 = none */
+    uint8_t  flags;                    /* [1:0] resource type, [3:2] tile team+1, [6:4] adjacent_city_tiles */
+    uint8_t  road_q;                   /* Cell.road * 4 */
+    uint8_t  tile_cd;                  /* CityTile.cooldown */
+    uint8_t  city_slot;                /* index into cities[] */
+    uint16_t key;                      /* index in City.city_cells */
+} LuxCell;
+
+typedef struct LuxUnit {              /* unit.py:15-35 */
+    int32_t  id;                       /* N of "u_N" */
+    uint8_t  x, y;
+    uint8_t  team_type;                /* bit0 team, bit1 cart */
+    uint8_t  cd_q;                     /* cooldown * 4 */
+    uint16_t wood, coal, uranium;
+    uint16_t pad;
+} LuxUnit;
+
+typedef struct LuxCity {              /* city.py:15-50 */
+    int32_t  id;                       /* N of "c_N" */
+    int32_t  fuel;
+    uint16_t ntiles;
+    uint16_t adjsum;                   /* sum of adjacent_city_tiles over the city's tiles */
+    uint8_t  team;
+    uint8_t  pad[3];
+} LuxCity;
+#pragma pack(pop)
+
+typedef struct LuxBatch {
+    int32_t n_matches;
+    int32_t size;                      /* map side (12/16/24/32; any 4..32 accepted) */
+    int32_t u_cap, c_cap, t_cap, r_cap;
+    LuxHeader* hdr;
+    LuxCell*   cells;
+    LuxUnit*   units;
+    LuxCity*   cities;
+    uint16_t*  tiles;
+    uint16_t*  res;
+} LuxBatch;
+
+/* Library / build identification; also reports whether a CUDA device is usable. */
+int lux_b200_version(void);
+int lux_b200_device_count(void);
+
+/* Dynamic shared memory one match needs in lux_b200_step for these capacities. */
+size_t lux_b200_step_smem_bytes(int size, int u_cap, int c_cap, int t_cap, int r_cap);
+
+/*
+ * One turn for every live match of the batch.
+ * Replaces: Game.run_turn_with_actions(actions) -> bool, luxai2021/game/game.py:390-535
+ * (phases: validate_command :646-723, handle_movement_actions :1104-1195, CityTile.turn
+ * city.py:96-120, Worker/Cart.turn unit.py:162-269, distribute_all_resources :868-1001,
+ * handle_resource_deposit :1003-1023, handle_night :537-558, regenerate_trees :1081-1102,
+ * match_over :570-592, run_cooldowns :560-568), applied to the action list
+ *   [tile_actions[m][p] for p in canonical tile order] + [unit_actions[m][i] for i in slot order].
+ * unit_actions: [n][u_cap] uint32, tile_actions: [n][t_cap] uint8 (device).  Matches whose
+ * hdr.done is set are left untouched.  The bool return value lands in hdr.done, the
+ * winner (get_winning_team :594-634, coin flip reported as LUX_WIN_TIE) in hdr.winner.
+ */
+int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions,
+                  void* cuda_stream);
+
+/*
+ * Same call with HOST action buffers and HOST result buffers (pinned or pageable):
+ * copies the actions to the device staging buffers the caller provides, steps, and
+ * copies back done[n] (uint8) and the headers (n*128 B) if the pointers are non-NULL.
+ * Synchronises the stream before returning.
+ */
+int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,
+                       const uint8_t* tile_actions_host, uint32_t* unit_actions_dev,
+                       uint8_t* tile_actions_dev, uint8_t* done_host, LuxHeader* hdr_host,
+                       void* cuda_stream);
+
+/*
+ * Canonical seeded action stream, written as packed action
+ * tensors for every live match: action = f(hash64(seed, match_id_base+m, turn, kind, key)).
+ * Harness utility (benchmarks, parity tests); a policy normally fills the tensors itself.
+ */
+int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t match_id_base,
+                         uint32_t* unit_actions, uint8_t* tile_actions, void* cuda_stream);
+
+/*
+ * Per-entity observation tensors for team `team_sel[m]` of every match.
+ * Replaces: AgentPolicy.get_observation, examples/agent_policy.py:188-424, called once
+ * per actionable entity by LuxEnvironment.step (luxai2021/env/lux_env.py:146).  Entity
+ * order is MatchController's yield order (match_controller.py:271-289): the team's units
+ * with can_act() in dict order, then its city tiles with can_act() in cities x cells order.
+ * obs: [n][e_cap][85] float32, ent_slot: [n][e_cap] int16 (unit slot, or 0x4000|tile
+ * position), ent_count: [n] int32.
+ */
+int lux_b200_observe(const LuxBatch* b, const uint8_t* team_sel, float* obs, int16_t* ent_slot,
+                     int32_t* ent_count, int e_cap, void* cuda_stream);
+
+/*
+ * Replace every finished match (hdr.done != 0) by a fresh one copied from a pool of
+ * initial states (same size/capacities), round-robin from `pool_cursor[0]`.
+ * Replaces: Game.reset(), luxai2021/game/game.py:76-157 (map generation itself stays on
+ * the host: luxpythonenvgym_b200/mapgen.py).  reset_count (device int32[1]) += resets.
+ */
+int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, int32_t* pool_cursor,
+                        int32_t* reset_count, void* cuda_stream);
+
+/*
+ * Episode statistics summed over the batch into out[16] (device int64):
+ * [0] live matches, [1] finished, [2] wins A, [3] wins B, [4] ties, [5] sum turn,
+ * [6] sum fuelGenerated, [7] sum units, [8] sum city tiles, [9] sum cities,
+ * [10] matches with status != 0, [11] algorithmic bytes of one turn over live matches.
+ * This is the vector NCCL all-reduces across GPUs.
+ */
+int lux_b200_stats(const LuxBatch* b, int64_t* out16, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUX_B200_H */

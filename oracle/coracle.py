@@ -1,0 +1,94 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/lux_oracle.c (the CPU checker)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+    return os.path.join(_HERE, "_build", "liblux_oracle.so")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "_build", "liblux_oracle.so")
+        src = os.path.join(_HERE, "lux_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            build()
+        _LIB = ctypes.CDLL(path)
+        _LIB.lux_oracle_hash.restype = ctypes.c_uint64
+        _LIB.lux_oracle_hash.argtypes = [ctypes.c_uint64] * 5
+    return _LIB
+
+
+def _p(arr):
+    return arr.ctypes.data_as(ctypes.c_void_p) if arr is not None else None
+
+
+def step(ms, unit_words=None, tile_bytes=None):
+    """One turn of one MatchState in place (lux_oracle_step)."""
+    L = lib()
+    hdr = ms.hdr.reshape(1)
+    if unit_words is not None:
+        unit_words = np.ascontiguousarray(unit_words, dtype=np.uint32)
+        assert len(unit_words) >= len(ms.units)
+    if tile_bytes is not None:
+        tile_bytes = np.ascontiguousarray(tile_bytes, dtype=np.uint8)
+        assert len(tile_bytes) >= len(ms.tiles)
+    rc = L.lux_oracle_step(_p(hdr), _p(ms.cells), _p(ms.units), _p(ms.cities), _p(ms.tiles), _p(ms.res),
+                           _p(unit_words), _p(tile_bytes), len(ms.units), len(ms.cities), len(ms.tiles))
+    ms.hdr = hdr[0]
+    if rc != 0:
+        raise RuntimeError("lux_oracle_step -> %d" % rc)
+    return bool(ms.hdr["done"])
+
+
+def gen_actions(ms, seed, match_id):
+    L = lib()
+    uw = np.zeros(len(ms.units), dtype=np.uint32)
+    tb = np.zeros(len(ms.tiles), dtype=np.uint8)
+    hdr = ms.hdr.reshape(1)
+    rc = L.lux_oracle_gen_actions(_p(hdr), _p(ms.cells), _p(ms.units), _p(ms.tiles),
+                                  ctypes.c_uint64(seed), ctypes.c_uint64(match_id), _p(uw), _p(tb),
+                                  len(ms.units), len(ms.tiles))
+    if rc != 0:
+        raise RuntimeError("lux_oracle_gen_actions -> %d" % rc)
+    return uw, tb
+
+
+class LuxBatchC(ctypes.Structure):
+    _fields_ = [("n_matches", ctypes.c_int32), ("size", ctypes.c_int32),
+                ("u_cap", ctypes.c_int32), ("c_cap", ctypes.c_int32),
+                ("t_cap", ctypes.c_int32), ("r_cap", ctypes.c_int32),
+                ("hdr", ctypes.c_void_p), ("cells", ctypes.c_void_p), ("units", ctypes.c_void_p),
+                ("cities", ctypes.c_void_p), ("tiles", ctypes.c_void_p), ("res", ctypes.c_void_p)]
+
+
+def batch_desc(size, caps, arrays, n):
+    """arrays: dict of C-contiguous numpy uint8 arrays hdr/cells/units/cities/tiles/res with leading dim n."""
+    b = LuxBatchC(n, size, caps["units"], caps["cities"], caps["tiles"], caps["res"],
+                  *[arrays[k].ctypes.data for k in ("hdr", "cells", "units", "cities", "tiles", "res")])
+    return b
+
+
+def step_batch(desc, unit_actions, tile_actions, first=0, count=None):
+    L = lib()
+    count = desc.n_matches if count is None else count
+    rc = L.lux_oracle_step_batch(ctypes.byref(desc), _p(unit_actions), _p(tile_actions), first, count)
+    if rc != 0:
+        raise RuntimeError("lux_oracle_step_batch -> %d" % rc)
+
+
+def gen_actions_batch(desc, seed, match_id_base, unit_actions, tile_actions, first=0, count=None):
+    L = lib()
+    count = desc.n_matches if count is None else count
+    rc = L.lux_oracle_gen_actions_batch(ctypes.byref(desc), ctypes.c_uint64(seed), ctypes.c_uint64(match_id_base),
+                                        _p(unit_actions), _p(tile_actions), first, count)
+    if rc != 0:
+        raise RuntimeError("lux_oracle_gen_actions_batch -> %d" % rc)

@@ -1,0 +1,173 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):  python -m oracle.make_golden
+Everything stored is output of the reference engine itself (luxai2021.game.game.Game,
+imported through oracle/refshim.py); the packed encoding is oracle/flatten.py.
+
+  maps.npz     100 seeded maps (seeds of luxai2021/tests/testmaps.json, test_map.py:107-144):
+               initial packed state of Game({seed}) -- pins the host map generator.
+  replays.npz  the 7 Kaggle episodes of luxai2021/tests/replays_for_test (test_replay.py):
+               initial state, per-turn packed actions, per-turn state digests, full states
+               every 40 turns.
+  random.npz   seeded random-action matches on 12/16/24/32 maps (canonical stream,
+               oracle/stream.py): initial state, per-turn digests, final state.
+  dense.npz    replay states imported at turns 80/200/300 (process_updates, game.py:159-262)
+               continued for 45 turns with the canonical stream: digests + final state.
+"""
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import flatten, refshim, stream  # noqa: E402
+
+CAPS = dict(units=252, cities=256, tiles=512, res=384)
+OUT = os.path.join(ROOT, "tests", "golden")
+SECTIONS = ("hdr", "cells", "units", "cities", "tiles", "res")
+
+
+def put(store, prefix, ms):
+    for name, arr in ms.to_bytes().items():
+        store["%s/%s" % (prefix, name)] = arr
+
+
+def stamp_done(want, game, over):
+    if over:
+        want.hdr["done"] = 1
+        want.hdr["winner"] = flatten.winner_code(game)
+    return want
+
+
+def make_maps(ref):
+    tm = json.load(open(os.path.join(refshim.REFERENCE_ROOT, "luxai2021/tests/testmaps.json")))
+    store = {}
+    seeds = []
+    for seed, rows in tm.items():
+        g = refshim.new_game(seed=seed)
+        # the reference's own assertion (test_map.py:120-143)
+        assert len(rows) == g.map.height and len(rows[0]) == g.map.width
+        for y, row in enumerate(rows):
+            for x, want in enumerate(row):
+                cell = g.map.get_cell(x, y)
+                assert cell.is_city_tile() == want["citytile"]
+                if want["resource"] is None:
+                    assert not cell.has_resource()
+                else:
+                    assert cell.resource.type == want["resource"]["type"]
+                    assert cell.resource.amount == want["resource"]["amount"]
+        ms = flatten.flatten(g, caps=CAPS)
+        seeds.append(int(seed))
+        store["%d/size" % int(seed)] = np.array(ms.size)
+        put(store, "%d" % int(seed), ms)
+    store["seeds"] = np.array(seeds)
+    np.savez_compressed(os.path.join(OUT, "maps.npz"), **store)
+    print("maps.npz", len(seeds))
+
+
+def make_replays(ref):
+    store = {}
+    ids = []
+    files = sorted(glob.glob(os.path.join(refshim.REFERENCE_ROOT, "luxai2021/tests/replays_for_test/*[0-9].json")))
+    for f in files:
+        rid = os.path.basename(f)[:-5]
+        rep = json.load(open(f))
+        g = refshim.game_from_replay(rep)
+        ms = flatten.flatten(g, caps=CAPS)
+        store["%s/size" % rid] = np.array(ms.size)
+        put(store, "%s/init" % rid, ms)
+        ua, ta, digests = [], [], []
+        for turn in range(len(rep["steps"]) - 1):
+            cmds = [rep["steps"][turn + 1][t]["action"] for t in (0, 1)]
+            uw, tb, _ = flatten.commands_to_words(g, cmds, ms)
+            for s in np.nonzero(uw)[0]:
+                ua.append((turn, s, uw[s]))
+            for s in np.nonzero(tb)[0]:
+                ta.append((turn, s, tb[s]))
+            over = g.run_turn_with_actions(flatten.words_to_actions(ref, g, uw, tb))
+            # the reference's own per-turn assertion (match_controller.py:323-324)
+            g.process_updates(rep["steps"][turn + 1][0]["observation"]["updates"], assign=False)
+            ms = stamp_done(flatten.flatten(g, caps=CAPS), g, over)
+            digests.append(ms.digest())
+            if (turn + 1) % 40 == 0 or over:
+                put(store, "%s/t%d" % (rid, turn + 1), ms)
+            if over:
+                break
+        store["%s/unit_actions" % rid] = np.array(ua, dtype=np.uint32).reshape(-1, 3)
+        store["%s/tile_actions" % rid] = np.array(ta, dtype=np.uint32).reshape(-1, 3)
+        store["%s/digests" % rid] = np.array(digests, dtype=np.uint64)
+        ids.append(rid)
+        print("replay", rid, ms.size, len(digests))
+    store["ids"] = np.array(ids)
+    np.savez_compressed(os.path.join(OUT, "replays.npz"), **store)
+
+
+def run_stream(ref, g, ms, seed, match_id, max_turns):
+    digests = []
+    for _ in range(max_turns):
+        uw, tb = stream.gen_actions(ms, seed, match_id)
+        over = g.run_turn_with_actions(flatten.words_to_actions(ref, g, uw, tb))
+        ms = stamp_done(flatten.flatten(g, caps=CAPS), g, over)
+        digests.append(ms.digest())
+        if over:
+            break
+    return ms, np.array(digests, dtype=np.uint64)
+
+
+def make_random(ref, n=32, stream_seed=777):
+    store = {}
+    for k in range(n):
+        size = [12, 16, 24, 32][k % 4]
+        g = refshim.new_game(seed=5000 + k, width=size, height=size)
+        ms = flatten.flatten(g, caps=CAPS)
+        store["%d/size" % k] = np.array(size)
+        put(store, "%d/init" % k, ms)
+        ms, digests = run_stream(ref, g, ms, stream_seed, k, 360)
+        put(store, "%d/final" % k, ms)
+        store["%d/digests" % k] = digests
+        print("random", k, size, len(digests), int(ms.hdr["n_units"]))
+    store["n"] = np.array(n)
+    store["stream_seed"] = np.array(stream_seed)
+    np.savez_compressed(os.path.join(OUT, "random.npz"), **store)
+
+
+def make_dense(ref, stream_seed=31337):
+    store = {}
+    names = []
+    files = sorted(glob.glob(os.path.join(refshim.REFERENCE_ROOT, "luxai2021/tests/replays_for_test/*[0-9].json")))
+    for f in files:
+        rid = os.path.basename(f)[:-5]
+        rep = json.load(open(f))
+        for start in (80, 200, 300):
+            g = refshim.game_from_replay(rep, step=start)
+            ms = flatten.flatten(g, caps=CAPS)
+            name = "%s@%d" % (rid, start)
+            store["%s/size" % name] = np.array(ms.size)
+            put(store, "%s/init" % name, ms)
+            ms, digests = run_stream(ref, g, ms, stream_seed, start, 45)
+            put(store, "%s/final" % name, ms)
+            store["%s/digests" % name] = digests
+            names.append(name)
+            print("dense", name, len(digests), int(ms.hdr["n_units"]))
+    store["names"] = np.array(names)
+    store["stream_seed"] = np.array(stream_seed)
+    np.savez_compressed(os.path.join(OUT, "dense.npz"), **store)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    os.chdir("/tmp")
+    ref = refshim.load()
+    make_maps(ref)
+    make_replays(ref)
+    make_random(ref)
+    make_dense(ref)
+
+
+if __name__ == "__main__":
+    main()
