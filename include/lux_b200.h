@@ -46,8 +46,10 @@ enum { LUX_WIN_A = 0, LUX_WIN_B = 1, LUX_WIN_TIE = 2, LUX_WIN_NONE = 255 };
 /* error codes */
 enum { LUX_OK = 0, LUX_E_ARG = -1, LUX_E_CAPACITY = -2, LUX_E_CUDA = -3, LUX_E_NO_DEVICE = -4 };
 
-#pragma pack(push, 1)
-typedef struct LuxHeader {            /* game.py:85-147 */
+/* Every field is naturally aligned; the aligned attribute lets device code move a record with
+ * one 8/16-byte access.  Section base addresses must be 16-byte aligned. */
+#define LUX_ALIGNED(n) __attribute__((aligned(n)))
+typedef struct LUX_ALIGNED(16) LuxHeader {            /* game.py:85-147 */
     int32_t  turn;
     int32_t  unit_id_count;            /* Game.global_unit_id_count */
     int32_t  city_id_count;            /* Game.global_city_id_count */
@@ -67,7 +69,7 @@ typedef struct LuxHeader {            /* game.py:85-147 */
     uint8_t  pad[28];
 } LuxHeader;
 
-typedef struct LuxCell {              /* cell.py:20-33, city.py:53-66 */
+typedef struct LUX_ALIGNED(8) LuxCell {              /* cell.py:20-33, city.py:53-66 */
     uint16_t amount;                   /* Resource.amount, 0 = none */
     uint8_t  flags;                    /* [1:0] resource type, [3:2] tile team+1, [6:4] adjacent_city_tiles */
     uint8_t  road_q;                   /* Cell.road * 4 */
@@ -76,7 +78,7 @@ typedef struct LuxCell {              /* cell.py:20-33, city.py:53-66 */
     uint16_t key;                      /* index in City.city_cells */
 } LuxCell;
 
-typedef struct LuxUnit {              /* unit.py:15-35 */
+typedef struct LUX_ALIGNED(16) LuxUnit {              /* unit.py:15-35 */
     int32_t  id;                       /* N of "u_N" */
     uint8_t  x, y;
     uint8_t  team_type;                /* bit0 team, bit1 cart */
@@ -85,7 +87,7 @@ typedef struct LuxUnit {              /* unit.py:15-35 */
     uint16_t pad;
 } LuxUnit;
 
-typedef struct LuxCity {              /* city.py:15-50 */
+typedef struct LUX_ALIGNED(16) LuxCity {              /* city.py:15-50 */
     int32_t  id;                       /* N of "c_N" */
     int32_t  fuel;
     uint16_t ntiles;
@@ -93,7 +95,14 @@ typedef struct LuxCity {              /* city.py:15-50 */
     uint8_t  team;
     uint8_t  pad[3];
 } LuxCity;
-#pragma pack(pop)
+
+#ifdef __cplusplus
+static_assert(sizeof(LuxHeader) == 128 && sizeof(LuxCell) == 8 && sizeof(LuxUnit) == 16 && sizeof(LuxCity) == 16,
+              "packed state layout");
+#else
+_Static_assert(sizeof(LuxHeader) == 128 && sizeof(LuxCell) == 8 && sizeof(LuxUnit) == 16 && sizeof(LuxCity) == 16,
+               "packed state layout");
+#endif
 
 typedef struct LuxBatch {
     int32_t n_matches;

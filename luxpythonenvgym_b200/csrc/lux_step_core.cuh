@@ -1,0 +1,902 @@
+// lux_step_core.cuh -- one Lux AI 2021 turn for one match, executed by one warp.
+//
+// The match's whole state (header, cell grid, units, cities, tile and resource lists,
+// action words) is staged in the warp's slice of shared memory, every phase of
+// Game.run_turn_with_actions (reference: luxai2021/game/game.py:390-535) runs there with
+// lanes striding over units / city tiles / resource cells, and the result is written back.
+// There is no block-level synchronisation: warps (matches) of a CTA are independent.
+//
+// This is a parallel re-derivation, not a transcription, of the reference's sequential
+// algorithm; oracle/lux_oracle.c keeps the sequential form and the tests compare the two:
+//   * spawn-cap validation (game.py:696-718) = per-team ordered prefix via ballots;
+//   * collision pruning (game.py:1104-1195)  = static seeds + fixpoint over per-cell flags;
+//   * collection (game.py:868-1001)          = per-resource-cell water-filling on a packed
+//     histogram of request amounts, then per-worker gather (the iterative equal split is
+//     closed-form: request i receives min(amount_i, final level));
+//   * order-dependent actions (transfer, build city, pillage; unit.py:162-197) run in unit
+//     order on lane 0, everything else is lane-parallel;
+//   * dead units / cities are compacted and the canonical orders (team A then B units,
+//     cities x city_cells tiles) rebuilt while storing.
+#pragma once
+#include "../../include/lux_b200.h"
+#include "lux_warp.cuh"
+
+// ---- game constants (luxai2021/game/game_constants.json:18-57) -------------------------
+#define LUX_DAY_LENGTH 30
+#define LUX_CYCLE_LENGTH 40
+#define LUX_MAX_DAYS 360
+#define LUX_UPKEEP_CITY 23
+#define LUX_UPKEEP_WORKER 4
+#define LUX_UPKEEP_CART 10
+#define LUX_MAX_WOOD 500
+#define LUX_CITY_BUILD_COST 100
+#define LUX_ADJ_BONUS 5
+#define LUX_CAP_WORKER 100
+#define LUX_CAP_CART 2000
+#define LUX_RESEARCH_COAL 50
+#define LUX_RESEARCH_URANIUM 200
+#define LUX_CITY_ACTION_COOLDOWN 10
+#define LUX_MAX_ROAD_Q 24
+#define LUX_ROAD_DEV_Q 3
+#define LUX_PILLAGE_Q 2
+
+// per-cell flag plane p1 (movement phase)
+#define P1_IN1 0x01u      // >= 1 validated move targets the cell
+#define P1_IN2 0x02u      // >= 2
+#define P1_STILL 0x04u    // a unit without a validated move stands here
+#define P1_BLOCKED 0x08u  // a reverted mover stays here
+#define P1_HAS1 0x10u     // >= 1 unit stands here
+#define P1_HAS2 0x20u     // >= 2
+
+// per-unit scratch byte ust: [2:0] held action kind, [5:3] move direction, flags
+#define UST_REVERTED 0x40u
+#define UST_FAILED 0x80u  // transfer raised KeyError in the reference: no cooldown, no cart road
+
+struct LuxSmemLayout {
+    int hdr, cells, units, cities, tiles, res, uact, tact, p1, occ, utgt, ust, umine, tmask, cprefix, cremap, total;
+};
+
+LUX_DEV int lux_align16(int x) { return (x + 15) & ~15; }
+
+#ifdef LUX_EMULATE
+static inline
+#else
+__host__ __device__ inline
+#endif
+LuxSmemLayout lux_smem_layout(int size, int u_cap, int c_cap, int t_cap, int r_cap) {
+    LuxSmemLayout L;
+    int ncell = size * size;
+    int o = 0;
+#define LUX_TAKE(field, bytes) L.field = o; o += (((bytes) + 15) & ~15);
+    LUX_TAKE(hdr, LUX_HDR_BYTES)
+    LUX_TAKE(cells, ncell * 8)
+    LUX_TAKE(units, u_cap * 16)
+    LUX_TAKE(cities, c_cap * 16)
+    LUX_TAKE(tiles, t_cap * 2)
+    LUX_TAKE(res, r_cap * 2)
+    LUX_TAKE(uact, u_cap * 4)
+    LUX_TAKE(tact, t_cap)
+    LUX_TAKE(p1, ncell)
+    LUX_TAKE(occ, ncell)
+    LUX_TAKE(utgt, u_cap * 2)
+    LUX_TAKE(ust, u_cap)
+    LUX_TAKE(umine, u_cap)
+    LUX_TAKE(tmask, t_cap * 4)
+    LUX_TAKE(cprefix, (c_cap + 1) * 2)
+    LUX_TAKE(cremap, c_cap)
+#undef LUX_TAKE
+    L.total = o;
+    return L;
+}
+
+struct LuxMatch {
+    LuxHeader* hdr;
+    LuxCell* cells;
+    LuxUnit* units;
+    LuxCity* cities;
+    uint16_t* tiles;
+    uint16_t* res;
+    uint32_t* uact;
+    uint8_t* tact;
+    uint8_t* p1;
+    uint8_t* occ;
+    uint16_t* utgt;
+    uint8_t* ust;
+    uint8_t* umine;
+    uint32_t* tmask;
+    uint16_t* cprefix;
+    uint8_t* cremap;
+    int S, ncell, u_cap, c_cap, t_cap, r_cap;
+};
+
+LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayout& L, int size, int u_cap,
+                            int c_cap, int t_cap, int r_cap) {
+    M.hdr = (LuxHeader*)(smem + L.hdr);
+    M.cells = (LuxCell*)(smem + L.cells);
+    M.units = (LuxUnit*)(smem + L.units);
+    M.cities = (LuxCity*)(smem + L.cities);
+    M.tiles = (uint16_t*)(smem + L.tiles);
+    M.res = (uint16_t*)(smem + L.res);
+    M.uact = (uint32_t*)(smem + L.uact);
+    M.tact = (uint8_t*)(smem + L.tact);
+    M.p1 = (uint8_t*)(smem + L.p1);
+    M.occ = (uint8_t*)(smem + L.occ);
+    M.utgt = (uint16_t*)(smem + L.utgt);
+    M.ust = (uint8_t*)(smem + L.ust);
+    M.umine = (uint8_t*)(smem + L.umine);
+    M.tmask = (uint32_t*)(smem + L.tmask);
+    M.cprefix = (uint16_t*)(smem + L.cprefix);
+    M.cremap = (uint8_t*)(smem + L.cremap);
+    M.S = size; M.ncell = size * size;
+    M.u_cap = u_cap; M.c_cap = c_cap; M.t_cap = t_cap; M.r_cap = r_cap;
+}
+
+// ---- staging a match into shared memory with plain 16-byte loads --------------------------
+// (the CUDA build normally uses cp.async.bulk instead, see lux_step.cu; this form is what the
+//  host emulation runs and the device falls back to when LUX_NO_TMA is defined)
+LUX_DEV void lux_copy16(void* dst, const void* src, int bytes) {   // bytes rounded up to 16
+    int lane = lux_lane();
+    const uint64_t* s = (const uint64_t*)src;
+    uint64_t* d = (uint64_t*)dst;
+    int n = (bytes + 15) / 16;
+    for (int i = lane; i < n; i += 32) { uint64_t a = s[2 * i], b = s[2 * i + 1]; d[2 * i] = a; d[2 * i + 1] = b; }
+}
+
+// ---- cell accessors ----------------------------------------------------------------------
+LUX_DEV int cell_is_tile(const LuxCell& c) { return (c.flags & 0x0C) != 0; }
+LUX_DEV int cell_tile_team(const LuxCell& c) { return ((c.flags >> 2) & 3) - 1; }
+LUX_DEV int cell_res_type(const LuxCell& c) { return c.flags & 3; }
+LUX_DEV int cell_adj(const LuxCell& c) { return (c.flags >> 4) & 7; }
+
+LUX_DEV int unit_team(const LuxUnit& u) { return u.team_type & 1; }
+LUX_DEV int unit_is_cart(const LuxUnit& u) { return (u.team_type >> 1) & 1; }
+LUX_DEV int unit_space(const LuxUnit& u) {   // unit.py:43-52
+    return (unit_is_cart(u) ? LUX_CAP_CART : LUX_CAP_WORKER) - ((int)u.wood + (int)u.coal + (int)u.uranium);
+}
+LUX_DEV int lux_dx(int dir) { return dir == LUX_DIR_EAST ? 1 : dir == LUX_DIR_WEST ? -1 : 0; }
+LUX_DEV int lux_dy(int dir) { return dir == LUX_DIR_SOUTH ? 1 : dir == LUX_DIR_NORTH ? -1 : 0; }
+
+// the five cells a worker mines from: own, N, E, S, W (game.py:950-951, game_map.py:484-508)
+LUX_DEV int lux_cell5(int S, int x, int y, int k) {
+    if (k == 0) return y * S + x;
+    if (k == 1) return y > 0 ? (y - 1) * S + x : -1;
+    if (k == 2) return x < S - 1 ? y * S + x + 1 : -1;
+    if (k == 3) return y < S - 1 ? (y + 1) * S + x : -1;
+    return x > 0 ? y * S + x - 1 : -1;
+}
+
+LUX_DEV void lux_zero16(void* p, int bytes) {   // bytes multiple of 16, p 16-byte aligned
+    int lane = lux_lane();
+    uint64_t* q = (uint64_t*)p;
+    for (int i = lane; i < bytes / 16; i += 32) { q[2 * i] = 0; q[2 * i + 1] = 0; }
+}
+
+// ---- collection of one resource type (game.py:882-1001) -----------------------------------
+LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researched0, int researched1) {
+    const int lane = lux_lane();
+    const int S = M.S;
+    LuxHeader* h = M.hdr;
+    const int rate = rtype == LUX_RES_WOOD ? 20 : rtype == LUX_RES_COAL ? 5 : 2;
+    const int fuel_rate = rtype == LUX_RES_WOOD ? 1 : rtype == LUX_RES_COAL ? 10 : 40;
+    const int n_res = h->n_res;
+
+    // W1: every eligible worker computes its request amount (create_resource_requests :933-967)
+    for (int u = lane; u < n_units; u += 32) {
+        LuxUnit& U = M.units[u];
+        int mine = 0xFF;
+        int team = unit_team(U);
+        if (!unit_is_cart(U) && (team ? researched1 : researched0)) {
+            int k = 0;
+            for (int j = 0; j < 5; j++) {
+                int c = lux_cell5(S, U.x, U.y, j);
+                if (c >= 0 && cell_res_type(M.cells[c]) == rtype && M.cells[c].amount > 0) k++;
+            }
+            if (k > 0) {
+                int space = unit_space(U);
+                mine = (space + k - 1) / k;
+                if (mine > rate) mine = rate;
+                int ucell = U.y * S + U.x;
+                const LuxCell& C = M.cells[ucell];
+                if (cell_is_tile(C)) {
+                    // requests from one city tile are de-duplicated by amount (:920-931, :964-966)
+                    int t = M.cprefix[C.city_slot] + C.key;
+                    lux_atomic_or(&M.tmask[t], 1u << mine);
+                }
+            }
+        }
+        M.umine[u] = (uint8_t)mine;
+    }
+    lux_sync();
+
+    // C: every resource cell of this type resolves its requests (resolve_resource_requests :969-1001)
+    for (int r = lane; r < n_res; r += 32) {
+        int c = M.res[r];
+        LuxCell& C = M.cells[c];
+        if (cell_res_type(C) != rtype) continue;
+        int level = 0;
+        if (C.amount > 0) {
+            int x = c % S, y = c / S;
+            // histogram of request amounts 0..20, 3 bits each (at most one request per amount and source cell)
+            uint64_t hist = 0;
+            int n = 0, sum = 0;
+            for (int j = 0; j < 5; j++) {
+                int p = lux_cell5(S, x, y, j);
+                if (p < 0) continue;
+                const LuxCell& P = M.cells[p];
+                if (cell_is_tile(P)) {
+                    unsigned mask = M.tmask[M.cprefix[P.city_slot] + P.key];
+                    while (mask) {
+                        int a = lux_ffs(mask) - 1;
+                        mask &= mask - 1;
+                        hist += (uint64_t)1 << (3 * a);
+                        n++; sum += a;
+                    }
+                } else {
+                    int o = M.occ[p];
+                    if (o) {
+                        int a = M.umine[o - 1];
+                        if (a != 0xFF) { hist += (uint64_t)1 << (3 * a); n++; sum += a; }
+                    }
+                }
+            }
+            if (n > 0 && sum > 0) {
+                int left = C.amount;
+                for (int a = 0; a <= 20 && n > 0 && left > 0; a++) {
+                    int cnt = (int)((hist >> (3 * a)) & 7);
+                    if (!cnt) continue;
+                    int minrem = a - level;
+                    int q = left / n;
+                    if (q >= minrem) {
+                        left -= minrem * n;
+                        level = a;
+                        if (left < n) left = 0;
+                        n -= cnt;
+                    } else {
+                        level += q;
+                        left = 0;
+                    }
+                }
+                C.amount = (uint16_t)left;
+                // city-tile requests are credited here (game.py:988-990)
+                if (level > 0) {
+                    for (int j = 0; j < 5; j++) {
+                        int p = lux_cell5(S, x, y, j);
+                        if (p < 0) continue;
+                        const LuxCell& P = M.cells[p];
+                        if (!cell_is_tile(P)) continue;
+                        unsigned mask = M.tmask[M.cprefix[P.city_slot] + P.key];
+                        int got = 0;
+                        while (mask) {
+                            int a = lux_ffs(mask) - 1;
+                            mask &= mask - 1;
+                            got += a < level ? a : level;
+                        }
+                        if (got) {
+                            LuxCity& city = M.cities[P.city_slot];
+                            lux_atomic_add(&city.fuel, got * fuel_rate);
+                            lux_atomic_add(&h->collected[city.team][rtype - 1], got);
+                        }
+                    }
+                }
+            }
+        }
+        M.p1[c] = (uint8_t)level;
+    }
+    lux_sync();
+
+    // W2: workers off city tiles take min(request, level) from each cell, capped by cargo space
+    int got0 = 0, got1 = 0;
+    for (int u = lane; u < n_units; u += 32) {
+        LuxUnit& U = M.units[u];
+        int mine = M.umine[u];
+        if (mine == 0xFF) continue;
+        int ucell = U.y * S + U.x;
+        const LuxCell& C = M.cells[ucell];
+        if (cell_is_tile(C)) {
+            M.tmask[M.cprefix[C.city_slot] + C.key] = 0;   // leave the mask plane clean for the next type
+            continue;
+        }
+        int gain = 0;
+        for (int j = 0; j < 5; j++) {
+            int c = lux_cell5(S, U.x, U.y, j);
+            if (c >= 0 && cell_res_type(M.cells[c]) == rtype) {
+                int lv = M.p1[c];
+                gain += mine < lv ? mine : lv;
+            }
+        }
+        int space = unit_space(U);
+        if (gain > space) gain = space;
+        if (rtype == LUX_RES_WOOD) U.wood = (uint16_t)(U.wood + gain);
+        else if (rtype == LUX_RES_COAL) U.coal = (uint16_t)(U.coal + gain);
+        else U.uranium = (uint16_t)(U.uranium + gain);
+        if (unit_team(U)) got1 += gain; else got0 += gain;
+    }
+    got0 = lux_reduce_add(got0);
+    got1 = lux_reduce_add(got1);
+    if (lane == 0) {
+        h->collected[0][rtype - 1] += got0;
+        h->collected[1][rtype - 1] += got1;
+    }
+    lux_sync();
+}
+
+// exclusive prefix of city tile counts -> M.cprefix[0..n_cities]
+LUX_DEV void lux_city_prefix(LuxMatch& M, int n_cities) {
+    const int lane = lux_lane();
+    int run = 0;
+    for (int base = 0; base < n_cities; base += 32) {
+        int s = base + lane;
+        int v = s < n_cities ? M.cities[s].ntiles : 0;
+        int tot;
+        int ex = lux_exscan_add(v, &tot);
+        if (s < n_cities) M.cprefix[s] = (uint16_t)(run + ex);
+        run += tot;
+    }
+    if (lane == 0) M.cprefix[n_cities] = (uint16_t)run;
+    lux_sync();
+}
+
+// ---- build a city tile under unit `u` (spawn_city_tile game.py:798-854); lane 0 only ---------
+LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tiles) {
+    LuxHeader* h = M.hdr;
+    LuxUnit& U = M.units[u];
+    const int S = M.S;
+    const int team = unit_team(U);
+    const int idx = U.y * S + U.x;
+    LuxCell& C = M.cells[idx];
+    int same[4], nsame = 0, found[4], nfound = 0;
+    for (int j = 1; j < 5; j++) {
+        int p = lux_cell5(S, U.x, U.y, j);
+        if (p < 0) continue;
+        const LuxCell& P = M.cells[p];
+        if (cell_is_tile(P) && cell_tile_team(P) == team) {
+            same[nsame++] = p;
+            int seen = 0;
+            for (int f = 0; f < nfound; f++) seen |= (found[f] == P.city_slot);
+            if (!seen) found[nfound++] = P.city_slot;
+        }
+    }
+    if (n_tiles >= M.t_cap) { h->status |= LUX_ST_TILE_OVERFLOW; return; }
+    if (nsame == 0) {
+        if (n_cities >= M.c_cap) { h->status |= LUX_ST_CITY_OVERFLOW; return; }
+        LuxCity& city = M.cities[n_cities];
+        city.id = ++h->city_id_count;
+        city.fuel = 0; city.ntiles = 1; city.adjsum = 0; city.team = (uint8_t)team;
+        city.pad[0] = city.pad[1] = city.pad[2] = 0;
+        C.flags = (uint8_t)((C.flags & 0x03) | ((team + 1) << 2));
+        C.tile_cd = 0; C.city_slot = (uint8_t)n_cities; C.key = 0;
+        M.tiles[n_tiles++] = (uint16_t)idx;
+        n_cities++;
+        return;
+    }
+    const int cid = found[0];
+    LuxCity& city = M.cities[cid];
+    C.flags = (uint8_t)((C.flags & 0x03) | ((team + 1) << 2) | (nsame << 4));
+    C.tile_cd = 0; C.city_slot = (uint8_t)cid; C.key = city.ntiles;
+    for (int k = 0; k < nsame; k++) M.cells[same[k]].flags = (uint8_t)(M.cells[same[k]].flags + 0x10);
+    city.ntiles = (uint16_t)(city.ntiles + 1);
+    city.adjsum = (uint16_t)(city.adjsum + 2 * nsame);
+    M.tiles[n_tiles++] = (uint16_t)idx;
+    for (int f = 1; f < nfound; f++) {      // merge the other adjacent cities (:844-852)
+        LuxCity& old = M.cities[found[f]];
+        int base = city.ntiles;
+        for (int t = 0; t < n_tiles; t++) {
+            LuxCell& T = M.cells[M.tiles[t]];
+            if (cell_is_tile(T) && T.city_slot == found[f]) {
+                T.city_slot = (uint8_t)cid;
+                T.key = (uint16_t)(T.key + base);
+            }
+        }
+        city.ntiles = (uint16_t)(city.ntiles + old.ntiles);
+        city.adjsum = (uint16_t)(city.adjsum + old.adjsum);
+        city.fuel += old.fuel;
+        old.ntiles = 0; old.adjsum = 0; old.fuel = 0;
+    }
+}
+
+// ---- the turn ------------------------------------------------------------------------------
+// On entry the match is staged in shared memory (M.hdr, cells, units[0..n_units), cities,
+// tiles, res, uact, tact) and hdr.done == 0.  On exit shared memory holds the post-turn
+// cells/header/cities(uncompacted)/units(uncompacted, ust says who died); the caller's
+// store routine (lux_store_match) compacts while writing.  Returns packed flags:
+//   bit0 tiles list must be rewritten, [31:16] n_units (incl. spawned), others via hdr.
+struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; };
+
+LUX_DEV LuxTurnOut lux_turn(LuxMatch& M) {
+    const int lane = lux_lane();
+    const unsigned lt = lux_lanemask_lt();
+    LuxHeader* h = M.hdr;
+    const int S = M.S;
+    const int n_units0 = h->n_units;
+    const int n_tiles0 = h->n_tiles;
+    int n_cities = h->n_cities;
+    int n_tiles = n_tiles0;
+    const int turn = h->turn;
+    const int night = (turn % LUX_CYCLE_LENGTH) >= LUX_DAY_LENGTH;   // game.py:1197-1204
+    const int mult = night ? 2 : 1;
+    int tiles_dirty = 0;
+
+    lux_zero16(M.p1, lux_align16(M.ncell));
+    lux_zero16(M.tmask, lux_align16(M.t_cap * 4));
+
+    // ---- team city-tile counts (worker_unit_cap_reached game.py:725-735)
+    int tt0 = 0, tt1 = 0;
+    for (int s = lane; s < n_cities; s += 32) {
+        if (M.cities[s].team) tt1 += M.cities[s].ntiles; else tt0 += M.cities[s].ntiles;
+    }
+    tt0 = lux_reduce_add(tt0);
+    tt1 = lux_reduce_add(tt1);
+    const int tu0 = h->n_team_units[0], tu1 = h->n_team_units[1];
+
+    // ---- unit action validation (validate_command game.py:646-695), lanes over units
+    for (int u = lane; u < n_units0; u += 32) {
+        const LuxUnit& U = M.units[u];
+        unsigned w = M.uact[u];
+        int kind = w & 7;
+        int ucell = U.y * S + U.x;
+        const LuxCell& C = M.cells[ucell];
+        unsigned st = 0;
+        int tgt = ucell;
+        if (kind == LUX_UA_BCITY) {
+            if (!cell_is_tile(C) && C.amount == 0 && U.cd_q < 4 &&
+                (int)U.wood + (int)U.coal + (int)U.uranium >= LUX_CITY_BUILD_COST) st = kind;
+        } else if (kind == LUX_UA_MOVE) {
+            int dir = (w >> 3) & 7;
+            if (U.cd_q < 4 && dir <= 4) {
+                int ok = 1;
+                if (dir != LUX_DIR_CENTER) {
+                    int nx = U.x + lux_dx(dir), ny = U.y + lux_dy(dir);
+                    if (nx < 0 || ny < 0 || nx >= S || ny >= S) ok = 0;
+                    else {
+                        tgt = ny * S + nx;
+                        const LuxCell& T = M.cells[tgt];
+                        if (cell_is_tile(T) && cell_tile_team(T) != unit_team(U)) ok = 0;
+                    }
+                }
+                if (ok) st = kind | (dir << 3);
+            }
+        } else if (kind == LUX_UA_PILLAGE || kind == LUX_UA_TRANSFER) {
+            st = kind;                                             // game.py:721-723: no check
+        }
+        M.ust[u] = (uint8_t)st;
+        M.utgt[u] = (uint16_t)tgt;
+    }
+    lux_sync();
+
+    // ---- collision pruning (handle_movement_actions game.py:1104-1195)
+    for (int u = lane; u < n_units0; u += 32) {
+        const LuxUnit& U = M.units[u];
+        int ucell = U.y * S + U.x;
+        unsigned st = M.ust[u];
+        int moving = (st & 7) == LUX_UA_MOVE;
+        unsigned old = lux_atomic_or_byte(M.p1, ucell, P1_HAS1 | (moving ? 0u : P1_STILL));
+        if (old & P1_HAS1) lux_atomic_or_byte(M.p1, ucell, P1_HAS2);
+        if (moving) {
+            int t = M.utgt[u];
+            old = lux_atomic_or_byte(M.p1, t, P1_IN1);
+            if (old & P1_IN1) lux_atomic_or_byte(M.p1, t, P1_IN2);
+        }
+    }
+    lux_sync();
+    // seeds: >= 2 moves into a non-city cell, or one move into a non-city cell whose single
+    // occupant is not moving (:1164-1179)
+    for (int u = lane; u < n_units0; u += 32) {
+        unsigned st = M.ust[u];
+        if ((st & 7) != LUX_UA_MOVE) continue;
+        int t = M.utgt[u];
+        if (cell_is_tile(M.cells[t])) continue;
+        unsigned f = M.p1[t];
+        if ((f & P1_IN2) || ((f & P1_HAS1) && !(f & P1_HAS2) && (f & P1_STILL))) {
+            M.ust[u] = (uint8_t)(st | UST_REVERTED);
+            const LuxUnit& U = M.units[u];
+            int o = U.y * S + U.x;
+            if (!cell_is_tile(M.cells[o])) lux_atomic_or_byte(M.p1, o, P1_BLOCKED);
+        }
+    }
+    lux_sync();
+    // cascade (revert_action :1138-1156): a reverted mover blocks its own non-city cell
+    for (;;) {
+        int changed = 0;
+        for (int u = lane; u < n_units0; u += 32) {
+            unsigned st = M.ust[u];
+            if ((st & 7) != LUX_UA_MOVE || (st & UST_REVERTED)) continue;
+            int t = M.utgt[u];
+            if (cell_is_tile(M.cells[t])) continue;
+            if (M.p1[t] & P1_BLOCKED) {
+                M.ust[u] = (uint8_t)(st | UST_REVERTED);
+                const LuxUnit& U = M.units[u];
+                int o = U.y * S + U.x;
+                if (!cell_is_tile(M.cells[o])) lux_atomic_or_byte(M.p1, o, P1_BLOCKED);
+                changed = 1;
+            }
+        }
+        lux_sync();
+        if (!lux_any(changed)) break;
+    }
+
+    // ---- city tiles: spawn validation (game.py:696-718) + CityTile.turn (city.py:96-120)
+    int n_units = n_units0;
+    {
+        int acc0 = 0, acc1 = 0, spawned = 0, rp0 = 0, rp1 = 0;
+        int wb0 = 0, wb1 = 0, cb0 = 0, cb1 = 0;
+        const int uid0 = h->unit_id_count;
+        const int room = M.u_cap - n_units0;
+        for (int base = 0; base < n_tiles0; base += 32) {
+            int p = base + lane;
+            int valid = p < n_tiles0;
+            int code = valid ? M.tact[p] : 0;
+            int cell = valid ? M.tiles[p] : 0;
+            LuxCell& C = M.cells[cell];
+            int team = valid ? cell_tile_team(C) : 0;
+            int cd = C.tile_cd;
+            int cand = valid && (code == LUX_TA_BUILD_WORKER || code == LUX_TA_BUILD_CART) && cd < 1;
+            unsigned m0 = lux_ballot(cand && team == 0), m1 = lux_ballot(cand && team == 1);
+            int rank = team ? acc1 + lux_popc(m1 & lt) : acc0 + lux_popc(m0 & lt);
+            int ok = cand && ((team ? tu1 : tu0) + rank < (team ? tt1 : tt0));
+            acc0 += lux_popc(m0); acc1 += lux_popc(m1);
+            unsigned mok = lux_ballot(ok);
+            int srank = spawned + lux_popc(mok & lt);
+            spawned += lux_popc(mok);
+            int research = valid && code == LUX_TA_RESEARCH;
+            int acted = research;
+            if (ok) {
+                if (srank < room) {
+                    LuxUnit& N = M.units[n_units0 + srank];
+                    N.id = uid0 + 1 + srank;
+                    N.x = (uint8_t)(cell % S); N.y = (uint8_t)(cell / S);
+                    N.team_type = (uint8_t)(team | (code == LUX_TA_BUILD_CART ? 2 : 0));
+                    N.cd_q = 0; N.wood = 0; N.coal = 0; N.uranium = 0; N.pad = 0;
+                    M.ust[n_units0 + srank] = 0;
+                    M.uact[n_units0 + srank] = 0;
+                }
+                acted = 1;
+            }
+            int okroom = ok && srank < room;
+            wb0 += lux_popc(lux_ballot(okroom && team == 0 && code == LUX_TA_BUILD_WORKER));
+            wb1 += lux_popc(lux_ballot(okroom && team == 1 && code == LUX_TA_BUILD_WORKER));
+            cb0 += lux_popc(lux_ballot(okroom && team == 0 && code == LUX_TA_BUILD_CART));
+            cb1 += lux_popc(lux_ballot(okroom && team == 1 && code == LUX_TA_BUILD_CART));
+            rp0 += lux_popc(lux_ballot(research && team == 0));
+            rp1 += lux_popc(lux_ballot(research && team == 1));
+            if (valid) {
+                if (acted) cd = LUX_CITY_ACTION_COOLDOWN;
+                if (cd > 0) cd -= 1;
+                C.tile_cd = (uint8_t)cd;
+            }
+        }
+        int made = spawned < room ? spawned : room;
+        if (made < 0) made = 0;
+        n_units = n_units0 + made;
+        if (lane == 0) {
+            if (spawned > room) h->status |= LUX_ST_UNIT_OVERFLOW;
+            h->unit_id_count = uid0 + made;
+            h->workers_built[0] += wb0; h->workers_built[1] += wb1;
+            h->carts_built[0] += cb0; h->carts_built[1] += cb1;
+            h->research[0] += rp0; h->research[1] += rp1;
+        }
+    }
+    lux_sync();
+
+    // ---- unit turns (Worker.turn unit.py:162-197, Cart.turn :234-269)
+    // moves are conflict-free after pruning: lane-parallel
+    for (int u = lane; u < n_units0; u += 32) {
+        unsigned st = M.ust[u];
+        if ((st & 7) != LUX_UA_MOVE) continue;
+        int dir = (st >> 3) & 7;
+        if ((st & UST_REVERTED) || dir == LUX_DIR_CENTER) { M.ust[u] = 0; continue; }   // game.py:462-465
+        LuxUnit& U = M.units[u];
+        U.x = (uint8_t)(U.x + lux_dx(dir));
+        U.y = (uint8_t)(U.y + lux_dy(dir));
+    }
+    lux_sync();
+    // transfer / build city / pillage depend on unit order (team A then B == slot order)
+    for (int base = 0; base < n_units0; base += 32) {
+        int u = base + lane;
+        int k = u < n_units0 ? (M.ust[u] & 7) : 0;
+        unsigned pend = lux_ballot(k == LUX_UA_TRANSFER || k == LUX_UA_BCITY || k == LUX_UA_PILLAGE);
+        while (pend) {
+            int j = lux_ffs(pend) - 1;
+            pend &= pend - 1;
+            int su = base + j;
+            int kind = M.ust[su] & 7;
+            if (kind == LUX_UA_TRANSFER) {                           // transfer_resources game.py:1039-1057
+                unsigned w = M.uact[su];
+                int dest_id = (int)(w >> 17);
+                int steam = unit_team(M.units[su]);
+                int dest = -1;
+                for (int cb = 0; cb < n_units; cb += 32) {
+                    int v = cb + lane;
+                    int hit = v < n_units && M.units[v].id == dest_id && unit_team(M.units[v]) == steam;
+                    unsigned hm = lux_ballot(hit);
+                    if (hm) { dest = cb + lux_ffs(hm) - 1; break; }
+                }
+                if (lane == 0) {
+                    int r = (int)((w >> 3) & 3);
+                    if (dest < 0 || r > 2) {
+                        M.ust[su] = (uint8_t)(kind | UST_FAILED);
+                    } else {
+                        LuxUnit& A = M.units[su];
+                        LuxUnit& B = M.units[dest];
+                        uint16_t* ca = r == 0 ? &A.wood : r == 1 ? &A.coal : &A.uranium;
+                        int amt = (int)((w >> 6) & 2047);
+                        if (*ca < amt) amt = *ca;
+                        int sp = unit_space(B);
+                        if (sp < amt) amt = sp;
+                        *ca = (uint16_t)(*ca - amt);
+                        uint16_t* cbp = r == 0 ? &B.wood : r == 1 ? &B.coal : &B.uranium;
+                        *cbp = (uint16_t)(*cbp + amt);
+                    }
+                }
+            } else if (lane == 0) {
+                LuxUnit& U = M.units[su];
+                if (!unit_is_cart(U)) {
+                    if (kind == LUX_UA_BCITY) {
+                        lux_build_city_lane0(M, su, n_cities, n_tiles);
+                        int spent = 0;                                // expend_resources_for_city unit.py:146-160
+                        uint16_t* cg[3] = {&U.wood, &U.coal, &U.uranium};
+                        for (int r = 0; r < 3; r++) {
+                            if (spent + *cg[r] > LUX_CITY_BUILD_COST) { *cg[r] = (uint16_t)(*cg[r] - (LUX_CITY_BUILD_COST - spent)); break; }
+                            spent += *cg[r];
+                            *cg[r] = 0;
+                        }
+                    } else {                                          // pillage unit.py:188-192
+                        LuxCell& C = M.cells[U.y * S + U.x];
+                        C.road_q = (uint8_t)(C.road_q > LUX_PILLAGE_Q ? C.road_q - LUX_PILLAGE_Q : 0);
+                    }
+                }
+            }
+            lux_sync();
+        }
+    }
+    n_cities = lux_shfl(n_cities, 0);
+    n_tiles = lux_shfl(n_tiles, 0);
+    if (n_tiles != n_tiles0) tiles_dirty = 1;
+    // cooldowns of the acting units, then the carts' automatic roads (unit.py:196-197, :257-269)
+    {
+        int rb0 = 0, rb1 = 0;
+        for (int u = lane; u < n_units0; u += 32) {
+            unsigned st = M.ust[u];
+            LuxUnit& U = M.units[u];
+            int cart = unit_is_cart(U);
+            if ((st & 7) != 0 && !(st & UST_FAILED)) U.cd_q = (uint8_t)(U.cd_q + (cart ? 12 : 8) * mult);
+            if (cart && !(st & UST_FAILED)) {
+                LuxCell& C = M.cells[U.y * S + U.x];
+                if (!cell_is_tile(C) && C.road_q < LUX_MAX_ROAD_Q) {
+                    int r = C.road_q + LUX_ROAD_DEV_Q;
+                    C.road_q = (uint8_t)(r > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : r);
+                    if (unit_team(U)) rb1 += LUX_ROAD_DEV_Q; else rb0 += LUX_ROAD_DEV_Q;
+                }
+            }
+            M.ust[u] = 0;
+        }
+        rb0 = lux_reduce_add(rb0);
+        rb1 = lux_reduce_add(rb1);
+        if (lane == 0) { h->roads_built_q[0] += rb0; h->roads_built_q[1] += rb1; }
+    }
+    lux_sync();
+
+    // ---- resource collection: uranium, coal, wood (distribute_all_resources game.py:868-880)
+    {
+        lux_zero16(M.occ, lux_align16(M.ncell));
+        lux_city_prefix(M, n_cities);     // also syncs
+        int bad = 0;
+        for (int u = lane; u < n_units; u += 32) {
+            const LuxUnit& U = M.units[u];
+            int c = U.y * S + U.x;
+            if (!cell_is_tile(M.cells[c])) {
+                if (M.occ[c]) bad = 1;     // cannot happen in play: a non-city cell holds one unit
+                M.occ[c] = (uint8_t)(u + 1);
+            }
+        }
+        if (lux_any(bad) && lane == 0) h->status |= LUX_ST_BAD_STATE;
+        lux_sync();
+        int rp0 = h->research[0], rp1 = h->research[1];
+        if (rp0 >= LUX_RESEARCH_URANIUM || rp1 >= LUX_RESEARCH_URANIUM)
+            lux_collect_type(M, LUX_RES_URANIUM, n_units, rp0 >= LUX_RESEARCH_URANIUM, rp1 >= LUX_RESEARCH_URANIUM);
+        if (rp0 >= LUX_RESEARCH_COAL || rp1 >= LUX_RESEARCH_COAL)
+            lux_collect_type(M, LUX_RES_COAL, n_units, rp0 >= LUX_RESEARCH_COAL, rp1 >= LUX_RESEARCH_COAL);
+        lux_collect_type(M, LUX_RES_WOOD, n_units, 1, 1);
+    }
+
+    // ---- deposit (handle_resource_deposit game.py:1003-1023)
+    {
+        int fg0 = 0, fg1 = 0;
+        for (int u = lane; u < n_units; u += 32) {
+            LuxUnit& U = M.units[u];
+            const LuxCell& C = M.cells[U.y * S + U.x];
+            int team = unit_team(U);
+            if (cell_is_tile(C) && cell_tile_team(C) == team) {
+                int fuel = U.wood + 10 * U.coal + 40 * U.uranium;
+                if (fuel) lux_atomic_add(&M.cities[C.city_slot].fuel, fuel);
+                if (team) fg1 += fuel; else fg0 += fuel;
+                U.wood = 0; U.coal = 0; U.uranium = 0;
+            }
+        }
+        fg0 = lux_reduce_add(fg0);
+        fg1 = lux_reduce_add(fg1);
+        if (lane == 0) { h->fuel_generated[0] += fg0; h->fuel_generated[1] += fg1; }
+    }
+    lux_sync();
+
+    // ---- night (handle_night game.py:537-558)
+    if (night) {
+        int died = 0;
+        for (int s = lane; s < n_cities; s += 32) {
+            LuxCity& city = M.cities[s];
+            M.cremap[s] = 0;
+            if (city.ntiles == 0) continue;
+            int upkeep = LUX_UPKEEP_CITY * city.ntiles - LUX_ADJ_BONUS * city.adjsum;   // city.py:34-50
+            if (city.fuel < upkeep) { M.cremap[s] = 1; died = 1; }
+            else city.fuel -= upkeep;
+        }
+        lux_sync();
+        if (lux_any(died)) {
+            tiles_dirty = 1;
+            for (int t = lane; t < n_tiles; t += 32) {                // destroy_city :1059-1070
+                LuxCell& C = M.cells[M.tiles[t]];
+                if (cell_is_tile(C) && M.cremap[C.city_slot]) {
+                    C.flags &= 0x03;
+                    C.tile_cd = 0; C.city_slot = 0; C.key = 0;
+                    C.road_q = 0;
+                }
+            }
+            lux_sync();
+            for (int s = lane; s < n_cities; s += 32)
+                if (M.cremap[s]) { M.cities[s].ntiles = 0; M.cities[s].fuel = 0; M.cities[s].adjsum = 0; }
+            lux_sync();
+        }
+        for (int u = lane; u < n_units; u += 32) {                    // spend_fuel_to_survive unit.py:64-98
+            LuxUnit& U = M.units[u];
+            if (cell_is_tile(M.cells[U.y * S + U.x])) continue;
+            int need = unit_is_cart(U) ? LUX_UPKEEP_CART : LUX_UPKEEP_WORKER;
+            int used = U.wood < need ? U.wood : need;
+            need -= used; U.wood = (uint16_t)(U.wood - used);
+            if (need > 0) {
+                int want = (need + 9) / 10;
+                used = U.coal < want ? U.coal : want;
+                need -= used * 10; U.coal = (uint16_t)(U.coal - used);
+            }
+            if (need > 0) {
+                int want = (need + 39) / 40;
+                used = U.uranium < want ? U.uranium : want;
+                need -= used * 40; U.uranium = (uint16_t)(U.uranium - used);
+            }
+            if (need > 0) M.ust[u] = UST_FAILED;                      // dead: dropped while storing
+        }
+        lux_sync();
+    }
+
+    // ---- depleted cells leave the list (game.py:498-510), trees regrow (:1081-1102)
+    {
+        int n_res = h->n_res;
+        for (int r = lane; r < n_res; r += 32) {
+            LuxCell& C = M.cells[M.res[r]];
+            if (C.amount == 0) { C.flags &= 0xFC; continue; }
+            if (cell_res_type(C) == LUX_RES_WOOD && C.amount < LUX_MAX_WOOD) {
+                int a = (41 * (int)C.amount + 39) / 40;               // == ceil(min(a*1.025, 500)), tests/test_oracle_golden.py
+                C.amount = (uint16_t)(a > LUX_MAX_WOOD ? LUX_MAX_WOOD : a);
+            }
+        }
+    }
+    lux_sync();
+
+    LuxTurnOut out;
+    out.n_units = n_units; out.n_cities = n_cities; out.n_tiles = n_tiles; out.tiles_dirty = tiles_dirty;
+    return out;
+}
+
+// ---- epilogue: compaction, match_over, cooldowns, canonical tile order, store ---------------
+// g_* are the match's sections in global memory.
+LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g_hdr, LuxCell* g_cells,
+                                  LuxUnit* g_units, LuxCity* g_cities, uint16_t* g_tiles) {
+    const int lane = lux_lane();
+    const unsigned lt = lux_lanemask_lt();
+    LuxHeader* h = M.hdr;
+    const int S = M.S;
+
+    // cities: drop the dead (ntiles == 0), keep order
+    int n_alive = 0, nc0 = 0, nc1 = 0, tl0 = 0, tl1 = 0;
+    for (int base = 0; base < T.n_cities; base += 32) {
+        int s = base + lane;
+        int alive = s < T.n_cities && M.cities[s].ntiles > 0;
+        unsigned m = lux_ballot(alive);
+        if (s < T.n_cities) M.cremap[s] = (uint8_t)(alive ? n_alive + lux_popc(m & lt) : 0xFF);
+        n_alive += lux_popc(m);
+        int team = alive ? M.cities[s].team : 0;
+        nc0 += alive && team == 0; nc1 += alive && team == 1;
+        if (alive) { if (team) tl1 += M.cities[s].ntiles; else tl0 += M.cities[s].ntiles; }
+    }
+    nc0 = lux_reduce_add(nc0); nc1 = lux_reduce_add(nc1);
+    tl0 = lux_reduce_add(tl0); tl1 = lux_reduce_add(tl1);
+    lux_sync();
+    const int cities_moved = n_alive != T.n_cities;
+    if (cities_moved) {
+        for (int t = lane; t < T.n_tiles; t += 32) {
+            LuxCell& C = M.cells[M.tiles[t]];
+            if (cell_is_tile(C)) C.city_slot = M.cremap[C.city_slot];
+        }
+    }
+    // store cities compacted
+    for (int s = lane; s < T.n_cities; s += 32) {
+        int ns = M.cremap[s];
+        if (ns != 0xFF) g_cities[ns] = M.cities[s];
+    }
+    // canonical tile list: position = prefix[new slot] + key
+    int n_tiles_live = tl0 + tl1;
+    if (T.tiles_dirty || cities_moved) {
+        int run = 0;
+        for (int base = 0; base < T.n_cities; base += 32) {
+            int s = base + lane;
+            int v = (s < T.n_cities) ? M.cities[s].ntiles : 0;   // dead cities have 0 tiles
+            int tot;
+            int ex = lux_exscan_add(v, &tot);
+            if (s < T.n_cities && v > 0) M.cprefix[M.cremap[s]] = (uint16_t)(run + ex);
+            run += tot;
+        }
+        lux_sync();
+        for (int t = lane; t < T.n_tiles; t += 32) {
+            int cell = M.tiles[t];
+            const LuxCell& C = M.cells[cell];
+            if (cell_is_tile(C)) g_tiles[M.cprefix[C.city_slot] + C.key] = (uint16_t)cell;
+        }
+    }
+
+    // match_over (game.py:570-592) is evaluated before the turn counter moves (:515-517)
+    int alive0 = 0, alive1 = 0;
+    for (int u = lane; u < T.n_units; u += 32) {
+        if (M.ust[u] & UST_FAILED) continue;
+        if (unit_team(M.units[u])) alive1++; else alive0++;
+    }
+    alive0 = lux_reduce_add(alive0);
+    alive1 = lux_reduce_add(alive1);
+    int over = h->turn >= LUX_MAX_DAYS - 1 || (alive0 + nc0 == 0) || (alive1 + nc1 == 0);
+
+    // run_cooldowns (game.py:560-568) and the stable partition team A | team B while storing
+    int run0 = 0, run1 = 0;
+    for (int base = 0; base < T.n_units; base += 32) {
+        int u = base + lane;
+        int valid = u < T.n_units && !(M.ust[u] & UST_FAILED);
+        int team = valid ? unit_team(M.units[u]) : 0;
+        unsigned m0 = lux_ballot(valid && team == 0), m1 = lux_ballot(valid && team == 1);
+        if (valid) {
+            LuxUnit U = M.units[u];
+            const LuxCell& C = M.cells[U.y * S + U.x];
+            int road = cell_is_tile(C) ? LUX_MAX_ROAD_Q : C.road_q;    // cell.py:77-85
+            int cd = (int)U.cd_q - road - 4;
+            U.cd_q = (uint8_t)(cd > 0 ? cd : 0);
+            U.pad = 0;
+            int dst = team ? alive0 + run1 + lux_popc(m1 & lt) : run0 + lux_popc(m0 & lt);
+            g_units[dst] = U;
+        }
+        run0 += lux_popc(m0); run1 += lux_popc(m1);
+    }
+
+    if (lane == 0) {
+        h->turn += 1;
+        h->n_units = (uint16_t)(alive0 + alive1);
+        h->n_team_units[0] = (uint16_t)alive0;
+        h->n_team_units[1] = (uint16_t)alive1;
+        h->n_cities = (uint16_t)n_alive;
+        h->n_tiles = (uint16_t)n_tiles_live;
+        if (over) {
+            h->done = 1;
+            int w;                                                     // get_winning_team game.py:594-634
+            if (tl0 != tl1) w = tl0 > tl1 ? LUX_WIN_A : LUX_WIN_B;
+            else if (alive0 != alive1) w = alive0 > alive1 ? LUX_WIN_A : LUX_WIN_B;
+            else if (h->fuel_generated[0] != h->fuel_generated[1])
+                w = h->fuel_generated[0] > h->fuel_generated[1] ? LUX_WIN_A : LUX_WIN_B;
+            else w = LUX_WIN_TIE;
+            h->winner = (uint8_t)w;
+        }
+    }
+    lux_sync();
+    // cells and header: straight 16-byte copies
+    {
+        const uint64_t* s = (const uint64_t*)M.cells;
+        uint64_t* d = (uint64_t*)g_cells;
+        for (int i = lane; i < M.ncell; i += 32) d[i] = s[i];
+        const uint64_t* hs = (const uint64_t*)M.hdr;
+        uint64_t* hd = (uint64_t*)g_hdr;
+        if (lane < LUX_HDR_BYTES / 8) hd[lane] = hs[lane];
+    }
+}

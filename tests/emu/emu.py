@@ -1,0 +1,53 @@
+"""TEST INFRASTRUCTURE ONLY -- builds/loads the host emulation of the CUDA turn engine.
+
+tests/emu/emu_step.cpp compiles luxpythonenvgym_b200/csrc/lux_step_core.cuh with g++ and a
+32-fiber warp emulator, so the kernel's logic can be diffed against the oracle on CPU.
+Nothing in the product imports this.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from oracle.coracle import LuxBatchC, _p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        out = os.path.join(_HERE, "_build", "liblux_emu.so")
+        csrc = os.path.join(_ROOT, "luxpythonenvgym_b200", "csrc")
+        srcs = [os.path.join(_HERE, "emu_step.cpp"), os.path.join(_HERE, "warp_emu.h"),
+                os.path.join(_ROOT, "include", "lux_b200.h")]
+        srcs += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+        if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.run(["g++", "-O2", "-g", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas",
+                            "-I", _HERE, "-o", out, srcs[0]], check=True)
+        _LIB = ctypes.CDLL(out)
+    return _LIB
+
+
+def step(ms, unit_words, tile_bytes):
+    """One turn of one MatchState in place through the emulated kernel."""
+    L = lib()
+    hdr = ms.hdr.reshape(1)
+    uw = np.zeros(len(ms.units), dtype=np.uint32)
+    tb = np.zeros(len(ms.tiles), dtype=np.uint8)
+    if unit_words is not None:
+        uw[:] = unit_words[: len(uw)]
+    if tile_bytes is not None:
+        tb[:] = tile_bytes[: len(tb)]
+    b = LuxBatchC(1, ms.size, len(ms.units), len(ms.cities), len(ms.tiles), len(ms.res),
+                  hdr.ctypes.data, ms.cells.ctypes.data, ms.units.ctypes.data, ms.cities.ctypes.data,
+                  ms.tiles.ctypes.data, ms.res.ctypes.data)
+    rc = L.lux_emu_step(ctypes.byref(b), _p(uw), _p(tb))
+    ms.hdr = hdr[0]
+    if rc != 0:
+        raise RuntimeError("lux_emu_step -> %d" % rc)
+    return bool(ms.hdr["done"])

@@ -1,0 +1,66 @@
+// emu_step.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the CUDA turn engine's source (luxpythonenvgym_b200/csrc/lux_step_core.cuh) for the
+// host with the warp emulator of warp_emu.h and exposes it with the same batch signature as
+// lux_b200_step, so tests can diff the kernel's logic against the oracle without a GPU.
+// Built by tests/emu/build.py into tests/emu/_build/ ; never loaded by the product.
+#define LUX_EMULATE 1
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../luxpythonenvgym_b200/csrc/lux_step_core.cuh"
+
+struct EmuArgs {
+    const LuxBatch* b;
+    int m;
+    const uint32_t* ua;
+    const uint8_t* ta;
+    unsigned char* smem;
+    LuxSmemLayout L;
+};
+
+static void emu_lane(void* p) {
+    EmuArgs* a = (EmuArgs*)p;
+    const LuxBatch* b = a->b;
+    int m = a->m;
+    int ncell = b->size * b->size;
+    LuxMatch M;
+    lux_match_bind(M, a->smem, a->L, b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    LuxHeader* g_hdr = b->hdr + m;
+    LuxCell* g_cells = b->cells + (size_t)m * ncell;
+    LuxUnit* g_units = b->units + (size_t)m * b->u_cap;
+    LuxCity* g_cities = b->cities + (size_t)m * b->c_cap;
+    uint16_t* g_tiles = b->tiles + (size_t)m * b->t_cap;
+    uint16_t* g_res = b->res + (size_t)m * b->r_cap;
+    lux_copy16(M.hdr, g_hdr, LUX_HDR_BYTES);
+    lux_sync();
+    if (M.hdr->done) return;
+    lux_copy16(M.cells, g_cells, ncell * 8);
+    lux_copy16(M.units, g_units, M.hdr->n_units * 16);
+    lux_copy16(M.cities, g_cities, M.hdr->n_cities * 16);
+    lux_copy16(M.tiles, g_tiles, M.hdr->n_tiles * 2);
+    lux_copy16(M.res, g_res, M.hdr->n_res * 2);
+    lux_copy16(M.uact, a->ua + (size_t)m * b->u_cap, M.hdr->n_units * 4);
+    lux_copy16(M.tact, a->ta + (size_t)m * b->t_cap, M.hdr->n_tiles);
+    lux_sync();
+    LuxTurnOut T = lux_turn(M);
+    lux_finish_and_store(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
+}
+
+extern "C" size_t lux_emu_smem_bytes(int size, int u_cap, int c_cap, int t_cap, int r_cap) {
+    return (size_t)lux_smem_layout(size, u_cap, c_cap, t_cap, r_cap).total;
+}
+
+extern "C" int lux_emu_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions) {
+    if (!b || !unit_actions || !tile_actions) return LUX_E_ARG;
+    EmuArgs a;
+    a.b = b; a.ua = unit_actions; a.ta = tile_actions;
+    a.L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    a.smem = (unsigned char*)aligned_alloc(16, a.L.total);
+    for (int m = 0; m < b->n_matches; m++) {
+        memset(a.smem, 0xA5, a.L.total);   // shared memory is not zero-initialised on the device either
+        a.m = m;
+        warp_emu::run_warp(emu_lane, &a);
+    }
+    free(a.smem);
+    return 0;
+}
