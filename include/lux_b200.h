@@ -120,6 +120,10 @@ typedef struct LuxBatch {
 int lux_b200_version(void);
 int lux_b200_device_count(void);
 
+/* Tuning knobs: "tma" (1 = cp.async.bulk staging, 0 = plain vector loads/stores),
+ * "warps_per_cta" (0 = automatic).  Returns LUX_E_ARG for an unknown name. */
+int lux_b200_set_option(const char* name, int value);
+
 /* Dynamic shared memory one match needs in lux_b200_step for these capacities. */
 size_t lux_b200_step_smem_bytes(int size, int u_cap, int c_cap, int t_cap, int r_cap);
 
@@ -153,9 +157,12 @@ int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,
  * Canonical seeded action stream, written as packed action
  * tensors for every live match: action = f(hash64(seed, match_id_base+m, turn, kind, key)).
  * Harness utility (benchmarks, parity tests); a policy normally fills the tensors itself.
+ * counters (device uint64[2], may be NULL): [0] += live matches, [1] += algorithmic bytes of
+ * the turn about to run, 2*(8*S^2 + 16*U + 16*K + 64) + 4*(U+T) per live match.
  */
 int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t match_id_base,
-                         uint32_t* unit_actions, uint8_t* tile_actions, void* cuda_stream);
+                         uint32_t* unit_actions, uint8_t* tile_actions, uint64_t* counters,
+                         void* cuda_stream);
 
 /*
  * Per-entity observation tensors for team `team_sel[m]` of every match.
@@ -171,11 +178,12 @@ int lux_b200_observe(const LuxBatch* b, const uint8_t* team_sel, float* obs, int
 
 /*
  * Replace every finished match (hdr.done != 0) by a fresh one copied from a pool of
- * initial states (same size/capacities), round-robin from `pool_cursor[0]`.
+ * initial states (same size/capacities); the pool entry is a hash of (match index, epoch)
+ * so that a run is replayable.
  * Replaces: Game.reset(), luxai2021/game/game.py:76-157 (map generation itself stays on
- * the host: luxpythonenvgym_b200/mapgen.py).  reset_count (device int32[1]) += resets.
+ * the host: luxpythonenvgym_b200/mapgen.py).  reset_count (device int32[1], may be NULL) += resets.
  */
-int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, int32_t* pool_cursor,
+int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, uint32_t epoch,
                         int32_t* reset_count, void* cuda_stream);
 
 /*

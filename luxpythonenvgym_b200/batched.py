@@ -1,0 +1,120 @@
+"""BatchedGame: thousands of independent Lux AI 2021 matches resident on one GPU.
+
+Host-side mirror of the reference's `Game` for the per-turn path
+(luxai2021/game/game.py:390 `run_turn_with_actions`), batched: `step(unit_actions,
+tile_actions)` advances every live match by one turn with one kernel launch.  State lives
+in six torch uint8 tensors (one per section of luxpythonenvgym_b200/state.py); torch is
+only the allocator / stream provider, all compute is in _lux_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import state as S
+
+
+class BatchedGame:
+    def __init__(self, n_matches, size, caps=None, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedGame needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.n = int(n_matches)
+        self.size = int(size)
+        self.caps = dict(S.default_caps(size), **(caps or {}))
+        self.device = torch.device(device)
+        c = self.caps
+        ncell = size * size
+        z = lambda *shape: torch.zeros(shape, dtype=torch.uint8, device=self.device)
+        self.hdr = z(self.n, S.HDR_BYTES)
+        self.cells = z(self.n, ncell * 8)
+        self.units = z(self.n, c["units"] * 16)
+        self.cities = z(self.n, c["cities"] * 16)
+        self.tiles = z(self.n, c["tiles"] * 2)
+        self.res = z(self.n, c["res"] * 2)
+        self.unit_actions = torch.zeros((self.n, c["units"]), dtype=torch.int32, device=self.device)
+        self.tile_actions = z(self.n, c["tiles"])
+        self._stats = torch.zeros(16, dtype=torch.int64, device=self.device)
+        self._desc = self._make_desc()
+        # a fresh batch is "done" until states are loaded
+        self.hdr[:, 24] = 1
+
+    # ------------------------------------------------------------------ plumbing
+    def _make_desc(self):
+        c = self.caps
+        return _lib.LuxBatch(self.n, self.size, c["units"], c["cities"], c["tiles"], c["res"],
+                             self.hdr.data_ptr(), self.cells.data_ptr(), self.units.data_ptr(),
+                             self.cities.data_ptr(), self.tiles.data_ptr(), self.res.data_ptr())
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sections(self):
+        return {"hdr": self.hdr, "cells": self.cells, "units": self.units, "cities": self.cities,
+                "tiles": self.tiles, "res": self.res}
+
+    # ------------------------------------------------------------------ state import / export
+    def load_states(self, states, first=0):
+        """Copy a list of MatchState (host) into matches first..first+len-1."""
+        k = len(states)
+        host = {name: np.zeros((k,) + tuple(t.shape[1:]), dtype=np.uint8) for name, t in self.sections().items()}
+        for i, ms in enumerate(states):
+            assert ms.size == self.size
+            for name, arr in ms.to_bytes().items():
+                assert arr.size <= host[name].shape[1], "MatchState %s exceeds batch capacity" % name
+                host[name][i, : arr.size] = arr
+        for name, t in self.sections().items():
+            t[first:first + k].copy_(torch.from_numpy(host[name]))
+
+    def export_states(self, indices=None):
+        """MatchState copies (host) of the given matches (default: all)."""
+        idx = list(range(self.n)) if indices is None else list(indices)
+        it = torch.as_tensor(idx, device=self.device, dtype=torch.long)
+        host = {name: t.index_select(0, it).cpu().numpy() for name, t in self.sections().items()}
+        return [S.MatchState.from_arrays(self.size, {name: host[name][i] for name in host}) for i in range(len(idx))]
+
+    def headers(self):
+        """Structured numpy view of all headers (one D2H copy)."""
+        return self.hdr.cpu().numpy().view(S.header_dtype).reshape(self.n)
+
+    # ------------------------------------------------------------------ the hot path
+    def step(self, unit_actions=None, tile_actions=None):
+        """One turn for every live match.  Actions default to this object's action tensors."""
+        ua = self.unit_actions if unit_actions is None else unit_actions
+        ta = self.tile_actions if tile_actions is None else tile_actions
+        assert ua.is_cuda and ta.is_cuda and ua.is_contiguous() and ta.is_contiguous()
+        assert ua.numel() == self.n * self.caps["units"] and ua.element_size() == 4
+        assert ta.numel() == self.n * self.caps["tiles"] and ta.element_size() == 1
+        _lib.check(self.lib.lux_b200_step(ctypes.byref(self._desc), ua.data_ptr(), ta.data_ptr(), self._stream()),
+                   "lux_b200_step")
+
+    def step_host(self, unit_actions_host, tile_actions_host, hdr_host=None, done_host=None):
+        """The same turn from HOST (pinned) action buffers; copies back headers/done flags."""
+        _lib.check(self.lib.lux_b200_step_host(
+            ctypes.byref(self._desc), unit_actions_host.data_ptr(), tile_actions_host.data_ptr(),
+            self.unit_actions.data_ptr(), self.tile_actions.data_ptr(),
+            done_host.data_ptr() if done_host is not None else None,
+            hdr_host.data_ptr() if hdr_host is not None else None, self._stream()), "lux_b200_step_host")
+
+    def gen_actions(self, seed, match_id_base=0, unit_actions=None, tile_actions=None, counters=None):
+        """Fill the action tensors from the canonical seeded stream (harness utility)."""
+        ua = self.unit_actions if unit_actions is None else unit_actions
+        ta = self.tile_actions if tile_actions is None else tile_actions
+        _lib.check(self.lib.lux_b200_gen_actions(ctypes.byref(self._desc), seed, match_id_base,
+                                                 ua.data_ptr(), ta.data_ptr(),
+                                                 counters.data_ptr() if counters is not None else None,
+                                                 self._stream()), "lux_b200_gen_actions")
+
+    def reset_done(self, pool, epoch, reset_count=None):
+        """Replace finished matches by pool entries chosen by hash(match, epoch)."""
+        _lib.check(self.lib.lux_b200_reset_done(ctypes.byref(self._desc), ctypes.byref(pool._desc),
+                                                int(epoch) & 0xFFFFFFFF,
+                                                reset_count.data_ptr() if reset_count is not None else None,
+                                                self._stream()), "lux_b200_reset_done")
+
+    def stats(self):
+        """Device int64[16] episode statistics (see include/lux_b200.h lux_b200_stats)."""
+        _lib.check(self.lib.lux_b200_stats(ctypes.byref(self._desc), self._stats.data_ptr(), self._stream()),
+                   "lux_b200_stats")
+        return self._stats

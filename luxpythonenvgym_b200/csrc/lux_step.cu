@@ -1,0 +1,427 @@
+// lux_step.cu -- sm_100a kernels and the C ABI (include/lux_b200.h) of the batched turn engine.
+//
+// lux_step_kernel: one warp per match.  The warp's slice of dynamic shared memory holds the
+// whole match; it is filled by the TMA unit (cp.async.bulk global->shared, completion on a
+// per-warp mbarrier: 128-byte header first, then the live prefixes of every section), the
+// turn runs in shared memory (lux_step_core.cuh), and the cell grid + header go back with
+// cp.async.bulk shared->global while the compacted unit/city/tile lists are written with
+// plain vector stores.  No CPU fallback exists: without a device the entry points return
+// LUX_E_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "lux_step_core.cuh"
+
+#define LUX_B200_VERSION 100
+
+// ---------------------------------------------------------------- PTX helpers (TMA bulk copy + mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---------------------------------------------------------------- the step kernel
+template <bool kTma>
+__global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions,
+                                const uint8_t* __restrict__ tile_actions, LuxSmemLayout L) {
+    extern __shared__ __align__(128) unsigned char lux_smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (m >= b.n_matches) return;
+    unsigned char* smem = lux_smem + (size_t)warp * L.total;
+    const int ncell = b.size * b.size;
+    LuxMatch M;
+    lux_match_bind(M, smem, L, b.size, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
+    LuxHeader* g_hdr = b.hdr + m;
+    LuxCell* g_cells = b.cells + (size_t)m * ncell;
+    LuxUnit* g_units = b.units + (size_t)m * b.u_cap;
+    LuxCity* g_cities = b.cities + (size_t)m * b.c_cap;
+    uint16_t* g_tiles = b.tiles + (size_t)m * b.t_cap;
+    const uint16_t* g_res = b.res + (size_t)m * b.r_cap;
+    const uint32_t* g_ua = unit_actions + (size_t)m * b.u_cap;
+    const uint8_t* g_ta = tile_actions + (size_t)m * b.t_cap;
+
+    if (kTma) {
+        uint64_t* bar = (uint64_t*)(smem + L.mbar);
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(bar, LUX_HDR_BYTES);
+            tma_g2s(M.hdr, g_hdr, LUX_HDR_BYTES, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);
+        if (M.hdr->done) return;
+        const uint32_t nu = M.hdr->n_units, nc = M.hdr->n_cities, nt = M.hdr->n_tiles, nr = M.hdr->n_res;
+        const uint32_t b_cells = ncell * 8, b_units = nu * 16, b_cities = nc * 16;
+        const uint32_t b_tiles = (nt * 2 + 15) & ~15u, b_res = (nr * 2 + 15) & ~15u;
+        const uint32_t b_ua = (nu * 4 + 15) & ~15u, b_ta = (nt + 15) & ~15u;
+        if (lane == 0) {
+            mbar_expect_tx(bar, b_cells + b_units + b_cities + b_tiles + b_res + b_ua + b_ta);
+            tma_g2s(M.cells, g_cells, b_cells, bar);
+            if (b_units) tma_g2s(M.units, g_units, b_units, bar);
+            if (b_cities) tma_g2s(M.cities, g_cities, b_cities, bar);
+            if (b_tiles) tma_g2s(M.tiles, g_tiles, b_tiles, bar);
+            if (b_res) tma_g2s(M.res, g_res, b_res, bar);
+            if (b_ua) tma_g2s(M.uact, g_ua, b_ua, bar);
+            if (b_ta) tma_g2s(M.tact, g_ta, b_ta, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 1);
+    } else {
+        lux_copy16(M.hdr, g_hdr, LUX_HDR_BYTES);
+        __syncwarp();
+        if (M.hdr->done) return;
+        lux_copy16(M.cells, g_cells, ncell * 8);
+        lux_copy16(M.units, g_units, M.hdr->n_units * 16);
+        lux_copy16(M.cities, g_cities, M.hdr->n_cities * 16);
+        lux_copy16(M.tiles, g_tiles, M.hdr->n_tiles * 2);
+        lux_copy16(M.res, g_res, M.hdr->n_res * 2);
+        lux_copy16(M.uact, g_ua, M.hdr->n_units * 4);
+        lux_copy16(M.tact, g_ta, M.hdr->n_tiles);
+        __syncwarp();
+    }
+
+    LuxTurnOut T = lux_turn(M);
+
+    if (kTma) {
+        lux_finish_and_store<false>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
+        // every lane orders its own shared-memory writes before the async proxy reads them
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma_s2g(g_cells, M.cells, ncell * 8);
+            tma_s2g(g_hdr, M.hdr, LUX_HDR_BYTES);
+            tma_commit();
+            tma_wait_read0();
+        }
+    } else {
+        lux_finish_and_store<true>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
+    }
+}
+
+// ---------------------------------------------------------------- canonical action stream
+__device__ __forceinline__ uint64_t lux_mix64(uint64_t z) {
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+    z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return z;
+}
+__device__ __forceinline__ uint64_t lux_hash(uint64_t seed, uint64_t match, uint64_t turn, uint64_t kind, uint64_t key) {
+    const uint64_t G = 0x9E3779B97F4A7C15ULL;
+    uint64_t x = seed;
+    x = lux_mix64(x + G * (match + 1));
+    x = lux_mix64(x + G * (turn + 1));
+    x = lux_mix64(x + G * (kind + 1));
+    x = lux_mix64(x + G * (key + 1));
+    return x;
+}
+
+// one warp per match, state read in place from global memory (harness kernel, not the hot path)
+__global__ void lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match_id_base,
+                                       uint32_t* __restrict__ unit_actions, uint8_t* __restrict__ tile_actions,
+                                       unsigned long long* counters) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (m >= b.n_matches) return;
+    const int ncell = b.size * b.size, S = b.size;
+    const LuxHeader* h = b.hdr + m;
+    const LuxCell* cells = b.cells + (size_t)m * ncell;
+    const LuxUnit* units = b.units + (size_t)m * b.u_cap;
+    const uint16_t* tiles = b.tiles + (size_t)m * b.t_cap;
+    uint32_t* ua = unit_actions + (size_t)m * b.u_cap;
+    uint8_t* ta = tile_actions + (size_t)m * b.t_cap;
+    const int nu = h->n_units, nt = h->n_tiles, turn = h->turn, done = h->done;
+    if (counters && lane == 0 && !done) {
+        // live match-turns and their algorithmic bytes for the turn about to run
+        atomicAdd(counters, 1ULL);
+        atomicAdd(counters + 1, (unsigned long long)(2 * (8 * ncell + 16 * nu + 16 * (int)h->n_cities + 64) + 4 * (nu + nt)));
+    }
+    const uint64_t mid = match_id_base + (uint64_t)m;
+    for (int i = lane; i < b.u_cap; i += 32) {
+        uint32_t w = 0;
+        if (!done && i < nu) {
+            const LuxUnit U = units[i];
+            uint64_t r = lux_hash(seed, mid, (uint64_t)turn, 0, (uint64_t)U.id);
+            int can_act = U.cd_q < 4;
+            if (can_act || ((r >> 32) & 15) == 0) {
+                unsigned p = (unsigned)(r % 100);
+                const LuxCell C = cells[U.y * S + U.x];
+                int cargo = U.wood + U.coal + U.uranium;
+                int night = (turn % 40) >= 30;
+                int on_tile = (C.flags & 0x0C) != 0;
+                int can_build = !(U.team_type & 2) && cargo >= 100 && !on_tile && C.amount == 0;
+                if (can_build && ((r >> 40) & 3) != 0) w = LUX_UA_BCITY;
+                else if (night && on_tile && ((r >> 42) & 7) != 0) w = 0;
+                else if (p < 40) w = 0;
+                else if (p < 80) w = LUX_UA_MOVE | ((1 + ((r >> 8) & 3)) << 3);
+                else if (p < 85) w = LUX_UA_BCITY;
+                else if (p < 88) w = LUX_UA_PILLAGE;
+                else {
+                    int best_id = 0x7fffffff;
+                    for (int j = 0; j < nu; j++) {
+                        const LuxUnit V = units[j];
+                        if (j == i || ((V.team_type ^ U.team_type) & 1)) continue;
+                        int d = abs((int)V.x - (int)U.x) + abs((int)V.y - (int)U.y);
+                        if (d <= 1 && V.id < best_id) best_id = V.id;
+                    }
+                    if (best_id != 0x7fffffff) {
+                        uint32_t res = (uint32_t)((r >> 8) % 3), amount = 1 + (uint32_t)((r >> 16) % 100);
+                        w = LUX_UA_TRANSFER | (res << 3) | (amount << 6) | ((uint32_t)best_id << 17);
+                    }
+                }
+            }
+        }
+        ua[i] = w;
+    }
+    for (int p = lane; p < b.t_cap; p += 32) {
+        uint8_t code = 0;
+        if (!done && p < nt) {
+            int cell = tiles[p];
+            uint64_t r = lux_hash(seed, mid, (uint64_t)turn, 1, (uint64_t)cell);
+            int can_act = cells[cell].tile_cd < 1;
+            if (can_act || ((r >> 32) & 15) == 0) {
+                unsigned q = (unsigned)(r % 100);
+                code = q < 45 ? LUX_TA_BUILD_WORKER : q < 50 ? LUX_TA_BUILD_CART : q < 90 ? LUX_TA_RESEARCH : LUX_TA_NONE;
+            }
+        }
+        ta[p] = code;
+    }
+}
+
+// ---------------------------------------------------------------- episode statistics
+__global__ void lux_stats_kernel(LuxBatch b, unsigned long long* out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    long long v[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) v[k] = 0;
+    if (m < b.n_matches) {
+        const LuxHeader* h = b.hdr + m;
+        int done = h->done;
+        v[0] = !done; v[1] = done;
+        v[2] = done && h->winner == LUX_WIN_A; v[3] = done && h->winner == LUX_WIN_B; v[4] = done && h->winner == LUX_WIN_TIE;
+        v[5] = h->turn;
+        v[6] = (long long)h->fuel_generated[0] + h->fuel_generated[1];
+        v[7] = h->n_units; v[8] = h->n_tiles; v[9] = h->n_cities;
+        v[10] = h->status != 0;
+        // algorithmic bytes of one turn: 2*(8*S^2 + 16*U + 16*K + 64) + 4*(U+T)
+        v[11] = done ? 0 : 2LL * (8LL * b.size * b.size + 16LL * h->n_units + 16LL * h->n_cities + 64) + 4LL * (h->n_units + h->n_tiles);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        long long x = v[k];
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(out + k, (unsigned long long)x);
+    }
+}
+
+// ---------------------------------------------------------------- reset finished matches from a pool
+__global__ void lux_reset_done_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch, int* reset_count) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (m >= b.n_matches) return;
+    if (!b.hdr[m].done) return;
+    int src = 0;
+    if (lane == 0) {
+        // deterministic choice (replayable trajectories): a hash of (match, epoch)
+        uint32_t hsh = (uint32_t)m * 0x9E3779B1u + epoch * 0x85EBCA6Bu;
+        hsh ^= hsh >> 15; hsh *= 0x2C1B3C6Du; hsh ^= hsh >> 12;
+        src = (int)(hsh % (uint32_t)pool.n_matches);
+        if (reset_count) atomicAdd(reset_count, 1);
+    }
+    src = __shfl_sync(0xffffffffu, src, 0);
+    const int ncell = b.size * b.size;
+    auto copy = [&](void* d, const void* s, size_t bytes) {
+        const uint4* sp = (const uint4*)s;
+        uint4* dp = (uint4*)d;
+        for (size_t i = lane; i < bytes / 16; i += 32) dp[i] = sp[i];
+    };
+    copy(b.cells + (size_t)m * ncell, pool.cells + (size_t)src * ncell, (size_t)ncell * 8);
+    copy(b.units + (size_t)m * b.u_cap, pool.units + (size_t)src * b.u_cap, (size_t)pool.hdr[src].n_units * 16);
+    copy(b.cities + (size_t)m * b.c_cap, pool.cities + (size_t)src * b.c_cap, (size_t)pool.hdr[src].n_cities * 16);
+    copy(b.tiles + (size_t)m * b.t_cap, pool.tiles + (size_t)src * b.t_cap, ((size_t)pool.hdr[src].n_tiles * 2 + 15) & ~(size_t)15);
+    copy(b.res + (size_t)m * b.r_cap, pool.res + (size_t)src * b.r_cap, ((size_t)pool.hdr[src].n_res * 2 + 15) & ~(size_t)15);
+    __syncwarp();
+    copy(b.hdr + m, pool.hdr + src, LUX_HDR_BYTES);
+}
+
+// ---------------------------------------------------------------- C ABI
+static int check_batch(const LuxBatch* b) {
+    if (!b) return LUX_E_ARG;
+    if (b->n_matches < 0 || b->size < 4 || b->size > 32 || (b->size & 1)) return LUX_E_ARG;
+    if (b->u_cap < 4 || b->u_cap > 252 || (b->u_cap & 3)) return LUX_E_CAPACITY;
+    if (b->c_cap < 1 || b->c_cap > 255) return LUX_E_CAPACITY;
+    if (b->t_cap < 16 || b->t_cap > 1024 || (b->t_cap & 15)) return LUX_E_CAPACITY;
+    if (b->r_cap < 8 || b->r_cap > 1024 || (b->r_cap & 7)) return LUX_E_CAPACITY;
+    if (!b->hdr || !b->cells || !b->units || !b->cities || !b->tiles || !b->res) return LUX_E_ARG;
+    if (((uintptr_t)b->hdr | (uintptr_t)b->cells | (uintptr_t)b->units | (uintptr_t)b->cities | (uintptr_t)b->tiles |
+         (uintptr_t)b->res) & 15)
+        return LUX_E_ARG;
+    return LUX_OK;
+}
+
+static int cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return LUX_OK;
+    fprintf(stderr, "lux_b200: %s: %s\n", what, cudaGetErrorString(e));
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? LUX_E_NO_DEVICE : LUX_E_CUDA;
+}
+
+extern "C" int lux_b200_version(void) { return LUX_B200_VERSION; }
+
+extern "C" int lux_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" size_t lux_b200_step_smem_bytes(int size, int u_cap, int c_cap, int t_cap, int r_cap) {
+    return (size_t)lux_smem_layout(size, u_cap, c_cap, t_cap, r_cap).total;
+}
+
+static int g_use_tma = 1;
+static int g_warps_per_cta = 0;   // 0 = automatic
+// tuning / fallback knobs (tests flip them to cover both staging paths)
+extern "C" int lux_b200_set_option(const char* name, int value) {
+    if (!name) return LUX_E_ARG;
+    if (!strcmp(name, "tma")) { g_use_tma = value != 0; return LUX_OK; }
+    if (!strcmp(name, "warps_per_cta")) { g_warps_per_cta = value; return LUX_OK; }
+    return LUX_E_ARG;
+}
+
+extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions,
+                             void* cuda_stream) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!unit_actions || !tile_actions) return LUX_E_ARG;
+    if (((uintptr_t)unit_actions | (uintptr_t)tile_actions) & 15) return LUX_E_ARG;
+    if (b->n_matches == 0) return LUX_OK;
+    if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
+    LuxSmemLayout L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    int wpc = g_warps_per_cta;
+    if (wpc <= 0) {
+        wpc = (64 * 1024) / L.total;
+        if (wpc < 1) wpc = 1;
+        if (wpc > 4) wpc = 4;
+    }
+    size_t smem = (size_t)L.total * wpc;
+    if (smem > 227 * 1024) return LUX_E_CAPACITY;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int grid = (b->n_matches + wpc - 1) / wpc;
+    if (g_use_tma) {
+        rc = cuda_ok(cudaFuncSetAttribute(lux_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        if (rc) return rc;
+        lux_step_kernel<true><<<grid, 32 * wpc, smem, st>>>(*b, unit_actions, tile_actions, L);
+    } else {
+        rc = cuda_ok(cudaFuncSetAttribute(lux_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        if (rc) return rc;
+        lux_step_kernel<false><<<grid, 32 * wpc, smem, st>>>(*b, unit_actions, tile_actions, L);
+    }
+    return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
+}
+
+extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,
+                                  const uint8_t* tile_actions_host, uint32_t* unit_actions_dev,
+                                  uint8_t* tile_actions_dev, uint8_t* done_host, LuxHeader* hdr_host,
+                                  void* cuda_stream) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!unit_actions_host || !tile_actions_host || !unit_actions_dev || !tile_actions_dev) return LUX_E_ARG;
+    if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    size_t n = (size_t)b->n_matches;
+    rc = cuda_ok(cudaMemcpyAsync(unit_actions_dev, unit_actions_host, n * b->u_cap * 4, cudaMemcpyHostToDevice, st), "h2d unit actions");
+    if (rc) return rc;
+    rc = cuda_ok(cudaMemcpyAsync(tile_actions_dev, tile_actions_host, n * b->t_cap, cudaMemcpyHostToDevice, st), "h2d tile actions");
+    if (rc) return rc;
+    rc = lux_b200_step(b, unit_actions_dev, tile_actions_dev, cuda_stream);
+    if (rc) return rc;
+    if (hdr_host) {
+        rc = cuda_ok(cudaMemcpyAsync(hdr_host, b->hdr, n * LUX_HDR_BYTES, cudaMemcpyDeviceToHost, st), "d2h headers");
+        if (rc) return rc;
+    }
+    rc = cuda_ok(cudaStreamSynchronize(st), "step sync");
+    if (rc) return rc;
+    if (done_host && hdr_host)
+        for (size_t i = 0; i < n; i++) done_host[i] = hdr_host[i].done;
+    return LUX_OK;
+}
+
+extern "C" int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t match_id_base,
+                                    uint32_t* unit_actions, uint8_t* tile_actions, uint64_t* counters,
+                                    void* cuda_stream) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!unit_actions || !tile_actions) return LUX_E_ARG;
+    if (b->n_matches == 0) return LUX_OK;
+    if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
+    const int wpc = 4;
+    lux_gen_actions_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, 0, (cudaStream_t)cuda_stream>>>(
+        *b, seed, match_id_base, unit_actions, tile_actions, (unsigned long long*)counters);
+    return cuda_ok(cudaGetLastError(), "lux_gen_actions_kernel launch");
+}
+
+extern "C" int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, uint32_t epoch,
+                                   int32_t* reset_count, void* cuda_stream) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    rc = check_batch(pool);
+    if (rc) return rc;
+    if (pool->n_matches < 1) return LUX_E_ARG;
+    if (pool->size != b->size || pool->u_cap != b->u_cap || pool->c_cap != b->c_cap || pool->t_cap != b->t_cap ||
+        pool->r_cap != b->r_cap)
+        return LUX_E_ARG;
+    if (b->n_matches == 0) return LUX_OK;
+    if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
+    const int wpc = 4;
+    lux_reset_done_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, 0, (cudaStream_t)cuda_stream>>>(
+        *b, *pool, epoch, reset_count);
+    return cuda_ok(cudaGetLastError(), "lux_reset_done_kernel launch");
+}
+
+extern "C" int lux_b200_stats(const LuxBatch* b, int64_t* out16, void* cuda_stream) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!out16) return LUX_E_ARG;
+    if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    rc = cuda_ok(cudaMemsetAsync(out16, 0, 16 * sizeof(int64_t), st), "stats memset");
+    if (rc) return rc;
+    if (b->n_matches == 0) return LUX_OK;
+    lux_stats_kernel<<<(b->n_matches + 127) / 128, 128, 0, st>>>(*b, (unsigned long long*)out16);
+    return cuda_ok(cudaGetLastError(), "lux_stats_kernel launch");
+}

@@ -53,7 +53,7 @@
 #define UST_FAILED 0x80u  // transfer raised KeyError in the reference: no cooldown, no cart road
 
 struct LuxSmemLayout {
-    int hdr, cells, units, cities, tiles, res, uact, tact, p1, occ, utgt, ust, umine, tmask, cprefix, cremap, total;
+    int hdr, cells, units, cities, tiles, res, uact, tact, p1, occ, utgt, ust, umine, tmask, cprefix, cremap, mbar, total;
 };
 
 LUX_DEV int lux_align16(int x) { return (x + 15) & ~15; }
@@ -84,6 +84,7 @@ LuxSmemLayout lux_smem_layout(int size, int u_cap, int c_cap, int t_cap, int r_c
     LUX_TAKE(tmask, t_cap * 4)
     LUX_TAKE(cprefix, (c_cap + 1) * 2)
     LUX_TAKE(cremap, c_cap)
+    LUX_TAKE(mbar, 16)
 #undef LUX_TAKE
     L.total = o;
     return L;
@@ -787,6 +788,8 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M) {
 
 // ---- epilogue: compaction, match_over, cooldowns, canonical tile order, store ---------------
 // g_* are the match's sections in global memory.
+// With kStoreGrid == false the caller moves the cell grid and the header itself (bulk copy).
+template <bool kStoreGrid>
 LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g_hdr, LuxCell* g_cells,
                                   LuxUnit* g_units, LuxCity* g_cities, uint16_t* g_tiles) {
     const int lane = lux_lane();
@@ -890,8 +893,8 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
         }
     }
     lux_sync();
-    // cells and header: straight 16-byte copies
-    {
+    // cells and header: straight copies
+    if (kStoreGrid) {
         const uint64_t* s = (const uint64_t*)M.cells;
         uint64_t* d = (uint64_t*)g_cells;
         for (int i = lane; i < M.ncell; i += 32) d[i] = s[i];

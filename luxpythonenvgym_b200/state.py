@@ -99,13 +99,21 @@ assert city_dtype.itemsize == 16
 
 
 def default_caps(size):
-    """Capacities (units, cities, tiles, resource cells) for a map side."""
+    """Capacities (units, cities, tiles, resource cells) for a map side.
+
+    Constraints of the C ABI: units % 4 == 0 and <= 252, cities <= 255, tiles % 16 == 0,
+    res % 8 == 0 (16-byte granules of the bulk copies).  The largest populations in the
+    reference's fixtures are 112 units / 133 tiles / 70 cities on 32x32.
+    """
     cells = size * size
-    units = min(252, max(32, cells // 4))
-    units = (units + 3) // 4 * 4
-    tiles = min(512, max(32, cells // 2)) if size < 32 else 384
-    cities = min(256, max(16, cells // 8))
-    res = min(384, max(48, cells // 4))
+
+    def up(x, m):
+        return (x + m - 1) // m * m
+
+    units = up(min(252, max(64, cells // 2)), 4)
+    tiles = up(min(384, max(64, cells)), 16)
+    cities = min(255, max(32, cells // 4))
+    res = up(min(256, max(48, cells // 3)), 8)
     return dict(units=units, cities=cities, tiles=tiles, res=res)
 
 

@@ -1,0 +1,183 @@
+"""-m gpu: the CUDA turn engine (through the C ABI) against the oracle and the golden vectors.
+
+Bar: bit-exact on every state field, every turn.
+"""
+import numpy as np
+import pytest
+import torch
+
+from luxpythonenvgym_b200 import _lib, mapgen
+from luxpythonenvgym_b200 import state as S
+from tests import golden_util as G
+from tests import gpu_util
+
+pytestmark = pytest.mark.gpu
+
+BIG = dict(units=252, cities=255, tiles=512, res=384)
+
+
+def _game(n, size, caps=None):
+    from luxpythonenvgym_b200.batched import BatchedGame
+    return BatchedGame(n, size, caps)
+
+
+def _recap(ms, caps):
+    o = S.MatchState(ms.size, caps)
+    o.hdr, o.cells = ms.hdr.copy(), ms.cells.copy()
+    for name in ("units", "cities", "tiles", "res"):
+        dst = getattr(o, name)
+        src = getattr(ms, name)
+        k = min(len(dst), len(src))
+        dst[:k] = src[:k]
+    return o
+
+
+@pytest.mark.parametrize("tma", [1, 0])
+def test_replays_bit_exact(tma):
+    """The 7 Kaggle episodes of the reference's test_replay.py, 360 turns each."""
+    lib = _lib.load()
+    lib.lux_b200_set_option(b"tma", tma)
+    try:
+        z = G.npz("replays")
+        for rid in G.replay_ids():
+            init = G.get_state(z, rid + "/init")
+            U, T = G.replay_actions(z, rid, init)
+            g = _game(1, init.size, BIG)
+            g.load_states([_recap(init, BIG)])
+            digests = z[rid + "/digests"]
+            ua = torch.from_numpy(U[:, : BIG["units"]].astype(np.int64).astype(np.int32)).cuda()
+            ta = torch.from_numpy(T[:, : BIG["tiles"]]).cuda()
+            for turn in range(len(digests)):
+                g.step(ua[turn].contiguous().view(1, -1), ta[turn].contiguous().view(1, -1))
+                if turn % 20 == 19 or turn == len(digests) - 1:
+                    ms = g.export_states([0])[0]
+                    assert ms.digest() == int(digests[turn]), "replay %s turn %d" % (rid, turn)
+            assert g.headers()["done"][0] == 1
+    finally:
+        lib.lux_b200_set_option(b"tma", 1)
+
+
+def test_random_and_dense_fixtures():
+    """Golden random-stream and dense fixtures: device action generator + device step."""
+    for fixture, names, base_of in (
+            ("random", [str(k) for k in range(int(G.npz("random")["n"]))], lambda nm: int(nm)),
+            ("dense", G.dense_names(), lambda nm: int(nm.split("@")[1]))):
+        z = G.npz(fixture)
+        seed = int(z["stream_seed"])
+        for nm in names:
+            init = G.get_state(z, nm + "/init")
+            digests = z[nm + "/digests"]
+            g = _game(1, init.size, BIG)
+            g.load_states([_recap(init, BIG)])
+            for turn in range(len(digests)):
+                g.gen_actions(seed, base_of(nm))
+                g.step()
+            ms = g.export_states([0])[0]
+            assert ms.digest() == int(digests[-1]), "%s %s" % (fixture, nm)
+            assert _recap(G.get_state(z, nm + "/final"), BIG).diff(ms) == []
+
+
+@pytest.mark.parametrize("size,n,turns", [(12, 4096, 360), (16, 1024, 200), (24, 512, 200), (32, 1024, 360)])
+def test_batch_vs_oracle_every_turn(size, n, turns):
+    """Config 2 of BASELINE.json (4096 parallel 12x12 matches) and the larger sizes:
+    per-turn bit-exact diff of every match against the C oracle."""
+    n_maps = 32
+    maps = [mapgen.generate(1000 + i, size=size) for i in range(n_maps)]
+    g = _game(n, size)
+    g.load_states([maps[i % n_maps] for i in range(n)])
+    host = gpu_util.HostBatch(g)
+    seed = 20211 + size
+    for turn in range(turns):
+        g.gen_actions(seed, 0)
+        host.gen_actions(seed, 0)
+        if turn % 50 == 0:
+            assert np.array_equal(g.unit_actions.cpu().numpy().view(np.uint32), host.ua), "action stream differs"
+            assert np.array_equal(g.tile_actions.cpu().numpy(), host.ta)
+        g.step()
+        host.step()
+        bad = gpu_util.diff_batches(host, g)
+        assert len(bad) == 0, "turn %d: %d matches differ, first %d: %s" % (
+            turn, len(bad), bad[0], gpu_util.explain(host, g, int(bad[0])))
+    hh = host.hdr()
+    assert (hh["status"] == 0).all()
+    assert hh["done"].sum() > 0
+
+
+def test_dense_pool_vs_oracle():
+    """Dense late-game states (replay imports) tiled over a batch with different action streams."""
+    z = G.npz("dense")
+    names = [nm for nm in G.dense_names() if int(z[nm + "/size"]) == 32]
+    caps = S.default_caps(32)
+    inits = [_recap(G.get_state(z, nm + "/init"), caps) for nm in names]
+    n = 512
+    g = _game(n, 32)
+    g.load_states([inits[i % len(inits)] for i in range(n)])
+    host = gpu_util.HostBatch(g)
+    for turn in range(60):
+        g.gen_actions(99, 0)
+        host.gen_actions(99, 0)
+        g.step()
+        host.step()
+        bad = gpu_util.diff_batches(host, g)
+        assert len(bad) == 0, "turn %d: %s" % (turn, gpu_util.explain(host, g, int(bad[0])))
+    assert (host.hdr()["status"] == 0).all()
+
+
+def test_done_matches_are_untouched_and_reset():
+    size = 12
+    maps = [mapgen.generate(50 + i, size=size) for i in range(8)]
+    g = _game(64, size)
+    g.load_states([maps[i % 8] for i in range(64)])
+    pool = _game(8, size)
+    pool.load_states(maps)
+    for _ in range(120):
+        g.gen_actions(5, 0)
+        g.step()
+    before = {k: t.clone() for k, t in g.sections().items()}
+    done = g.headers()["done"].astype(bool)
+    assert done.any() and not done.all()
+    g.gen_actions(5, 0)
+    g.step()
+    for k, t in g.sections().items():
+        assert torch.equal(t[torch.from_numpy(done).cuda()], before[k][torch.from_numpy(done).cuda()]), k
+    st = g.stats().cpu().numpy()
+    assert st[0] + st[1] == 64 and st[1] == done.sum()
+    count = torch.zeros(1, dtype=torch.int32, device="cuda")
+    g.reset_done(pool, 7, count)
+    assert int(count.item()) == int(done.sum())
+    hh = g.headers()
+    assert (hh["done"] == 0).all() and (hh["turn"][done] == 0).all()
+
+
+def test_step_host_matches_device_step():
+    size = 16
+    maps = [mapgen.generate(300 + i, size=size) for i in range(4)]
+    a, b = _game(32, size), _game(32, size)
+    for g in (a, b):
+        g.load_states([maps[i % 4] for i in range(32)])
+    ua_h = torch.zeros_like(a.unit_actions, device="cpu").pin_memory()
+    ta_h = torch.zeros_like(a.tile_actions, device="cpu").pin_memory()
+    hdr_h = torch.zeros_like(a.hdr, device="cpu").pin_memory()
+    done_h = torch.zeros(32, dtype=torch.uint8).pin_memory()
+    for turn in range(40):
+        a.gen_actions(3, 0)
+        ua_h.copy_(a.unit_actions)
+        ta_h.copy_(a.tile_actions)
+        a.step()
+        b.step_host(ua_h, ta_h, hdr_h, done_h)
+        assert torch.equal(hdr_h, a.hdr.cpu())
+    for k in a.sections():
+        assert torch.equal(a.sections()[k], b.sections()[k]), k
+
+
+def test_bad_arguments_are_rejected():
+    import ctypes
+    lib = _lib.load()
+    g = _game(4, 12)
+    d = _lib.LuxBatch(4, 13, 32, 16, 32, 48, g.hdr.data_ptr(), g.cells.data_ptr(), g.units.data_ptr(),
+                      g.cities.data_ptr(), g.tiles.data_ptr(), g.res.data_ptr())
+    assert lib.lux_b200_step(ctypes.byref(d), g.unit_actions.data_ptr(), g.tile_actions.data_ptr(), None) == _lib.LUX_E_ARG
+    d.size, d.u_cap = 12, 33
+    assert lib.lux_b200_step(ctypes.byref(d), g.unit_actions.data_ptr(), g.tile_actions.data_ptr(), None) == _lib.LUX_E_CAPACITY
+    d.u_cap = 32
+    assert lib.lux_b200_step(ctypes.byref(d), None, g.tile_actions.data_ptr(), None) == _lib.LUX_E_ARG
