@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- match-turns/sec of the batched Lux AI 2021 turn engine on N B200s.
+
+Contract (see DESIGN.md "Measurement"):
+  python bench.py --gpus N --steps K --warmup W          our arm (one rank per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N ...          CPU arm: the oracle port on the host cores
+
+A "step" is one turn of every resident match: canonical seeded action stream
+(lux_b200_gen_actions) -> lux_b200_step -> lux_b200_reset_done (finished matches are
+replaced from a pool of pre-generated maps).  `value` counts only LIVE match-turns.
+Workload: BASELINE.json config 5's per-GPU shape -- 32x32 maps, 16384 resident matches per
+GPU (state 230+ MB > the 126 MB L2, so no L2 flush is needed between steps), seeded random
+actions.  Matches shard independently over ranks (weak scaling); the only collective is
+the NCCL all-reduce of the episode-statistics vector.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE = 32
+MATCHES_PER_GPU = 16384
+POOL_MAPS = 128
+BURN_IN_TURNS = 400          # untimed: brings the batch to a steady mix of match ages
+STREAM_SEED = 20211019
+METRIC = "match-turns/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--matches", type=int, default=MATCHES_PER_GPU)
+    ap.add_argument("--size", type=int, default=SIZE)
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(args, n_gpus):
+    return {"workload": "BASELINE.json config 5 per-GPU shape: %dx%d maps, %d resident matches per GPU, "
+                        "canonical seeded random action stream, finished matches reset from a %d-map pool"
+                        % (args.size, args.size, args.matches, POOL_MAPS),
+            "map_size": args.size, "matches_per_gpu": args.matches, "n_gpus": n_gpus,
+            "burn_in_turns": BURN_IN_TURNS, "stream_seed": STREAM_SEED,
+            "l2": "state+actions per GPU exceed the 126 MB L2 (inputs larger than L2, no flush)",
+            "parallelism": "independent matches sharded over ranks (dp%d), NCCL all-reduce of stats only" % n_gpus}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        try:  # in-process NVML: a few hundred samples even in a sub-second timed region
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(hnd, pynvml.NVML_CLOCK_SM)
+            bits = ((pynvml.nvmlClocksThrottleReasonHwSlowdown, 2), (pynvml.nvmlClocksThrottleReasonHwThermalSlowdown, 3),
+                    (pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, 4), (pynvml.nvmlClocksThrottleReasonSwPowerCap, 5))
+            while not self.stop_flag:
+                sm = pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
+                row = [str(sm), str(mx), "", "", "", ""]
+                for bit, col in bits:
+                    row[col] = "Active" if reasons & bit else "Not Active"
+                self.rows.append(row)
+                time.sleep(0.002)
+            return
+        except Exception:
+            pass
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_pool_states(size, count, seed0=424242):
+    from luxpythonenvgym_b200 import mapgen
+    return [mapgen.generate(seed0 + i, size=size) for i in range(count)]
+
+
+# ------------------------------------------------------------------------------------------------
+class CpuPort:
+    """The oracle port (oracle/lux_oracle.c) on `threads` host threads over a bounded sample of
+    the same workload: same maps, same action stream, same pool reset rule.  Only the step
+    calls are timed (action construction is not), one C call per thread per `run`."""
+
+    def __init__(self, size, n_matches, threads, pool_states):
+        from luxpythonenvgym_b200 import state as S
+        from oracle import coracle
+        self.coracle = coracle
+        coracle.lib()
+        self.n, self.threads = n_matches, threads
+        caps = S.default_caps(size)
+
+        def alloc(k):
+            return {name: np.zeros((k, width), dtype=np.uint8) for name, width in (
+                ("hdr", 128), ("cells", size * size * 8), ("units", caps["units"] * 16),
+                ("cities", caps["cities"] * 16), ("tiles", caps["tiles"] * 2), ("res", caps["res"] * 2))}
+
+        self.arr, self.parr = alloc(n_matches), alloc(len(pool_states))
+        for i, ms in enumerate(pool_states):
+            for name, b in ms.to_bytes().items():
+                self.parr[name][i, : b.size] = b
+        for name in self.arr:
+            self.arr[name][:] = self.parr[name][np.arange(n_matches) % len(pool_states)]
+        self.desc = coracle.batch_desc(size, caps, self.arr, n_matches)
+        self.pdesc = coracle.batch_desc(size, caps, self.parr, len(pool_states))
+        self.ua = np.zeros((n_matches, caps["units"]), dtype=np.uint32)
+        self.ta = np.zeros((n_matches, caps["tiles"]), dtype=np.uint8)
+        self.epoch = 0
+
+    def run(self, turns):
+        """-> (match_turns_per_sec, live_match_turns, step_seconds of the slowest thread)."""
+        from concurrent.futures import ThreadPoolExecutor
+        chunks = [(t * self.n // self.threads, (t + 1) * self.n // self.threads) for t in range(self.threads)]
+
+        def work(rng):
+            lo, hi = rng
+            return self.coracle.run_batch(self.desc, self.pdesc, STREAM_SEED, 0, self.ua, self.ta, lo, hi - lo,
+                                          turns, self.epoch)
+
+        with ThreadPoolExecutor(self.threads) as ex:
+            res = list(ex.map(work, chunks))
+        self.epoch += turns
+        live = sum(r[1] for r in res)
+        secs = max(r[0] for r in res)
+        return live / secs, live, secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_matches, turns_per_step = 256 * threads, 40
+    port = CpuPort(args.size, n_matches, threads, make_pool_states(args.size, 32))
+    port.run(BURN_IN_TURNS)
+    vals, budget = [], 150.0
+    t_begin = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        v, live, secs = port.run(turns_per_step)
+        if i >= args.warmup:
+            vals.append((live, secs))
+        if time.perf_counter() - t_begin > budget and len(vals) >= 3:
+            break
+    value = sum(l for l, _ in vals) / sum(s for _, s in vals)
+    sample = ("oracle/lux_oracle.c: %d matches x %d turns per step (after %d burn-in turns, pool resets on), "
+              "%d host threads, step calls only" % (n_matches, turns_per_step, BURN_IN_TURNS, threads))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "match-turns/s", "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([s for _, s in vals])),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": config_dict(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "match-turns/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "match-turns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference is pure Python (no compiled path) and /root/reference does not travel to the GPU "
+                    "box, so this arm times the C port of the same algorithm; the unmodified Python engine measured "
+                    "1-8 k match-turns/s per core in the build container (BASELINE.md section 2)"}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from luxpythonenvgym_b200.batched import BatchedGame
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    n, size = args.matches, args.size
+    pool_states = make_pool_states(size, POOL_MAPS, seed0=424242 + 100000 * rank)
+    game = BatchedGame(n, size, device=dev)
+    pool = BatchedGame(POOL_MAPS, size, device=dev)
+    pool.load_states(pool_states)
+    game.load_states([pool_states[i % POOL_MAPS] for i in range(n)])
+    base = rank * n
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    resets = torch.zeros(1, dtype=torch.int32, device=dev)
+    epoch = [0]
+
+    def one_step(count=None):
+        game.gen_actions(STREAM_SEED, base, counters=count)
+        game.step()
+        game.reset_done(pool, epoch[0], resets)
+        epoch[0] += 1
+
+    for _ in range(BURN_IN_TURNS):
+        one_step()
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device-timed, per-step events around the step kernel
+    K = args.steps
+    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    counters.zero_()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t_start.record()
+    for k in range(K):
+        game.gen_actions(STREAM_SEED, base, counters=counters)
+        ev_a[k].record()
+        game.step()
+        ev_b[k].record()
+        game.reset_done(pool, epoch[0], resets)
+        epoch[0] += 1
+    t_end.record()
+    barrier()
+    sampler.stop_flag = True
+    total_ms = t_start.elapsed_time(t_end)
+    step_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / K
+    live_turns, alg_bytes = [int(x) for x in counters.cpu().tolist()]
+
+    # ---- end to end through the host-buffer entry point: pinned host actions in, headers out
+    E = min(args.e2e_steps, K)
+    snap = {k: t.clone() for k, t in game.sections().items()}
+    epoch0 = epoch[0]
+    ua_h = torch.empty((E, n, game.caps["units"]), dtype=torch.int32).pin_memory()
+    ta_h = torch.empty((E, n, game.caps["tiles"]), dtype=torch.uint8).pin_memory()
+    for k in range(E):                       # untimed: record the action tensors of E turns on the host
+        game.gen_actions(STREAM_SEED, base)
+        ua_h[k].copy_(game.unit_actions)
+        ta_h[k].copy_(game.tile_actions)
+        game.step()
+        game.reset_done(pool, epoch[0], resets)
+        epoch[0] += 1
+    torch.cuda.synchronize()
+    final_hdr_device_path = game.hdr.clone()
+    for k, t in game.sections().items():     # rewind
+        t.copy_(snap[k])
+    epoch[0] = epoch0
+    hdr_h = torch.empty((n, 128), dtype=torch.uint8).pin_memory()
+    done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    barrier()
+    w0 = time.perf_counter()
+    for k in range(E):
+        game.step_host(ua_h[k], ta_h[k], hdr_h, done_h)      # H2D actions, step, D2H headers, sync
+        game.reset_done(pool, epoch[0], resets)
+        epoch[0] += 1
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    assert torch.equal(game.hdr, final_hdr_device_path), "host-buffer path diverged from the device path"
+    # live match-turns of those E steps = the same trajectory the device path ran
+    h2d = n * (game.caps["units"] * 4 + game.caps["tiles"])
+    d2h = n * 128
+
+    # ---- reduce over ranks: time = max, work = sum; stats vector all-reduced with NCCL
+    stats = game.stats().clone()
+    red = torch.tensor([total_ms, step_ms, e2e_s], dtype=torch.float64, device=dev)
+    work = torch.tensor([live_turns, alg_bytes, n * E], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    total_ms, step_ms, e2e_s = red.cpu().tolist()
+    live_all, bytes_all, e2e_turns = work.cpu().tolist()
+    st = stats.cpu().tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        value = live_all / (total_ms * 1e-3)
+        # per-GPU: bytes of one launch on one GPU / that launch's duration
+        achieved = (bytes_all / world / K) / (step_ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": "match-turns/s", "n_gpus": world, "steps": K,
+                "warmup": max(args.warmup, 3), "ms_per_step": total_ms / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": config_dict(args, world),
+                "gpu_launches": 3 * K,
+                "kernel_ms": {"lux_step_kernel": step_ms, "whole_step": total_ms / K},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "kernel": "lux_step_kernel<true>",
+                             "algorithmic_bytes_per_launch": bytes_all / world / K,
+                             "live_match_turns_per_launch": live_all / world / K},
+                "e2e": {"value": e2e_turns / e2e_s, "unit": "match-turns/s", "h2d_bytes_per_step": h2d * world,
+                        "d2h_bytes_per_step": d2h * world, "steps": E,
+                        "note": "lux_b200_step_host: pinned host action tensors -> device, step, headers -> host, "
+                                "sync every step; counts resident matches per step (finished ones are reset the same step)"},
+                "clocks": sampler.summary(),
+                "stats": {"live": st[0], "finished_pending": st[1], "sum_units": st[7], "sum_city_tiles": st[8],
+                          "status_nonzero": st[10], "resets": int(resets.item())}}
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+            line["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            port = CpuPort(size, 256 * threads, threads, pool_states[:32])
+            port.run(BURN_IN_TURNS)
+            live_sum, sec_sum, turns_sum = 0, 0.0, 0
+            while sec_sum < 1.5 and turns_sum < 40000:          # ~1.5 s x threads of CPU work
+                v, live, secs = port.run(600)
+                live_sum, sec_sum, turns_sum = live_sum + live, sec_sum + secs, turns_sum + 600
+            line["cpu_baseline"] = {"value": live_sum / sec_sum, "unit": "match-turns/s", "cores": threads, "kind": "port",
+                                    "sample": "oracle/lux_oracle.c, %d matches x %d turns after %d burn-in turns, same maps / "
+                                              "action stream / pool resets, %d host threads, step calls only (%.1f s of "
+                                              "stepping per thread)" % (256 * threads, turns_sum, BURN_IN_TURNS, threads, sec_sum)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

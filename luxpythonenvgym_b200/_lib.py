@@ -55,8 +55,7 @@ def load():
     lib.lux_b200_step.argtypes = [bp, vp, vp, vp]
     lib.lux_b200_step_host.argtypes = [bp, vp, vp, vp, vp, vp, vp, vp]
     lib.lux_b200_gen_actions.argtypes = [bp, u64, u64, vp, vp, vp, vp]
-    if hasattr(lib, "lux_b200_observe"):
-        lib.lux_b200_observe.argtypes = [bp, vp, vp, vp, vp, i32, vp]
+    lib.lux_b200_observe.argtypes = [bp, vp, vp, vp, vp, i32, vp]
     lib.lux_b200_reset_done.argtypes = [bp, bp, ctypes.c_uint32, vp, vp]
     lib.lux_b200_stats.argtypes = [bp, vp, vp]
     _lib = lib

@@ -113,6 +113,27 @@ class BatchedGame:
                                                 reset_count.data_ptr() if reset_count is not None else None,
                                                 self._stream()), "lux_b200_reset_done")
 
+    def observe(self, team_sel, e_cap=None):
+        """Per-entity observation rows for team `team_sel[m]` of every match.
+
+        Returns (obs float32 [n, e_cap, 85], ent int16 [n, e_cap], count int32 [n]); entity codes are
+        unit slots, or 0x4000 | tile position for city tiles.  Rows beyond count[m] are unspecified.
+        """
+        e_cap = int(e_cap or (self.caps["units"] + self.caps["tiles"]))
+        key = ("obs", e_cap)
+        if getattr(self, "_obs_key", None) != key:
+            self._obs = torch.empty((self.n, e_cap, 85), dtype=torch.float32, device=self.device)
+            self._ent = torch.empty((self.n, e_cap), dtype=torch.int16, device=self.device)
+            self._cnt = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+            self._obs_key = key
+        if not torch.is_tensor(team_sel):
+            team_sel = torch.full((self.n,), int(team_sel), dtype=torch.uint8, device=self.device)
+        assert team_sel.dtype == torch.uint8 and team_sel.numel() == self.n and team_sel.is_cuda
+        _lib.check(self.lib.lux_b200_observe(ctypes.byref(self._desc), team_sel.data_ptr(), self._obs.data_ptr(),
+                                             self._ent.data_ptr(), self._cnt.data_ptr(), e_cap, self._stream()),
+                   "lux_b200_observe")
+        return self._obs, self._ent, self._cnt
+
     def stats(self):
         """Device int64[16] episode statistics (see include/lux_b200.h lux_b200_stats)."""
         _lib.check(self.lib.lux_b200_stats(ctypes.byref(self._desc), self._stats.data_ptr(), self._stream()),

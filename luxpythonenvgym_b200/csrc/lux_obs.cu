@@ -1,0 +1,82 @@
+// lux_obs.cu -- lux_b200_observe: per-entity observation tensors (see lux_obs_core.cuh).
+// One warp per match; the match is staged in shared memory with cp.async.bulk (TMA) exactly like
+// the step kernel, rows leave through a shared-memory staging tile with coalesced stores.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "lux_obs_core.cuh"
+#include "lux_tma.cuh"
+
+struct LuxObsLayoutDev { LuxObsLayout L; int mbar; int total; };
+
+__global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_sel, float* __restrict__ obs,
+                                   int16_t* __restrict__ ent_slot, int32_t* __restrict__ ent_count, int e_cap,
+                                   LuxObsLayoutDev D) {
+    extern __shared__ __align__(128) unsigned char lux_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (m >= b.n_matches) return;
+    unsigned char* smem = lux_smem + (size_t)warp * D.total;
+    const int ncell = b.size * b.size;
+    LuxObsMatch M;
+    lux_obs_bind(M, smem, D.L, b.size);
+    uint64_t* bar = (uint64_t*)(smem + D.mbar);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, LUX_HDR_BYTES);
+        tma_g2s(M.hdr, b.hdr + m, LUX_HDR_BYTES, bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    if (M.hdr->done) {
+        if (lane == 0) ent_count[m] = 0;
+        return;
+    }
+    const uint32_t nu = M.hdr->n_units, nc = M.hdr->n_cities, nt = M.hdr->n_tiles, nr = M.hdr->n_res;
+    const uint32_t b_cells = ncell * 8, b_units = nu * 16, b_cities = nc * 16;
+    const uint32_t b_tiles = (nt * 2 + 15) & ~15u, b_res = (nr * 2 + 15) & ~15u;
+    if (lane == 0) {
+        mbar_expect_tx(bar, b_cells + b_units + b_cities + b_tiles + b_res);
+        tma_g2s(M.cells, b.cells + (size_t)m * ncell, b_cells, bar);
+        if (b_units) tma_g2s(M.units, b.units + (size_t)m * b.u_cap, b_units, bar);
+        if (b_cities) tma_g2s(M.cities, b.cities + (size_t)m * b.c_cap, b_cities, bar);
+        if (b_tiles) tma_g2s(M.tiles, b.tiles + (size_t)m * b.t_cap, b_tiles, bar);
+        if (b_res) tma_g2s(M.res, b.res + (size_t)m * b.r_cap, b_res, bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 1);
+    int n = lux_observe(M, team_sel[m] & 1, obs + (size_t)m * e_cap * LUX_OBS_DIM, ent_slot + (size_t)m * e_cap, e_cap);
+    if (lane == 0) ent_count[m] = n < e_cap ? n : e_cap;
+}
+
+extern "C" int lux_b200_device_count(void);
+
+extern "C" int lux_b200_observe(const LuxBatch* b, const uint8_t* team_sel, float* obs, int16_t* ent_slot,
+                                int32_t* ent_count, int e_cap, void* cuda_stream) {
+    if (!b || !team_sel || !obs || !ent_slot || !ent_count || e_cap < 1) return LUX_E_ARG;
+    if (b->n_matches < 0 || b->size < 4 || b->size > 32 || (b->size & 1)) return LUX_E_ARG;
+    if (b->u_cap < 4 || b->u_cap > 252 || (b->u_cap & 3) || b->c_cap < 1 || b->c_cap > 255 || b->t_cap < 16 ||
+        b->t_cap > 1024 || (b->t_cap & 15) || b->r_cap < 8 || b->r_cap > 1024 || (b->r_cap & 7))
+        return LUX_E_CAPACITY;
+    if (!b->hdr || !b->cells || !b->units || !b->cities || !b->tiles || !b->res) return LUX_E_ARG;
+    if (b->n_matches == 0) return LUX_OK;
+    if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
+    LuxObsLayoutDev D;
+    D.L = lux_obs_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    D.mbar = D.L.total;
+    D.total = D.L.total + 16;
+    int wpc = (96 * 1024) / D.total;
+    if (wpc < 1) wpc = 1;
+    if (wpc > 4) wpc = 4;
+    size_t smem = (size_t)D.total * wpc;
+    if (smem > 227 * 1024) return LUX_E_CAPACITY;
+    cudaError_t e = cudaFuncSetAttribute(lux_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { fprintf(stderr, "lux_b200: observe smem attr: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
+    lux_observe_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, smem, (cudaStream_t)cuda_stream>>>(
+        *b, team_sel, obs, ent_slot, ent_count, e_cap, D);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { fprintf(stderr, "lux_b200: lux_observe_kernel launch: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
+    return LUX_OK;
+}

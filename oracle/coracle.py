@@ -92,3 +92,44 @@ def gen_actions_batch(desc, seed, match_id_base, unit_actions, tile_actions, fir
                                         _p(unit_actions), _p(tile_actions), first, count)
     if rc != 0:
         raise RuntimeError("lux_oracle_gen_actions_batch -> %d" % rc)
+
+
+def run_batch(desc, pool_desc, seed, match_id_base, unit_actions, tile_actions, first, count, turns, epoch0=0):
+    """lux_oracle_run_batch: (step_seconds, live_match_turns) for matches [first, first+count)."""
+    L = lib()
+    secs = ctypes.c_double(0.0)
+    live = ctypes.c_longlong(0)
+    rc = L.lux_oracle_run_batch(ctypes.byref(desc), ctypes.byref(pool_desc) if pool_desc is not None else None,
+                                ctypes.c_uint64(seed), ctypes.c_uint64(match_id_base), _p(unit_actions),
+                                _p(tile_actions), first, count, turns, ctypes.c_uint32(epoch0),
+                                ctypes.byref(secs), ctypes.byref(live))
+    if rc != 0:
+        raise RuntimeError("lux_oracle_run_batch -> %d" % rc)
+    return secs.value, live.value
+
+
+def observe(ms, team, e_cap=640):
+    """lux_oracle_observe for one MatchState -> (obs float32 [E,85], ent codes int16 [E])."""
+    L = lib()
+    obs = np.zeros((e_cap, 85), dtype=np.float32)
+    ent = np.zeros(e_cap, dtype=np.int16)
+    cnt = ctypes.c_int32(0)
+    hdr = ms.hdr.reshape(1)
+    rc = L.lux_oracle_observe(_p(hdr), _p(ms.cells), _p(ms.units), _p(ms.cities), _p(ms.tiles), _p(ms.res),
+                              int(team), _p(obs), _p(ent), ctypes.byref(cnt), e_cap)
+    if rc != 0:
+        raise RuntimeError("lux_oracle_observe -> %d" % rc)
+    return obs[: cnt.value].copy(), ent[: cnt.value].copy()
+
+
+def observe_batch(desc, team_sel, e_cap):
+    L = lib()
+    n = desc.n_matches
+    obs = np.zeros((n, e_cap, 85), dtype=np.float32)
+    ent = np.zeros((n, e_cap), dtype=np.int16)
+    cnt = np.zeros(n, dtype=np.int32)
+    team_sel = np.ascontiguousarray(team_sel, dtype=np.uint8)
+    rc = L.lux_oracle_observe_batch(ctypes.byref(desc), _p(team_sel), _p(obs), _p(ent), _p(cnt), e_cap)
+    if rc != 0:
+        raise RuntimeError("lux_oracle_observe_batch -> %d" % rc)
+    return obs, ent, cnt

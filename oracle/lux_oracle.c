@@ -770,3 +770,212 @@ int lux_oracle_gen_actions_batch(const LuxBatch* b, uint64_t seed, uint64_t matc
     }
     return 0;
 }
+
+/* ---------------------------------------------------------------- timed multi-turn driver (CPU baseline)
+ * Runs `turns` turns of matches [first, first+count) with the canonical action stream entirely in C
+ * (one call per host thread).  Only the step calls are timed; action construction is not.
+ * Finished matches are replaced by pool entries exactly like lux_b200_reset_done
+ * (hash of match index and epoch) when pool != NULL. */
+#include <time.h>
+
+static double now_sec(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+int lux_oracle_run_batch(const LuxBatch* b, const LuxBatch* pool, uint64_t seed, uint64_t match_id_base,
+                         uint32_t* unit_actions, uint8_t* tile_actions, int first, int count, int turns,
+                         uint32_t epoch0, double* step_seconds, long long* live_turns) {
+    if (!b || !unit_actions || !tile_actions || !step_seconds || !live_turns) return LUX_E_ARG;
+    int ncell = b->size * b->size;
+    double spent = 0.0;
+    long long live = 0;
+    for (int t = 0; t < turns; t++) {
+        int rc = lux_oracle_gen_actions_batch(b, seed, match_id_base, unit_actions, tile_actions, first, count);
+        if (rc) return rc;
+        for (int m = first; m < first + count && m < b->n_matches; m++) live += !b->hdr[m].done;
+        double t0 = now_sec();
+        rc = lux_oracle_step_batch(b, unit_actions, tile_actions, first, count);
+        spent += now_sec() - t0;
+        if (rc) return rc;
+        if (pool) {
+            for (int m = first; m < first + count && m < b->n_matches; m++) {
+                if (!b->hdr[m].done) continue;
+                uint32_t hsh = (uint32_t)m * 0x9E3779B1u + (epoch0 + (uint32_t)t) * 0x85EBCA6Bu;
+                hsh ^= hsh >> 15; hsh *= 0x2C1B3C6Du; hsh ^= hsh >> 12;
+                int src = (int)(hsh % (uint32_t)pool->n_matches);
+                memcpy(b->cells + (size_t)m * ncell, pool->cells + (size_t)src * ncell, (size_t)ncell * 8);
+                memcpy(b->units + (size_t)m * b->u_cap, pool->units + (size_t)src * b->u_cap, (size_t)b->u_cap * 16);
+                memcpy(b->cities + (size_t)m * b->c_cap, pool->cities + (size_t)src * b->c_cap, (size_t)b->c_cap * 16);
+                memcpy(b->tiles + (size_t)m * b->t_cap, pool->tiles + (size_t)src * b->t_cap, (size_t)b->t_cap * 2);
+                memcpy(b->res + (size_t)m * b->r_cap, pool->res + (size_t)src * b->r_cap, (size_t)b->r_cap * 2);
+                b->hdr[m] = pool->hdr[src];
+            }
+        }
+    }
+    *step_seconds = spent;
+    *live_turns = live;
+    return 0;
+}
+
+/* ---------------------------------------------------------------- observations
+ * Restatement of AgentPolicy.get_observation, /root/reference/examples/agent_policy.py:188-424, for
+ * every entity MatchController would yield for `team` (match_controller.py:271-289): the team's
+ * units with can_act() in dict order, then its city tiles with can_act() in cities x cells order.
+ * Keeps the reference's structure: per-key node lists (:197-247), np.delete of the closest node for
+ * the self-exclusion (:328-336), argmin/argmax of squared distance with first-index ties (:17-22),
+ * greedy direction_to (position.py:48-66).  float64 arithmetic, stored as float32. */
+#define OBS_DIM 85
+
+typedef struct { int n; int x[MAXCELLS], y[MAXCELLS]; } NodeList;
+
+static int obs_direction_slot(int px, int py, int tx, int ty) {
+    /* position.py:48-66 checks N, E, S, W and keeps the first strict improvement;
+       agent_policy.py:349-355 maps c,n,w,s,e -> 0,1,2,3,4 */
+    int best = abs(tx - px) + abs(ty - py), dir = 0;
+    const int cx[4] = {0, 1, 0, -1}, cy[4] = {-1, 0, 1, 0}, slot[4] = {1, 4, 3, 2};
+    for (int k = 0; k < 4; k++) {
+        int d = abs(tx - (px + cx[k])) + abs(ty - (py + cy[k]));
+        if (d < best) { best = d; dir = slot[k]; }
+    }
+    return dir;
+}
+
+static int obs_arg(const NodeList* l, int px, int py, int furthest) {
+    int best = -1; long bd = 0;
+    for (int i = 0; i < l->n; i++) {
+        long d = (long)(l->x[i] - px) * (l->x[i] - px) + (long)(l->y[i] - py) * (l->y[i] - py);
+        if (best < 0 || (furthest ? d > bd : d < bd)) { best = i; bd = d; }
+    }
+    return best;
+}
+
+int lux_oracle_observe(const LuxHeader* h, const LuxCell* cells, const LuxUnit* units, const LuxCity* cities,
+                       const uint16_t* tiles, const uint16_t* res, int team, float* obs, int16_t* ent_slot,
+                       int32_t* ent_count, int e_cap) {
+    if (!h || !cells || !units || !cities || !tiles || !res || !obs || !ent_slot || !ent_count) return LUX_E_ARG;
+    *ent_count = 0;
+    if (h->done) return 0;
+    int S = h->size;
+    static __thread NodeList nodes[5];      /* wood, coal, uranium, own city tiles, own workers */
+    for (int k = 0; k < 5; k++) nodes[k].n = 0;
+    for (int r = 0; r < h->n_res; r++) {     /* game.map.resources order; depleted cells are not in the list */
+        const LuxCell* c = &cells[res[r]];
+        if (c->amount == 0) continue;
+        NodeList* l = &nodes[res_type(c) - 1];
+        l->x[l->n] = res[r] % S; l->y[l->n] = res[r] / S; l->n++;
+    }
+    int own_workers = 0, own_carts = 0, own_tiles = 0, opp_tiles = 0;
+    for (int i = 0; i < h->n_units; i++) {
+        const LuxUnit* u = &units[i];
+        if ((u->team_type & 1) != team) continue;
+        if (u->team_type & 2) { own_carts++; continue; }
+        NodeList* l = &nodes[4];
+        l->x[l->n] = u->x; l->y[l->n] = u->y; l->n++;
+        own_workers++;
+    }
+    for (int p = 0; p < h->n_tiles; p++) {
+        const LuxCell* c = &cells[tiles[p]];
+        if (tile_team(c) != team) { opp_tiles++; continue; }
+        NodeList* l = &nodes[3];
+        l->x[l->n] = tiles[p] % S; l->y[l->n] = tiles[p] / S; l->n++;
+        own_tiles++;
+    }
+    int night = is_night(h);
+    int n_ent = 0;
+    int total = h->n_units + h->n_tiles;
+    for (int e = 0; e < total; e++) {
+        int is_unit = e < h->n_units;
+        int px, py, kind, slot_code, ucell_units = 0;
+        const LuxUnit* U = NULL;
+        if (is_unit) {
+            U = &units[e];
+            if ((U->team_type & 1) != team || !(U->cd_q < 4)) continue;
+            px = U->x; py = U->y; kind = (U->team_type & 2) ? 1 : 0; slot_code = e;
+            for (int i = 0; i < h->n_units; i++) ucell_units += (units[i].x == px && units[i].y == py);
+        } else {
+            int p = e - h->n_units;
+            const LuxCell* c = &cells[tiles[p]];
+            if (tile_team(c) != team || !(c->tile_cd < 1)) continue;
+            px = tiles[p] % S; py = tiles[p] / S; kind = 2; slot_code = 0x4000 | p;
+        }
+        if (n_ent >= e_cap) return LUX_E_CAPACITY;
+        float* o = obs + (size_t)n_ent * OBS_DIM;
+        for (int k = 0; k < OBS_DIM; k++) o[k] = 0.0f;
+        o[kind] = 1.0f;
+        int at = 3;
+        for (int furthest = 0; furthest < 2; furthest++) {
+            for (int key = 0; key < 5; key++, at += 7) {
+                const NodeList* full = &nodes[key];
+                if (full->n == 0) continue;                               /* key not in object_nodes */
+                static __thread NodeList filt;
+                const NodeList* l = full;
+                if ((key == 3 && kind == 2) || (kind == 0 && key == 4 && ucell_units <= 1)) {
+                    int drop = obs_arg(full, px, py, 0);                  /* np.delete(closest) :333-334 */
+                    filt.n = 0;
+                    for (int i = 0; i < full->n; i++)
+                        if (i != drop) { filt.x[filt.n] = full->x[i]; filt.y[filt.n] = full->y[i]; filt.n++; }
+                    l = &filt;
+                }
+                if (l->n == 0) { o[at + 5] = 1.0f; continue; }
+                int idx = obs_arg(l, px, py, furthest);
+                int tx = l->x[idx], ty = l->y[idx];
+                o[at + obs_direction_slot(px, py, tx, ty)] = 1.0f;
+                double dist = (double)(abs(tx - px) + abs(ty - py)) / 20.0;
+                o[at + 5] = (float)(dist < 1.0 ? dist : 1.0);
+                const LuxCell* tc = &cells[ty * S + tx];
+                double v;
+                if (key == 3) {
+                    const LuxCity* city = &cities[tc->city_slot];
+                    double upkeep = (double)(city->ntiles * UPKEEP_CITY - city->adjsum * ADJ_BONUS);
+                    v = (double)city->fuel / (upkeep * 200.0);
+                } else if (key < 3) {
+                    v = (double)tc->amount / 500.0;
+                } else {
+                    /* first unit in that cell's dict (:380-381); every unit standing on a cell gives the same
+                       value in reachable states, the first in slot order is taken */
+                    const LuxUnit* f = NULL;
+                    for (int i = 0; i < h->n_units && !f; i++)
+                        if (units[i].x == tx && units[i].y == ty) f = &units[i];
+                    int space = ((f->team_type & 2) ? CAP_CART : CAP_WORKER) - (f->wood + f->coal + f->uranium);
+                    v = (double)space / 100.0;
+                }
+                o[at + 6] = (float)(v < 1.0 ? v : 1.0);
+            }
+        }
+        if (is_unit) {
+            int space = ((U->team_type & 2) ? CAP_CART : CAP_WORKER) - (U->wood + U->coal + U->uranium);
+            o[73] = (float)((double)space / 100.0);
+        }
+        o[74] = night ? 1.0f : 0.0f;
+        o[75] = (float)((double)h->turn / 360.0);
+        o[76] = (float)((double)own_tiles / 30.0);
+        o[77] = (float)((double)opp_tiles / 30.0);
+        o[78] = (float)((double)own_workers / 30.0);
+        o[79] = (float)((double)own_workers / 30.0);   /* agent_policy.py:214-215 iterates the own team twice */
+        o[80] = (float)((double)own_carts / 30.0);
+        o[81] = (float)((double)own_carts / 30.0);
+        o[82] = (float)((double)h->research[team] / 200.0);
+        o[83] = h->research[team] >= RESEARCH_COAL ? 1.0f : 0.0f;
+        o[84] = h->research[team] >= RESEARCH_URANIUM ? 1.0f : 0.0f;
+        ent_slot[n_ent] = (int16_t)slot_code;
+        n_ent++;
+    }
+    *ent_count = n_ent;
+    return 0;
+}
+
+int lux_oracle_observe_batch(const LuxBatch* b, const uint8_t* team_sel, float* obs, int16_t* ent_slot,
+                             int32_t* ent_count, int e_cap) {
+    if (!b || !team_sel) return LUX_E_ARG;
+    int ncell = b->size * b->size;
+    for (int m = 0; m < b->n_matches; m++) {
+        int rc = lux_oracle_observe(&b->hdr[m], b->cells + (size_t)m * ncell, b->units + (size_t)m * b->u_cap,
+                                    b->cities + (size_t)m * b->c_cap, b->tiles + (size_t)m * b->t_cap,
+                                    b->res + (size_t)m * b->r_cap, team_sel[m], obs + (size_t)m * e_cap * OBS_DIM,
+                                    ent_slot + (size_t)m * e_cap, ent_count + m, e_cap);
+        if (rc) return rc;
+    }
+    return 0;
+}

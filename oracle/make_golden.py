@@ -159,6 +159,55 @@ def make_dense(ref, stream_seed=31337):
     np.savez_compressed(os.path.join(OUT, "dense.npz"), **store)
 
 
+def make_obs(ref, stream_seed=4711):
+    """obs.npz: AgentPolicy.get_observation (examples/agent_policy.py:188-424) of every actionable
+    entity of both teams on replay states (turn 80/200/300, +12 turns of the canonical stream so that
+    cooldowns/cargo/roads are mixed) and on seeded random matches at turn 25 and 60."""
+    store = {}
+    names = []
+    agent = refshim.agent_policy()
+
+    def snap(name, g):
+        ms = flatten.flatten(g, caps=CAPS)
+        store["%s/size" % name] = np.array(ms.size)
+        put(store, "%s/state" % name, ms)
+        for team in (0, 1):
+            obs, codes = refshim.reference_observations(g, team, agent)
+            store["%s/obs%d" % (name, team)] = obs.astype(np.float32)
+            store["%s/obs64_%d" % (name, team)] = obs
+            store["%s/ent%d" % (name, team)] = codes
+        names.append(name)
+        print("obs", name, [len(store["%s/ent%d" % (name, t)]) for t in (0, 1)])
+
+    files = sorted(glob.glob(os.path.join(refshim.REFERENCE_ROOT, "luxai2021/tests/replays_for_test/*[0-9].json")))
+    for f in files:
+        rid = os.path.basename(f)[:-5]
+        rep = json.load(open(f))
+        for start in (80, 200, 300):
+            g = refshim.game_from_replay(rep, step=start)
+            snap("%s@%d" % (rid, start), g)
+            ms = flatten.flatten(g, caps=CAPS)
+            for _ in range(12):
+                uw, tb = stream.gen_actions(ms, stream_seed, start)
+                g.run_turn_with_actions(flatten.words_to_actions(ref, g, uw, tb))
+                ms = flatten.flatten(g, caps=CAPS)
+            snap("%s@%d+12" % (rid, start), g)
+    for k in range(8):
+        size = [12, 16, 24, 32][k % 4]
+        g = refshim.new_game(seed=5000 + k, width=size, height=size)
+        snap("rand%d@0" % k, g)
+        ms = flatten.flatten(g, caps=CAPS)
+        for turn in range(60):
+            uw, tb = stream.gen_actions(ms, stream_seed, k)
+            if g.run_turn_with_actions(flatten.words_to_actions(ref, g, uw, tb)):
+                break
+            ms = flatten.flatten(g, caps=CAPS)
+            if turn in (24, 59):
+                snap("rand%d@%d" % (k, turn + 1), g)
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "obs.npz"), **store)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     os.chdir("/tmp")
@@ -167,6 +216,7 @@ def main():
     make_replays(ref)
     make_random(ref)
     make_dense(ref)
+    make_obs(ref)
 
 
 if __name__ == "__main__":

@@ -190,3 +190,40 @@ def game_from_replay(replay, step=0):
     g.global_city_id_count = obs["globalCityIDCount"]
     g.state["turn"] = obs["step"]
     return g
+
+
+def agent_policy():
+    """The reference's example AgentPolicy (examples/agent_policy.py), train mode, no model."""
+    load()
+    examples = os.path.join(REFERENCE_ROOT, "examples")
+    if examples not in sys.path:
+        sys.path.insert(0, examples)
+    import agent_policy as ap
+    return ap.AgentPolicy(mode="train")
+
+
+def reference_observations(game, team, agent=None):
+    """obs rows + entity codes in MatchController's yield order (match_controller.py:271-289)."""
+    import numpy as np
+    agent = agent or agent_policy()
+    rows, codes = [], []
+    new_turn = True
+    units = game.state["teamStates"][team]["units"]
+    slot = 0
+    for t in (0, 1):
+        for unit in game.state["teamStates"][t]["units"].values():
+            if t == team and unit.can_act():
+                rows.append(agent.get_observation(game, unit, None, team, new_turn))
+                codes.append(slot)
+                new_turn = False
+            slot += 1
+    pos = 0
+    for city in game.cities.values():
+        for cell in city.city_cells:
+            if city.team == team and cell.city_tile.can_act():
+                rows.append(agent.get_observation(game, None, cell.city_tile, team, new_turn))
+                codes.append(0x4000 | pos)
+                new_turn = False
+            pos += 1
+    obs = np.array(rows, dtype=np.float64).reshape(len(rows), 85)
+    return obs, np.array(codes, dtype=np.int16)

@@ -51,3 +51,20 @@ def step(ms, unit_words, tile_bytes):
     if rc != 0:
         raise RuntimeError("lux_emu_step -> %d" % rc)
     return bool(ms.hdr["done"])
+
+
+def observe(ms, team, e_cap=640):
+    """Observation rows of one MatchState through the emulated kernel."""
+    L = lib()
+    hdr = ms.hdr.reshape(1)
+    b = LuxBatchC(1, ms.size, len(ms.units), len(ms.cities), len(ms.tiles), len(ms.res),
+                  hdr.ctypes.data, ms.cells.ctypes.data, ms.units.ctypes.data, ms.cities.ctypes.data,
+                  ms.tiles.ctypes.data, ms.res.ctypes.data)
+    obs = np.zeros((e_cap, 85), dtype=np.float32)
+    ent = np.zeros(e_cap, dtype=np.int16)
+    cnt = np.zeros(1, dtype=np.int32)
+    sel = np.array([team], dtype=np.uint8)
+    rc = L.lux_emu_observe(ctypes.byref(b), _p(sel), _p(obs), _p(ent), _p(cnt), e_cap)
+    if rc != 0:
+        raise RuntimeError("lux_emu_observe -> %d" % rc)
+    return obs[: cnt[0]].copy(), ent[: cnt[0]].copy()

@@ -64,3 +64,45 @@ extern "C" int lux_emu_step(const LuxBatch* b, const uint32_t* unit_actions, con
     free(a.smem);
     return 0;
 }
+
+// ---- observations through the emulated warp ------------------------------------------------
+#include "../../luxpythonenvgym_b200/csrc/lux_obs_core.cuh"
+
+struct EmuObsArgs {
+    const LuxBatch* b; int m; const uint8_t* team_sel; float* obs; int16_t* ent; int32_t* cnt; int e_cap;
+    unsigned char* smem; LuxObsLayout L;
+};
+
+static void emu_obs_lane(void* p) {
+    EmuObsArgs* a = (EmuObsArgs*)p;
+    const LuxBatch* b = a->b;
+    int m = a->m, ncell = b->size * b->size;
+    LuxObsMatch M;
+    lux_obs_bind(M, a->smem, a->L, b->size);
+    lux_copy16(M.hdr, b->hdr + m, LUX_HDR_BYTES);
+    lux_sync();
+    if (M.hdr->done) { if (lux_lane() == 0) a->cnt[m] = 0; return; }
+    lux_copy16(M.cells, b->cells + (size_t)m * ncell, ncell * 8);
+    lux_copy16(M.units, b->units + (size_t)m * b->u_cap, M.hdr->n_units * 16);
+    lux_copy16(M.cities, b->cities + (size_t)m * b->c_cap, M.hdr->n_cities * 16);
+    lux_copy16(M.tiles, b->tiles + (size_t)m * b->t_cap, M.hdr->n_tiles * 2);
+    lux_copy16(M.res, b->res + (size_t)m * b->r_cap, M.hdr->n_res * 2);
+    lux_sync();
+    int n = lux_observe(M, a->team_sel[m], a->obs + (size_t)m * a->e_cap * LUX_OBS_DIM, a->ent + (size_t)m * a->e_cap, a->e_cap);
+    if (lux_lane() == 0) a->cnt[m] = n < a->e_cap ? n : a->e_cap;
+}
+
+extern "C" int lux_emu_observe(const LuxBatch* b, const uint8_t* team_sel, float* obs, int16_t* ent, int32_t* cnt, int e_cap) {
+    if (!b || !team_sel || !obs || !ent || !cnt) return LUX_E_ARG;
+    EmuObsArgs a;
+    a.b = b; a.team_sel = team_sel; a.obs = obs; a.ent = ent; a.cnt = cnt; a.e_cap = e_cap;
+    a.L = lux_obs_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    a.smem = (unsigned char*)aligned_alloc(16, a.L.total);
+    for (int m = 0; m < b->n_matches; m++) {
+        memset(a.smem, 0xA5, a.L.total);
+        a.m = m;
+        warp_emu::run_warp(emu_obs_lane, &a);
+    }
+    free(a.smem);
+    return 0;
+}

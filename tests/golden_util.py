@@ -37,3 +37,7 @@ def replay_actions(z, rid, ms):
 
 def dense_names():
     return [str(x) for x in npz("dense")["names"]]
+
+
+def obs_names():
+    return [str(x) for x in npz("obs")["names"]]

@@ -1,0 +1,73 @@
+"""CUDA kernel LOGIC on the CPU: luxpythonenvgym_b200/csrc/*.cuh compiled for the host with a
+32-fiber warp emulator (tests/emu/) and compared with the oracle / golden vectors.  This is a
+development aid for a container without a GPU -- the product never runs this build; the real
+parity tests are tests/test_gpu_parity.py (-m gpu)."""
+import numpy as np
+import pytest
+
+from luxpythonenvgym_b200 import state as S
+from oracle import coracle
+from tests import golden_util as G
+from tests.emu import emu
+
+CAPS = dict(units=252, cities=255, tiles=512, res=384)
+
+
+def recap(ms):
+    o = S.MatchState(ms.size, CAPS)
+    o.hdr, o.cells = ms.hdr.copy(), ms.cells.copy()
+    for name in ("units", "cities", "tiles", "res"):
+        dst, src = getattr(o, name), getattr(ms, name)
+        k = min(len(dst), len(src))
+        dst[:k] = src[:k]
+    return o
+
+
+@pytest.mark.parametrize("rid", G.replay_ids()[:3])
+def test_emulated_step_replays(rid):
+    z = G.npz("replays")
+    init = G.get_state(z, rid + "/init")
+    U, T = G.replay_actions(z, rid, init)
+    ms = recap(init)
+    digests = z[rid + "/digests"]
+    for turn in range(len(digests)):
+        emu.step(ms, U[turn], T[turn])
+        assert ms.digest() == int(digests[turn]), "replay %s turn %d" % (rid, turn)
+
+
+@pytest.mark.parametrize("name", G.dense_names())
+def test_emulated_step_dense(name):
+    z = G.npz("dense")
+    seed, start = int(z["stream_seed"]), int(name.split("@")[1])
+    a = recap(G.get_state(z, name + "/init"))
+    b = a.copy()
+    digests = z[name + "/digests"]
+    for turn in range(len(digests)):
+        uw, tb = coracle.gen_actions(a, seed, start)
+        coracle.step(a, uw, tb)
+        emu.step(b, uw, tb)
+        assert a.diff(b) == []
+        assert b.digest() == int(digests[turn])
+
+
+@pytest.mark.parametrize("k", range(0, 32, 3))
+def test_emulated_step_random(k):
+    z = G.npz("random")
+    seed = int(z["stream_seed"])
+    ms = recap(G.get_state(z, "%d/init" % k))
+    digests = z["%d/digests" % k]
+    for turn in range(len(digests)):
+        uw, tb = coracle.gen_actions(ms, seed, k)
+        emu.step(ms, uw, tb)
+        assert ms.digest() == int(digests[turn]), "match %d turn %d" % (k, turn)
+
+
+@pytest.mark.parametrize("name", G.obs_names())
+def test_emulated_observations(name):
+    z = G.npz("obs")
+    ms = recap(G.get_state(z, name + "/state"))
+    for team in (0, 1):
+        want, codes = z["%s/obs%d" % (name, team)], z["%s/ent%d" % (name, team)]
+        got, got_codes = emu.observe(ms, team)
+        assert np.array_equal(codes, got_codes)
+        assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), np.argwhere(want != got)[:5]

@@ -181,3 +181,42 @@ def test_bad_arguments_are_rejected():
     assert lib.lux_b200_step(ctypes.byref(d), g.unit_actions.data_ptr(), g.tile_actions.data_ptr(), None) == _lib.LUX_E_CAPACITY
     d.u_cap = 32
     assert lib.lux_b200_step(ctypes.byref(d), None, g.tile_actions.data_ptr(), None) == _lib.LUX_E_ARG
+
+
+def test_observations_golden_and_oracle():
+    """lux_b200_observe against the reference's AgentPolicy.get_observation (golden rows, bit-exact)
+    and against the observation oracle on a large mixed batch."""
+    from oracle import coracle
+    z = G.npz("obs")
+    for size in (12, 16, 24, 32):
+        names = [nm for nm in G.obs_names() if int(z[nm + "/size"]) == size]
+        states = [_recap(G.get_state(z, nm + "/state"), BIG) for nm in names]
+        g = _game(2 * len(states), size, BIG)
+        g.load_states(states + states)
+        sel = torch.tensor([0] * len(states) + [1] * len(states), dtype=torch.uint8, device="cuda")
+        obs, ent, cnt = g.observe(sel)
+        obs, ent, cnt = obs.cpu().numpy(), ent.cpu().numpy(), cnt.cpu().numpy()
+        for i, nm in enumerate(names):
+            for team in (0, 1):
+                m = i + team * len(states)
+                want, codes = z["%s/obs%d" % (nm, team)], z["%s/ent%d" % (nm, team)]
+                assert cnt[m] == len(codes), (nm, team)
+                assert np.array_equal(ent[m, : cnt[m]], codes)
+                assert np.array_equal(obs[m, : cnt[m]].view(np.uint32), want.view(np.uint32)), (nm, team)
+    # large batch after some play, vs the oracle
+    maps = [mapgen.generate(2000 + i, size=24) for i in range(16)]
+    g = _game(512, 24)
+    g.load_states([maps[i % 16] for i in range(512)])
+    for turn in range(90):
+        g.gen_actions(11, 0)
+        g.step()
+    host = gpu_util.HostBatch(g)
+    sel_np = (np.arange(512) % 2).astype(np.uint8)
+    e_cap = g.caps["units"] + g.caps["tiles"]
+    obs, ent, cnt = g.observe(torch.from_numpy(sel_np).cuda())
+    o_obs, o_ent, o_cnt = coracle.observe_batch(host.desc, sel_np, e_cap)
+    cnt = cnt.cpu().numpy()
+    assert np.array_equal(cnt, o_cnt)
+    live = np.arange(e_cap)[None, :] < cnt[:, None]
+    assert np.array_equal(ent.cpu().numpy()[live], o_ent[live])
+    assert np.array_equal(obs.cpu().numpy().view(np.uint32)[live], o_obs.view(np.uint32)[live])
