@@ -43,6 +43,8 @@ enum { LUX_TA_NONE = 0, LUX_TA_BUILD_WORKER = 1, LUX_TA_BUILD_CART = 2, LUX_TA_R
 enum { LUX_ST_UNIT_OVERFLOW = 1, LUX_ST_CITY_OVERFLOW = 2, LUX_ST_TILE_OVERFLOW = 4, LUX_ST_BAD_STATE = 8 };
 /* LuxHeader.winner */
 enum { LUX_WIN_A = 0, LUX_WIN_B = 1, LUX_WIN_TIE = 2, LUX_WIN_NONE = 255 };
+/* lux_b200_step flags */
+enum { LUX_STEP_PREVALIDATE = 1 };
 /* error codes */
 enum { LUX_OK = 0, LUX_E_ARG = -1, LUX_E_CAPACITY = -2, LUX_E_CUDA = -3, LUX_E_NO_DEVICE = -4 };
 
@@ -66,7 +68,8 @@ typedef struct LUX_ALIGNED(16) LuxHeader {            /* game.py:85-147 */
     int32_t  carts_built[2];
     int32_t  roads_built_q[2];         /* roadsBuilt * 4 */
     int32_t  city_tiles_built[2];
-    uint8_t  pad[28];
+    uint16_t n_team_tiles[2];          /* city tiles per team (derived from cities[]) */
+    uint8_t  pad[24];
 } LuxHeader;
 
 typedef struct LUX_ALIGNED(8) LuxCell {              /* cell.py:20-33, city.py:53-66 */
@@ -138,9 +141,13 @@ size_t lux_b200_step_smem_bytes(int size, int u_cap, int c_cap, int t_cap, int r
  * unit_actions: [n][u_cap] uint32, tile_actions: [n][t_cap] uint8 (device).  Matches whose
  * hdr.done is set are left untouched.  The bool return value lands in hdr.done, the
  * winner (get_winning_team :594-634, coin flip reported as LUX_WIN_TIE) in hdr.winner.
+ * flags: LUX_STEP_PREVALIDATE first applies MatchController.take_action's Action.is_valid filter
+ * (luxai2021/game/match_controller.py:137-187, actions.py:58-438) to the action tensors: of the
+ * same-team moves into one non-city cell only the first in unit order survives, transfers need an
+ * acting source and an adjacent destination on the team, pillage / research need can_act().
  */
 int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions,
-                  void* cuda_stream);
+                  uint32_t flags, void* cuda_stream);
 
 /*
  * Same call with HOST action buffers and HOST result buffers (pinned or pageable):
@@ -151,7 +158,7 @@ int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t
 int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,
                        const uint8_t* tile_actions_host, uint32_t* unit_actions_dev,
                        uint8_t* tile_actions_dev, uint8_t* done_host, LuxHeader* hdr_host,
-                       void* cuda_stream);
+                       uint32_t flags, void* cuda_stream);
 
 /*
  * Canonical seeded action stream, written as packed action
@@ -175,6 +182,27 @@ int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t match_id_bas
  */
 int lux_b200_observe(const LuxBatch* b, const uint8_t* team_sel, float* obs, int16_t* ent_slot,
                      int32_t* ent_count, int e_cap, void* cuda_stream);
+
+/*
+ * AgentPolicy action codes -> packed action tensors for the entities lux_b200_observe listed.
+ * Replaces: AgentPolicy.action_code_to_action, examples/agent_policy.py:426-470 with the action
+ * tables :117-132 (unit code % 9: center, n, w, s, e, transfer to a nearby cart, transfer to a nearby
+ * worker (smart_transfer_to_nearby :24-100), build city, pillage; tile code % 3: build worker, build
+ * cart, research).  codes: [n][e_cap] int32.  Slots without an entity get "no action".
+ */
+int lux_b200_encode_actions(const LuxBatch* b, const int16_t* ent_slot, const int32_t* ent_count,
+                            const int32_t* codes, int e_cap, uint32_t* unit_actions, uint8_t* tile_actions,
+                            void* cuda_stream);
+
+/*
+ * Per-turn reward of team `team_sel[m]`.
+ * Replaces: AgentPolicy.get_reward, examples/agent_policy.py:494-560 evaluated at a turn boundary:
+ * 0.05*d(units) + 0.1*d(city tiles) + d(fuelGenerated)/20000 (+ city tiles when the match just ended).
+ * reward_state: [n][4] int32 in/out (units_last, city_tiles_last, fuel_collected_last, unused; zero it
+ * at match start like game_start :480-492), reward: [n] float64.
+ */
+int lux_b200_reward(const LuxBatch* b, const uint8_t* team_sel, int32_t* reward_state, double* reward,
+                    void* cuda_stream);
 
 /*
  * Replace every finished match (hdr.done != 0) by a fresh one copied from a pool of

@@ -9,6 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "_lux_b200.so")
 
+LUX_STEP_PREVALIDATE = 1
 LUX_OK, LUX_E_ARG, LUX_E_CAPACITY, LUX_E_CUDA, LUX_E_NO_DEVICE = 0, -1, -2, -3, -4
 _ERR = {LUX_E_ARG: "bad argument", LUX_E_CAPACITY: "capacity out of range",
         LUX_E_CUDA: "CUDA error", LUX_E_NO_DEVICE: "no CUDA device"}
@@ -16,7 +17,7 @@ _ERR = {LUX_E_ARG: "bad argument", LUX_E_CAPACITY: "capacity out of range",
 # every symbol include/lux_b200.h declares
 EXPORTS = ("lux_b200_version", "lux_b200_device_count", "lux_b200_set_option", "lux_b200_step_smem_bytes",
            "lux_b200_step", "lux_b200_step_host", "lux_b200_gen_actions", "lux_b200_observe",
-           "lux_b200_reset_done", "lux_b200_stats")
+           "lux_b200_reset_done", "lux_b200_stats", "lux_b200_encode_actions", "lux_b200_reward")
 
 
 class LuxError(RuntimeError):
@@ -52,12 +53,14 @@ def load():
     lib.lux_b200_set_option.argtypes = [ctypes.c_char_p, i32]
     lib.lux_b200_step_smem_bytes.restype = ctypes.c_size_t
     lib.lux_b200_step_smem_bytes.argtypes = [i32] * 5
-    lib.lux_b200_step.argtypes = [bp, vp, vp, vp]
-    lib.lux_b200_step_host.argtypes = [bp, vp, vp, vp, vp, vp, vp, vp]
+    lib.lux_b200_step.argtypes = [bp, vp, vp, ctypes.c_uint32, vp]
+    lib.lux_b200_step_host.argtypes = [bp, vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp]
     lib.lux_b200_gen_actions.argtypes = [bp, u64, u64, vp, vp, vp, vp]
     lib.lux_b200_observe.argtypes = [bp, vp, vp, vp, vp, i32, vp]
     lib.lux_b200_reset_done.argtypes = [bp, bp, ctypes.c_uint32, vp, vp]
     lib.lux_b200_stats.argtypes = [bp, vp, vp]
+    lib.lux_b200_encode_actions.argtypes = [bp, vp, vp, vp, i32, vp, vp, vp]
+    lib.lux_b200_reward.argtypes = [bp, vp, vp, vp, vp]
     _lib = lib
     return lib
 

@@ -79,23 +79,25 @@ class BatchedGame:
         return self.hdr.cpu().numpy().view(S.header_dtype).reshape(self.n)
 
     # ------------------------------------------------------------------ the hot path
-    def step(self, unit_actions=None, tile_actions=None):
+    def step(self, unit_actions=None, tile_actions=None, prevalidate=False):
         """One turn for every live match.  Actions default to this object's action tensors."""
         ua = self.unit_actions if unit_actions is None else unit_actions
         ta = self.tile_actions if tile_actions is None else tile_actions
         assert ua.is_cuda and ta.is_cuda and ua.is_contiguous() and ta.is_contiguous()
         assert ua.numel() == self.n * self.caps["units"] and ua.element_size() == 4
         assert ta.numel() == self.n * self.caps["tiles"] and ta.element_size() == 1
-        _lib.check(self.lib.lux_b200_step(ctypes.byref(self._desc), ua.data_ptr(), ta.data_ptr(), self._stream()),
+        _lib.check(self.lib.lux_b200_step(ctypes.byref(self._desc), ua.data_ptr(), ta.data_ptr(),
+                                          _lib.LUX_STEP_PREVALIDATE if prevalidate else 0, self._stream()),
                    "lux_b200_step")
 
-    def step_host(self, unit_actions_host, tile_actions_host, hdr_host=None, done_host=None):
+    def step_host(self, unit_actions_host, tile_actions_host, hdr_host=None, done_host=None, prevalidate=False):
         """The same turn from HOST (pinned) action buffers; copies back headers/done flags."""
         _lib.check(self.lib.lux_b200_step_host(
             ctypes.byref(self._desc), unit_actions_host.data_ptr(), tile_actions_host.data_ptr(),
             self.unit_actions.data_ptr(), self.tile_actions.data_ptr(),
             done_host.data_ptr() if done_host is not None else None,
-            hdr_host.data_ptr() if hdr_host is not None else None, self._stream()), "lux_b200_step_host")
+            hdr_host.data_ptr() if hdr_host is not None else None,
+            _lib.LUX_STEP_PREVALIDATE if prevalidate else 0, self._stream()), "lux_b200_step_host")
 
     def gen_actions(self, seed, match_id_base=0, unit_actions=None, tile_actions=None, counters=None):
         """Fill the action tensors from the canonical seeded stream (harness utility)."""
@@ -133,6 +135,23 @@ class BatchedGame:
                                              self._ent.data_ptr(), self._cnt.data_ptr(), e_cap, self._stream()),
                    "lux_b200_observe")
         return self._obs, self._ent, self._cnt
+
+    def encode_actions(self, ent, count, codes, unit_actions=None, tile_actions=None):
+        """AgentPolicy action codes (int32 [n, e_cap]) of the observed entities -> action tensors."""
+        ua = self.unit_actions if unit_actions is None else unit_actions
+        ta = self.tile_actions if tile_actions is None else tile_actions
+        assert codes.dtype == torch.int32 and codes.is_contiguous() and codes.shape == ent.shape
+        _lib.check(self.lib.lux_b200_encode_actions(ctypes.byref(self._desc), ent.data_ptr(), count.data_ptr(),
+                                                    codes.data_ptr(), ent.shape[1], ua.data_ptr(), ta.data_ptr(),
+                                                    self._stream()), "lux_b200_encode_actions")
+
+    def reward(self, team_sel, reward_state, out=None):
+        """Per-turn AgentPolicy reward (float64 [n]); reward_state is int32 [n, 4], updated in place."""
+        if out is None:
+            out = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.lux_b200_reward(ctypes.byref(self._desc), team_sel.data_ptr(), reward_state.data_ptr(),
+                                            out.data_ptr(), self._stream()), "lux_b200_reward")
+        return out
 
     def stats(self):
         """Device int64[16] episode statistics (see include/lux_b200.h lux_b200_stats)."""

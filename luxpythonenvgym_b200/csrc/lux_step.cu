@@ -20,7 +20,7 @@
 // ---------------------------------------------------------------- the step kernel
 template <bool kTma>
 __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions,
-                                const uint8_t* __restrict__ tile_actions, LuxSmemLayout L) {
+                                const uint8_t* __restrict__ tile_actions, LuxSmemLayout L, unsigned flags) {
     extern __shared__ __align__(128) unsigned char lux_smem[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -80,7 +80,7 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
         __syncwarp();
     }
 
-    LuxTurnOut T = lux_turn(M);
+    LuxTurnOut T = lux_turn(M, flags);
 
     if (kTma) {
         lux_finish_and_store<false>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
@@ -287,7 +287,7 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
 }
 
 extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions,
-                             void* cuda_stream) {
+                             uint32_t flags, void* cuda_stream) {
     int rc = check_batch(b);
     if (rc) return rc;
     if (!unit_actions || !tile_actions) return LUX_E_ARG;
@@ -308,11 +308,11 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
     if (g_use_tma) {
         rc = cuda_ok(cudaFuncSetAttribute(lux_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
         if (rc) return rc;
-        lux_step_kernel<true><<<grid, 32 * wpc, smem, st>>>(*b, unit_actions, tile_actions, L);
+        lux_step_kernel<true><<<grid, 32 * wpc, smem, st>>>(*b, unit_actions, tile_actions, L, flags);
     } else {
         rc = cuda_ok(cudaFuncSetAttribute(lux_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
         if (rc) return rc;
-        lux_step_kernel<false><<<grid, 32 * wpc, smem, st>>>(*b, unit_actions, tile_actions, L);
+        lux_step_kernel<false><<<grid, 32 * wpc, smem, st>>>(*b, unit_actions, tile_actions, L, flags);
     }
     return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
 }
@@ -320,7 +320,7 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
 extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,
                                   const uint8_t* tile_actions_host, uint32_t* unit_actions_dev,
                                   uint8_t* tile_actions_dev, uint8_t* done_host, LuxHeader* hdr_host,
-                                  void* cuda_stream) {
+                                  uint32_t flags, void* cuda_stream) {
     int rc = check_batch(b);
     if (rc) return rc;
     if (!unit_actions_host || !tile_actions_host || !unit_actions_dev || !tile_actions_dev) return LUX_E_ARG;
@@ -331,7 +331,7 @@ extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_action
     if (rc) return rc;
     rc = cuda_ok(cudaMemcpyAsync(tile_actions_dev, tile_actions_host, n * b->t_cap, cudaMemcpyHostToDevice, st), "h2d tile actions");
     if (rc) return rc;
-    rc = lux_b200_step(b, unit_actions_dev, tile_actions_dev, cuda_stream);
+    rc = lux_b200_step(b, unit_actions_dev, tile_actions_dev, flags, cuda_stream);
     if (rc) return rc;
     if (hdr_host) {
         rc = cuda_ok(cudaMemcpyAsync(hdr_host, b->hdr, n * LUX_HDR_BYTES, cudaMemcpyDeviceToHost, st), "d2h headers");

@@ -47,6 +47,8 @@
 #define P1_BLOCKED 0x08u  // a reverted mover stays here
 #define P1_HAS1 0x10u     // >= 1 unit stands here
 #define P1_HAS2 0x20u     // >= 2
+#define P1_CLAIM0 0x40u   // pre-validation: team 0 / team 1 already holds a validated move into the cell
+#define P1_CLAIM1 0x80u
 
 // per-unit scratch byte ust: [2:0] held action kind, [5:3] move direction, flags
 #define UST_REVERTED 0x40u
@@ -403,7 +405,7 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
 //   bit0 tiles list must be rewritten, [31:16] n_units (incl. spawned), others via hdr.
 struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; };
 
-LUX_DEV LuxTurnOut lux_turn(LuxMatch& M) {
+LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     const int lane = lux_lane();
     const unsigned lt = lux_lanemask_lt();
     LuxHeader* h = M.hdr;
@@ -458,11 +460,53 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M) {
             }
         } else if (kind == LUX_UA_PILLAGE || kind == LUX_UA_TRANSFER) {
             st = kind;                                             // game.py:721-723: no check
+            if (flags & LUX_STEP_PREVALIDATE) {
+                // Action.is_valid (actions.py:322-345, :368-385): the acting unit can act; a transfer
+                // names another unit of the team standing at Manhattan distance <= 1
+                if (!(U.cd_q < 4)) st = 0;
+                if (st && kind == LUX_UA_TRANSFER) {
+                    int dest_id = (int)(w >> 17), found = 0;
+                    for (int v = 0; v < n_units0; v++) {
+                        const LuxUnit& V = M.units[v];
+                        if (V.id == dest_id && unit_team(V) == unit_team(U) && v != u) {
+                            int d = (V.x > U.x ? V.x - U.x : U.x - V.x) + (V.y > U.y ? V.y - U.y : U.y - V.y);
+                            found = d <= 1;
+                            break;
+                        }
+                    }
+                    if (!found) st = 0;
+                }
+            }
         }
         M.ust[u] = (uint8_t)st;
         M.utgt[u] = (uint16_t)tgt;
     }
     lux_sync();
+
+    // ---- MatchController pre-validation of moves (MoveAction.is_valid actions.py:58-116): of the
+    // same-team moves into one non-city cell only the first in unit order is buffered; a CENTER
+    // move is the do-nothing action and never changes the outcome, so it is dropped here
+    if (flags & LUX_STEP_PREVALIDATE) {
+        for (int base = 0; base < n_units0; base += 32) {
+            int u = base + lane;
+            unsigned st = u < n_units0 ? M.ust[u] : 0;
+            int is_move = (st & 7) == LUX_UA_MOVE;
+            int center = is_move && ((st >> 3) & 7) == LUX_DIR_CENTER;
+            int t = is_move ? M.utgt[u] : 0;
+            int team = is_move ? unit_team(M.units[u]) : 0;
+            int cand = is_move && !center && !cell_is_tile(M.cells[t]);
+            unsigned peers = lux_match_any(cand ? ((t << 1) | team) : (int)(0x40000000 | lane));
+            if (center) M.ust[u] = 0;
+            if (cand) {
+                unsigned bit = team ? P1_CLAIM1 : P1_CLAIM0;
+                int first = lux_ffs(peers) - 1 == lane;
+                if (!first || (M.p1[t] & bit)) M.ust[u] = 0;
+            }
+            lux_sync();
+            if (cand && M.ust[u]) lux_atomic_or_byte(M.p1, t, team ? P1_CLAIM1 : P1_CLAIM0);
+            lux_sync();
+        }
+    }
 
     // ---- collision pruning (handle_movement_actions game.py:1104-1195)
     for (int u = lane; u < n_units0; u += 32) {
@@ -538,7 +582,8 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M) {
             unsigned mok = lux_ballot(ok);
             int srank = spawned + lux_popc(mok & lt);
             spawned += lux_popc(mok);
-            int research = valid && code == LUX_TA_RESEARCH;
+            int research = valid && code == LUX_TA_RESEARCH &&
+                           (!(flags & LUX_STEP_PREVALIDATE) || cd < 1);   // ResearchAction.is_valid actions.py:412-438
             int acted = research;
             if (ok) {
                 if (srank < room) {
@@ -881,6 +926,8 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
         h->n_team_units[1] = (uint16_t)alive1;
         h->n_cities = (uint16_t)n_alive;
         h->n_tiles = (uint16_t)n_tiles_live;
+        h->n_team_tiles[0] = (uint16_t)tl0;
+        h->n_team_tiles[1] = (uint16_t)tl1;
         if (over) {
             h->done = 1;
             int w;                                                     // get_winning_team game.py:594-634

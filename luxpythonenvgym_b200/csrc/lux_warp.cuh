@@ -20,6 +20,7 @@ LUX_DEV int lux_any(int pred) { return __any_sync(0xffffffffu, pred); }
 LUX_DEV int lux_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 LUX_DEV int lux_reduce_add(int v) { return __reduce_add_sync(0xffffffffu, v); }
 LUX_DEV int lux_popc(unsigned v) { return __popc(v); }
+LUX_DEV unsigned lux_match_any(int key) { return __match_any_sync(0xffffffffu, key); }
 LUX_DEV int lux_ffs(unsigned v) { return __ffs(v); }
 LUX_DEV unsigned lux_atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
 LUX_DEV int lux_atomic_add(int* p, int v) { return atomicAdd(p, v); }

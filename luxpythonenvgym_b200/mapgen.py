@@ -269,6 +269,7 @@ def generate(seed, size=None, caps=None):
     hd["city_id_count"] = 2
     hd["n_units"], hd["n_cities"], hd["n_tiles"] = 2, 2, 2
     hd["n_team_units"] = (1, 1)
+    hd["n_team_tiles"] = (1, 1)
     hd["workers_built"] = (1, 1)
     assert len(res_list) <= len(ms.res), "resource capacity too small for this map"
     ms.res[: len(res_list)] = res_list

@@ -60,7 +60,8 @@ header_dtype = np.dtype([
     ("carts_built", "<i4", (2,)),
     ("roads_built_q", "<i4", (2,)),     # stats.roadsBuilt in quarter units
     ("city_tiles_built", "<i4", (2,)),  # only process_updates touches it (game.py:247)
-    ("pad", "u1", (28,)),
+    ("n_team_tiles", "<u2", (2,)),      # city tiles per team (derived; kept for rewards / win rule)
+    ("pad", "u1", (24,)),
 ])
 assert header_dtype.itemsize == HDR_BYTES
 

@@ -133,3 +133,40 @@ def observe_batch(desc, team_sel, e_cap):
     if rc != 0:
         raise RuntimeError("lux_oracle_observe_batch -> %d" % rc)
     return obs, ent, cnt
+
+
+def prevalidate(ms, unit_words, tile_bytes):
+    """lux_oracle_prevalidate in place on copies; returns (unit_words, tile_bytes)."""
+    L = lib()
+    uw = np.ascontiguousarray(unit_words, dtype=np.uint32).copy()
+    tb = np.ascontiguousarray(tile_bytes, dtype=np.uint8).copy()
+    hdr = ms.hdr.reshape(1)
+    rc = L.lux_oracle_prevalidate(_p(hdr), _p(ms.cells), _p(ms.units), _p(ms.tiles), _p(uw), _p(tb))
+    if rc != 0:
+        raise RuntimeError("lux_oracle_prevalidate -> %d" % rc)
+    return uw, tb
+
+
+def encode_actions(ms, ent, codes):
+    L = lib()
+    uw = np.zeros(len(ms.units), dtype=np.uint32)
+    tb = np.zeros(len(ms.tiles), dtype=np.uint8)
+    ent = np.ascontiguousarray(ent, dtype=np.int16)
+    codes = np.ascontiguousarray(codes, dtype=np.int32)
+    hdr = ms.hdr.reshape(1)
+    rc = L.lux_oracle_encode_actions(_p(hdr), _p(ms.units), _p(ent), len(ent), _p(codes), _p(uw), _p(tb),
+                                     len(ms.units), len(ms.tiles))
+    if rc != 0:
+        raise RuntimeError("lux_oracle_encode_actions -> %d" % rc)
+    return uw, tb
+
+
+def reward(ms, team, last):
+    """lux_oracle_reward; `last` is an int32[3] array updated in place."""
+    L = lib()
+    r = ctypes.c_double(0.0)
+    hdr = ms.hdr.reshape(1)
+    rc = L.lux_oracle_reward(_p(hdr), int(team), _p(last), ctypes.byref(r))
+    if rc != 0:
+        raise RuntimeError("lux_oracle_reward -> %d" % rc)
+    return r.value

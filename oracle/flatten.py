@@ -59,6 +59,8 @@ def flatten(game, caps=None):
         c["adjsum"] = adjsum
     h["n_cities"] = len(game.cities)
     h["n_tiles"] = ntile
+    for city in game.cities.values():
+        h["n_team_tiles"][city.team] += len(city.city_cells)
 
     # cells: resources and roads
     for y in range(size):

@@ -126,6 +126,13 @@ static void unpack(Game* g, LuxHeader* h, LuxCell* cells, LuxUnit* units, LuxCit
     }
 }
 
+static int team_tile_count_packed(Game* g, int team) {
+    int n = 0;
+    for (int s = 0; s < g->ncities; s++)
+        if (g->cities[s].alive && g->cities[s].team == team) n += g->cities[s].ncells;
+    return n;
+}
+
 static void pack(Game* g, LuxUnit* units, LuxCity* cities, uint16_t* tiles) {
     LuxHeader* h = g->h;
     int n = 0;
@@ -165,6 +172,8 @@ static void pack(Game* g, LuxUnit* units, LuxCity* cities, uint16_t* tiles) {
     }
     h->n_cities = (uint16_t)slot;
     h->n_tiles = (uint16_t)nt;
+    h->n_team_tiles[0] = (uint16_t)team_tile_count_packed(g, 0);
+    h->n_team_tiles[1] = (uint16_t)team_tile_count_packed(g, 1);
 }
 
 /* ---------------------------------------------------------------- helpers */
@@ -977,5 +986,134 @@ int lux_oracle_observe_batch(const LuxBatch* b, const uint8_t* team_sel, float* 
                                     ent_slot + (size_t)m * e_cap, ent_count + m, e_cap);
         if (rc) return rc;
     }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- MatchController layer
+ * lux_oracle_prevalidate: Action.is_valid as MatchController.take_action applies it
+ * (match_controller.py:137-187) to each decision in yield order -- per team, units in dict order and
+ * then city tiles -- against the actions already buffered this turn.  Invalid actions are zeroed in
+ * the packed tensors; lux_oracle_step then sees what Game.run_turn_with_actions would be handed.
+ * Spawn and build-city decisions need no filtering here: their is_valid (actions.py:159-194,
+ * :256-285) equals validate_command (game.py:656-718) in the canonical order. */
+int lux_oracle_prevalidate(const LuxHeader* h, const LuxCell* cells, const LuxUnit* units, const uint16_t* tiles,
+                           uint32_t* ua, uint8_t* ta) {
+    if (!h || !cells || !units || !tiles || !ua || !ta) return LUX_E_ARG;
+    int S = h->size, n = h->n_units;
+    static __thread int buffered_target[MAXU];      /* target cell of a buffered move, -1 none */
+    for (int i = 0; i < n; i++) buffered_target[i] = -1;
+    for (int i = 0; i < n; i++) {                    /* slot order == team A then team B, dict order */
+        const LuxUnit* u = &units[i];
+        int team = u->team_type & 1;
+        int kind = ua[i] & 7;
+        int can_act = u->cd_q < 4;
+        if (kind == LUX_UA_MOVE) {                   /* MoveAction.is_valid actions.py:58-116 */
+            int dir = (ua[i] >> 3) & 7, ok = can_act && dir <= 4;
+            int nx = u->x, ny = u->y;
+            if (ok) { nx += DX[dir]; ny += DY[dir]; ok = nx >= 0 && ny >= 0 && nx < S && ny < S; }
+            if (ok) {
+                int tgt = ny * S + nx;
+                const LuxCell* tc = &cells[tgt];
+                if (is_tile(tc) && tile_team(tc) != team) ok = 0;
+                if (ok && !is_tile(tc)) {
+                    int around[5], na = adjacent_cells(S, tgt, around);
+                    around[na++] = tgt;
+                    for (int k = 0; k < na && ok; k++)
+                        for (int j = 0; j < n && ok; j++) {
+                            const LuxUnit* v = &units[j];
+                            if (j == i || (v->team_type & 1) != team || v->y * S + v->x != around[k]) continue;
+                            if (buffered_target[j] == tgt) ok = 0;          /* :104-108 */
+                            if (nx == u->x && ny == u->y) ok = 0;           /* :110-113 (compares with the mover) */
+                        }
+                }
+                if (ok) buffered_target[i] = tgt;
+            }
+            if (!ok) ua[i] = 0;
+        } else if (kind == LUX_UA_TRANSFER) {        /* TransferAction.is_valid actions.py:322-345 */
+            int dest = (int)(ua[i] >> 17), ok = 0;
+            for (int j = 0; j < n; j++) {
+                const LuxUnit* v = &units[j];
+                if ((v->team_type & 1) == team && v->id == dest) {
+                    ok = j != i && can_act && abs((int)v->x - (int)u->x) + abs((int)v->y - (int)u->y) <= 1;
+                    break;
+                }
+            }
+            if (!ok) ua[i] = 0;
+        } else if (kind == LUX_UA_PILLAGE) {         /* PillageAction.is_valid actions.py:368-385 */
+            if (!can_act) ua[i] = 0;
+        }
+    }
+    for (int p = 0; p < h->n_tiles; p++)             /* ResearchAction.is_valid actions.py:412-438 */
+        if (ta[p] == LUX_TA_RESEARCH && !(cells[tiles[p]].tile_cd < 1)) ta[p] = 0;
+    return 0;
+}
+
+/* AgentPolicy.action_code_to_action (examples/agent_policy.py:117-132, :426-470) for the entities of
+ * one team in observation order: unit codes % 9 = center, n, w, s, e, transfer->cart, transfer->worker,
+ * build city, pillage; tile codes % 3 = build worker, build cart, research.  Transfers follow
+ * smart_transfer_to_nearby (:24-100). */
+static int smart_transfer(const LuxHeader* h, const LuxUnit* units, int i, int want_cart, uint32_t* word) {
+    const LuxUnit* u = &units[i];
+    int S = h->size, team = u->team_type & 1;
+    int amounts[3] = {u->wood, u->uranium, u->coal};          /* cargo dict order: wood, uranium, coal */
+    const int codes[3] = {0, 2, 1};                           /* packed resource field: wood 0, coal 1, uranium 2 */
+    int rtype = -1, ramount = 0;
+    for (int k = 0; k < 3; k++) if (amounts[k] > ramount) { rtype = codes[k]; ramount = amounts[k]; }
+    int adj[4], na = adjacent_cells(S, u->y * S + u->x, adj), target = -1;
+    for (int k = 0; k < na; k++)
+        for (int j = 0; j < h->n_units; j++) {                /* cell.units order: slot order stands in for arrival order */
+            const LuxUnit* v = &units[j];
+            if (v->y * S + v->x != adj[k] || ((v->team_type >> 1) & 1) != want_cart || (v->team_type & 1) != team) continue;
+            if (target < 0) { target = j; continue; }
+            int sv = (want_cart ? CAP_CART : CAP_WORKER) - (v->wood + v->coal + v->uranium);
+            const LuxUnit* t = &units[target];
+            int st = (want_cart ? CAP_CART : CAP_WORKER) - (t->wood + t->coal + t->uranium);
+            if (sv >= ramount && st >= ramount) { if (sv < st) target = j; }
+            else if (st >= ramount) { }
+            else if (sv > st) target = j;
+        }
+    if (target < 0 || rtype < 0) return 0;                    /* TransferAction with None fields: is_valid False */
+    const LuxUnit* t = &units[target];
+    int st = (want_cart ? CAP_CART : CAP_WORKER) - (t->wood + t->coal + t->uranium);
+    if (st < ramount) ramount = st;
+    if (ramount > 2047) ramount = 2047;
+    *word = LUX_UA_TRANSFER | ((uint32_t)rtype << 3) | ((uint32_t)ramount << 6) | ((uint32_t)t->id << 17);
+    return 1;
+}
+
+int lux_oracle_encode_actions(const LuxHeader* h, const LuxUnit* units, const int16_t* ent_slot, int ent_count,
+                              const int32_t* codes, uint32_t* ua, uint8_t* ta, int u_cap, int t_cap) {
+    if (!h || !units || !ent_slot || !codes || !ua || !ta) return LUX_E_ARG;
+    memset(ua, 0, sizeof(uint32_t) * u_cap);
+    memset(ta, 0, t_cap);
+    if (h->done) return 0;
+    static const int dirs[5] = {LUX_DIR_CENTER, LUX_DIR_NORTH, LUX_DIR_WEST, LUX_DIR_SOUTH, LUX_DIR_EAST};
+    for (int e = 0; e < ent_count; e++) {
+        int code = codes[e], slot = ent_slot[e];
+        if (slot & 0x4000) { ta[slot & 0x3FFF] = (uint8_t)(1 + ((code % 3) + 3) % 3); continue; }
+        int c = ((code % 9) + 9) % 9;
+        uint32_t w = 0;
+        if (c < 5) w = LUX_UA_MOVE | (dirs[c] << 3);
+        else if (c == 5) smart_transfer(h, units, slot, 1, &w);
+        else if (c == 6) smart_transfer(h, units, slot, 0, &w);
+        else if (c == 7) w = LUX_UA_BCITY;
+        else w = LUX_UA_PILLAGE;
+        ua[slot] = w;
+    }
+    return 0;
+}
+
+/* AgentPolicy.get_reward (examples/agent_policy.py:494-560) evaluated once per turn for `team`:
+ * last[3] = units_last, city_tiles_last, fuel_collected_last (game_start :480-492 zeroes them). */
+int lux_oracle_reward(const LuxHeader* h, int team, int32_t* last, double* reward) {
+    if (!h || !last || !reward) return LUX_E_ARG;
+    int units_now = h->n_team_units[team], tiles_now = h->n_team_tiles[team], fuel = h->fuel_generated[team];
+    double r = 0.0;
+    r += (double)(units_now - last[0]) * 0.05;
+    r += (double)(tiles_now - last[1]) * 0.1;
+    r += (double)(fuel - last[2]) / 20000.0;
+    r += h->done ? (double)tiles_now : 0.0;
+    last[0] = units_now; last[1] = tiles_now; last[2] = fuel;
+    *reward = r;
     return 0;
 }

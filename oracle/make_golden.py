@@ -208,6 +208,144 @@ def make_obs(ref, stream_seed=4711):
     np.savez_compressed(os.path.join(OUT, "obs.npz"), **store)
 
 
+def make_env(ref, stream_seed=90210, n=8):
+    """env.npz: the reference's LuxEnvironment (luxai2021/env/lux_env.py:73-183) driven decision by
+    decision: learning agent = examples/agent_policy.py AgentPolicy("train"), opponent = idle Agent(),
+    action code of every decision = hash64(stream_seed, match, turn, kind, key) % 9.  Stored per match:
+    initial state, learning team, per decision (turn, entity code, action code, returned reward, done),
+    per game turn the state digest, and the observation rows of the first 50 turns."""
+    import random
+    from luxai2021.env.agent import Agent
+    from luxai2021.env.lux_env import LuxEnvironment
+    store = {}
+    for k in range(n):
+        size = [12, 16, 24, 32][k % 4]
+        random.seed(4000 + k)
+        agent = refshim.agent_policy()
+        cfg = dict(ref.LuxMatchConfigs_Default)
+        cfg.update(seed=7000 + k, width=size, height=size)
+        env = LuxEnvironment(configs=cfg, learning_agent=agent, opponent_agent=Agent())
+        game = env.game
+        game.log = lambda text: None
+        digests = []
+        orig = game.run_turn_with_actions
+
+        def wrapped(actions, orig=orig, game=game, digests=digests):
+            over = orig(actions)
+            digests.append(stamp_done(flatten.flatten(game, caps=CAPS), game, over).digest())
+            return over
+
+        game.run_turn_with_actions = wrapped
+        obs = env.reset()
+        init = flatten.flatten(game, caps=CAPS)
+        team = agent.team
+        decisions, obs_rows = [], []
+        done = False
+        while not done:
+            unit, tile, t, _ = env.last_observation_object
+            assert t == team
+            turn = game.state["turn"]
+            if unit is not None:
+                slot = 0
+                for tt in (0, 1):
+                    for u in game.state["teamStates"][tt]["units"].values():
+                        if u is unit:
+                            ent = slot
+                        slot += 1
+                kind, key = 2, int(unit.id.split("_")[1])
+            else:
+                pos = 0
+                for city in game.cities.values():
+                    for cell in city.city_cells:
+                        if cell.city_tile is tile:
+                            ent = 0x4000 | pos
+                        pos += 1
+                kind, key = 3, tile.pos.y * size + tile.pos.x
+            code = stream.hash64(stream_seed, k, turn, kind, key) % 9
+            if turn < 50:
+                obs_rows.append(np.asarray(obs, dtype=np.float64))
+            obs, reward, done, _ = env.step(code)
+            decisions.append((turn, ent, code, reward, float(done)))
+        store["%d/size" % k] = np.array(size)
+        store["%d/team" % k] = np.array(team)
+        put(store, "%d/init" % k, init)
+        store["%d/decisions" % k] = np.array(decisions, dtype=np.float64).reshape(-1, 5)
+        store["%d/digests" % k] = np.array(digests, dtype=np.uint64)
+        store["%d/obs" % k] = np.array(obs_rows, dtype=np.float32).reshape(-1, 85)
+        print("env", k, size, "team", team, "turns", len(digests), "decisions", len(decisions))
+    # dense episodes: the same decision loop (MatchController.run_to_next_observation +
+    # AgentPolicy.take_action / get_reward, i.e. the body of LuxEnvironment.step) started from
+    # replay states, so that many units of one team compete for cells (MoveAction.is_valid :87-113)
+    from luxai2021.game.match_controller import MatchController
+    files = sorted(glob.glob(os.path.join(refshim.REFERENCE_ROOT, "luxai2021/tests/replays_for_test/*[0-9].json")))
+    k = n
+    for f in files:
+        rep = json.load(open(f))
+        for start in (120, 250):
+            random.seed(5000 + k)
+            game = refshim.game_from_replay(rep, step=start)
+            size = game.map.width
+            agent = refshim.agent_policy()
+            mc = MatchController(game, agents=[agent, Agent()])
+            team = agent.team
+            digests = []
+            orig = game.run_turn_with_actions
+
+            def wrapped(actions, orig=orig, game=game, digests=digests):
+                over = orig(actions)
+                digests.append(stamp_done(flatten.flatten(game, caps=CAPS), game, over).digest())
+                return over
+
+            game.run_turn_with_actions = wrapped
+            init = flatten.flatten(game, caps=CAPS)
+            gen = mc.run_to_next_observation()
+            decisions = []
+            try:
+                unit, tile, t, new_turn = next(gen)
+                while len(digests) < 30:
+                    turn = game.state["turn"]
+                    if unit is not None:
+                        slot = 0
+                        for tt in (0, 1):
+                            for u in game.state["teamStates"][tt]["units"].values():
+                                if u is unit:
+                                    ent = slot
+                                slot += 1
+                        kind, key = 2, int(unit.id.split("_")[1])
+                    else:
+                        pos = 0
+                        for city in game.cities.values():
+                            for cell in city.city_cells:
+                                if cell.city_tile is tile:
+                                    ent = 0x4000 | pos
+                                pos += 1
+                        kind, key = 3, tile.pos.y * size + tile.pos.x
+                    code = stream.hash64(stream_seed, k, turn, kind, key) % 9
+                    agent.take_action(code, game, unit=unit, city_tile=tile, team=t)
+                    done = False
+                    try:
+                        unit, tile, t, new_turn = next(gen)
+                    except StopIteration:
+                        done, new_turn = True, True
+                    reward = agent.get_reward(game, done, new_turn, False)
+                    decisions.append((turn, ent, code, reward, float(done)))
+                    if done:
+                        break
+            except StopIteration:
+                pass
+            store["%d/size" % k] = np.array(size)
+            store["%d/team" % k] = np.array(team)
+            put(store, "%d/init" % k, init)
+            store["%d/decisions" % k] = np.array(decisions, dtype=np.float64).reshape(-1, 5)
+            store["%d/digests" % k] = np.array(digests, dtype=np.uint64)
+            store["%d/obs" % k] = np.zeros((0, 85), dtype=np.float32)
+            print("env-dense", k, os.path.basename(f), start, "team", team, "turns", len(digests), "decisions", len(decisions))
+            k += 1
+    store["n"] = np.array(k)
+    store["stream_seed"] = np.array(stream_seed)
+    np.savez_compressed(os.path.join(OUT, "env.npz"), **store)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     os.chdir("/tmp")
@@ -217,6 +355,7 @@ def main():
     make_random(ref)
     make_dense(ref)
     make_obs(ref)
+    make_env(ref)
 
 
 if __name__ == "__main__":

@@ -33,7 +33,7 @@ def lib():
     return _LIB
 
 
-def step(ms, unit_words, tile_bytes):
+def step(ms, unit_words, tile_bytes, flags=0):
     """One turn of one MatchState in place through the emulated kernel."""
     L = lib()
     hdr = ms.hdr.reshape(1)
@@ -46,7 +46,7 @@ def step(ms, unit_words, tile_bytes):
     b = LuxBatchC(1, ms.size, len(ms.units), len(ms.cities), len(ms.tiles), len(ms.res),
                   hdr.ctypes.data, ms.cells.ctypes.data, ms.units.ctypes.data, ms.cities.ctypes.data,
                   ms.tiles.ctypes.data, ms.res.ctypes.data)
-    rc = L.lux_emu_step(ctypes.byref(b), _p(uw), _p(tb))
+    rc = L.lux_emu_step(ctypes.byref(b), _p(uw), _p(tb), int(flags))
     ms.hdr = hdr[0]
     if rc != 0:
         raise RuntimeError("lux_emu_step -> %d" % rc)

@@ -16,6 +16,7 @@ struct EmuArgs {
     const uint8_t* ta;
     unsigned char* smem;
     LuxSmemLayout L;
+    unsigned flags;
 };
 
 static void emu_lane(void* p) {
@@ -42,7 +43,7 @@ static void emu_lane(void* p) {
     lux_copy16(M.uact, a->ua + (size_t)m * b->u_cap, M.hdr->n_units * 4);
     lux_copy16(M.tact, a->ta + (size_t)m * b->t_cap, M.hdr->n_tiles);
     lux_sync();
-    LuxTurnOut T = lux_turn(M);
+    LuxTurnOut T = lux_turn(M, a->flags);
     lux_finish_and_store<true>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
 }
 
@@ -50,10 +51,10 @@ extern "C" size_t lux_emu_smem_bytes(int size, int u_cap, int c_cap, int t_cap, 
     return (size_t)lux_smem_layout(size, u_cap, c_cap, t_cap, r_cap).total;
 }
 
-extern "C" int lux_emu_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions) {
+extern "C" int lux_emu_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions, unsigned flags) {
     if (!b || !unit_actions || !tile_actions) return LUX_E_ARG;
     EmuArgs a;
-    a.b = b; a.ua = unit_actions; a.ta = tile_actions;
+    a.b = b; a.ua = unit_actions; a.ta = tile_actions; a.flags = flags;
     a.L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
     a.smem = (unsigned char*)aligned_alloc(16, a.L.total);
     for (int m = 0; m < b->n_matches; m++) {

@@ -125,6 +125,15 @@ static inline int lux_reduce_add(int v) {
     warp_emu::barrier();
     return (int)r;
 }
+static inline unsigned lux_match_any(int key) {
+    warp_emu::State& s = warp_emu::st();
+    s.vals[s.cur] = key;
+    warp_emu::barrier();
+    unsigned m = 0;
+    for (int i = 0; i < 32; i++) m |= (unsigned)(s.vals[i] == key) << i;
+    warp_emu::barrier();
+    return m;
+}
 static inline int lux_popc(unsigned v) { return __builtin_popcount(v); }
 static inline int lux_ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline unsigned lux_atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }

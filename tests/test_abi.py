@@ -64,7 +64,7 @@ def test_no_device_is_an_error_not_a_fallback():
     desc = _lib.LuxBatch(n, size, caps["units"], caps["cities"], caps["tiles"], caps["res"], *ptrs)
     ua = np.zeros(n * caps["units"] + 4, dtype=np.uint32)
     ta = np.zeros(n * caps["tiles"] + 16, dtype=np.uint8)
-    rc = lib.lux_b200_step(ctypes.byref(desc), (ua.ctypes.data + 15) & ~15, (ta.ctypes.data + 15) & ~15, None)
+    rc = lib.lux_b200_step(ctypes.byref(desc), (ua.ctypes.data + 15) & ~15, (ta.ctypes.data + 15) & ~15, 0, None)
     assert rc == _lib.LUX_E_NO_DEVICE
     with pytest.raises(RuntimeError):
         from luxpythonenvgym_b200.batched import BatchedGame

@@ -71,3 +71,17 @@ def test_emulated_observations(name):
         got, got_codes = emu.observe(ms, team)
         assert np.array_equal(codes, got_codes)
         assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), np.argwhere(want != got)[:5]
+
+
+@pytest.mark.parametrize("k", [0, 7, 10, 12, 16, 19])
+def test_emulated_env_flow(k):
+    """Pre-validation (LUX_STEP_PREVALIDATE) inside the emulated step kernel + emulated observations
+    on the LuxEnvironment fixtures; action decoding / reward come from the oracle here."""
+    from tests import env_util
+
+    def step_turn(ms, ent, codes):
+        uw, tb = coracle.encode_actions(ms, ent, codes)
+        emu.step(ms, uw, tb, flags=1)
+
+    ms = recap(G.get_state(G.npz("env"), "%d/init" % k))
+    env_util.check_episode(k, ms, emu.observe, step_turn, coracle.reward)

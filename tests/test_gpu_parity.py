@@ -176,11 +176,11 @@ def test_bad_arguments_are_rejected():
     g = _game(4, 12)
     d = _lib.LuxBatch(4, 13, 32, 16, 32, 48, g.hdr.data_ptr(), g.cells.data_ptr(), g.units.data_ptr(),
                       g.cities.data_ptr(), g.tiles.data_ptr(), g.res.data_ptr())
-    assert lib.lux_b200_step(ctypes.byref(d), g.unit_actions.data_ptr(), g.tile_actions.data_ptr(), None) == _lib.LUX_E_ARG
+    assert lib.lux_b200_step(ctypes.byref(d), g.unit_actions.data_ptr(), g.tile_actions.data_ptr(), 0, None) == _lib.LUX_E_ARG
     d.size, d.u_cap = 12, 33
-    assert lib.lux_b200_step(ctypes.byref(d), g.unit_actions.data_ptr(), g.tile_actions.data_ptr(), None) == _lib.LUX_E_CAPACITY
+    assert lib.lux_b200_step(ctypes.byref(d), g.unit_actions.data_ptr(), g.tile_actions.data_ptr(), 0, None) == _lib.LUX_E_CAPACITY
     d.u_cap = 32
-    assert lib.lux_b200_step(ctypes.byref(d), None, g.tile_actions.data_ptr(), None) == _lib.LUX_E_ARG
+    assert lib.lux_b200_step(ctypes.byref(d), None, g.tile_actions.data_ptr(), 0, None) == _lib.LUX_E_ARG
 
 
 def test_observations_golden_and_oracle():
@@ -220,3 +220,99 @@ def test_observations_golden_and_oracle():
     live = np.arange(e_cap)[None, :] < cnt[:, None]
     assert np.array_equal(ent.cpu().numpy()[live], o_ent[live])
     assert np.array_equal(obs.cpu().numpy().view(np.uint32)[live], o_obs.view(np.uint32)[live])
+
+
+def test_env_flow_on_device():
+    """observe -> encode_actions -> step(prevalidate) -> reward on the GPU against the golden episodes
+    recorded from the reference's LuxEnvironment.step loop (tests/golden/env.npz)."""
+    from tests import env_util
+    z = G.npz("env")
+    for k in env_util.env_ids():
+        init = _recap(G.get_state(z, "%d/init" % k), BIG)
+        g = _game(1, init.size, BIG)
+        g.load_states([init])
+        team = int(z["%d/team" % k])
+        sel = torch.full((1,), team, dtype=torch.uint8, device="cuda")
+        rstate = torch.zeros((1, 4), dtype=torch.int32, device="cuda")
+
+        def observe(ms, t):
+            obs, ent, cnt = g.observe(sel)
+            c = int(cnt.item())
+            return obs[0, :c].cpu().numpy(), ent[0, :c].cpu().numpy()
+
+        def step_turn(ms, ent, codes):
+            obs, ent_t, cnt = g._obs, g._ent, g._cnt
+            ct = torch.zeros((1, ent_t.shape[1]), dtype=torch.int32, device="cuda")
+            ct[0, : len(codes)] = torch.from_numpy(codes).cuda()
+            g.encode_actions(ent_t, cnt, ct)
+            g.step(prevalidate=True)
+            new = g.export_states([0])[0]
+            for name in S.MatchState.SECTIONS:
+                setattr(ms, name, getattr(new, name))
+
+        def reward(ms, t, last):
+            return float(g.reward(sel, rstate).item())
+
+        env_util.check_episode(k, g.export_states([0])[0], observe, step_turn, reward)
+
+
+def test_game_adapter_replays_reference_episode():
+    """The single-match `Game` adapter (reference API names) driven by Kaggle command strings."""
+    from luxpythonenvgym_b200.game import Game
+    from luxpythonenvgym_b200 import actions as A
+    z = G.npz("replays")
+    rid = G.replay_ids()[0]
+    init = G.get_state(z, rid + "/init")
+    game = Game({"seed": 1, "width": init.size})
+    game.reset(state=init)
+    U, T = G.replay_actions(z, rid, init)
+    digests = z[rid + "/digests"]
+    for turn in range(120):
+        ms = game.packed_state()
+        acts = []
+        for p in np.nonzero(T[turn])[0]:
+            cell = int(ms.tiles[p])
+            team = ((int(ms.cells["flags"][cell]) >> 2) & 3) - 1
+            cls = {1: A.SpawnWorkerAction, 2: A.SpawnCartAction}.get(int(T[turn][p]))
+            x, y = cell % ms.size, cell // ms.size
+            acts.append(cls(team, None, x, y) if cls else A.ResearchAction(team, x, y, None))
+        for s in np.nonzero(U[turn])[0]:
+            d = S.decode_unit_action(U[turn][s])
+            team, uid = int(ms.units["team_type"][s]) & 1, "u_%d" % int(ms.units["id"][s])
+            if d["kind"] == S.UA_MOVE:
+                acts.append(A.MoveAction(team, uid, S.DIR_CHARS[d["dir"]]))
+            elif d["kind"] == S.UA_BCITY:
+                acts.append(A.SpawnCityAction(team, uid))
+            elif d["kind"] == S.UA_PILLAGE:
+                acts.append(A.PillageAction(team, uid))
+            else:
+                acts.append(A.TransferAction(team, uid, "u_%d" % d["dest"], S.RES_NAMES[d["res"]], d["amount"]))
+        over = game.run_turn_with_actions(acts)
+        assert not over
+        assert game.packed_state().digest() == int(digests[turn]), turn
+    assert game.state["turn"] == 120 and len(game.cities) > 0
+    assert sum(len(c.city_cells) for c in game.cities.values()) == int(game.packed_state().hdr["n_tiles"])
+    assert game.map.get_map_string().count("\n") == init.size
+
+
+def test_lux_environment_single_and_batched():
+    from luxpythonenvgym_b200.env import BatchedLuxEnvironment, LuxEnvironment
+    env = LuxEnvironment({"seed": 7000, "width": 12, "team_seed": 3})
+    obs = env.reset()
+    assert obs.shape == (85,)
+    total, steps, done = 0.0, 0, False
+    while not done and steps < 3000:
+        obs, r, done, _ = env.step((steps * 7) % 9)
+        total += r
+        steps += 1
+    assert done and steps > 10 and total != 0.0
+    benv = BatchedLuxEnvironment(256, size=16, seed=100, pool_maps=16)
+    obs, ent, cnt = benv.reset()
+    assert obs.shape == (256, benv.e_cap, 85) and int(cnt.min()) >= 1
+    finished = 0
+    for t in range(120):
+        codes = torch.randint(0, 9, ent.shape, dtype=torch.int32, device="cuda")
+        (obs, ent, cnt), reward, done = benv.step(codes)
+        finished += int(done.sum())
+        assert reward.dtype == torch.float64 and torch.isfinite(reward).all()
+    assert finished > 0 and (benv.game.headers()["status"] == 0).all()
