@@ -18,7 +18,14 @@
 #define LUX_B200_VERSION 100
 
 // ---------------------------------------------------------------- the step kernel
-template <bool kTma>
+// Speculative first batch: these many leading records of each list travel together with the header
+// and the cell grid, so a typical (sparse) match needs ONE global->shared round trip; only matches
+// with more entities issue a second batch for the remainder.
+#define LUX_PRE_UNITS 32
+#define LUX_PRE_CITIES 16
+#define LUX_PRE_TILES 32
+
+template <bool kTma, int kS>
 __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions,
                                 const uint8_t* __restrict__ tile_actions, LuxSmemLayout L, unsigned flags) {
     extern __shared__ __align__(128) unsigned char lux_smem[];
@@ -27,9 +34,10 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
     if (m >= b.n_matches) return;
     unsigned char* smem = lux_smem + (size_t)warp * L.total;
-    const int ncell = b.size * b.size;
+    const int size = kS > 0 ? kS : b.size;
+    const int ncell = size * size;
     LuxMatch M;
-    lux_match_bind(M, smem, L, b.size, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
+    lux_match_bind(M, smem, L, size, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
     LuxHeader* g_hdr = b.hdr + m;
     LuxCell* g_cells = b.cells + (size_t)m * ncell;
     LuxUnit* g_units = b.units + (size_t)m * b.u_cap;
@@ -41,31 +49,40 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
 
     if (kTma) {
         uint64_t* bar = (uint64_t*)(smem + L.mbar);
+        const uint32_t pu = min(b.u_cap, LUX_PRE_UNITS), pc = min(b.c_cap, LUX_PRE_CITIES), pt = min(b.t_cap, LUX_PRE_TILES);
+        const uint32_t b_cells = ncell * 8, b_res = b.r_cap * 2;
         if (lane == 0) {
             mbar_init(bar, 1);
             fence_mbar_init();
-            mbar_expect_tx(bar, LUX_HDR_BYTES);
+            mbar_expect_tx(bar, LUX_HDR_BYTES + b_cells + b_res + pu * 16 + pc * 16 + pt * 2 + pu * 4 + pt);
             tma_g2s(M.hdr, g_hdr, LUX_HDR_BYTES, bar);
+            tma_g2s(M.cells, g_cells, b_cells, bar);
+            tma_g2s(M.res, g_res, b_res, bar);
+            tma_g2s(M.units, g_units, pu * 16, bar);
+            tma_g2s(M.cities, g_cities, pc * 16, bar);
+            tma_g2s(M.tiles, g_tiles, pt * 2, bar);
+            tma_g2s(M.uact, g_ua, pu * 4, bar);
+            tma_g2s(M.tact, g_ta, pt, bar);
         }
         __syncwarp();
         mbar_wait(bar, 0);
         if (M.hdr->done) return;
-        const uint32_t nu = M.hdr->n_units, nc = M.hdr->n_cities, nt = M.hdr->n_tiles, nr = M.hdr->n_res;
-        const uint32_t b_cells = ncell * 8, b_units = nu * 16, b_cities = nc * 16;
-        const uint32_t b_tiles = (nt * 2 + 15) & ~15u, b_res = (nr * 2 + 15) & ~15u;
-        const uint32_t b_ua = (nu * 4 + 15) & ~15u, b_ta = (nt + 15) & ~15u;
-        if (lane == 0) {
-            mbar_expect_tx(bar, b_cells + b_units + b_cities + b_tiles + b_res + b_ua + b_ta);
-            tma_g2s(M.cells, g_cells, b_cells, bar);
-            if (b_units) tma_g2s(M.units, g_units, b_units, bar);
-            if (b_cities) tma_g2s(M.cities, g_cities, b_cities, bar);
-            if (b_tiles) tma_g2s(M.tiles, g_tiles, b_tiles, bar);
-            if (b_res) tma_g2s(M.res, g_res, b_res, bar);
-            if (b_ua) tma_g2s(M.uact, g_ua, b_ua, bar);
-            if (b_ta) tma_g2s(M.tact, g_ta, b_ta, bar);
+        const uint32_t nu = M.hdr->n_units, nc = M.hdr->n_cities, nt = M.hdr->n_tiles;
+        if (nu > pu || nc > pc || nt > pt) {                      // warp-uniform
+            const uint32_t ru = nu > pu ? nu - pu : 0, rc = nc > pc ? nc - pc : 0;
+            const uint32_t rt2 = nt > pt ? ((nt - pt) * 2 + 15) & ~15u : 0;
+            const uint32_t rua = nu > pu ? ((nu - pu) * 4 + 15) & ~15u : 0, rta = nt > pt ? ((nt - pt) + 15) & ~15u : 0;
+            if (lane == 0) {
+                mbar_expect_tx(bar, ru * 16 + rc * 16 + rt2 + rua + rta);
+                if (ru) tma_g2s(M.units + pu, g_units + pu, ru * 16, bar);
+                if (rc) tma_g2s(M.cities + pc, g_cities + pc, rc * 16, bar);
+                if (rt2) tma_g2s(M.tiles + pt, g_tiles + pt, rt2, bar);
+                if (rua) tma_g2s(M.uact + pu, g_ua + pu, rua, bar);
+                if (rta) tma_g2s(M.tact + pt, g_ta + pt, rta, bar);
+            }
+            __syncwarp();
+            mbar_wait(bar, 1);
         }
-        __syncwarp();
-        mbar_wait(bar, 1);
     } else {
         lux_copy16(M.hdr, g_hdr, LUX_HDR_BYTES);
         __syncwarp();
@@ -80,10 +97,10 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
         __syncwarp();
     }
 
-    LuxTurnOut T = lux_turn(M, flags);
+    LuxTurnOut T = lux_turn<kS>(M, flags);
 
     if (kTma) {
-        lux_finish_and_store<false>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
+        lux_finish_and_store<false, kS>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
         // every lane orders its own shared-memory writes before the async proxy reads them
         fence_proxy_async();
         __syncwarp();
@@ -94,8 +111,17 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
             tma_wait_read0();
         }
     } else {
-        lux_finish_and_store<true>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
+        lux_finish_and_store<true, kS>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
     }
+}
+
+template <bool kTma, int kS>
+static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L, unsigned flags,
+                       int grid, int wpc, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return LUX_E_CUDA;
+    lux_step_kernel<kTma, kS><<<grid, 32 * wpc, smem, st>>>(*b, ua, ta, L, flags);
+    return LUX_OK;
 }
 
 // ---------------------------------------------------------------- canonical action stream
@@ -297,23 +323,27 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
     LuxSmemLayout L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
     int wpc = g_warps_per_cta;
     if (wpc <= 0) {
-        wpc = (64 * 1024) / L.total;
-        if (wpc < 1) wpc = 1;
-        if (wpc > 4) wpc = 4;
+        // one match per CTA measured fastest for staged footprints of 8 KB and more (independent
+        // CTAs spread better over the SMs' instruction caches); pair small matches to lift the
+        // 32-CTA-per-SM limit
+        wpc = L.total >= 8 * 1024 ? 1 : 2;
     }
     size_t smem = (size_t)L.total * wpc;
     if (smem > 227 * 1024) return LUX_E_CAPACITY;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int grid = (b->n_matches + wpc - 1) / wpc;
     if (g_use_tma) {
-        rc = cuda_ok(cudaFuncSetAttribute(lux_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-        if (rc) return rc;
-        lux_step_kernel<true><<<grid, 32 * wpc, smem, st>>>(*b, unit_actions, tile_actions, L, flags);
+        switch (b->size) {
+            case 12: rc = launch_step<true, 12>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st); break;
+            case 16: rc = launch_step<true, 16>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st); break;
+            case 24: rc = launch_step<true, 24>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st); break;
+            case 32: rc = launch_step<true, 32>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st); break;
+            default: rc = launch_step<true, 0>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st); break;
+        }
     } else {
-        rc = cuda_ok(cudaFuncSetAttribute(lux_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-        if (rc) return rc;
-        lux_step_kernel<false><<<grid, 32 * wpc, smem, st>>>(*b, unit_actions, tile_actions, L, flags);
+        rc = launch_step<false, 0>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st);
     }
+    if (rc) { fprintf(stderr, "lux_b200: step kernel attribute: %s\n", cudaGetErrorString(cudaGetLastError())); return rc; }
     return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
 }
 

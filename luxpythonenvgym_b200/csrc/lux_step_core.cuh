@@ -55,7 +55,7 @@
 #define UST_FAILED 0x80u  // transfer raised KeyError in the reference: no cooldown, no cart road
 
 struct LuxSmemLayout {
-    int hdr, cells, units, cities, tiles, res, uact, tact, p1, occ, utgt, ust, umine, tmask, cprefix, cremap, mbar, total;
+    int hdr, cells, units, cities, tiles, res, uact, tact, p1, occ, utgt, ust, umine, tmask, cprefix, cremap, reqlist, mbar, total;
 };
 
 LUX_DEV int lux_align16(int x) { return (x + 15) & ~15; }
@@ -86,6 +86,7 @@ LuxSmemLayout lux_smem_layout(int size, int u_cap, int c_cap, int t_cap, int r_c
     LUX_TAKE(tmask, t_cap * 4)
     LUX_TAKE(cprefix, (c_cap + 1) * 2)
     LUX_TAKE(cremap, c_cap)
+    LUX_TAKE(reqlist, r_cap * 2 + 16)   // cells requested this collection pass (+ counter)
     LUX_TAKE(mbar, 16)
 #undef LUX_TAKE
     L.total = o;
@@ -109,6 +110,8 @@ struct LuxMatch {
     uint32_t* tmask;
     uint16_t* cprefix;
     uint8_t* cremap;
+    uint16_t* reqlist;
+    int* reqcnt;
     int S, ncell, u_cap, c_cap, t_cap, r_cap;
 };
 
@@ -130,9 +133,17 @@ LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayou
     M.tmask = (uint32_t*)(smem + L.tmask);
     M.cprefix = (uint16_t*)(smem + L.cprefix);
     M.cremap = (uint8_t*)(smem + L.cremap);
+    M.reqcnt = (int*)(smem + L.reqlist);
+    M.reqlist = (uint16_t*)(smem + L.reqlist + 16);
     M.S = size; M.ncell = size * size;
     M.u_cap = u_cap; M.c_cap = c_cap; M.t_cap = t_cap; M.r_cap = r_cap;
 }
+
+#ifdef LUX_EMULATE
+#define LUX_NOINLINE static __attribute__((noinline))
+#else
+#define LUX_NOINLINE __device__ __noinline__
+#endif
 
 // ---- staging a match into shared memory with plain 16-byte loads --------------------------
 // (the CUDA build normally uses cp.async.bulk instead, see lux_step.cu; this form is what the
@@ -142,6 +153,7 @@ LUX_DEV void lux_copy16(void* dst, const void* src, int bytes) {   // bytes roun
     const uint64_t* s = (const uint64_t*)src;
     uint64_t* d = (uint64_t*)dst;
     int n = (bytes + 15) / 16;
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) { uint64_t a = s[2 * i], b = s[2 * i + 1]; d[2 * i] = a; d[2 * i + 1] = b; }
 }
 
@@ -171,28 +183,39 @@ LUX_DEV int lux_cell5(int S, int x, int y, int k) {
 LUX_DEV void lux_zero16(void* p, int bytes) {   // bytes multiple of 16, p 16-byte aligned
     int lane = lux_lane();
     uint64_t* q = (uint64_t*)p;
+#pragma unroll 1
     for (int i = lane; i < bytes / 16; i += 32) { q[2 * i] = 0; q[2 * i + 1] = 0; }
 }
 
 // ---- collection of one resource type (game.py:882-1001) -----------------------------------
+// One inlined copy inside a rolled loop over the resource types, inner loops rolled: the kernel is
+// instruction-fetch sensitive (flat, once-through code far larger than the instruction caches).
+template <int kS>
 LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researched0, int researched1) {
     const int lane = lux_lane();
-    const int S = M.S;
+    const int S = kS > 0 ? kS : M.S;
     LuxHeader* h = M.hdr;
     const int rate = rtype == LUX_RES_WOOD ? 20 : rtype == LUX_RES_COAL ? 5 : 2;
     const int fuel_rate = rtype == LUX_RES_WOOD ? 1 : rtype == LUX_RES_COAL ? 10 : 40;
-    const int n_res = h->n_res;
+
+    lux_zero16(M.p1, lux_align16(M.ncell));      // p1 becomes the "requested / fill level" plane
+    if (lane == 0) *M.reqcnt = 0;
+    lux_sync();
 
     // W1: every eligible worker computes its request amount (create_resource_requests :933-967)
+    // and registers the cells it mines from in the request list
+#pragma unroll 1
     for (int u = lane; u < n_units; u += 32) {
         LuxUnit& U = M.units[u];
         int mine = 0xFF;
         int team = unit_team(U);
         if (!unit_is_cart(U) && (team ? researched1 : researched0)) {
             int k = 0;
+            unsigned minable = 0;
+#pragma unroll 1
             for (int j = 0; j < 5; j++) {
                 int c = lux_cell5(S, U.x, U.y, j);
-                if (c >= 0 && cell_res_type(M.cells[c]) == rtype && M.cells[c].amount > 0) k++;
+                if (c >= 0 && cell_res_type(M.cells[c]) == rtype && M.cells[c].amount > 0) { k++; minable |= 1u << j; }
             }
             if (k > 0) {
                 int space = unit_space(U);
@@ -205,80 +228,89 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                     int t = M.cprefix[C.city_slot] + C.key;
                     lux_atomic_or(&M.tmask[t], 1u << mine);
                 }
+#pragma unroll 1
+                for (int j = 0; j < 5; j++) {
+                    if (!(minable & (1u << j))) continue;
+                    int c = lux_cell5(S, U.x, U.y, j);
+                    unsigned old = lux_atomic_or_byte(M.p1, c, 0x80u);
+                    if (!(old & 0x80u)) M.reqlist[lux_atomic_add(M.reqcnt, 1)] = (uint16_t)c;
+                }
             }
         }
         M.umine[u] = (uint8_t)mine;
     }
     lux_sync();
 
-    // C: every resource cell of this type resolves its requests (resolve_resource_requests :969-1001)
-    for (int r = lane; r < n_res; r += 32) {
-        int c = M.res[r];
+    // C: every requested cell resolves its requests (resolve_resource_requests :969-1001)
+    const int n_req = *M.reqcnt;
+#pragma unroll 1
+    for (int q = lane; q < n_req; q += 32) {
+        int c = M.reqlist[q];
         LuxCell& C = M.cells[c];
-        if (cell_res_type(C) != rtype) continue;
         int level = 0;
-        if (C.amount > 0) {
-            int x = c % S, y = c / S;
-            // histogram of request amounts 0..20, 3 bits each (at most one request per amount and source cell)
-            uint64_t hist = 0;
-            int n = 0, sum = 0;
-            for (int j = 0; j < 5; j++) {
-                int p = lux_cell5(S, x, y, j);
-                if (p < 0) continue;
-                const LuxCell& P = M.cells[p];
-                if (cell_is_tile(P)) {
+        int x = c % S, y = c / S;
+        // histogram of request amounts 0..20, 3 bits each (at most one request per amount and source cell)
+        uint64_t hist = 0;
+        int n = 0, sum = 0;
+#pragma unroll 1
+        for (int j = 0; j < 5; j++) {
+            int p = lux_cell5(S, x, y, j);
+            if (p < 0) continue;
+            const LuxCell& P = M.cells[p];
+            if (cell_is_tile(P)) {
+                unsigned mask = M.tmask[M.cprefix[P.city_slot] + P.key];
+                while (mask) {
+                    int a = lux_ffs(mask) - 1;
+                    mask &= mask - 1;
+                    hist += (uint64_t)1 << (3 * a);
+                    n++; sum += a;
+                }
+            } else {
+                int o = M.occ[p];
+                if (o) {
+                    int a = M.umine[o - 1];
+                    if (a != 0xFF) { hist += (uint64_t)1 << (3 * a); n++; sum += a; }
+                }
+            }
+        }
+        if (n > 0 && sum > 0) {
+            int left = C.amount;
+#pragma unroll 1
+            for (int a = 0; a <= 20 && n > 0 && left > 0; a++) {
+                int cnt = (int)((hist >> (3 * a)) & 7);
+                if (!cnt) continue;
+                int minrem = a - level;
+                int qq = left / n;
+                if (qq >= minrem) {
+                    left -= minrem * n;
+                    level = a;
+                    if (left < n) left = 0;
+                    n -= cnt;
+                } else {
+                    level += qq;
+                    left = 0;
+                }
+            }
+            C.amount = (uint16_t)left;
+            // city-tile requests are credited here (game.py:988-990)
+            if (level > 0) {
+#pragma unroll 1
+                for (int j = 0; j < 5; j++) {
+                    int p = lux_cell5(S, x, y, j);
+                    if (p < 0) continue;
+                    const LuxCell& P = M.cells[p];
+                    if (!cell_is_tile(P)) continue;
                     unsigned mask = M.tmask[M.cprefix[P.city_slot] + P.key];
+                    int got = 0;
                     while (mask) {
                         int a = lux_ffs(mask) - 1;
                         mask &= mask - 1;
-                        hist += (uint64_t)1 << (3 * a);
-                        n++; sum += a;
+                        got += a < level ? a : level;
                     }
-                } else {
-                    int o = M.occ[p];
-                    if (o) {
-                        int a = M.umine[o - 1];
-                        if (a != 0xFF) { hist += (uint64_t)1 << (3 * a); n++; sum += a; }
-                    }
-                }
-            }
-            if (n > 0 && sum > 0) {
-                int left = C.amount;
-                for (int a = 0; a <= 20 && n > 0 && left > 0; a++) {
-                    int cnt = (int)((hist >> (3 * a)) & 7);
-                    if (!cnt) continue;
-                    int minrem = a - level;
-                    int q = left / n;
-                    if (q >= minrem) {
-                        left -= minrem * n;
-                        level = a;
-                        if (left < n) left = 0;
-                        n -= cnt;
-                    } else {
-                        level += q;
-                        left = 0;
-                    }
-                }
-                C.amount = (uint16_t)left;
-                // city-tile requests are credited here (game.py:988-990)
-                if (level > 0) {
-                    for (int j = 0; j < 5; j++) {
-                        int p = lux_cell5(S, x, y, j);
-                        if (p < 0) continue;
-                        const LuxCell& P = M.cells[p];
-                        if (!cell_is_tile(P)) continue;
-                        unsigned mask = M.tmask[M.cprefix[P.city_slot] + P.key];
-                        int got = 0;
-                        while (mask) {
-                            int a = lux_ffs(mask) - 1;
-                            mask &= mask - 1;
-                            got += a < level ? a : level;
-                        }
-                        if (got) {
-                            LuxCity& city = M.cities[P.city_slot];
-                            lux_atomic_add(&city.fuel, got * fuel_rate);
-                            lux_atomic_add(&h->collected[city.team][rtype - 1], got);
-                        }
+                    if (got) {
+                        LuxCity& city = M.cities[P.city_slot];
+                        lux_atomic_add(&city.fuel, got * fuel_rate);
+                        lux_atomic_add(&h->collected[city.team][rtype - 1], got);
                     }
                 }
             }
@@ -289,6 +321,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
 
     // W2: workers off city tiles take min(request, level) from each cell, capped by cargo space
     int got0 = 0, got1 = 0;
+#pragma unroll 1
     for (int u = lane; u < n_units; u += 32) {
         LuxUnit& U = M.units[u];
         int mine = M.umine[u];
@@ -300,10 +333,11 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
             continue;
         }
         int gain = 0;
+#pragma unroll 1
         for (int j = 0; j < 5; j++) {
             int c = lux_cell5(S, U.x, U.y, j);
             if (c >= 0 && cell_res_type(M.cells[c]) == rtype) {
-                int lv = M.p1[c];
+                int lv = M.p1[c] & 0x7F;
                 gain += mine < lv ? mine : lv;
             }
         }
@@ -327,6 +361,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
 LUX_DEV void lux_city_prefix(LuxMatch& M, int n_cities) {
     const int lane = lux_lane();
     int run = 0;
+#pragma unroll 1
     for (int base = 0; base < n_cities; base += 32) {
         int s = base + lane;
         int v = s < n_cities ? M.cities[s].ntiles : 0;
@@ -340,10 +375,11 @@ LUX_DEV void lux_city_prefix(LuxMatch& M, int n_cities) {
 }
 
 // ---- build a city tile under unit `u` (spawn_city_tile game.py:798-854); lane 0 only ---------
+template <int kS>
 LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tiles) {
     LuxHeader* h = M.hdr;
     LuxUnit& U = M.units[u];
-    const int S = M.S;
+    const int S = kS > 0 ? kS : M.S;
     const int team = unit_team(U);
     const int idx = U.y * S + U.x;
     LuxCell& C = M.cells[idx];
@@ -383,6 +419,7 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
     for (int f = 1; f < nfound; f++) {      // merge the other adjacent cities (:844-852)
         LuxCity& old = M.cities[found[f]];
         int base = city.ntiles;
+#pragma unroll 1
         for (int t = 0; t < n_tiles; t++) {
             LuxCell& T = M.cells[M.tiles[t]];
             if (cell_is_tile(T) && T.city_slot == found[f]) {
@@ -405,11 +442,12 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
 //   bit0 tiles list must be rewritten, [31:16] n_units (incl. spawned), others via hdr.
 struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; };
 
+template <int kS>
 LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     const int lane = lux_lane();
     const unsigned lt = lux_lanemask_lt();
     LuxHeader* h = M.hdr;
-    const int S = M.S;
+    const int S = kS > 0 ? kS : M.S;
     const int n_units0 = h->n_units;
     const int n_tiles0 = h->n_tiles;
     int n_cities = h->n_cities;
@@ -420,10 +458,15 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     int tiles_dirty = 0;
 
     lux_zero16(M.p1, lux_align16(M.ncell));
-    lux_zero16(M.tmask, lux_align16(M.t_cap * 4));
+    {
+        int nt = n_tiles0 + n_units0;                 // tile indices that can exist during this turn
+        if (nt > M.t_cap) nt = M.t_cap;
+        lux_zero16(M.tmask, lux_align16(nt * 4));
+    }
 
     // ---- team city-tile counts (worker_unit_cap_reached game.py:725-735)
     int tt0 = 0, tt1 = 0;
+#pragma unroll 1
     for (int s = lane; s < n_cities; s += 32) {
         if (M.cities[s].team) tt1 += M.cities[s].ntiles; else tt0 += M.cities[s].ntiles;
     }
@@ -432,6 +475,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     const int tu0 = h->n_team_units[0], tu1 = h->n_team_units[1];
 
     // ---- unit action validation (validate_command game.py:646-695), lanes over units
+#pragma unroll 1
     for (int u = lane; u < n_units0; u += 32) {
         const LuxUnit& U = M.units[u];
         unsigned w = M.uact[u];
@@ -487,6 +531,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     // same-team moves into one non-city cell only the first in unit order is buffered; a CENTER
     // move is the do-nothing action and never changes the outcome, so it is dropped here
     if (flags & LUX_STEP_PREVALIDATE) {
+#pragma unroll 1
         for (int base = 0; base < n_units0; base += 32) {
             int u = base + lane;
             unsigned st = u < n_units0 ? M.ust[u] : 0;
@@ -509,6 +554,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     }
 
     // ---- collision pruning (handle_movement_actions game.py:1104-1195)
+#pragma unroll 1
     for (int u = lane; u < n_units0; u += 32) {
         const LuxUnit& U = M.units[u];
         int ucell = U.y * S + U.x;
@@ -525,6 +571,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     lux_sync();
     // seeds: >= 2 moves into a non-city cell, or one move into a non-city cell whose single
     // occupant is not moving (:1164-1179)
+#pragma unroll 1
     for (int u = lane; u < n_units0; u += 32) {
         unsigned st = M.ust[u];
         if ((st & 7) != LUX_UA_MOVE) continue;
@@ -540,8 +587,10 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     }
     lux_sync();
     // cascade (revert_action :1138-1156): a reverted mover blocks its own non-city cell
+#pragma unroll 1
     for (;;) {
         int changed = 0;
+#pragma unroll 1
         for (int u = lane; u < n_units0; u += 32) {
             unsigned st = M.ust[u];
             if ((st & 7) != LUX_UA_MOVE || (st & UST_REVERTED)) continue;
@@ -566,6 +615,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         int wb0 = 0, wb1 = 0, cb0 = 0, cb1 = 0;
         const int uid0 = h->unit_id_count;
         const int room = M.u_cap - n_units0;
+#pragma unroll 1
         for (int base = 0; base < n_tiles0; base += 32) {
             int p = base + lane;
             int valid = p < n_tiles0;
@@ -625,6 +675,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 
     // ---- unit turns (Worker.turn unit.py:162-197, Cart.turn :234-269)
     // moves are conflict-free after pruning: lane-parallel
+#pragma unroll 1
     for (int u = lane; u < n_units0; u += 32) {
         unsigned st = M.ust[u];
         if ((st & 7) != LUX_UA_MOVE) continue;
@@ -636,6 +687,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     }
     lux_sync();
     // transfer / build city / pillage depend on unit order (team A then B == slot order)
+#pragma unroll 1
     for (int base = 0; base < n_units0; base += 32) {
         int u = base + lane;
         int k = u < n_units0 ? (M.ust[u] & 7) : 0;
@@ -650,6 +702,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 int dest_id = (int)(w >> 17);
                 int steam = unit_team(M.units[su]);
                 int dest = -1;
+#pragma unroll 1
                 for (int cb = 0; cb < n_units; cb += 32) {
                     int v = cb + lane;
                     int hit = v < n_units && M.units[v].id == dest_id && unit_team(M.units[v]) == steam;
@@ -677,9 +730,10 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 LuxUnit& U = M.units[su];
                 if (!unit_is_cart(U)) {
                     if (kind == LUX_UA_BCITY) {
-                        lux_build_city_lane0(M, su, n_cities, n_tiles);
+                        lux_build_city_lane0<kS>(M, su, n_cities, n_tiles);
                         int spent = 0;                                // expend_resources_for_city unit.py:146-160
                         uint16_t* cg[3] = {&U.wood, &U.coal, &U.uranium};
+#pragma unroll 1
                         for (int r = 0; r < 3; r++) {
                             if (spent + *cg[r] > LUX_CITY_BUILD_COST) { *cg[r] = (uint16_t)(*cg[r] - (LUX_CITY_BUILD_COST - spent)); break; }
                             spent += *cg[r];
@@ -700,6 +754,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     // cooldowns of the acting units, then the carts' automatic roads (unit.py:196-197, :257-269)
     {
         int rb0 = 0, rb1 = 0;
+#pragma unroll 1
         for (int u = lane; u < n_units0; u += 32) {
             unsigned st = M.ust[u];
             LuxUnit& U = M.units[u];
@@ -726,6 +781,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         lux_zero16(M.occ, lux_align16(M.ncell));
         lux_city_prefix(M, n_cities);     // also syncs
         int bad = 0;
+#pragma unroll 1
         for (int u = lane; u < n_units; u += 32) {
             const LuxUnit& U = M.units[u];
             int c = U.y * S + U.x;
@@ -737,16 +793,18 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         if (lux_any(bad) && lane == 0) h->status |= LUX_ST_BAD_STATE;
         lux_sync();
         int rp0 = h->research[0], rp1 = h->research[1];
-        if (rp0 >= LUX_RESEARCH_URANIUM || rp1 >= LUX_RESEARCH_URANIUM)
-            lux_collect_type(M, LUX_RES_URANIUM, n_units, rp0 >= LUX_RESEARCH_URANIUM, rp1 >= LUX_RESEARCH_URANIUM);
-        if (rp0 >= LUX_RESEARCH_COAL || rp1 >= LUX_RESEARCH_COAL)
-            lux_collect_type(M, LUX_RES_COAL, n_units, rp0 >= LUX_RESEARCH_COAL, rp1 >= LUX_RESEARCH_COAL);
-        lux_collect_type(M, LUX_RES_WOOD, n_units, 1, 1);
+#pragma unroll 1
+        for (int rtype = LUX_RES_URANIUM; rtype >= LUX_RES_WOOD; rtype--) {
+            int need = rtype == LUX_RES_WOOD ? 0 : rtype == LUX_RES_COAL ? LUX_RESEARCH_COAL : LUX_RESEARCH_URANIUM;
+            if (rp0 < need && rp1 < need) continue;           // nobody may mine this type yet
+            lux_collect_type<kS>(M, rtype, n_units, rp0 >= need, rp1 >= need);
+        }
     }
 
     // ---- deposit (handle_resource_deposit game.py:1003-1023)
     {
         int fg0 = 0, fg1 = 0;
+#pragma unroll 1
         for (int u = lane; u < n_units; u += 32) {
             LuxUnit& U = M.units[u];
             const LuxCell& C = M.cells[U.y * S + U.x];
@@ -767,6 +825,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     // ---- night (handle_night game.py:537-558)
     if (night) {
         int died = 0;
+#pragma unroll 1
         for (int s = lane; s < n_cities; s += 32) {
             LuxCity& city = M.cities[s];
             M.cremap[s] = 0;
@@ -778,6 +837,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         lux_sync();
         if (lux_any(died)) {
             tiles_dirty = 1;
+#pragma unroll 1
             for (int t = lane; t < n_tiles; t += 32) {                // destroy_city :1059-1070
                 LuxCell& C = M.cells[M.tiles[t]];
                 if (cell_is_tile(C) && M.cremap[C.city_slot]) {
@@ -787,10 +847,12 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 }
             }
             lux_sync();
+#pragma unroll 1
             for (int s = lane; s < n_cities; s += 32)
                 if (M.cremap[s]) { M.cities[s].ntiles = 0; M.cities[s].fuel = 0; M.cities[s].adjsum = 0; }
             lux_sync();
         }
+#pragma unroll 1
         for (int u = lane; u < n_units; u += 32) {                    // spend_fuel_to_survive unit.py:64-98
             LuxUnit& U = M.units[u];
             if (cell_is_tile(M.cells[U.y * S + U.x])) continue;
@@ -815,6 +877,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     // ---- depleted cells leave the list (game.py:498-510), trees regrow (:1081-1102)
     {
         int n_res = h->n_res;
+#pragma unroll 1
         for (int r = lane; r < n_res; r += 32) {
             LuxCell& C = M.cells[M.res[r]];
             if (C.amount == 0) { C.flags &= 0xFC; continue; }
@@ -834,16 +897,17 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 // ---- epilogue: compaction, match_over, cooldowns, canonical tile order, store ---------------
 // g_* are the match's sections in global memory.
 // With kStoreGrid == false the caller moves the cell grid and the header itself (bulk copy).
-template <bool kStoreGrid>
+template <bool kStoreGrid, int kS>
 LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g_hdr, LuxCell* g_cells,
                                   LuxUnit* g_units, LuxCity* g_cities, uint16_t* g_tiles) {
     const int lane = lux_lane();
     const unsigned lt = lux_lanemask_lt();
     LuxHeader* h = M.hdr;
-    const int S = M.S;
+    const int S = kS > 0 ? kS : M.S;
 
     // cities: drop the dead (ntiles == 0), keep order
     int n_alive = 0, nc0 = 0, nc1 = 0, tl0 = 0, tl1 = 0;
+#pragma unroll 1
     for (int base = 0; base < T.n_cities; base += 32) {
         int s = base + lane;
         int alive = s < T.n_cities && M.cities[s].ntiles > 0;
@@ -859,12 +923,14 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
     lux_sync();
     const int cities_moved = n_alive != T.n_cities;
     if (cities_moved) {
+#pragma unroll 1
         for (int t = lane; t < T.n_tiles; t += 32) {
             LuxCell& C = M.cells[M.tiles[t]];
             if (cell_is_tile(C)) C.city_slot = M.cremap[C.city_slot];
         }
     }
     // store cities compacted
+#pragma unroll 1
     for (int s = lane; s < T.n_cities; s += 32) {
         int ns = M.cremap[s];
         if (ns != 0xFF) g_cities[ns] = M.cities[s];
@@ -873,6 +939,7 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
     int n_tiles_live = tl0 + tl1;
     if (T.tiles_dirty || cities_moved) {
         int run = 0;
+#pragma unroll 1
         for (int base = 0; base < T.n_cities; base += 32) {
             int s = base + lane;
             int v = (s < T.n_cities) ? M.cities[s].ntiles : 0;   // dead cities have 0 tiles
@@ -882,6 +949,7 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
             run += tot;
         }
         lux_sync();
+#pragma unroll 1
         for (int t = lane; t < T.n_tiles; t += 32) {
             int cell = M.tiles[t];
             const LuxCell& C = M.cells[cell];
@@ -891,6 +959,7 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
 
     // match_over (game.py:570-592) is evaluated before the turn counter moves (:515-517)
     int alive0 = 0, alive1 = 0;
+#pragma unroll 1
     for (int u = lane; u < T.n_units; u += 32) {
         if (M.ust[u] & UST_FAILED) continue;
         if (unit_team(M.units[u])) alive1++; else alive0++;
@@ -901,6 +970,7 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
 
     // run_cooldowns (game.py:560-568) and the stable partition team A | team B while storing
     int run0 = 0, run1 = 0;
+#pragma unroll 1
     for (int base = 0; base < T.n_units; base += 32) {
         int u = base + lane;
         int valid = u < T.n_units && !(M.ust[u] & UST_FAILED);
@@ -944,6 +1014,7 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
     if (kStoreGrid) {
         const uint64_t* s = (const uint64_t*)M.cells;
         uint64_t* d = (uint64_t*)g_cells;
+#pragma unroll 1
         for (int i = lane; i < M.ncell; i += 32) d[i] = s[i];
         const uint64_t* hs = (const uint64_t*)M.hdr;
         uint64_t* hd = (uint64_t*)g_hdr;

@@ -43,8 +43,8 @@ static void emu_lane(void* p) {
     lux_copy16(M.uact, a->ua + (size_t)m * b->u_cap, M.hdr->n_units * 4);
     lux_copy16(M.tact, a->ta + (size_t)m * b->t_cap, M.hdr->n_tiles);
     lux_sync();
-    LuxTurnOut T = lux_turn(M, a->flags);
-    lux_finish_and_store<true>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
+    LuxTurnOut T = b->size == 32 ? lux_turn<32>(M, a->flags) : lux_turn<0>(M, a->flags);
+    lux_finish_and_store<true, 0>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
 }
 
 extern "C" size_t lux_emu_smem_bytes(int size, int u_cap, int c_cap, int t_cap, int r_cap) {
