@@ -25,15 +25,23 @@
 #define LUX_PRE_CITIES 16
 #define LUX_PRE_TILES 32
 
+// Launch modes.  The staged footprint of a match is dominated by capacity, not by content: with the
+// default 32x32 capacities (252 units / 255 cities / 384 tiles) a match needs 25 KB of shared memory and
+// only 8 warps fit on an SM, although a typical match holds a dozen entities.  So a step is two launches:
+//   kSmall : every match; shared memory is sized for `stage` capacities (e.g. 64/64/96); a match whose
+//            populations could outgrow them during this turn is appended to a retry list instead;
+//   kList  : the retry list, full capacities, grid-stride over the list.
+// kAll is the single full-capacity launch (small maps, dense batches, the non-TMA path).
+enum { kAll = 0, kSmall = 1, kList = 2 };
+
+struct LuxStage { int u, c, t; };      // shared-memory staging capacities (units, cities, tiles)
+
 template <bool kTma, int kS>
-__global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions,
-                                const uint8_t* __restrict__ tile_actions, LuxSmemLayout L, unsigned flags) {
-    extern __shared__ __align__(128) unsigned char lux_smem[];
-    const int warp = threadIdx.x >> 5;
+__device__ __forceinline__ bool lux_step_match(const LuxBatch& b, int m, const uint32_t* __restrict__ unit_actions,
+                                               const uint8_t* __restrict__ tile_actions, const LuxSmemLayout& L,
+                                               unsigned char* smem, unsigned flags, const LuxStage& stage,
+                                               bool check_fit, uint32_t& phase) {
     const int lane = threadIdx.x & 31;
-    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (m >= b.n_matches) return;
-    unsigned char* smem = lux_smem + (size_t)warp * L.total;
     const int size = kS > 0 ? kS : b.size;
     const int ncell = size * size;
     LuxMatch M;
@@ -49,11 +57,9 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
 
     if (kTma) {
         uint64_t* bar = (uint64_t*)(smem + L.mbar);
-        const uint32_t pu = min(b.u_cap, LUX_PRE_UNITS), pc = min(b.c_cap, LUX_PRE_CITIES), pt = min(b.t_cap, LUX_PRE_TILES);
+        const uint32_t pu = min(stage.u, LUX_PRE_UNITS), pc = min(stage.c, LUX_PRE_CITIES), pt = min(stage.t, LUX_PRE_TILES);
         const uint32_t b_cells = ncell * 8, b_res = b.r_cap * 2;
         if (lane == 0) {
-            mbar_init(bar, 1);
-            fence_mbar_init();
             mbar_expect_tx(bar, LUX_HDR_BYTES + b_cells + b_res + pu * 16 + pc * 16 + pt * 2 + pu * 4 + pt);
             tma_g2s(M.hdr, g_hdr, LUX_HDR_BYTES, bar);
             tma_g2s(M.cells, g_cells, b_cells, bar);
@@ -65,9 +71,13 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
             tma_g2s(M.tact, g_ta, pt, bar);
         }
         __syncwarp();
-        mbar_wait(bar, 0);
-        if (M.hdr->done) return;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        if (M.hdr->done) return true;
         const uint32_t nu = M.hdr->n_units, nc = M.hdr->n_cities, nt = M.hdr->n_tiles;
+        // worst case growth inside one turn: every tile spawns, every unit founds a city
+        if (check_fit && (nu + nt > (uint32_t)stage.u || nc + nu > (uint32_t)stage.c || nt + nu > (uint32_t)stage.t))
+            return false;
         if (nu > pu || nc > pc || nt > pt) {                      // warp-uniform
             const uint32_t ru = nu > pu ? nu - pu : 0, rc = nc > pc ? nc - pc : 0;
             const uint32_t rt2 = nt > pt ? ((nt - pt) * 2 + 15) & ~15u : 0;
@@ -81,12 +91,13 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
                 if (rta) tma_g2s(M.tact + pt, g_ta + pt, rta, bar);
             }
             __syncwarp();
-            mbar_wait(bar, 1);
+            mbar_wait(bar, phase);
+            phase ^= 1;
         }
     } else {
         lux_copy16(M.hdr, g_hdr, LUX_HDR_BYTES);
         __syncwarp();
-        if (M.hdr->done) return;
+        if (M.hdr->done) return true;
         lux_copy16(M.cells, g_cells, ncell * 8);
         lux_copy16(M.units, g_units, M.hdr->n_units * 16);
         lux_copy16(M.cities, g_cities, M.hdr->n_cities * 16);
@@ -113,15 +124,61 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
     } else {
         lux_finish_and_store<true, kS>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
     }
+    return true;
 }
 
-template <bool kTma, int kS>
+// retry: [0] number of entries, [1..] match indices; retry_next[0] is cleared for the following step
+template <bool kTma, int kS, int kMode>
+__global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions,
+                                const uint8_t* __restrict__ tile_actions, LuxSmemLayout L, unsigned flags,
+                                LuxStage stage, int* __restrict__ retry, int* __restrict__ retry_next) {
+    extern __shared__ __align__(128) unsigned char lux_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    unsigned char* smem = lux_smem + (size_t)warp * L.total;
+    uint32_t phase = 0;
+    if (kTma) {
+        if (lane == 0) {
+            mbar_init((uint64_t*)(smem + L.mbar), 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+    }
+    if (kMode == kList) {
+        const int count = retry[0];
+        for (int idx = blockIdx.x * wpc + warp; idx < count; idx += gridDim.x * wpc) {
+            lux_step_match<kTma, kS>(b, retry[1 + idx], unit_actions, tile_actions, L, smem, flags, stage, false, phase);
+            __syncwarp();
+        }
+        return;
+    }
+    const int m = blockIdx.x * wpc + warp;
+    if (kMode == kSmall && m == 0 && lane == 0) retry_next[0] = 0;
+    if (m >= b.n_matches) return;
+    bool ok = lux_step_match<kTma, kS>(b, m, unit_actions, tile_actions, L, smem, flags, stage, kMode == kSmall, phase);
+    if (kMode == kSmall && !ok && lane == 0) retry[1 + atomicAdd(&retry[0], 1)] = m;
+}
+
+template <bool kTma, int kS, int kMode>
 static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L, unsigned flags,
-                       int grid, int wpc, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                       LuxStage stage, int* retry, int* retry_next, int grid, int wpc, cudaStream_t st) {
+    size_t smem = (size_t)L.total * wpc;
+    cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return LUX_E_CUDA;
-    lux_step_kernel<kTma, kS><<<grid, 32 * wpc, smem, st>>>(*b, ua, ta, L, flags);
+    lux_step_kernel<kTma, kS, kMode><<<grid, 32 * wpc, smem, st>>>(*b, ua, ta, L, flags, stage, retry, retry_next);
     return LUX_OK;
+}
+
+template <bool kTma, int kMode>
+static int launch_step_size(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L, unsigned flags,
+                            LuxStage stage, int* retry, int* retry_next, int grid, int wpc, cudaStream_t st) {
+    switch (kTma ? b->size : 0) {
+        case 12: return launch_step<kTma, 12, kMode>(b, ua, ta, L, flags, stage, retry, retry_next, grid, wpc, st);
+        case 16: return launch_step<kTma, 16, kMode>(b, ua, ta, L, flags, stage, retry, retry_next, grid, wpc, st);
+        case 24: return launch_step<kTma, 24, kMode>(b, ua, ta, L, flags, stage, retry, retry_next, grid, wpc, st);
+        case 32: return launch_step<kTma, 32, kMode>(b, ua, ta, L, flags, stage, retry, retry_next, grid, wpc, st);
+        default: return launch_step<kTma, 0, kMode>(b, ua, ta, L, flags, stage, retry, retry_next, grid, wpc, st);
+    }
 }
 
 // ---------------------------------------------------------------- canonical action stream
@@ -304,12 +361,38 @@ extern "C" size_t lux_b200_step_smem_bytes(int size, int u_cap, int c_cap, int t
 
 static int g_use_tma = 1;
 static int g_warps_per_cta = 0;   // 0 = automatic
-// tuning / fallback knobs (tests flip them to cover both staging paths)
+static int g_two_class = -1;      // -1 automatic, 0 off, 1 always
+// tuning / fallback knobs (tests flip them to cover every launch path)
 extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!name) return LUX_E_ARG;
     if (!strcmp(name, "tma")) { g_use_tma = value != 0; return LUX_OK; }
     if (!strcmp(name, "warps_per_cta")) { g_warps_per_cta = value; return LUX_OK; }
+    if (!strcmp(name, "two_class")) { g_two_class = value; return LUX_OK; }
     return LUX_E_ARG;
+}
+
+// per-process scratch of the two-class launch: two retry lists used alternately (the small-class
+// kernel of one step clears the counter of the next) and a pinned word that trails the retry count
+static int* g_retry[2] = {nullptr, nullptr};
+static int g_retry_cap = 0, g_retry_dev = -1, g_retry_flip = 0;
+static int* g_retry_seen = nullptr;   // pinned host copy of a recent retry count (may be stale)
+static int g_dense_hold = 0;          // steps left in single-launch mode after a dense observation
+
+static int ensure_retry(int n_matches) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return LUX_E_CUDA;
+    if (g_retry[0] && g_retry_cap >= n_matches + 1 && g_retry_dev == dev) return LUX_OK;
+    for (int k = 0; k < 2; k++) { if (g_retry[k]) cudaFree(g_retry[k]); g_retry[k] = nullptr; }
+    if (!g_retry_seen && cudaMallocHost(&g_retry_seen, sizeof(int)) != cudaSuccess) return LUX_E_CUDA;
+    *g_retry_seen = 0;
+    for (int k = 0; k < 2; k++) {
+        if (cudaMalloc(&g_retry[k], sizeof(int) * (size_t)(n_matches + 1)) != cudaSuccess) return LUX_E_CUDA;
+        if (cudaMemset(g_retry[k], 0, sizeof(int)) != cudaSuccess) return LUX_E_CUDA;
+    }
+    g_retry_cap = n_matches + 1;
+    g_retry_dev = dev;
+    g_retry_flip = 0;
+    return LUX_OK;
 }
 
 extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions,
@@ -320,31 +403,48 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
     if (((uintptr_t)unit_actions | (uintptr_t)tile_actions) & 15) return LUX_E_ARG;
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
-    LuxSmemLayout L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
-    int wpc = g_warps_per_cta;
-    if (wpc <= 0) {
-        // one match per CTA measured fastest for staged footprints of 8 KB and more (independent
-        // CTAs spread better over the SMs' instruction caches); pair small matches to lift the
-        // 32-CTA-per-SM limit
-        wpc = L.total >= 8 * 1024 ? 1 : 2;
-    }
-    size_t smem = (size_t)L.total * wpc;
-    if (smem > 227 * 1024) return LUX_E_CAPACITY;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    int grid = (b->n_matches + wpc - 1) / wpc;
-    if (g_use_tma) {
-        switch (b->size) {
-            case 12: rc = launch_step<true, 12>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st); break;
-            case 16: rc = launch_step<true, 16>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st); break;
-            case 24: rc = launch_step<true, 24>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st); break;
-            case 32: rc = launch_step<true, 32>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st); break;
-            default: rc = launch_step<true, 0>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st); break;
-        }
-    } else {
-        rc = launch_step<false, 0>(b, unit_actions, tile_actions, L, flags, grid, wpc, smem, st);
+    LuxSmemLayout L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    LuxStage full = {b->u_cap, b->c_cap, b->t_cap};
+    if ((size_t)L.total > 227 * 1024) return LUX_E_CAPACITY;
+    // one match per CTA measured fastest for staged footprints of 8 KB and more; pair small matches to
+    // lift the 32-CTA-per-SM limit
+    int wpc = g_warps_per_cta > 0 ? g_warps_per_cta : (L.total >= 8 * 1024 ? 1 : 2);
+    if ((size_t)L.total * wpc > 227 * 1024) wpc = 1;
+
+    // small staging class: worth it when it at least halves... the footprint is dominated by capacity
+    LuxStage small = {64 < b->u_cap ? 64 : b->u_cap, 64 < b->c_cap ? 64 : b->c_cap, 96 < b->t_cap ? 96 : b->t_cap};
+    LuxSmemLayout Ls = lux_smem_layout(b->size, small.u, small.c, small.t, b->r_cap);
+    bool two = g_use_tma && g_two_class != 0 && (g_two_class == 1 || (L.total >= 12 * 1024 && Ls.total * 4 <= L.total * 3));
+    if (two && g_two_class < 0 && g_dense_hold > 0) { g_dense_hold--; two = false; }
+    if (two) {
+        rc = ensure_retry(b->n_matches);
+        if (rc) return rc;
+        if (g_two_class < 0 && *g_retry_seen * 2 > b->n_matches) { g_dense_hold = 64; *g_retry_seen = 0; two = false; }
     }
-    if (rc) { fprintf(stderr, "lux_b200: step kernel attribute: %s\n", cudaGetErrorString(cudaGetLastError())); return rc; }
-    return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
+    if (!two) {
+        int grid = (b->n_matches + wpc - 1) / wpc;
+        rc = g_use_tma ? launch_step_size<true, kAll>(b, unit_actions, tile_actions, L, flags, full, nullptr, nullptr, grid, wpc, st)
+                       : launch_step_size<false, kAll>(b, unit_actions, tile_actions, L, flags, full, nullptr, nullptr, grid, wpc, st);
+        if (rc) return rc;
+        return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
+    }
+    int* retry = g_retry[g_retry_flip];
+    int* retry_next = g_retry[g_retry_flip ^ 1];
+    g_retry_flip ^= 1;
+    int wpc_s = g_warps_per_cta > 0 ? g_warps_per_cta : (Ls.total >= 8 * 1024 ? 1 : 2);
+    rc = launch_step_size<true, kSmall>(b, unit_actions, tile_actions, Ls, flags, small, retry, retry_next,
+                                        (b->n_matches + wpc_s - 1) / wpc_s, wpc_s, st);
+    if (rc) return rc;
+    rc = cuda_ok(cudaGetLastError(), "lux_step_kernel (small class) launch");
+    if (rc) return rc;
+    int grid_l = b->n_matches < 148 * 8 ? b->n_matches : 148 * 8;
+    rc = launch_step_size<true, kList>(b, unit_actions, tile_actions, L, flags, full, retry, nullptr, grid_l, 1, st);
+    if (rc) return rc;
+    rc = cuda_ok(cudaGetLastError(), "lux_step_kernel (retry list) launch");
+    if (rc) return rc;
+    // trail the retry count to the host without synchronising; a stale value only delays the mode switch
+    return cuda_ok(cudaMemcpyAsync(g_retry_seen, retry, sizeof(int), cudaMemcpyDeviceToHost, st), "retry count copy");
 }
 
 extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,

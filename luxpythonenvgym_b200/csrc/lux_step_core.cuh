@@ -173,11 +173,10 @@ LUX_DEV int lux_dy(int dir) { return dir == LUX_DIR_SOUTH ? 1 : dir == LUX_DIR_N
 
 // the five cells a worker mines from: own, N, E, S, W (game.py:950-951, game_map.py:484-508)
 LUX_DEV int lux_cell5(int S, int x, int y, int k) {
-    if (k == 0) return y * S + x;
-    if (k == 1) return y > 0 ? (y - 1) * S + x : -1;
-    if (k == 2) return x < S - 1 ? y * S + x + 1 : -1;
-    if (k == 3) return y < S - 1 ? (y + 1) * S + x : -1;
-    return x > 0 ? y * S + x - 1 : -1;
+    // branch-free: (dx, dy) + 1 packed two bits per direction, k = 0..4 -> c, n, e, s, w
+    int nx = x + (int)((0x065u >> (2 * k)) & 3u) - 1;
+    int ny = y + (int)((0x191u >> (2 * k)) & 3u) - 1;
+    return ((unsigned)nx < (unsigned)S && (unsigned)ny < (unsigned)S) ? ny * S + nx : -1;
 }
 
 LUX_DEV void lux_zero16(void* p, int bytes) {   // bytes multiple of 16, p 16-byte aligned
@@ -251,6 +250,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         int x = c % S, y = c / S;
         // histogram of request amounts 0..20, 3 bits each (at most one request per amount and source cell)
         uint64_t hist = 0;
+        unsigned present = 0;                         // amounts that occur
         int n = 0, sum = 0;
 #pragma unroll 1
         for (int j = 0; j < 5; j++) {
@@ -263,22 +263,24 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                     int a = lux_ffs(mask) - 1;
                     mask &= mask - 1;
                     hist += (uint64_t)1 << (3 * a);
+                    present |= 1u << a;
                     n++; sum += a;
                 }
             } else {
                 int o = M.occ[p];
                 if (o) {
                     int a = M.umine[o - 1];
-                    if (a != 0xFF) { hist += (uint64_t)1 << (3 * a); n++; sum += a; }
+                    if (a != 0xFF) { hist += (uint64_t)1 << (3 * a); present |= 1u << a; n++; sum += a; }
                 }
             }
         }
         if (n > 0 && sum > 0) {
             int left = C.amount;
 #pragma unroll 1
-            for (int a = 0; a <= 20 && n > 0 && left > 0; a++) {
+            while (present && n > 0 && left > 0) {        // ascending over the amounts that occur
+                int a = lux_ffs(present) - 1;
+                present &= present - 1;
                 int cnt = (int)((hist >> (3 * a)) & 7);
-                if (!cnt) continue;
                 int minrem = a - level;
                 int qq = left / n;
                 if (qq >= minrem) {

@@ -32,11 +32,13 @@ def _recap(ms, caps):
     return o
 
 
-@pytest.mark.parametrize("tma", [1, 0])
-def test_replays_bit_exact(tma):
-    """The 7 Kaggle episodes of the reference's test_replay.py, 360 turns each."""
+@pytest.mark.parametrize("tma,two_class", [(1, -1), (1, 1), (1, 0), (0, -1)])
+def test_replays_bit_exact(tma, two_class):
+    """The 7 Kaggle episodes of the reference's test_replay.py, 360 turns each, through every launch
+    path: TMA staging with the automatic / forced / disabled two-class launch, and plain loads."""
     lib = _lib.load()
     lib.lux_b200_set_option(b"tma", tma)
+    lib.lux_b200_set_option(b"two_class", two_class)
     try:
         z = G.npz("replays")
         for rid in G.replay_ids():
@@ -55,6 +57,7 @@ def test_replays_bit_exact(tma):
             assert g.headers()["done"][0] == 1
     finally:
         lib.lux_b200_set_option(b"tma", 1)
+        lib.lux_b200_set_option(b"two_class", -1)
 
 
 def test_random_and_dense_fixtures():
