@@ -153,12 +153,15 @@ int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t
  * Same call with HOST action buffers and HOST result buffers (pinned or pageable):
  * copies the actions to the device staging buffers the caller provides, steps, and
  * copies back done[n] (uint8) and the headers (n*128 B) if the pointers are non-NULL.
+ * Only the first u_used unit slots / t_used tile slots of every match are uploaded (0 = all of them);
+ * they must cover the live entities, e.g. the maxima of hdr.n_units / hdr.n_tiles seen in the headers
+ * the previous call returned (a freshly reset match holds 2 + 2).
  * Synchronises the stream before returning.
  */
 int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,
                        const uint8_t* tile_actions_host, uint32_t* unit_actions_dev,
                        uint8_t* tile_actions_dev, uint8_t* done_host, LuxHeader* hdr_host,
-                       uint32_t flags, void* cuda_stream);
+                       int u_used, int t_used, uint32_t flags, void* cuda_stream);
 
 /*
  * Canonical seeded action stream, written as packed action

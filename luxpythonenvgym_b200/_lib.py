@@ -54,7 +54,7 @@ def load():
     lib.lux_b200_step_smem_bytes.restype = ctypes.c_size_t
     lib.lux_b200_step_smem_bytes.argtypes = [i32] * 5
     lib.lux_b200_step.argtypes = [bp, vp, vp, ctypes.c_uint32, vp]
-    lib.lux_b200_step_host.argtypes = [bp, vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp]
+    lib.lux_b200_step_host.argtypes = [bp, vp, vp, vp, vp, vp, vp, i32, i32, ctypes.c_uint32, vp]
     lib.lux_b200_gen_actions.argtypes = [bp, u64, u64, vp, vp, vp, vp]
     lib.lux_b200_observe.argtypes = [bp, vp, vp, vp, vp, i32, vp]
     lib.lux_b200_reset_done.argtypes = [bp, bp, ctypes.c_uint32, vp, vp]

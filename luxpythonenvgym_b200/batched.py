@@ -90,13 +90,14 @@ class BatchedGame:
                                           _lib.LUX_STEP_PREVALIDATE if prevalidate else 0, self._stream()),
                    "lux_b200_step")
 
-    def step_host(self, unit_actions_host, tile_actions_host, hdr_host=None, done_host=None, prevalidate=False):
+    def step_host(self, unit_actions_host, tile_actions_host, hdr_host=None, done_host=None, prevalidate=False,
+                  u_used=0, t_used=0):
         """The same turn from HOST (pinned) action buffers; copies back headers/done flags."""
         _lib.check(self.lib.lux_b200_step_host(
             ctypes.byref(self._desc), unit_actions_host.data_ptr(), tile_actions_host.data_ptr(),
             self.unit_actions.data_ptr(), self.tile_actions.data_ptr(),
             done_host.data_ptr() if done_host is not None else None,
-            hdr_host.data_ptr() if hdr_host is not None else None,
+            hdr_host.data_ptr() if hdr_host is not None else None, int(u_used), int(t_used),
             _lib.LUX_STEP_PREVALIDATE if prevalidate else 0, self._stream()), "lux_b200_step_host")
 
     def gen_actions(self, seed, match_id_base=0, unit_actions=None, tile_actions=None, counters=None):

@@ -219,7 +219,10 @@ __global__ void lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match
         atomicAdd(counters + 1, (unsigned long long)(2 * (8 * ncell + 16 * nu + 16 * (int)h->n_cities + 64) + 4 * (nu + nt)));
     }
     const uint64_t mid = match_id_base + (uint64_t)m;
-    for (int i = lane; i < b.u_cap; i += 32) {
+    // only the live prefix (rounded up to the staging granule) is written: the step kernel never looks further
+    const int nu_w = done ? 0 : min(b.u_cap, max((nu + 3) & ~3, LUX_PRE_UNITS));
+    const int nt_w = done ? 0 : min(b.t_cap, max((nt + 15) & ~15, LUX_PRE_TILES));
+    for (int i = lane; i < nu_w; i += 32) {
         uint32_t w = 0;
         if (!done && i < nu) {
             const LuxUnit U = units[i];
@@ -255,7 +258,7 @@ __global__ void lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match
         }
         ua[i] = w;
     }
-    for (int p = lane; p < b.t_cap; p += 32) {
+    for (int p = lane; p < nt_w; p += 32) {
         uint8_t code = 0;
         if (!done && p < nt) {
             int cell = tiles[p];
@@ -450,16 +453,26 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
 extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,
                                   const uint8_t* tile_actions_host, uint32_t* unit_actions_dev,
                                   uint8_t* tile_actions_dev, uint8_t* done_host, LuxHeader* hdr_host,
-                                  uint32_t flags, void* cuda_stream) {
+                                  int u_used, int t_used, uint32_t flags, void* cuda_stream) {
     int rc = check_batch(b);
     if (rc) return rc;
     if (!unit_actions_host || !tile_actions_host || !unit_actions_dev || !tile_actions_dev) return LUX_E_ARG;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     size_t n = (size_t)b->n_matches;
-    rc = cuda_ok(cudaMemcpyAsync(unit_actions_dev, unit_actions_host, n * b->u_cap * 4, cudaMemcpyHostToDevice, st), "h2d unit actions");
+    // only the first u_used / t_used slots of every match travel (0 = all); the caller knows the largest
+    // live counts from the headers of the previous step
+    if (u_used <= 0 || u_used > b->u_cap) u_used = b->u_cap;
+    if (t_used <= 0 || t_used > b->t_cap) t_used = b->t_cap;
+    u_used = (u_used + 3) & ~3;
+    t_used = (t_used + 15) & ~15;
+    if (u_used > b->u_cap) u_used = b->u_cap;
+    if (t_used > b->t_cap) t_used = b->t_cap;
+    rc = cuda_ok(cudaMemcpy2DAsync(unit_actions_dev, (size_t)b->u_cap * 4, unit_actions_host, (size_t)b->u_cap * 4,
+                                   (size_t)u_used * 4, n, cudaMemcpyHostToDevice, st), "h2d unit actions");
     if (rc) return rc;
-    rc = cuda_ok(cudaMemcpyAsync(tile_actions_dev, tile_actions_host, n * b->t_cap, cudaMemcpyHostToDevice, st), "h2d tile actions");
+    rc = cuda_ok(cudaMemcpy2DAsync(tile_actions_dev, (size_t)b->t_cap, tile_actions_host, (size_t)b->t_cap,
+                                   (size_t)t_used, n, cudaMemcpyHostToDevice, st), "h2d tile actions");
     if (rc) return rc;
     rc = lux_b200_step(b, unit_actions_dev, tile_actions_dev, flags, cuda_stream);
     if (rc) return rc;

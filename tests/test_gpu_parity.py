@@ -93,9 +93,13 @@ def test_batch_vs_oracle_every_turn(size, n, turns):
     for turn in range(turns):
         g.gen_actions(seed, 0)
         host.gen_actions(seed, 0)
-        if turn % 50 == 0:
-            assert np.array_equal(g.unit_actions.cpu().numpy().view(np.uint32), host.ua), "action stream differs"
-            assert np.array_equal(g.tile_actions.cpu().numpy(), host.ta)
+        if turn % 50 == 0:   # the device stream equals the C statement on every live entity
+            hh = host.hdr()
+            live = (hh["done"] == 0)[:, None]          # finished matches are not written (nor read) at all
+            lu = (np.arange(host.ua.shape[1])[None, :] < hh["n_units"][:, None]) & live
+            lt = (np.arange(host.ta.shape[1])[None, :] < hh["n_tiles"][:, None]) & live
+            assert np.array_equal(g.unit_actions.cpu().numpy().view(np.uint32)[lu], host.ua[lu]), "action stream differs"
+            assert np.array_equal(g.tile_actions.cpu().numpy()[lt], host.ta[lt])
         g.step()
         host.step()
         bad = gpu_util.diff_batches(host, g)
@@ -167,7 +171,9 @@ def test_step_host_matches_device_step():
         ua_h.copy_(a.unit_actions)
         ta_h.copy_(a.tile_actions)
         a.step()
-        b.step_host(ua_h, ta_h, hdr_h, done_h)
+        hv = hdr_h.numpy().view(S.header_dtype).reshape(-1)
+        used = (0, 0) if turn == 0 else (int(hv["n_units"].max()), int(hv["n_tiles"].max()))
+        b.step_host(ua_h, ta_h, hdr_h, done_h, u_used=used[0], t_used=used[1])
         assert torch.equal(hdr_h, a.hdr.cpu())
     for k in a.sections():
         assert torch.equal(a.sections()[k], b.sections()[k]), k
