@@ -22,6 +22,11 @@ for warm in range(400):
     g.gen_actions(1, 0); g.step(); g.reset_done(pool, warm, count)
 torch.cuda.synchronize()
 print("smem/match", lib.lux_b200_step_smem_bytes(size, g.caps["units"], g.caps["cities"], g.caps["tiles"], g.caps["res"]), g.caps)
+import os
+for opt in os.environ.get("LUX_OPTS", "").split(","):
+    if "=" in opt:
+        k, v = opt.split("=")
+        print("option", k, v, lib.lux_b200_set_option(k.encode(), int(v)))
 for wpc in wpcs:
     lib.lux_b200_set_option(b"warps_per_cta", wpc)
     e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
