@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 SIZE = 32
 MATCHES_PER_GPU = 16384
-POOL_MAPS = 128
+POOL_MAPS = 1024
 BURN_IN_TURNS = 400          # untimed: brings the batch to a steady mix of match ages
 STREAM_SEED = 20211019
 METRIC = "match-turns/sec"
@@ -109,9 +109,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_pool_states(size, count, seed0=424242):
+def make_pool_arrays(size, count, seed0=424242):
+    """`count` distinct seeded maps as host section arrays (native generator, all host threads)."""
     from luxpythonenvgym_b200 import mapgen
-    return [mapgen.generate(seed0 + i, size=size) for i in range(count)]
+    return mapgen.generate_batch(np.arange(seed0, seed0 + count), size)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -120,7 +121,7 @@ class CpuPort:
     the same workload: same maps, same action stream, same pool reset rule.  Only the step
     calls are timed (action construction is not), one C call per thread per `run`."""
 
-    def __init__(self, size, n_matches, threads, pool_states):
+    def __init__(self, size, n_matches, threads, pool_arrays):
         from luxpythonenvgym_b200 import state as S
         from oracle import coracle
         self.coracle = coracle
@@ -133,14 +134,12 @@ class CpuPort:
                 ("hdr", 128), ("cells", size * size * 8), ("units", caps["units"] * 16),
                 ("cities", caps["cities"] * 16), ("tiles", caps["tiles"] * 2), ("res", caps["res"] * 2))}
 
-        self.arr, self.parr = alloc(n_matches), alloc(len(pool_states))
-        for i, ms in enumerate(pool_states):
-            for name, b in ms.to_bytes().items():
-                self.parr[name][i, : b.size] = b
+        n_pool = pool_arrays["hdr"].shape[0]
+        self.arr, self.parr = alloc(n_matches), {k: np.ascontiguousarray(v) for k, v in pool_arrays.items()}
         for name in self.arr:
-            self.arr[name][:] = self.parr[name][np.arange(n_matches) % len(pool_states)]
+            self.arr[name][:] = self.parr[name][np.arange(n_matches) % n_pool]
         self.desc = coracle.batch_desc(size, caps, self.arr, n_matches)
-        self.pdesc = coracle.batch_desc(size, caps, self.parr, len(pool_states))
+        self.pdesc = coracle.batch_desc(size, caps, self.parr, n_pool)
         self.ua = np.zeros((n_matches, caps["units"]), dtype=np.uint32)
         self.ta = np.zeros((n_matches, caps["tiles"]), dtype=np.uint8)
         self.epoch = 0
@@ -169,7 +168,7 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     n_matches, turns_per_step = 256 * threads, 40
-    port = CpuPort(args.size, n_matches, threads, make_pool_states(args.size, 32))
+    port = CpuPort(args.size, n_matches, threads, make_pool_arrays(args.size, POOL_MAPS))
     port.run(BURN_IN_TURNS)
     vals, budget = [], 150.0
     t_begin = time.perf_counter()
@@ -211,11 +210,15 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     n, size = args.matches, args.size
-    pool_states = make_pool_states(size, POOL_MAPS, seed0=424242 + 100000 * rank)
+    # every resident match starts on its own seeded map (seed = 10^6 * rank + match index); finished
+    # matches are replaced from a 1024-map pool.  Host generation: native generator, all host threads.
+    t_gen = time.perf_counter()
+    pool_arrays = make_pool_arrays(size, POOL_MAPS, seed0=424242 + 100000 * rank)
     game = BatchedGame(n, size, device=dev)
     pool = BatchedGame(POOL_MAPS, size, device=dev)
-    pool.load_states(pool_states)
-    game.load_states([pool_states[i % POOL_MAPS] for i in range(n)])
+    pool.load_arrays(pool_arrays)
+    game.load_arrays(make_pool_arrays(size, n, seed0=1000000 * (rank + 1)))
+    mapgen_s = time.perf_counter() - t_gen
     base = rank * n
     counters = torch.zeros(2, dtype=torch.int64, device=dev)
     resets = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -343,6 +346,7 @@ def run_b200(args):
                         "note": "lux_b200_step_host: pinned host action tensors -> device, step, headers -> host, "
                                 "sync every step; counts resident matches per step (finished ones are reset the same step)"},
                 "clocks": sampler.summary(),
+                "host_mapgen": {"maps": n + POOL_MAPS, "seconds": mapgen_s, "note": "untimed setup: native seeded generator"},
                 "stats": {"live": st[0], "finished_pending": st[1], "sum_units": st[7], "sum_city_tiles": st[8],
                           "status_nonzero": st[10], "resets": int(resets.item())}}
         try:
@@ -352,7 +356,7 @@ def run_b200(args):
             pass
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            port = CpuPort(size, 256 * threads, threads, pool_states[:32])
+            port = CpuPort(size, 256 * threads, threads, pool_arrays)
             port.run(BURN_IN_TURNS)
             live_sum, sec_sum, turns_sum = 0, 0.0, 0
             while sec_sum < 1.5 and turns_sum < 40000:          # ~1.5 s x threads of CPU work

@@ -67,6 +67,13 @@ class BatchedGame:
         for name, t in self.sections().items():
             t[first:first + k].copy_(torch.from_numpy(host[name]))
 
+    def load_arrays(self, arrays, first=0):
+        """Copy host section arrays ([k, bytes] uint8, e.g. from mapgen.generate_batch) into matches first.."""
+        for name, t in self.sections().items():
+            a = arrays[name]
+            assert a.shape[1] == t.shape[1], "section %s: capacity mismatch" % name
+            t[first:first + a.shape[0]].copy_(torch.from_numpy(a))
+
     def export_states(self, indices=None):
         """MatchState copies (host) of the given matches (default: all)."""
         idx = list(range(self.n)) if indices is None else list(indices)

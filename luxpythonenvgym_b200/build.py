@@ -20,7 +20,25 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+MAPGEN_OUT = os.path.join(HERE, "_lux_mapgen.so")
+
+
+def build_mapgen(force=False):
+    """Host-only native map generator (g++; no CUDA)."""
+    src = os.path.join(CSRC, "lux_mapgen.cpp")
+    hdr = os.path.join(HERE, "..", "include", "lux_b200.h")
+    if not force and os.path.exists(MAPGEN_OUT) and os.path.getmtime(MAPGEN_OUT) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return MAPGEN_OUT
+    cmd = ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", MAPGEN_OUT, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed for lux_mapgen.cpp")
+    return MAPGEN_OUT
+
+
 def build(force=False, verbose=False):
+    build_mapgen(force)
     if not force and not stale():
         return OUT
     cmd = [NVCC] + FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]

@@ -36,8 +36,13 @@ enum { kAll = 0, kSmall = 1, kList = 2 };
 
 struct LuxStage { int u, c, t; };      // shared-memory staging capacities (units, cities, tiles)
 
+// result of one match: skipped because finished, did not fit the staging class, or played
+// (LUX_M_HEAVY: its end-of-turn population is above the "schedule first next step" threshold)
+enum { LUX_M_DONE = 0, LUX_M_SPILL = 1, LUX_M_PLAYED = 2, LUX_M_HEAVY = 3 };
+#define LUX_HEAVY_THRESHOLD 28     // units + tiles
+
 template <bool kTma, int kS>
-__device__ __forceinline__ bool lux_step_match(const LuxBatch& b, int m, const uint32_t* __restrict__ unit_actions,
+__device__ __forceinline__ int lux_step_match(const LuxBatch& b, int m, const uint32_t* __restrict__ unit_actions,
                                                const uint8_t* __restrict__ tile_actions, const LuxSmemLayout& L,
                                                unsigned char* smem, unsigned flags, const LuxStage& stage,
                                                bool check_fit, uint32_t& phase) {
@@ -73,11 +78,10 @@ __device__ __forceinline__ bool lux_step_match(const LuxBatch& b, int m, const u
         __syncwarp();
         mbar_wait(bar, phase);
         phase ^= 1;
-        if (M.hdr->done) return true;
+        if (M.hdr->done) return LUX_M_DONE;
         const uint32_t nu = M.hdr->n_units, nc = M.hdr->n_cities, nt = M.hdr->n_tiles;
-        // worst case growth inside one turn: every tile spawns, every unit founds a city
-        if (check_fit && (nu + nt > (uint32_t)stage.u || nc + nu > (uint32_t)stage.c || nt + nu > (uint32_t)stage.t))
-            return false;
+        // the live lists themselves must fit the staging arrays before anything more is loaded
+        if (check_fit && (nu > (uint32_t)stage.u || nc > (uint32_t)stage.c || nt > (uint32_t)stage.t)) return LUX_M_SPILL;
         if (nu > pu || nc > pc || nt > pt) {                      // warp-uniform
             const uint32_t ru = nu > pu ? nu - pu : 0, rc = nc > pc ? nc - pc : 0;
             const uint32_t rt2 = nt > pt ? ((nt - pt) * 2 + 15) & ~15u : 0;
@@ -97,7 +101,7 @@ __device__ __forceinline__ bool lux_step_match(const LuxBatch& b, int m, const u
     } else {
         lux_copy16(M.hdr, g_hdr, LUX_HDR_BYTES);
         __syncwarp();
-        if (M.hdr->done) return true;
+        if (M.hdr->done) return LUX_M_DONE;
         lux_copy16(M.cells, g_cells, ncell * 8);
         lux_copy16(M.units, g_units, M.hdr->n_units * 16);
         lux_copy16(M.cities, g_cities, M.hdr->n_cities * 16);
@@ -106,6 +110,24 @@ __device__ __forceinline__ bool lux_step_match(const LuxBatch& b, int m, const u
         lux_copy16(M.uact, g_ua, M.hdr->n_units * 4);
         lux_copy16(M.tact, g_ta, M.hdr->n_tiles);
         __syncwarp();
+    }
+
+    if (check_fit) {
+        // growth inside this turn is bounded by the actions actually present: every spawn action may add
+        // a unit, every build-city action a tile and a city
+        int spawns = 0, builds = 0;
+        const int nu = M.hdr->n_units, nt = M.hdr->n_tiles, nc = M.hdr->n_cities;
+        for (int base = 0; base < nt; base += 32) {
+            int p = base + lane;
+            int code = p < nt ? M.tact[p] : 0;
+            spawns += __popc(__ballot_sync(0xffffffffu, code == LUX_TA_BUILD_WORKER || code == LUX_TA_BUILD_CART));
+        }
+        for (int base = 0; base < nu; base += 32) {
+            int u = base + lane;
+            int kind = u < nu ? (int)(M.uact[u] & 7) : 0;
+            builds += __popc(__ballot_sync(0xffffffffu, kind == LUX_UA_BCITY));
+        }
+        if (nu + spawns > stage.u || nc + builds > stage.c || nt + builds > stage.t) return LUX_M_SPILL;
     }
 
     LuxTurnOut T = lux_turn<kS>(M, flags);
@@ -124,14 +146,28 @@ __device__ __forceinline__ bool lux_step_match(const LuxBatch& b, int m, const u
     } else {
         lux_finish_and_store<true, kS>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
     }
-    return true;
+    return (!M.hdr->done && (int)M.hdr->n_units + (int)M.hdr->n_tiles > LUX_HEAVY_THRESHOLD) ? LUX_M_HEAVY : LUX_M_PLAYED;
 }
 
-// retry: [0] number of entries, [1..] match indices; retry_next[0] is cleared for the following step
+// Scheduling scratch (device pointers, owned by the library, see StepScratch below).
+//  * retry list: matches the small staging class could not hold this step (consumed by kList);
+//  * heavy list: matches whose population was above LUX_HEAVY_THRESHOLD at the end of the previous step.
+//    The first `hcap` CTAs of a launch take their match from this list, the remaining CTAs walk the
+//    matches in index order and skip the ones flagged in `hint_cur`: long jobs start first, which removes
+//    the tail a late-starting dense match would otherwise add to the launch (LPT scheduling).
+//    Lists and hints are hints only: a stale or empty list just means index order.
+struct LuxSched {
+    int* retry_cnt; int* retry_list;                 // this step
+    const int* heavy_cnt; const int* heavy_list; const uint8_t* hint_cur;   // built during the previous step
+    int* heavy_next_cnt; int* heavy_next; uint8_t* hint_next;               // built now
+    int* zero_a; int* zero_b;                        // counters to clear for the step after
+    int hcap;                                        // 0 = scheduling off
+};
+
 template <bool kTma, int kS, int kMode>
 __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions,
                                 const uint8_t* __restrict__ tile_actions, LuxSmemLayout L, unsigned flags,
-                                LuxStage stage, int* __restrict__ retry, int* __restrict__ retry_next) {
+                                LuxStage stage, LuxSched sc) {
     extern __shared__ __align__(128) unsigned char lux_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
@@ -145,55 +181,62 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
         __syncwarp();
     }
     if (kMode == kList) {
-        const int count = retry[0];
+        const int count = *sc.retry_cnt;
         for (int idx = blockIdx.x * wpc + warp; idx < count; idx += gridDim.x * wpc) {
-            lux_step_match<kTma, kS>(b, retry[1 + idx], unit_actions, tile_actions, L, smem, flags, stage, false, phase);
+            lux_step_match<kTma, kS>(b, sc.retry_list[idx], unit_actions, tile_actions, L, smem, flags, stage, false, phase);
             __syncwarp();
         }
         return;
     }
-    if (kMode == kSmall && blockIdx.x == 0 && threadIdx.x == 0) retry_next[0] = 0;
-    // grid-stride over the matches: with a grid of (resident CTAs per SM) x (SMs) the kernel is
-    // persistent (one mbarrier init / CTA launch per resident slot instead of one per match)
-    for (int m = blockIdx.x * wpc + warp; m < b.n_matches; m += gridDim.x * wpc) {
-        bool ok = lux_step_match<kTma, kS>(b, m, unit_actions, tile_actions, L, smem, flags, stage, kMode == kSmall, phase);
-        if (kMode == kSmall && !ok && lane == 0) retry[1 + atomicAdd(&retry[0], 1)] = m;
-        __syncwarp();
+    const int gidx = blockIdx.x * wpc + warp;
+    int m;
+    if (sc.zero_a && gidx == 0 && lane == 0) { *sc.zero_a = 0; *sc.zero_b = 0; }
+    if (sc.hcap > 0) {
+        if (gidx < sc.hcap) {
+            int cnt = *sc.heavy_cnt;
+            if (gidx >= (cnt < sc.hcap ? cnt : sc.hcap)) return;
+            m = sc.heavy_list[gidx];
+        } else {
+            m = gidx - sc.hcap;
+            if (m >= b.n_matches || sc.hint_cur[m]) return;
+        }
+    } else {
+        m = gidx;
+    }
+    if (m < 0 || m >= b.n_matches) return;
+    int r = lux_step_match<kTma, kS>(b, m, unit_actions, tile_actions, L, smem, flags, stage, kMode == kSmall, phase);
+    if (lane == 0) {
+        if (r == LUX_M_SPILL) sc.retry_list[atomicAdd(sc.retry_cnt, 1)] = m;
+        if (sc.hcap > 0) {
+            uint8_t heavy = 0;
+            if (r == LUX_M_SPILL || r == LUX_M_HEAVY) {
+                int i = atomicAdd(sc.heavy_next_cnt, 1);
+                if (i < sc.hcap) { sc.heavy_next[i] = m; heavy = 1; }
+            }
+            sc.hint_next[m] = heavy;
+        }
     }
 }
 
-static int g_persistent = 0;      // 1: grid = resident CTAs (grid-stride over matches; measured ~3% slower); 0: one CTA per wpc matches
-static int g_sm_count = 0;
-
 template <bool kTma, int kS, int kMode>
 static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L, unsigned flags,
-                       LuxStage stage, int* retry, int* retry_next, int grid, int wpc, cudaStream_t st) {
+                       LuxStage stage, const LuxSched& sc, int grid, int wpc, cudaStream_t st) {
     size_t smem = (size_t)L.total * wpc;
     cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return LUX_E_CUDA;
-    if (g_persistent && kMode != kList) {
-        int per_sm = 0;
-        if (!g_sm_count) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        }
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lux_step_kernel<kTma, kS, kMode>, 32 * wpc, smem);
-        if (e == cudaSuccess && per_sm > 0 && g_sm_count > 0 && per_sm * g_sm_count < grid) grid = per_sm * g_sm_count;
-    }
-    lux_step_kernel<kTma, kS, kMode><<<grid, 32 * wpc, smem, st>>>(*b, ua, ta, L, flags, stage, retry, retry_next);
+    lux_step_kernel<kTma, kS, kMode><<<grid, 32 * wpc, smem, st>>>(*b, ua, ta, L, flags, stage, sc);
     return LUX_OK;
 }
 
 template <bool kTma, int kMode>
 static int launch_step_size(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L, unsigned flags,
-                            LuxStage stage, int* retry, int* retry_next, int grid, int wpc, cudaStream_t st) {
+                            LuxStage stage, const LuxSched& sc, int grid, int wpc, cudaStream_t st) {
     switch (kTma ? b->size : 0) {
-        case 12: return launch_step<kTma, 12, kMode>(b, ua, ta, L, flags, stage, retry, retry_next, grid, wpc, st);
-        case 16: return launch_step<kTma, 16, kMode>(b, ua, ta, L, flags, stage, retry, retry_next, grid, wpc, st);
-        case 24: return launch_step<kTma, 24, kMode>(b, ua, ta, L, flags, stage, retry, retry_next, grid, wpc, st);
-        case 32: return launch_step<kTma, 32, kMode>(b, ua, ta, L, flags, stage, retry, retry_next, grid, wpc, st);
-        default: return launch_step<kTma, 0, kMode>(b, ua, ta, L, flags, stage, retry, retry_next, grid, wpc, st);
+        case 12: return launch_step<kTma, 12, kMode>(b, ua, ta, L, flags, stage, sc, grid, wpc, st);
+        case 16: return launch_step<kTma, 16, kMode>(b, ua, ta, L, flags, stage, sc, grid, wpc, st);
+        case 24: return launch_step<kTma, 24, kMode>(b, ua, ta, L, flags, stage, sc, grid, wpc, st);
+        case 32: return launch_step<kTma, 32, kMode>(b, ua, ta, L, flags, stage, sc, grid, wpc, st);
+        default: return launch_step<kTma, 0, kMode>(b, ua, ta, L, flags, stage, sc, grid, wpc, st);
     }
 }
 
@@ -215,12 +258,10 @@ __device__ __forceinline__ uint64_t lux_hash(uint64_t seed, uint64_t match, uint
 }
 
 // one warp per match, state read in place from global memory (harness kernel, not the hot path)
-__global__ void lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match_id_base,
-                                       uint32_t* __restrict__ unit_actions, uint8_t* __restrict__ tile_actions,
-                                       unsigned long long* counters) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (m >= b.n_matches) return;
+__device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, uint64_t seed, uint64_t match_id_base,
+                                                      uint32_t* __restrict__ unit_actions,
+                                                      uint8_t* __restrict__ tile_actions, unsigned long long* counters) {
+    const int lane = threadIdx.x & 31;
     const int ncell = b.size * b.size, S = b.size;
     const LuxHeader* h = b.hdr + m;
     const LuxCell* cells = b.cells + (size_t)m * ncell;
@@ -231,6 +272,7 @@ __global__ void lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match
     const int nu = h->n_units, nt = h->n_tiles, turn = h->turn, done = h->done;
     if (counters && lane == 0 && !done) {
         // live match-turns and their algorithmic bytes for the turn about to run
+        // (`counters` is the CTA's shared-memory pair here; one global add per CTA follows)
         atomicAdd(counters, 1ULL);
         atomicAdd(counters + 1, (unsigned long long)(2 * (8 * ncell + 16 * nu + 16 * (int)h->n_cities + 64) + 4 * (nu + nt)));
     }
@@ -287,6 +329,18 @@ __global__ void lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match
         }
         ta[p] = code;
     }
+}
+
+__global__ void lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match_id_base,
+                                       uint32_t* __restrict__ unit_actions, uint8_t* __restrict__ tile_actions,
+                                       unsigned long long* counters) {
+    __shared__ unsigned long long cta_counters[2];
+    if (threadIdx.x < 2) cta_counters[threadIdx.x] = 0;
+    __syncthreads();
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m < b.n_matches) lux_gen_actions_match(b, m, seed, match_id_base, unit_actions, tile_actions, counters ? cta_counters : nullptr);
+    __syncthreads();
+    if (counters && threadIdx.x < 2 && cta_counters[threadIdx.x]) atomicAdd(counters + threadIdx.x, cta_counters[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------- episode statistics
@@ -381,38 +435,58 @@ extern "C" size_t lux_b200_step_smem_bytes(int size, int u_cap, int c_cap, int t
 static int g_use_tma = 1;
 static int g_warps_per_cta = 0;   // 0 = automatic
 static int g_two_class = -1;      // -1 automatic, 0 off, 1 always
+static int g_heavy_first = 1;     // schedule the previous step's populous matches first
 // tuning / fallback knobs (tests flip them to cover every launch path)
 extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!name) return LUX_E_ARG;
     if (!strcmp(name, "tma")) { g_use_tma = value != 0; return LUX_OK; }
     if (!strcmp(name, "warps_per_cta")) { g_warps_per_cta = value; return LUX_OK; }
     if (!strcmp(name, "two_class")) { g_two_class = value; return LUX_OK; }
-    if (!strcmp(name, "persistent")) { g_persistent = value != 0; return LUX_OK; }
+    if (!strcmp(name, "heavy_first")) { g_heavy_first = value != 0; return LUX_OK; }
     return LUX_E_ARG;
 }
 
-// per-process scratch of the two-class launch: two retry lists used alternately (the small-class
-// kernel of one step clears the counter of the next) and a pinned word that trails the retry count
-static int* g_retry[2] = {nullptr, nullptr};
-static int g_retry_cap = 0, g_retry_dev = -1, g_retry_flip = 0;
-static int* g_retry_seen = nullptr;   // pinned host copy of a recent retry count (may be stale)
-static int g_dense_hold = 0;          // steps left in single-launch mode after a dense observation
+// Scheduling scratch of one batch (keyed by its header pointer; a few batches are cached so that
+// interleaved batches -- mixed map sizes, a pool -- each keep their own lists).
+struct StepScratch {
+    const void* key; int n; int dev;
+    int* counts;                 // [0..2] heavy counts (3-way rotation), [3..5] retry counts
+    int* lists;                  // heavy[2][n] then retry[n]
+    unsigned char* hints;        // [2][n]
+    int* seen;                   // pinned host copy of a recent retry count (may be stale)
+    unsigned step;
+    int dense_hold;              // steps left in single-launch mode after a dense observation
+};
+static StepScratch g_scratch[8];
+static unsigned g_scratch_clock = 0;
 
-static int ensure_retry(int n_matches) {
+static void scratch_free(StepScratch& s) {
+    if (s.counts) cudaFree(s.counts);
+    if (s.lists) cudaFree(s.lists);
+    if (s.hints) cudaFree(s.hints);
+    if (s.seen) cudaFreeHost(s.seen);
+    memset(&s, 0, sizeof s);
+}
+
+static StepScratch* scratch_get(const LuxBatch* b, cudaStream_t st) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return LUX_E_CUDA;
-    if (g_retry[0] && g_retry_cap >= n_matches + 1 && g_retry_dev == dev) return LUX_OK;
-    for (int k = 0; k < 2; k++) { if (g_retry[k]) cudaFree(g_retry[k]); g_retry[k] = nullptr; }
-    if (!g_retry_seen && cudaMallocHost(&g_retry_seen, sizeof(int)) != cudaSuccess) return LUX_E_CUDA;
-    *g_retry_seen = 0;
-    for (int k = 0; k < 2; k++) {
-        if (cudaMalloc(&g_retry[k], sizeof(int) * (size_t)(n_matches + 1)) != cudaSuccess) return LUX_E_CUDA;
-        if (cudaMemset(g_retry[k], 0, sizeof(int)) != cudaSuccess) return LUX_E_CUDA;
-    }
-    g_retry_cap = n_matches + 1;
-    g_retry_dev = dev;
-    g_retry_flip = 0;
-    return LUX_OK;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    StepScratch* slot = nullptr;
+    for (auto& s : g_scratch)
+        if (s.key == (const void*)b->hdr && s.n == b->n_matches && s.dev == dev) return &s;
+    for (auto& s : g_scratch)
+        if (!s.key) { slot = &s; break; }
+    if (!slot) { slot = &g_scratch[g_scratch_clock++ % 8]; cudaStreamSynchronize(st); scratch_free(*slot); }
+    size_t n = (size_t)b->n_matches;
+    if (cudaMalloc(&slot->counts, 8 * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&slot->lists, 3 * n * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&slot->hints, 2 * n) != cudaSuccess) return nullptr;
+    if (cudaMallocHost(&slot->seen, sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMemsetAsync(slot->counts, 0, 8 * sizeof(int), st) != cudaSuccess) return nullptr;
+    if (cudaMemsetAsync(slot->hints, 0, 2 * n, st) != cudaSuccess) return nullptr;
+    *slot->seen = 0;
+    slot->key = b->hdr; slot->n = b->n_matches; slot->dev = dev; slot->step = 0; slot->dense_hold = 0;
+    return slot;
 }
 
 extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions,
@@ -431,40 +505,62 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
     // lift the 32-CTA-per-SM limit
     int wpc = g_warps_per_cta > 0 ? g_warps_per_cta : (L.total >= 8 * 1024 ? 1 : 2);
     if ((size_t)L.total * wpc > 227 * 1024) wpc = 1;
-
-    // small staging class: worth it when it at least halves... the footprint is dominated by capacity
-    LuxStage small = {64 < b->u_cap ? 64 : b->u_cap, 64 < b->c_cap ? 64 : b->c_cap, 96 < b->t_cap ? 96 : b->t_cap};
-    LuxSmemLayout Ls = lux_smem_layout(b->size, small.u, small.c, small.t, b->r_cap);
-    bool two = g_use_tma && g_two_class != 0 && (g_two_class == 1 || (L.total >= 12 * 1024 && Ls.total * 4 <= L.total * 3));
-    if (two && g_two_class < 0 && g_dense_hold > 0) { g_dense_hold--; two = false; }
-    if (two) {
-        rc = ensure_retry(b->n_matches);
-        if (rc) return rc;
-        if (g_two_class < 0 && *g_retry_seen * 2 > b->n_matches) { g_dense_hold = 64; *g_retry_seen = 0; two = false; }
-    }
-    if (!two) {
-        int grid = (b->n_matches + wpc - 1) / wpc;
-        rc = g_use_tma ? launch_step_size<true, kAll>(b, unit_actions, tile_actions, L, flags, full, nullptr, nullptr, grid, wpc, st)
-                       : launch_step_size<false, kAll>(b, unit_actions, tile_actions, L, flags, full, nullptr, nullptr, grid, wpc, st);
+    LuxSched sc;
+    memset(&sc, 0, sizeof sc);
+    if (!g_use_tma) {
+        rc = launch_step_size<false, kAll>(b, unit_actions, tile_actions, L, flags, full, sc, (b->n_matches + wpc - 1) / wpc, wpc, st);
         if (rc) return rc;
         return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
     }
-    int* retry = g_retry[g_retry_flip];
-    int* retry_next = g_retry[g_retry_flip ^ 1];
-    g_retry_flip ^= 1;
+
+    // 96 / 64 / 96 is the largest staging class that still puts 14 matches of a 32x32 map on an SM
+    LuxStage small = {96 < b->u_cap ? 96 : b->u_cap, 64 < b->c_cap ? 64 : b->c_cap, 96 < b->t_cap ? 96 : b->t_cap};
+    LuxSmemLayout Ls = lux_smem_layout(b->size, small.u, small.c, small.t, b->r_cap);
+    bool two = g_two_class != 0 && (g_two_class == 1 || (L.total >= 12 * 1024 && Ls.total * 4 <= L.total * 3));
+    bool sched = g_heavy_first != 0;
+    StepScratch* S = (two || sched) ? scratch_get(b, st) : nullptr;
+    if ((two || sched) && !S) return LUX_E_CUDA;
+    if (two && g_two_class < 0) {
+        if (S->dense_hold > 0) { S->dense_hold--; two = false; }
+        else if (*S->seen * 2 > b->n_matches) { S->dense_hold = 64; *S->seen = 0; two = false; }
+    }
+    int hcap = 0;
+    if (S) {
+        const size_t n = (size_t)b->n_matches;
+        const unsigned t = S->step++;
+        sc.retry_cnt = S->counts + 3 + t % 3;
+        sc.retry_list = S->lists + 2 * n;
+        sc.heavy_cnt = S->counts + t % 3;
+        sc.heavy_list = S->lists + (t & 1) * n;
+        sc.hint_cur = S->hints + (t & 1) * n;
+        sc.heavy_next_cnt = S->counts + (t + 1) % 3;
+        sc.heavy_next = S->lists + ((t + 1) & 1) * n;
+        sc.hint_next = S->hints + ((t + 1) & 1) * n;
+        sc.zero_a = S->counts + (t + 2) % 3;
+        sc.zero_b = S->counts + 3 + (t + 1) % 3;
+        hcap = sched ? (b->n_matches / 4 + 64) : 0;
+        sc.hcap = hcap;
+    }
+    if (!two) {
+        // single full-capacity launch (small maps, dense batches); spills cannot happen
+        int grid = (b->n_matches + hcap + wpc - 1) / wpc;
+        rc = launch_step_size<true, kAll>(b, unit_actions, tile_actions, L, flags, full, sc, grid, wpc, st);
+        if (rc) return rc;
+        return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
+    }
     int wpc_s = g_warps_per_cta > 0 ? g_warps_per_cta : (Ls.total >= 8 * 1024 ? 1 : 2);
-    rc = launch_step_size<true, kSmall>(b, unit_actions, tile_actions, Ls, flags, small, retry, retry_next,
-                                        (b->n_matches + wpc_s - 1) / wpc_s, wpc_s, st);
+    rc = launch_step_size<true, kSmall>(b, unit_actions, tile_actions, Ls, flags, small, sc,
+                                        (b->n_matches + hcap + wpc_s - 1) / wpc_s, wpc_s, st);
     if (rc) return rc;
     rc = cuda_ok(cudaGetLastError(), "lux_step_kernel (small class) launch");
     if (rc) return rc;
     int grid_l = b->n_matches < 148 * 8 ? b->n_matches : 148 * 8;
-    rc = launch_step_size<true, kList>(b, unit_actions, tile_actions, L, flags, full, retry, nullptr, grid_l, 1, st);
+    rc = launch_step_size<true, kList>(b, unit_actions, tile_actions, L, flags, full, sc, grid_l, 1, st);
     if (rc) return rc;
     rc = cuda_ok(cudaGetLastError(), "lux_step_kernel (retry list) launch");
     if (rc) return rc;
     // trail the retry count to the host without synchronising; a stale value only delays the mode switch
-    return cuda_ok(cudaMemcpyAsync(g_retry_seen, retry, sizeof(int), cudaMemcpyDeviceToHost, st), "retry count copy");
+    return cuda_ok(cudaMemcpyAsync(S->seen, sc.retry_cnt, sizeof(int), cudaMemcpyDeviceToHost, st), "retry count copy");
 }
 
 extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,
@@ -512,7 +608,7 @@ extern "C" int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t m
     if (!unit_actions || !tile_actions) return LUX_E_ARG;
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
-    const int wpc = 4;
+    const int wpc = 8;
     lux_gen_actions_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, 0, (cudaStream_t)cuda_stream>>>(
         *b, seed, match_id_base, unit_actions, tile_actions, (unsigned long long*)counters);
     return cuda_ok(cudaGetLastError(), "lux_gen_actions_kernel launch");

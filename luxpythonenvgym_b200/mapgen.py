@@ -280,3 +280,51 @@ def generate(seed, size=None, caps=None):
 def natural_size(seed):
     """The map side the generator draws for this seed (first rng value, game_map.py:86)."""
     return MAP_SIZES[math.floor(Arc4Random("gen_%d" % int(seed)).random() * len(MAP_SIZES))]
+
+
+# ---------------------------------------------------------------------------------------------------
+# native generator (luxpythonenvgym_b200/csrc/lux_mapgen.cpp): same maps, ~100x faster, multithreaded
+_native = None
+
+
+def _native_lib():
+    global _native
+    if _native is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lux_mapgen.so")
+        if not os.path.exists(path):
+            from . import build
+            build.build_mapgen()
+        _native = ctypes.CDLL(path)
+        _native.lux_mapgen_natural_size.argtypes = [ctypes.c_int64]
+    return _native
+
+
+def generate_batch(seeds, size, caps=None, threads=0):
+    """Packed initial states for many seeds at once -> dict of host uint8 arrays [n, bytes] per section
+    (feed to BatchedGame.load_arrays).  `size` forces the map side (all maps of a batch share it)."""
+    import ctypes
+    from ._lib import LuxBatch
+    lib = _native_lib()
+    caps = dict(S.default_caps(size), **(caps or {}))
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    n = len(seeds)
+    arr = {name: np.zeros((n, width), dtype=np.uint8) for name, width in (
+        ("hdr", S.HDR_BYTES), ("cells", size * size * 8), ("units", caps["units"] * 16),
+        ("cities", caps["cities"] * 16), ("tiles", caps["tiles"] * 2), ("res", caps["res"] * 2))}
+    desc = LuxBatch(n, size, caps["units"], caps["cities"], caps["tiles"], caps["res"],
+                    *[arr[k].ctypes.data for k in ("hdr", "cells", "units", "cities", "tiles", "res")])
+    rc = lib.lux_mapgen_generate_batch(ctypes.byref(desc), seeds.ctypes.data_as(ctypes.c_void_p), int(threads))
+    if rc != 0:
+        raise RuntimeError("lux_mapgen_generate_batch -> %d" % rc)
+    return arr
+
+
+def generate_native(seed, size=None, caps=None):
+    """One map through the native generator, as a MatchState (size None = the seed's natural size)."""
+    if size is None:
+        size = int(_native_lib().lux_mapgen_natural_size(int(seed)))
+    caps = dict(S.default_caps(size), **(caps or {}))
+    arr = generate_batch([seed], size, caps, threads=1)
+    return S.MatchState.from_arrays(size, {k: v[0] for k, v in arr.items()})

@@ -32,13 +32,14 @@ def _recap(ms, caps):
     return o
 
 
-@pytest.mark.parametrize("tma,two_class", [(1, -1), (1, 1), (1, 0), (0, -1)])
-def test_replays_bit_exact(tma, two_class):
+@pytest.mark.parametrize("tma,two_class,heavy_first", [(1, -1, 1), (1, 1, 0), (1, 0, 1), (1, 0, 0), (0, -1, 1)])
+def test_replays_bit_exact(tma, two_class, heavy_first):
     """The 7 Kaggle episodes of the reference's test_replay.py, 360 turns each, through every launch
     path: TMA staging with the automatic / forced / disabled two-class launch, and plain loads."""
     lib = _lib.load()
     lib.lux_b200_set_option(b"tma", tma)
     lib.lux_b200_set_option(b"two_class", two_class)
+    lib.lux_b200_set_option(b"heavy_first", heavy_first)
     try:
         z = G.npz("replays")
         for rid in G.replay_ids():
@@ -58,6 +59,7 @@ def test_replays_bit_exact(tma, two_class):
     finally:
         lib.lux_b200_set_option(b"tma", 1)
         lib.lux_b200_set_option(b"two_class", -1)
+        lib.lux_b200_set_option(b"heavy_first", 1)
 
 
 def test_random_and_dense_fixtures():
