@@ -250,6 +250,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
+    launches0 = game.lib.lux_b200_launch_count()
     t_start.record()
     for k in range(K):
         game.gen_actions(STREAM_SEED, base, counters=counters)
@@ -259,6 +260,7 @@ def run_b200(args):
         game.reset_done(pool, epoch[0], resets)
         epoch[0] += 1
     t_end.record()
+    launches = game.lib.lux_b200_launch_count() - launches0
     barrier()
     sampler.stop_flag = True
     total_ms = t_start.elapsed_time(t_end)
@@ -335,7 +337,7 @@ def run_b200(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms / K, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": config_dict(args, world),
-                "gpu_launches": 3 * K,
+                "gpu_launches": int(launches) * world,
                 "kernel_ms": {"lux_step_kernel": step_ms, "whole_step": total_ms / K},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "kernel": "lux_step_kernel<true>",

@@ -127,6 +127,9 @@ int lux_b200_device_count(void);
  * "warps_per_cta" (0 = automatic).  Returns LUX_E_ARG for an unknown name. */
 int lux_b200_set_option(const char* name, int value);
 
+/* Number of kernels the step / gen_actions / reset_done / stats entry points have launched so far. */
+unsigned long long lux_b200_launch_count(void);
+
 /* Dynamic shared memory one match needs in lux_b200_step for these capacities. */
 size_t lux_b200_step_smem_bytes(int size, int u_cap, int c_cap, int t_cap, int r_cap);
 

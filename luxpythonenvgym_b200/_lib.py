@@ -17,7 +17,7 @@ _ERR = {LUX_E_ARG: "bad argument", LUX_E_CAPACITY: "capacity out of range",
 # every symbol include/lux_b200.h declares
 EXPORTS = ("lux_b200_version", "lux_b200_device_count", "lux_b200_set_option", "lux_b200_step_smem_bytes",
            "lux_b200_step", "lux_b200_step_host", "lux_b200_gen_actions", "lux_b200_observe",
-           "lux_b200_reset_done", "lux_b200_stats", "lux_b200_encode_actions", "lux_b200_reward")
+           "lux_b200_reset_done", "lux_b200_stats", "lux_b200_encode_actions", "lux_b200_reward", "lux_b200_launch_count")
 
 
 class LuxError(RuntimeError):
@@ -49,6 +49,7 @@ def load():
     vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
     bp = ctypes.POINTER(LuxBatch)
     lib.lux_b200_version.restype = i32
+    lib.lux_b200_launch_count.restype = ctypes.c_uint64
     lib.lux_b200_device_count.restype = i32
     lib.lux_b200_set_option.argtypes = [ctypes.c_char_p, i32]
     lib.lux_b200_step_smem_bytes.restype = ctypes.c_size_t

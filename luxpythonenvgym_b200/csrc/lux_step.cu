@@ -218,6 +218,11 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
     }
 }
 
+// kernels this library has launched (all entry points of this translation unit); bench.py reports the
+// difference over its timed region as "gpu_launches"
+static unsigned long long g_launches = 0;
+extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
+
 template <bool kTma, int kS, int kMode>
 static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L, unsigned flags,
                        LuxStage stage, const LuxSched& sc, int grid, int wpc, cudaStream_t st) {
@@ -225,6 +230,7 @@ static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta,
     cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return LUX_E_CUDA;
     lux_step_kernel<kTma, kS, kMode><<<grid, 32 * wpc, smem, st>>>(*b, ua, ta, L, flags, stage, sc);
+    g_launches++;
     return LUX_OK;
 }
 
@@ -611,6 +617,7 @@ extern "C" int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t m
     const int wpc = 8;
     lux_gen_actions_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, 0, (cudaStream_t)cuda_stream>>>(
         *b, seed, match_id_base, unit_actions, tile_actions, (unsigned long long*)counters);
+    g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_gen_actions_kernel launch");
 }
 
@@ -629,6 +636,7 @@ extern "C" int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, uint
     const int wpc = 4;
     lux_reset_done_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, 0, (cudaStream_t)cuda_stream>>>(
         *b, *pool, epoch, reset_count);
+    g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_reset_done_kernel launch");
 }
 
@@ -642,5 +650,6 @@ extern "C" int lux_b200_stats(const LuxBatch* b, int64_t* out16, void* cuda_stre
     if (rc) return rc;
     if (b->n_matches == 0) return LUX_OK;
     lux_stats_kernel<<<(b->n_matches + 127) / 128, 128, 0, st>>>(*b, (unsigned long long*)out16);
+    g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_stats_kernel launch");
 }

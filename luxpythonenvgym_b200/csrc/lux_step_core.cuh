@@ -55,7 +55,7 @@
 #define UST_FAILED 0x80u  // transfer raised KeyError in the reference: no cooldown, no cart road
 
 struct LuxSmemLayout {
-    int hdr, cells, units, cities, tiles, res, uact, tact, p1, occ, utgt, ust, umine, tmask, cprefix, cremap, reqlist, mbar, total;
+    int hdr, cells, units, cities, tiles, res, uact, tact, utgt, ust, umine, tmask, cprefix, cremap, reqlist, mbar, total;
 };
 
 LUX_DEV int lux_align16(int x) { return (x + 15) & ~15; }
@@ -78,8 +78,6 @@ LuxSmemLayout lux_smem_layout(int size, int u_cap, int c_cap, int t_cap, int r_c
     LUX_TAKE(res, r_cap * 2)
     LUX_TAKE(uact, u_cap * 4)
     LUX_TAKE(tact, t_cap)
-    LUX_TAKE(p1, ncell)
-    LUX_TAKE(occ, ncell)
     LUX_TAKE(utgt, u_cap * 2)
     LUX_TAKE(ust, u_cap)
     LUX_TAKE(umine, u_cap)
@@ -102,8 +100,6 @@ struct LuxMatch {
     uint16_t* res;
     uint32_t* uact;
     uint8_t* tact;
-    uint8_t* p1;
-    uint8_t* occ;
     uint16_t* utgt;
     uint8_t* ust;
     uint8_t* umine;
@@ -125,8 +121,6 @@ LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayou
     M.res = (uint16_t*)(smem + L.res);
     M.uact = (uint32_t*)(smem + L.uact);
     M.tact = (uint8_t*)(smem + L.tact);
-    M.p1 = (uint8_t*)(smem + L.p1);
-    M.occ = (uint8_t*)(smem + L.occ);
     M.utgt = (uint16_t*)(smem + L.utgt);
     M.ust = (uint8_t*)(smem + L.ust);
     M.umine = (uint8_t*)(smem + L.umine);
@@ -171,6 +165,18 @@ LUX_DEV int unit_space(const LuxUnit& u) {   // unit.py:43-52
 LUX_DEV int lux_dx(int dir) { return dir == LUX_DIR_EAST ? 1 : dir == LUX_DIR_WEST ? -1 : 0; }
 LUX_DEV int lux_dy(int dir) { return dir == LUX_DIR_SOUTH ? 1 : dir == LUX_DIR_NORTH ? -1 : 0; }
 
+// Per-cell scratch without extra planes: on a cell that is NOT a city tile the upper word of LuxCell
+// (tile_cd, city_slot, key) is unused, so the engine keeps its transient per-cell flags there --
+// byte 0 (tile_cd): movement flags P1_*, later the collection "requested / fill level" byte;
+// byte 1 (city_slot): index + 1 of the unit standing on the cell during collection.
+// Every such byte is cleared again before the grid is stored (canonical state has zeros there).
+LUX_DEV unsigned lux_scratch_or(LuxCell* cells, int c, int which, unsigned bits) {
+    unsigned* w = ((unsigned*)&cells[c]) + 1;
+    int sh = which * 8;
+    unsigned old = lux_atomic_or(w, bits << sh);
+    return (old >> sh) & 0xffu;
+}
+
 // the five cells a worker mines from: own, N, E, S, W (game.py:950-951, game_map.py:484-508)
 LUX_DEV int lux_cell5(int S, int x, int y, int k) {
     // branch-free: (dx, dy) + 1 packed two bits per direction, k = 0..4 -> c, n, e, s, w
@@ -197,7 +203,6 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
     const int rate = rtype == LUX_RES_WOOD ? 20 : rtype == LUX_RES_COAL ? 5 : 2;
     const int fuel_rate = rtype == LUX_RES_WOOD ? 1 : rtype == LUX_RES_COAL ? 10 : 40;
 
-    lux_zero16(M.p1, lux_align16(M.ncell));      // p1 becomes the "requested / fill level" plane
     if (lane == 0) *M.reqcnt = 0;
     lux_sync();
 
@@ -231,7 +236,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                 for (int j = 0; j < 5; j++) {
                     if (!(minable & (1u << j))) continue;
                     int c = lux_cell5(S, U.x, U.y, j);
-                    unsigned old = lux_atomic_or_byte(M.p1, c, 0x80u);
+                    unsigned old = lux_scratch_or(M.cells, c, 0, 0x80u);
                     if (!(old & 0x80u)) M.reqlist[lux_atomic_add(M.reqcnt, 1)] = (uint16_t)c;
                 }
             }
@@ -267,7 +272,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                     n++; sum += a;
                 }
             } else {
-                int o = M.occ[p];
+                int o = P.city_slot;                      // scratch: unit index + 1
                 if (o) {
                     int a = M.umine[o - 1];
                     if (a != 0xFF) { hist += (uint64_t)1 << (3 * a); present |= 1u << a; n++; sum += a; }
@@ -317,7 +322,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                 }
             }
         }
-        M.p1[c] = (uint8_t)level;
+        C.tile_cd = (uint8_t)level;                   // scratch: fill level (replaces the request mark)
     }
     lux_sync();
 
@@ -339,7 +344,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         for (int j = 0; j < 5; j++) {
             int c = lux_cell5(S, U.x, U.y, j);
             if (c >= 0 && cell_res_type(M.cells[c]) == rtype) {
-                int lv = M.p1[c] & 0x7F;
+                int lv = M.cells[c].tile_cd & 0x7F;
                 gain += mine < lv ? mine : lv;
             }
         }
@@ -459,7 +464,6 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     const int mult = night ? 2 : 1;
     int tiles_dirty = 0;
 
-    lux_zero16(M.p1, lux_align16(M.ncell));
     {
         int nt = n_tiles0 + n_units0;                 // tile indices that can exist during this turn
         if (nt > M.t_cap) nt = M.t_cap;
@@ -547,10 +551,10 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             if (cand) {
                 unsigned bit = team ? P1_CLAIM1 : P1_CLAIM0;
                 int first = lux_ffs(peers) - 1 == lane;
-                if (!first || (M.p1[t] & bit)) M.ust[u] = 0;
+                if (!first || (M.cells[t].tile_cd & bit)) M.ust[u] = 0;
             }
             lux_sync();
-            if (cand && M.ust[u]) lux_atomic_or_byte(M.p1, t, team ? P1_CLAIM1 : P1_CLAIM0);
+            if (cand && M.ust[u]) lux_scratch_or(M.cells, t, 0, team ? P1_CLAIM1 : P1_CLAIM0);
             lux_sync();
         }
     }
@@ -562,12 +566,17 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         int ucell = U.y * S + U.x;
         unsigned st = M.ust[u];
         int moving = (st & 7) == LUX_UA_MOVE;
-        unsigned old = lux_atomic_or_byte(M.p1, ucell, P1_HAS1 | (moving ? 0u : P1_STILL));
-        if (old & P1_HAS1) lux_atomic_or_byte(M.p1, ucell, P1_HAS2);
+        // flags are only ever read on non-city cells, and only those have the scratch byte
+        if (!cell_is_tile(M.cells[ucell])) {
+            unsigned old = lux_scratch_or(M.cells, ucell, 0, P1_HAS1 | (moving ? 0u : P1_STILL));
+            if (old & P1_HAS1) lux_scratch_or(M.cells, ucell, 0, P1_HAS2);
+        }
         if (moving) {
             int t = M.utgt[u];
-            old = lux_atomic_or_byte(M.p1, t, P1_IN1);
-            if (old & P1_IN1) lux_atomic_or_byte(M.p1, t, P1_IN2);
+            if (!cell_is_tile(M.cells[t])) {
+                unsigned old = lux_scratch_or(M.cells, t, 0, P1_IN1);
+                if (old & P1_IN1) lux_scratch_or(M.cells, t, 0, P1_IN2);
+            }
         }
     }
     lux_sync();
@@ -579,12 +588,12 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         if ((st & 7) != LUX_UA_MOVE) continue;
         int t = M.utgt[u];
         if (cell_is_tile(M.cells[t])) continue;
-        unsigned f = M.p1[t];
+        unsigned f = M.cells[t].tile_cd;
         if ((f & P1_IN2) || ((f & P1_HAS1) && !(f & P1_HAS2) && (f & P1_STILL))) {
             M.ust[u] = (uint8_t)(st | UST_REVERTED);
             const LuxUnit& U = M.units[u];
             int o = U.y * S + U.x;
-            if (!cell_is_tile(M.cells[o])) lux_atomic_or_byte(M.p1, o, P1_BLOCKED);
+            if (!cell_is_tile(M.cells[o])) lux_scratch_or(M.cells, o, 0, P1_BLOCKED);
         }
     }
     lux_sync();
@@ -598,17 +607,26 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             if ((st & 7) != LUX_UA_MOVE || (st & UST_REVERTED)) continue;
             int t = M.utgt[u];
             if (cell_is_tile(M.cells[t])) continue;
-            if (M.p1[t] & P1_BLOCKED) {
+            if (M.cells[t].tile_cd & P1_BLOCKED) {
                 M.ust[u] = (uint8_t)(st | UST_REVERTED);
                 const LuxUnit& U = M.units[u];
                 int o = U.y * S + U.x;
-                if (!cell_is_tile(M.cells[o])) lux_atomic_or_byte(M.p1, o, P1_BLOCKED);
+                if (!cell_is_tile(M.cells[o])) lux_scratch_or(M.cells, o, 0, P1_BLOCKED);
                 changed = 1;
             }
         }
         lux_sync();
         if (!lux_any(changed)) break;
     }
+    // the movement flags have served: clear the scratch byte of every cell a unit stands on or aimed at
+#pragma unroll 1
+    for (int u = lane; u < n_units0; u += 32) {
+        const LuxUnit& U = M.units[u];
+        int ucell = U.y * S + U.x, t = M.utgt[u];
+        if (!cell_is_tile(M.cells[ucell])) M.cells[ucell].tile_cd = 0;
+        if (!cell_is_tile(M.cells[t])) M.cells[t].tile_cd = 0;
+    }
+    lux_sync();
 
     // ---- city tiles: spawn validation (game.py:696-718) + CityTile.turn (city.py:96-120)
     int n_units = n_units0;
@@ -780,7 +798,6 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 
     // ---- resource collection: uranium, coal, wood (distribute_all_resources game.py:868-880)
     {
-        lux_zero16(M.occ, lux_align16(M.ncell));
         lux_city_prefix(M, n_cities);     // also syncs
         int bad = 0;
 #pragma unroll 1
@@ -788,8 +805,8 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             const LuxUnit& U = M.units[u];
             int c = U.y * S + U.x;
             if (!cell_is_tile(M.cells[c])) {
-                if (M.occ[c]) bad = 1;     // cannot happen in play: a non-city cell holds one unit
-                M.occ[c] = (uint8_t)(u + 1);
+                if (M.cells[c].city_slot) bad = 1;     // cannot happen in play: a non-city cell holds one unit
+                M.cells[c].city_slot = (uint8_t)(u + 1);
             }
         }
         if (lux_any(bad) && lane == 0) h->status |= LUX_ST_BAD_STATE;
@@ -801,6 +818,14 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             if (rp0 < need && rp1 < need) continue;           // nobody may mine this type yet
             lux_collect_type<kS>(M, rtype, n_units, rp0 >= need, rp1 >= need);
         }
+        // collection is over: drop the occupant marks again
+#pragma unroll 1
+        for (int u = lane; u < n_units; u += 32) {
+            const LuxUnit& U = M.units[u];
+            int c = U.y * S + U.x;
+            if (!cell_is_tile(M.cells[c])) M.cells[c].city_slot = 0;
+        }
+        lux_sync();
     }
 
     // ---- deposit (handle_resource_deposit game.py:1003-1023)
@@ -882,6 +907,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 #pragma unroll 1
         for (int r = lane; r < n_res; r += 32) {
             LuxCell& C = M.cells[M.res[r]];
+            if (!cell_is_tile(C)) C.tile_cd = 0;                          // collection scratch (fill level)
             if (C.amount == 0) { C.flags &= 0xFC; continue; }
             if (cell_res_type(C) == LUX_RES_WOOD && C.amount < LUX_MAX_WOOD) {
                 int a = (41 * (int)C.amount + 39) / 40;               // == ceil(min(a*1.025, 500)), tests/test_oracle_golden.py

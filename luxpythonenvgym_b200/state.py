@@ -114,7 +114,8 @@ def default_caps(size):
     units = up(min(252, max(64, cells // 2)), 4)
     tiles = up(min(384, max(64, cells)), 16)
     cities = min(255, max(32, cells // 4))
-    res = up(min(256, max(48, cells // 3)), 8)
+    # resource cells per generated map (20000 seeds per side): max 48 / 60 / 104 / 166 on 12 / 16 / 24 / 32
+    res = {12: 64, 16: 80, 24: 128, 32: 192}.get(size, up(min(256, max(64, cells // 4)), 8))
     return dict(units=units, cities=cities, tiles=tiles, res=res)
 
 
