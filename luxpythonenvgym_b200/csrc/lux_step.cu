@@ -263,6 +263,14 @@ __device__ __forceinline__ uint64_t lux_hash(uint64_t seed, uint64_t match, uint
     return x;
 }
 
+// r % m for a 64-bit r with 32-bit arithmetic only (2^32 = q*m + c): exact, and far cheaper than the
+// 64-bit remainder routine
+__device__ __forceinline__ unsigned lux_mod64(uint64_t r, unsigned m) {
+    unsigned hi = (unsigned)(r >> 32), lo = (unsigned)r;
+    unsigned c = (unsigned)(4294967296ULL % m);
+    return ((hi % m) * c + lo % m) % m;
+}
+
 // one warp per match, state read in place from global memory (harness kernel, not the hot path)
 __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, uint64_t seed, uint64_t match_id_base,
                                                       uint32_t* __restrict__ unit_actions,
@@ -293,7 +301,7 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
             uint64_t r = lux_hash(seed, mid, (uint64_t)turn, 0, (uint64_t)U.id);
             int can_act = U.cd_q < 4;
             if (can_act || ((r >> 32) & 15) == 0) {
-                unsigned p = (unsigned)(r % 100);
+                unsigned p = lux_mod64(r, 100);
                 const LuxCell C = cells[U.y * S + U.x];
                 int cargo = U.wood + U.coal + U.uranium;
                 int night = (turn % 40) >= 30;
@@ -314,7 +322,7 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
                         if (d <= 1 && V.id < best_id) best_id = V.id;
                     }
                     if (best_id != 0x7fffffff) {
-                        uint32_t res = (uint32_t)((r >> 8) % 3), amount = 1 + (uint32_t)((r >> 16) % 100);
+                        uint32_t res = lux_mod64(r >> 8, 3), amount = 1 + lux_mod64(r >> 16, 100);
                         w = LUX_UA_TRANSFER | (res << 3) | (amount << 6) | ((uint32_t)best_id << 17);
                     }
                 }
@@ -329,7 +337,7 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
             uint64_t r = lux_hash(seed, mid, (uint64_t)turn, 1, (uint64_t)cell);
             int can_act = cells[cell].tile_cd < 1;
             if (can_act || ((r >> 32) & 15) == 0) {
-                unsigned q = (unsigned)(r % 100);
+                unsigned q = lux_mod64(r, 100);
                 code = q < 45 ? LUX_TA_BUILD_WORKER : q < 50 ? LUX_TA_BUILD_CART : q < 90 ? LUX_TA_RESEARCH : LUX_TA_NONE;
             }
         }
@@ -391,10 +399,25 @@ __global__ void lux_reset_done_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch,
     }
     src = __shfl_sync(0xffffffffu, src, 0);
     const int ncell = b.size * b.size;
+    // 8 independent 16-byte loads in flight per lane before the stores: the copy of one match is a
+    // single warp's latency chain otherwise (measured 17 us for 9 KB)
     auto copy = [&](void* d, const void* s, size_t bytes) {
         const uint4* sp = (const uint4*)s;
         uint4* dp = (uint4*)d;
-        for (size_t i = lane; i < bytes / 16; i += 32) dp[i] = sp[i];
+        const size_t n16 = bytes / 16;
+        for (size_t base = 0; base < n16; base += 32 * 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                size_t i = base + (size_t)k * 32 + lane;
+                if (i < n16) v[k] = sp[i];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                size_t i = base + (size_t)k * 32 + lane;
+                if (i < n16) dp[i] = v[k];
+            }
+        }
     };
     copy(b.cells + (size_t)m * ncell, pool.cells + (size_t)src * ncell, (size_t)ncell * 8);
     copy(b.units + (size_t)m * b.u_cap, pool.units + (size_t)src * b.u_cap, (size_t)pool.hdr[src].n_units * 16);
