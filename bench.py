@@ -267,16 +267,21 @@ def run_b200(args):
     step_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / K
     live_turns, alg_bytes = [int(x) for x in counters.cpu().tolist()]
 
-    # ---- end to end through the host-buffer entry point: pinned host actions in, headers out
+    # ---- end to end through the host entry point: pinned host action LIST in, done flags + summary out
     E = min(args.e2e_steps, K)
     snap = {k: t.clone() for k, t in game.sections().items()}
     epoch0 = epoch[0]
-    ua_h = torch.empty((E, n, game.caps["units"]), dtype=torch.int32).pin_memory()
-    ta_h = torch.empty((E, n, game.caps["tiles"]), dtype=torch.uint8).pin_memory()
-    for k in range(E):                       # untimed: record the action tensors of E turns on the host
+    ent_cap = n * 24
+    ent_h = torch.zeros((E, ent_cap, 2), dtype=torch.int32).pin_memory()
+    ent_k = []
+    for k in range(E):                       # untimed: record the action LISTS of E turns on the host
+        game.unit_actions.zero_()
+        game.tile_actions.zero_()
         game.gen_actions(STREAM_SEED, base)
-        ua_h[k].copy_(game.unit_actions)
-        ta_h[k].copy_(game.tile_actions)
+        ent = game.pack_entries()
+        assert ent.shape[0] <= ent_cap
+        ent_h[k, : ent.shape[0]].copy_(ent)
+        ent_k.append(int(ent.shape[0]))
         game.step()
         game.reset_done(pool, epoch[0], resets)
         epoch[0] += 1
@@ -285,22 +290,17 @@ def run_b200(args):
     for k, t in game.sections().items():     # rewind
         t.copy_(snap[k])
     epoch[0] = epoch0
-    hdr_h = torch.empty((n, 128), dtype=torch.uint8).pin_memory()
+    game.unit_actions.zero_()
+    game.tile_actions.zero_()
     done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    summ_h = torch.zeros(4, dtype=torch.int32).pin_memory()
     barrier()
     w0 = time.perf_counter()
-    from luxpythonenvgym_b200 import state as S
-    hview = hdr_h.numpy().view(S.header_dtype).reshape(-1)
-    used_u = used_t = 0                                       # first step: upload every slot
     h2d_total = 0
     for k in range(E):
-        # H2D actions (only the slots that can hold a live entity, known from the previous headers),
-        # step, D2H headers, sync
-        game.step_host(ua_h[k], ta_h[k], hdr_h, done_h, u_used=used_u, t_used=used_t)
-        uu = game.caps["units"] if used_u == 0 else min(game.caps["units"], (used_u + 3) & ~3)
-        tt = game.caps["tiles"] if used_t == 0 else min(game.caps["tiles"], (used_t + 15) & ~15)
-        h2d_total += n * (uu * 4 + tt)
-        used_u, used_t = max(4, int(hview["n_units"].max())), max(4, int(hview["n_tiles"].max()))
+        # H2D: this turn's action list (8 bytes per action); step; D2H: done flags + summary; sync
+        game.step_host_sparse(ent_h[k], ent_k[k], done_h, summ_h)
+        h2d_total += 8 * ent_k[k]
         game.reset_done(pool, epoch[0], resets)
         epoch[0] += 1
     torch.cuda.synchronize()
@@ -308,7 +308,7 @@ def run_b200(args):
     assert torch.equal(game.hdr, final_hdr_device_path), "host-buffer path diverged from the device path"
     # live match-turns of those E steps = the same trajectory the device path ran
     h2d = h2d_total // max(E, 1)
-    d2h = n * 128
+    d2h = n + 16
 
     # ---- reduce over ranks: time = max, work = sum; stats vector all-reduced with NCCL
     stats = game.stats().clone()
@@ -345,8 +345,9 @@ def run_b200(args):
                              "live_match_turns_per_launch": live_all / world / K},
                 "e2e": {"value": e2e_turns / e2e_s, "unit": "match-turns/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "steps": E,
-                        "note": "lux_b200_step_host: pinned host action tensors -> device, step, headers -> host, "
-                                "sync every step; counts resident matches per step (finished ones are reset the same step)"},
+                        "note": "lux_b200_step_host_sparse: pinned host action LIST (8 B per action) -> device, scatter, "
+                                "step, done flags + summary -> host, sync every step; counts resident matches per step "
+                                "(finished ones are reset the same step)"},
                 "clocks": sampler.summary(),
                 "host_mapgen": {"maps": n + POOL_MAPS, "seconds": mapgen_s, "note": "untimed setup: native seeded generator"},
                 "stats": {"live": st[0], "finished_pending": st[1], "sum_units": st[7], "sum_city_tiles": st[8],

@@ -107,6 +107,34 @@ class BatchedGame:
             hdr_host.data_ptr() if hdr_host is not None else None, int(u_used), int(t_used),
             _lib.LUX_STEP_PREVALIDATE if prevalidate else 0, self._stream()), "lux_b200_step_host")
 
+    def step_host_sparse(self, entries_host, k, done_host=None, summary_host=None, prevalidate=False):
+        """One turn from a host action LIST: entries_host is an int32/uint32 [cap, 2] (pinned) tensor whose
+        first k rows are { tile<<31 | match<<10 | slot, action word }; see `pack_entries`."""
+        _lib.check(self.lib.lux_b200_step_host_sparse(
+            ctypes.byref(self._desc), entries_host.data_ptr(), int(k), self.unit_actions.data_ptr(),
+            self.tile_actions.data_ptr(), done_host.data_ptr() if done_host is not None else None,
+            summary_host.data_ptr() if summary_host is not None else None,
+            _lib.LUX_STEP_PREVALIDATE if prevalidate else 0, self._stream()), "lux_b200_step_host_sparse")
+
+    def pack_entries(self, unit_actions=None, tile_actions=None):
+        """Device helper: the non-zero live entries of dense action tensors as an int32 [k, 2] entry list
+        (the format step_host_sparse uploads).  Rows beyond the live prefixes are ignored."""
+        ua = self.unit_actions if unit_actions is None else unit_actions
+        ta = self.tile_actions if tile_actions is None else tile_actions
+        hdr = self.hdr.view(torch.int16)
+        nu = hdr[:, 6].to(torch.int64) & 0xFFFF          # n_units at byte 12
+        nt = hdr[:, 8].to(torch.int64) & 0xFFFF          # n_tiles at byte 16
+        live = self.hdr[:, 24] == 0
+        um = (torch.arange(ua.shape[1], device=self.device)[None, :] < nu[:, None]) & (ua != 0) & live[:, None]
+        tm = (torch.arange(ta.shape[1], device=self.device)[None, :] < nt[:, None]) & (ta != 0) & live[:, None]
+        ui, ti = um.nonzero(), tm.nonzero()
+        ukey = (ui[:, 0] << 10) | ui[:, 1]
+        tkey = (1 << 31) | (ti[:, 0] << 10) | ti[:, 1]
+        keys = torch.cat([ukey, tkey])
+        vals = torch.cat([ua[um].to(torch.int64) & 0xFFFFFFFF, ta[tm].to(torch.int64)])
+        ent = torch.stack([keys, vals], dim=1) & 0xFFFFFFFF
+        return ((ent + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32)      # the low 32 bits, as int32
+
     def gen_actions(self, seed, match_id_base=0, unit_actions=None, tile_actions=None, counters=None):
         """Fill the action tensors from the canonical seeded stream (harness utility)."""
         ua = self.unit_actions if unit_actions is None else unit_actions

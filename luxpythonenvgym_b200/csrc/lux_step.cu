@@ -483,6 +483,10 @@ struct StepScratch {
     int* lists;                  // heavy[2][n] then retry[n]
     unsigned char* hints;        // [2][n]
     int* seen;                   // pinned host copy of a recent retry count (may be stale)
+    uint2* entries[2];           // sparse host actions of this / the previous call (device copies)
+    int entries_cap, entries_prev_n, entries_flip;
+    uint8_t* done_dev;           // compact done flags for the host path
+    int* summary_dev;            // [0] max n_units, [1] max n_tiles, [2] live matches, [3] finished
     unsigned step;
     int dense_hold;              // steps left in single-launch mode after a dense observation
 };
@@ -494,6 +498,9 @@ static void scratch_free(StepScratch& s) {
     if (s.lists) cudaFree(s.lists);
     if (s.hints) cudaFree(s.hints);
     if (s.seen) cudaFreeHost(s.seen);
+    for (int k = 0; k < 2; k++) if (s.entries[k]) cudaFree(s.entries[k]);
+    if (s.done_dev) cudaFree(s.done_dev);
+    if (s.summary_dev) cudaFree(s.summary_dev);
     memset(&s, 0, sizeof s);
 }
 
@@ -627,6 +634,105 @@ extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_action
     if (done_host && hdr_host)
         for (size_t i = 0; i < n; i++) done_host[i] = hdr_host[i].done;
     return LUX_OK;
+}
+
+// ---------------------------------------------------------------- sparse host actions
+// entry.x = tile flag (bit 31) | match index (bits 30:10) | slot (bits 9:0), entry.y = action word / byte
+__global__ void lux_apply_entries_kernel(const uint2* __restrict__ entries, int k, int clear, uint32_t* __restrict__ ua,
+                                         uint8_t* __restrict__ ta, int u_cap, int t_cap, int n_matches) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    uint2 e = entries[i];
+    unsigned m = (e.x >> 10) & 0x1FFFFFu, slot = e.x & 1023u;
+    if ((int)m >= n_matches) return;
+    if (e.x >> 31) { if ((int)slot < t_cap) ta[(size_t)m * t_cap + slot] = clear ? 0 : (uint8_t)e.y; }
+    else if ((int)slot < u_cap) ua[(size_t)m * u_cap + slot] = clear ? 0u : e.y;
+}
+
+__global__ void lux_summary_kernel(LuxBatch b, uint8_t* __restrict__ done, int* __restrict__ summary) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    int nu = 0, nt = 0, live = 0, fin = 0;
+    if (m < b.n_matches) {
+        const LuxHeader* h = b.hdr + m;
+        int d = h->done;
+        done[m] = (uint8_t)d;
+        nu = h->n_units; nt = h->n_tiles; live = !d; fin = d;
+    }
+    nu = __reduce_max_sync(0xffffffffu, nu);
+    nt = __reduce_max_sync(0xffffffffu, nt);
+    live = __reduce_add_sync(0xffffffffu, live);
+    fin = __reduce_add_sync(0xffffffffu, fin);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(summary, nu); atomicMax(summary + 1, nt);
+        if (live) atomicAdd(summary + 2, live);
+        if (fin) atomicAdd(summary + 3, fin);
+    }
+}
+
+// The turn for a HOST caller that holds an action LIST (what Game.run_turn_with_actions takes): k entries
+// are uploaded, scattered into the device action tensors (the previous call's entries are cleared first),
+// the step runs, and done flags (n bytes) + a 4-int summary come back.  Per step this moves 8*k bytes up
+// and n + 16 bytes down instead of dense action tensors and full headers.
+extern "C" int lux_b200_step_host_sparse(const LuxBatch* b, const void* entries_host, int k, uint32_t* unit_actions_dev,
+                                         uint8_t* tile_actions_dev, uint8_t* done_host, int32_t* summary_host,
+                                         uint32_t flags, void* cuda_stream) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (k < 0 || (k > 0 && !entries_host) || !unit_actions_dev || !tile_actions_dev) return LUX_E_ARG;
+    if (b->n_matches >= (1 << 21)) return LUX_E_ARG;
+    if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    StepScratch* S = scratch_get(b, st);
+    if (!S) return LUX_E_CUDA;
+    if (!S->done_dev) {
+        if (cudaMalloc(&S->done_dev, (size_t)b->n_matches) != cudaSuccess) return LUX_E_CUDA;
+        if (cudaMalloc(&S->summary_dev, 4 * sizeof(int)) != cudaSuccess) return LUX_E_CUDA;
+    }
+    if (k > S->entries_cap) {
+        cudaStreamSynchronize(st);
+        int cap = k * 2 + 1024;
+        for (int j = 0; j < 2; j++) {
+            uint2* fresh = nullptr;
+            if (cudaMalloc(&fresh, (size_t)cap * sizeof(uint2)) != cudaSuccess) return LUX_E_CUDA;
+            if (S->entries[j]) {
+                cudaMemcpy(fresh, S->entries[j], (size_t)S->entries_cap * sizeof(uint2), cudaMemcpyDeviceToDevice);
+                cudaFree(S->entries[j]);
+            }
+            S->entries[j] = fresh;
+        }
+        S->entries_cap = cap;
+    }
+    uint2* prev = S->entries[S->entries_flip];
+    uint2* cur = S->entries[S->entries_flip ^ 1];
+    if (S->entries_prev_n > 0) {
+        lux_apply_entries_kernel<<<(S->entries_prev_n + 255) / 256, 256, 0, st>>>(prev, S->entries_prev_n, 1, unit_actions_dev,
+                                                                                  tile_actions_dev, b->u_cap, b->t_cap, b->n_matches);
+        g_launches++;
+    }
+    if (k > 0) {
+        rc = cuda_ok(cudaMemcpyAsync(cur, entries_host, (size_t)k * sizeof(uint2), cudaMemcpyHostToDevice, st), "h2d action entries");
+        if (rc) return rc;
+        lux_apply_entries_kernel<<<(k + 255) / 256, 256, 0, st>>>(cur, k, 0, unit_actions_dev, tile_actions_dev, b->u_cap,
+                                                                  b->t_cap, b->n_matches);
+        g_launches++;
+    }
+    S->entries_flip ^= 1;
+    S->entries_prev_n = k;
+    rc = lux_b200_step(b, unit_actions_dev, tile_actions_dev, flags, cuda_stream);
+    if (rc) return rc;
+    rc = cuda_ok(cudaMemsetAsync(S->summary_dev, 0, 4 * sizeof(int), st), "summary memset");
+    if (rc) return rc;
+    lux_summary_kernel<<<(b->n_matches + 255) / 256, 256, 0, st>>>(*b, S->done_dev, S->summary_dev);
+    g_launches++;
+    if (done_host) {
+        rc = cuda_ok(cudaMemcpyAsync(done_host, S->done_dev, (size_t)b->n_matches, cudaMemcpyDeviceToHost, st), "d2h done flags");
+        if (rc) return rc;
+    }
+    if (summary_host) {
+        rc = cuda_ok(cudaMemcpyAsync(summary_host, S->summary_dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, st), "d2h summary");
+        if (rc) return rc;
+    }
+    return cuda_ok(cudaStreamSynchronize(st), "step sync");
 }
 
 extern "C" int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t match_id_base,

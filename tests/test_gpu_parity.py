@@ -181,6 +181,33 @@ def test_step_host_matches_device_step():
         assert torch.equal(a.sections()[k], b.sections()[k]), k
 
 
+def test_step_host_sparse_matches_device_step():
+    size = 24
+    a, b = _game(48, size), _game(48, size)
+    arr = mapgen.generate_batch(np.arange(900, 948), size)
+    for g in (a, b):
+        g.load_arrays(arr)
+    ent_h = torch.zeros((48 * 64, 2), dtype=torch.int32).pin_memory()
+    done_h = torch.zeros(48, dtype=torch.uint8).pin_memory()
+    summ_h = torch.zeros(4, dtype=torch.int32).pin_memory()
+    for turn in range(60):
+        a.unit_actions.zero_()
+        a.tile_actions.zero_()
+        a.gen_actions(17, 0)
+        ent = a.pack_entries()
+        k = ent.shape[0]
+        ent_h[:k].copy_(ent)
+        a.step(prevalidate=True)
+        b.step_host_sparse(ent_h, k, done_h, summ_h, prevalidate=True)
+        hh = a.headers()
+        assert torch.equal(b.hdr, a.hdr), turn
+        assert np.array_equal(done_h.numpy(), hh["done"])
+        assert summ_h.tolist() == [int(hh["n_units"].max()), int(hh["n_tiles"].max()), int((hh["done"] == 0).sum()),
+                                   int((hh["done"] != 0).sum())]
+    for k in a.sections():
+        assert torch.equal(a.sections()[k], b.sections()[k]), k
+
+
 def test_bad_arguments_are_rejected():
     import ctypes
     lib = _lib.load()
