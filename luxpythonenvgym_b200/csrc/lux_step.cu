@@ -464,7 +464,7 @@ extern "C" size_t lux_b200_step_smem_bytes(int size, int u_cap, int c_cap, int t
 static int g_use_tma = 1;
 static int g_warps_per_cta = 0;   // 0 = automatic
 static int g_two_class = -1;      // -1 automatic, 0 off, 1 always
-static int g_heavy_first = 1;     // schedule the previous step's populous matches first
+static int g_heavy_first = 0;     // schedule the previous step's populous matches first (measured +-0: off)
 // tuning / fallback knobs (tests flip them to cover every launch path)
 extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!name) return LUX_E_ARG;

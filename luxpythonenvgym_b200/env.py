@@ -148,7 +148,8 @@ class LuxEnvironment:
     def reset(self):
         self.current_step = 0
         self._make()
-        team = int(self._rng.randint(0, 2))
+        # the reference flips a coin per reset (match_controller.py:118-122); configs["team"] pins it
+        team = int(self.configs["team"]) if self.configs.get("team") is not None else int(self._rng.randint(0, 2))
         self.learning_agent.set_team(team)
         self.opponent_agent.set_team(1 - team)
         self._team = torch.full((1,), team, dtype=torch.uint8, device=self.device)

@@ -354,3 +354,25 @@ def test_lux_environment_single_and_batched():
         finished += int(done.sum())
         assert reward.dtype == torch.float64 and torch.isfinite(reward).all()
     assert finished > 0 and (benv.game.headers()["status"] == 0).all()
+
+
+def test_lux_environment_matches_reference_decision_by_decision():
+    """The single-env `LuxEnvironment` (reset / step(code), one decision per step) against the episodes the
+    reference's own LuxEnvironment produced (tests/golden/env.npz fixtures 0-7): every observation row,
+    every returned reward and the done flag, decision by decision."""
+    from luxpythonenvgym_b200.env import LuxEnvironment
+    z = G.npz("env")
+    for k in range(8):
+        size, team = int(z["%d/size" % k]), int(z["%d/team" % k])
+        dec, want_obs = z["%d/decisions" % k], z["%d/obs" % k]
+        env = LuxEnvironment({"seed": 7000 + k, "width": size, "team": team})
+        obs = env.reset()
+        total = 0.0
+        for i in range(len(dec)):
+            if i < len(want_obs):
+                assert np.array_equal(np.asarray(obs, dtype=np.float32).view(np.uint32), want_obs[i].view(np.uint32)), (k, i)
+            obs, reward, done, _ = env.step(int(dec[i, 2]))
+            total += reward
+            assert abs(reward - float(dec[i, 3])) < 1e-9, (k, i, reward, dec[i, 3])
+            assert done == bool(dec[i, 4]), (k, i)
+        assert done
