@@ -480,6 +480,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     tt1 = lux_reduce_add(tt1);
     const int tu0 = h->n_team_units[0], tu1 = h->n_team_units[1];
 
+    int any_move = 0;
     // ---- unit action validation (validate_command game.py:646-695), lanes over units
 #pragma unroll 1
     for (int u = lane; u < n_units0; u += 32) {
@@ -530,13 +531,15 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         }
         M.ust[u] = (uint8_t)st;
         M.utgt[u] = (uint16_t)tgt;
+        any_move |= (st & 7) == LUX_UA_MOVE;
     }
     lux_sync();
+    any_move = lux_any(any_move);      // no validated move anywhere: the whole collision stage is a no-op
 
     // ---- MatchController pre-validation of moves (MoveAction.is_valid actions.py:58-116): of the
     // same-team moves into one non-city cell only the first in unit order is buffered; a CENTER
     // move is the do-nothing action and never changes the outcome, so it is dropped here
-    if (flags & LUX_STEP_PREVALIDATE) {
+    if ((flags & LUX_STEP_PREVALIDATE) && any_move) {
 #pragma unroll 1
         for (int base = 0; base < n_units0; base += 32) {
             int u = base + lane;
@@ -560,6 +563,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     }
 
     // ---- collision pruning (handle_movement_actions game.py:1104-1195)
+    if (any_move) {
 #pragma unroll 1
     for (int u = lane; u < n_units0; u += 32) {
         const LuxUnit& U = M.units[u];
@@ -627,6 +631,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         if (!cell_is_tile(M.cells[t])) M.cells[t].tile_cd = 0;
     }
     lux_sync();
+    }   // any_move
 
     // ---- city tiles: spawn validation (game.py:696-718) + CityTile.turn (city.py:96-120)
     int n_units = n_units0;
