@@ -198,20 +198,24 @@ int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t match_id_bas
  * with can_act() in dict order, then its city tiles with can_act() in cities x cells order.
  * obs: [n][e_cap][85] float32, ent_slot: [n][e_cap] int16 (unit slot, or 0x4000|tile
  * position), ent_count: [n] int32.
+ * Packed layout (row_offsets != NULL, int64[n+1], device): the rows of match m start at row
+ * row_offsets[m] of obs[R][85] / ent_slot[R] and may use up to row_offsets[m+1] - row_offsets[m] rows (an
+ * upper bound such as the team's units + tiles); unused rows of that range get ent_slot = -1.
  */
 int lux_b200_observe(const LuxBatch* b, const uint8_t* team_sel, float* obs, int16_t* ent_slot,
-                     int32_t* ent_count, int e_cap, void* cuda_stream);
+                     int32_t* ent_count, int e_cap, const int64_t* row_offsets, void* cuda_stream);
 
 /*
  * AgentPolicy action codes -> packed action tensors for the entities lux_b200_observe listed.
  * Replaces: AgentPolicy.action_code_to_action, examples/agent_policy.py:426-470 with the action
  * tables :117-132 (unit code % 9: center, n, w, s, e, transfer to a nearby cart, transfer to a nearby
  * worker (smart_transfer_to_nearby :24-100), build city, pillage; tile code % 3: build worker, build
- * cart, research).  codes: [n][e_cap] int32.  Slots without an entity get "no action".
+ * cart, research).  codes: [n][e_cap] int32, or [R] with the packed row_offsets of lux_b200_observe.
+ * Slots without an entity get "no action".
  */
 int lux_b200_encode_actions(const LuxBatch* b, const int16_t* ent_slot, const int32_t* ent_count,
-                            const int32_t* codes, int e_cap, uint32_t* unit_actions, uint8_t* tile_actions,
-                            void* cuda_stream);
+                            const int32_t* codes, int e_cap, const int64_t* row_offsets, uint32_t* unit_actions,
+                            uint8_t* tile_actions, void* cuda_stream);
 
 /*
  * Per-turn reward of team `team_sel[m]`.

@@ -58,10 +58,10 @@ def load():
     lib.lux_b200_step_host.argtypes = [bp, vp, vp, vp, vp, vp, vp, i32, i32, ctypes.c_uint32, vp]
     lib.lux_b200_step_host_sparse.argtypes = [bp, vp, i32, vp, vp, vp, vp, ctypes.c_uint32, vp]
     lib.lux_b200_gen_actions.argtypes = [bp, u64, u64, vp, vp, vp, vp]
-    lib.lux_b200_observe.argtypes = [bp, vp, vp, vp, vp, i32, vp]
+    lib.lux_b200_observe.argtypes = [bp, vp, vp, vp, vp, i32, vp, vp]
     lib.lux_b200_reset_done.argtypes = [bp, bp, ctypes.c_uint32, vp, vp]
     lib.lux_b200_stats.argtypes = [bp, vp, vp]
-    lib.lux_b200_encode_actions.argtypes = [bp, vp, vp, vp, i32, vp, vp, vp]
+    lib.lux_b200_encode_actions.argtypes = [bp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.lux_b200_reward.argtypes = [bp, vp, vp, vp, vp]
     _lib = lib
     return lib

@@ -168,18 +168,46 @@ class BatchedGame:
             team_sel = torch.full((self.n,), int(team_sel), dtype=torch.uint8, device=self.device)
         assert team_sel.dtype == torch.uint8 and team_sel.numel() == self.n and team_sel.is_cuda
         _lib.check(self.lib.lux_b200_observe(ctypes.byref(self._desc), team_sel.data_ptr(), self._obs.data_ptr(),
-                                             self._ent.data_ptr(), self._cnt.data_ptr(), e_cap, self._stream()),
+                                             self._ent.data_ptr(), self._cnt.data_ptr(), e_cap, None, self._stream()),
                    "lux_b200_observe")
         return self._obs, self._ent, self._cnt
 
-    def encode_actions(self, ent, count, codes, unit_actions=None, tile_actions=None):
-        """AgentPolicy action codes (int32 [n, e_cap]) of the observed entities -> action tensors."""
+    def observe_packed(self, team_sel):
+        """Observation rows without padding: returns (obs [R, 85], ent [R] int16 (-1 = unused row),
+        count [n] int32, offsets [n+1] int64).  Match m owns rows offsets[m] .. offsets[m+1]: an upper
+        bound of its team's units + tiles (from the headers), of which the first count[m] are entities."""
+        if not torch.is_tensor(team_sel):
+            team_sel = torch.full((self.n,), int(team_sel), dtype=torch.uint8, device=self.device)
+        h16 = self.hdr.view(torch.int16)
+        sel = team_sel.to(torch.int64)
+        tu = torch.gather(h16[:, 10:12].to(torch.int64) & 0xFFFF, 1, sel[:, None])[:, 0]      # n_team_units
+        tt = torch.gather(h16[:, 50:52].to(torch.int64) & 0xFFFF, 1, sel[:, None])[:, 0]      # n_team_tiles
+        offsets = torch.zeros(self.n + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(tu + tt, 0, out=offsets[1:])
+        rows = getattr(self, "_packed_rows", 0)
+        need = int(offsets[-1].item())
+        if need > rows:
+            rows = max(need * 5 // 4, 1024)
+            self._pobs = torch.empty((rows, 85), dtype=torch.float32, device=self.device)
+            self._pent = torch.empty(rows, dtype=torch.int16, device=self.device)
+            self._packed_rows = rows
+        if getattr(self, "_cnt", None) is None or self._cnt.numel() != self.n:
+            self._cnt = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.lux_b200_observe(ctypes.byref(self._desc), team_sel.data_ptr(), self._pobs.data_ptr(),
+                                             self._pent.data_ptr(), self._cnt.data_ptr(), 0, offsets.data_ptr(),
+                                             self._stream()), "lux_b200_observe")
+        return self._pobs[:need], self._pent[:need], self._cnt, offsets
+
+    def encode_actions(self, ent, count, codes, unit_actions=None, tile_actions=None, offsets=None):
+        """AgentPolicy action codes (int32 [n, e_cap], or [R] with the packed `offsets`) -> action tensors."""
         ua = self.unit_actions if unit_actions is None else unit_actions
         ta = self.tile_actions if tile_actions is None else tile_actions
         assert codes.dtype == torch.int32 and codes.is_contiguous() and codes.shape == ent.shape
         _lib.check(self.lib.lux_b200_encode_actions(ctypes.byref(self._desc), ent.data_ptr(), count.data_ptr(),
-                                                    codes.data_ptr(), ent.shape[1], ua.data_ptr(), ta.data_ptr(),
-                                                    self._stream()), "lux_b200_encode_actions")
+                                                    codes.data_ptr(), ent.shape[1] if offsets is None else 0,
+                                                    offsets.data_ptr() if offsets is not None else None,
+                                                    ua.data_ptr(), ta.data_ptr(), self._stream()),
+                   "lux_b200_encode_actions")
 
     def reward(self, team_sel, reward_state, out=None):
         """Per-turn AgentPolicy reward (float64 [n]); reward_state is int32 [n, 4], updated in place."""

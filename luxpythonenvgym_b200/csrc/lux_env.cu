@@ -49,8 +49,8 @@ __device__ uint32_t env_smart_transfer(const LuxUnit* units, int n_units, int S,
 
 __global__ void lux_encode_actions_kernel(LuxBatch b, const int16_t* __restrict__ ent_slot,
                                           const int32_t* __restrict__ ent_count, const int32_t* __restrict__ codes,
-                                          int e_cap, uint32_t* __restrict__ unit_actions,
-                                          uint8_t* __restrict__ tile_actions) {
+                                          int e_cap, const int64_t* __restrict__ row_offsets,
+                                          uint32_t* __restrict__ unit_actions, uint8_t* __restrict__ tile_actions) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
     if (m >= b.n_matches) return;
@@ -63,10 +63,12 @@ __global__ void lux_encode_actions_kernel(LuxBatch b, const int16_t* __restrict_
     if (h->done) return;
     const LuxUnit* units = b.units + (size_t)m * b.u_cap;
     const int n_units = h->n_units, S = b.size;
+    const size_t row0 = row_offsets ? (size_t)row_offsets[m] : (size_t)m * e_cap;
+    const int room = row_offsets ? (int)(row_offsets[m + 1] - row_offsets[m]) : e_cap;
     int n = ent_count[m];
-    if (n > e_cap) n = e_cap;
+    if (n > room) n = room;
     for (int e = lane; e < n; e += 32) {
-        int code = codes[(size_t)m * e_cap + e], slot = ent_slot[(size_t)m * e_cap + e];
+        int code = codes[row0 + e], slot = ent_slot[row0 + e];
         if (slot & 0x4000) {
             int p = slot & 0x3FFF;
             if (p < b.t_cap) ta[p] = (uint8_t)(1 + ((code % 3) + 3) % 3);
@@ -115,16 +117,16 @@ static int env_check(const LuxBatch* b) {
 }
 
 extern "C" int lux_b200_encode_actions(const LuxBatch* b, const int16_t* ent_slot, const int32_t* ent_count,
-                                       const int32_t* codes, int e_cap, uint32_t* unit_actions, uint8_t* tile_actions,
-                                       void* cuda_stream) {
+                                       const int32_t* codes, int e_cap, const int64_t* row_offsets,
+                                       uint32_t* unit_actions, uint8_t* tile_actions, void* cuda_stream) {
     int rc = env_check(b);
     if (rc) return rc;
-    if (!ent_slot || !ent_count || !codes || !unit_actions || !tile_actions || e_cap < 1) return LUX_E_ARG;
+    if (!ent_slot || !ent_count || !codes || !unit_actions || !tile_actions || (e_cap < 1 && !row_offsets)) return LUX_E_ARG;
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
     const int wpc = 4;
     lux_encode_actions_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, 0, (cudaStream_t)cuda_stream>>>(
-        *b, ent_slot, ent_count, codes, e_cap, unit_actions, tile_actions);
+        *b, ent_slot, ent_count, codes, e_cap, row_offsets, unit_actions, tile_actions);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { fprintf(stderr, "lux_b200: encode launch: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
     return LUX_OK;

@@ -12,7 +12,7 @@ struct LuxObsLayoutDev { LuxObsLayout L; int mbar; int total; };
 
 __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_sel, float* __restrict__ obs,
                                    int16_t* __restrict__ ent_slot, int32_t* __restrict__ ent_count, int e_cap,
-                                   LuxObsLayoutDev D) {
+                                   const int64_t* __restrict__ row_offsets, LuxObsLayoutDev D) {
     extern __shared__ __align__(128) unsigned char lux_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -30,8 +30,13 @@ __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_
     }
     __syncwarp();
     mbar_wait(bar, 0);
+    // padded layout: rows of match m start at m * e_cap; packed layout: at row_offsets[m], with room
+    // row_offsets[m + 1] - row_offsets[m] (the caller's upper bound, e.g. units + tiles of the team)
+    const size_t row0 = row_offsets ? (size_t)row_offsets[m] : (size_t)m * e_cap;
+    const int room = row_offsets ? (int)(row_offsets[m + 1] - row_offsets[m]) : e_cap;
     if (M.hdr->done) {
         if (lane == 0) ent_count[m] = 0;
+        if (row_offsets) for (int i = lane; i < room; i += 32) ent_slot[row0 + i] = -1;
         return;
     }
     const uint32_t nu = M.hdr->n_units, nc = M.hdr->n_cities, nt = M.hdr->n_tiles, nr = M.hdr->n_res;
@@ -47,15 +52,17 @@ __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_
     }
     __syncwarp();
     mbar_wait(bar, 1);
-    int n = lux_observe(M, team_sel[m] & 1, obs + (size_t)m * e_cap * LUX_OBS_DIM, ent_slot + (size_t)m * e_cap, e_cap);
-    if (lane == 0) ent_count[m] = n < e_cap ? n : e_cap;
+    int n = lux_observe(M, team_sel[m] & 1, obs + row0 * LUX_OBS_DIM, ent_slot + row0, room);
+    if (n > room) n = room;
+    if (lane == 0) ent_count[m] = n;
+    if (row_offsets) for (int i = n + lane; i < room; i += 32) ent_slot[row0 + i] = -1;      // gap rows
 }
 
 extern "C" int lux_b200_device_count(void);
 
 extern "C" int lux_b200_observe(const LuxBatch* b, const uint8_t* team_sel, float* obs, int16_t* ent_slot,
-                                int32_t* ent_count, int e_cap, void* cuda_stream) {
-    if (!b || !team_sel || !obs || !ent_slot || !ent_count || e_cap < 1) return LUX_E_ARG;
+                                int32_t* ent_count, int e_cap, const int64_t* row_offsets, void* cuda_stream) {
+    if (!b || !team_sel || !obs || !ent_slot || !ent_count || (e_cap < 1 && !row_offsets)) return LUX_E_ARG;
     if (b->n_matches < 0 || b->size < 4 || b->size > 32 || (b->size & 1)) return LUX_E_ARG;
     if (b->u_cap < 4 || b->u_cap > 252 || (b->u_cap & 3) || b->c_cap < 1 || b->c_cap > 255 || b->t_cap < 16 ||
         b->t_cap > 1024 || (b->t_cap & 15) || b->r_cap < 8 || b->r_cap > 1024 || (b->r_cap & 7))
@@ -75,7 +82,7 @@ extern "C" int lux_b200_observe(const LuxBatch* b, const uint8_t* team_sel, floa
     cudaError_t e = cudaFuncSetAttribute(lux_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { fprintf(stderr, "lux_b200: observe smem attr: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
     lux_observe_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, smem, (cudaStream_t)cuda_stream>>>(
-        *b, team_sel, obs, ent_slot, ent_count, e_cap, D);
+        *b, team_sel, obs, ent_slot, ent_count, e_cap, row_offsets, D);
     e = cudaGetLastError();
     if (e != cudaSuccess) { fprintf(stderr, "lux_b200: lux_observe_kernel launch: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
     return LUX_OK;

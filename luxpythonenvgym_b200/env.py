@@ -67,12 +67,13 @@ class AgentPolicy(Agent):
 
 
 class BatchedLuxEnvironment:
-    def __init__(self, n_envs, size=32, seed=0, pool_maps=64, device="cuda:0", team_seed=12345):
+    def __init__(self, n_envs, size=32, seed=0, pool_maps=64, device="cuda:0", team_seed=12345, packed=False):
         self.n, self.size, self.device = int(n_envs), int(size), torch.device(device)
+        self.packed = bool(packed)
         self.game = BatchedGame(self.n, size, device=device)
         self.pool = BatchedGame(pool_maps, size, device=device)
-        self._pool_states = [mapgen.generate(seed + i, size=size) for i in range(pool_maps)]
-        self.pool.load_states(self._pool_states)
+        self._pool_arrays = mapgen.generate_batch(np.arange(seed, seed + pool_maps), size)
+        self.pool.load_arrays(self._pool_arrays)
         self.e_cap = self.game.caps["units"] + self.game.caps["tiles"]
         self.team = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
         self.reward_state = torch.zeros((self.n, 4), dtype=torch.int32, device=self.device)
@@ -86,18 +87,32 @@ class BatchedLuxEnvironment:
         self.team = flips if mask is None else torch.where(mask, flips, self.team)
 
     def reset(self):
-        """All envs start a fresh match; returns (obs [n, e_cap, 85], ent [n, e_cap], count [n])."""
-        self.game.load_states([self._pool_states[i % len(self._pool_states)] for i in range(self.n)])
+        """All envs start a fresh match; returns (obs [n, e_cap, 85], ent [n, e_cap], count [n]), or with
+        packed=True (obs [R, 85], ent [R] (-1 = unused row), count [n], offsets [n+1])."""
+        k = self._pool_arrays["hdr"].shape[0]
+        idx = np.arange(self.n) % k
+        self.game.load_arrays({name: a[idx] for name, a in self._pool_arrays.items()})
         self.reward_state.zero_()
         self._draw_teams()
-        return self.game.observe(self.team, self.e_cap)
+        return self._observe()
+
+    def _observe(self):
+        if self.packed:
+            self._last = self.game.observe_packed(self.team)
+        else:
+            self._last = self.game.observe(self.team, self.e_cap)
+        return self._last
 
     def step(self, codes):
         """codes: int32 [n, e_cap], one AgentPolicy action code per observed entity row.
         Plays one turn everywhere.  Returns ((obs, ent, count), reward [n] float64, done [n] bool);
         finished envs are reset in place (their returned observation is the new match's first one)."""
         g = self.game
-        g.encode_actions(g._ent, g._cnt, codes)
+        if self.packed:
+            _, ent, cnt, offsets = self._last
+            g.encode_actions(ent, cnt, codes, offsets=offsets)
+        else:
+            g.encode_actions(g._ent, g._cnt, codes)
         g.step(prevalidate=True)
         reward = g.reward(self.team, self.reward_state)
         done = g.hdr[:, 24] != 0
@@ -106,7 +121,7 @@ class BatchedLuxEnvironment:
             self.reward_state[done] = 0
             self._draw_teams(done)
         self._epoch += 1
-        return g.observe(self.team, self.e_cap), reward, done
+        return self._observe(), reward, done
 
 
 class LuxEnvironment:

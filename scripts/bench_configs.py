@@ -86,6 +86,13 @@ class Policy(torch.nn.Module):
                                        torch.nn.Linear(64, 9))
 
     @torch.no_grad()
+    def act_packed(self, obs, ent):
+        """Packed rows: one forward pass over all rows; unused rows (ent == -1) get code 0 and are ignored."""
+        logits = self.net(obs)
+        codes = torch.multinomial(torch.softmax(logits, dim=-1), 1).squeeze(1).to(torch.int32)
+        return codes, int(obs.shape[0])
+
+    @torch.no_grad()
     def act(self, obs, cnt):
         n, e_cap, _ = obs.shape
         mask = torch.arange(e_cap, device=obs.device)[None, :] < cnt[:, None]
@@ -99,26 +106,30 @@ class Policy(torch.nn.Module):
 
 def config4(n_envs=16384, steps=100):
     torch.manual_seed(0)
-    env = BatchedLuxEnvironment(n_envs, size=32, seed=9000, pool_maps=64)
+    env = BatchedLuxEnvironment(n_envs, size=32, seed=9000, pool_maps=256, packed=True)
     policy = Policy().cuda()
-    obs, ent, cnt = env.reset()
+    obs, ent, cnt, offsets = env.reset()
     for w in range(20):
-        codes, _ = policy.act(obs, cnt)
-        (obs, ent, cnt), reward, done = env.step(codes)
+        codes, _ = policy.act_packed(obs, ent)
+        (obs, ent, cnt, offsets), reward, done = env.step(codes)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    decisions, ret = 0, 0.0
+    rows, decisions = 0, torch.zeros((), dtype=torch.int64, device="cuda")
     e0.record()
     for k in range(steps):
-        codes, nrows = policy.act(obs, cnt)
-        decisions += nrows
-        (obs, ent, cnt), reward, done = env.step(codes)
+        codes, nrows = policy.act_packed(obs, ent)
+        rows += nrows
+        decisions += cnt.sum()
+        (obs, ent, cnt, offsets), reward, done = env.step(codes)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    decisions = int(decisions.item())
     return {"envs": n_envs, "steps": steps, "ms_per_turn": ms / steps, "env_turns_per_s": n_envs * steps / (ms * 1e-3),
             "entity_decisions_per_s": decisions / (ms * 1e-3), "decisions_per_turn": decisions / steps,
-            "note": "includes observation kernel, torch MLP + multinomial sampling, encode, step(prevalidate), reward, resets"}
+            "policy_rows_per_turn": rows / steps,
+            "note": "packed observation rows; includes observation kernel, torch MLP + multinomial sampling, encode, "
+                    "step(prevalidate), reward, resets"}
 
 
 if __name__ == "__main__":

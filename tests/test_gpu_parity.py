@@ -376,3 +376,22 @@ def test_lux_environment_matches_reference_decision_by_decision():
             assert abs(reward - float(dec[i, 3])) < 1e-9, (k, i, reward, dec[i, 3])
             assert done == bool(dec[i, 4]), (k, i)
         assert done
+
+
+def test_packed_observations_equal_padded():
+    from luxpythonenvgym_b200.env import BatchedLuxEnvironment
+    env = BatchedLuxEnvironment(128, size=16, seed=500, pool_maps=16, packed=True)
+    obs, ent, cnt, off = env.reset()
+    for turn in range(40):
+        g = env.game
+        pobs, pent, pcnt, poff = g.observe_packed(env.team)
+        pobs, pent, pcnt, poff = pobs.clone(), pent.clone(), pcnt.clone(), poff.clone()
+        dobs, dent, dcnt = g.observe(env.team)
+        assert torch.equal(pcnt, dcnt)
+        for m in range(0, 128, 7):
+            c, o = int(dcnt[m]), int(poff[m])
+            assert torch.equal(pobs[o:o + c], dobs[m, :c]) and torch.equal(pent[o:o + c], dent[m, :c])
+            assert (pent[o + c:int(poff[m + 1])] == -1).all()
+        codes = torch.randint(0, 9, (obs.shape[0],), dtype=torch.int32, device="cuda")
+        (obs, ent, cnt, off), reward, done = env.step(codes)
+    assert (env.game.headers()["status"] == 0).all()
