@@ -1,12 +1,17 @@
 // lux_obs.cu -- lux_b200_observe: per-entity observation tensors (see lux_obs_core.cuh).
-// One warp per match; the match is staged in shared memory with cp.async.bulk (TMA) exactly like
-// the step kernel, rows leave through a shared-memory staging tile with coalesced stores.
+// One warp per match; header, cell grid, resource list and the leading unit / tile records are staged
+// in shared memory by one cp.async.bulk (TMA) batch exactly like the step kernel (a second batch only
+// for populous matches); cities are read in place; rows are zero-filled with coalesced 16-byte stores
+// and the non-zero features written by the owning lanes.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
 #include "lux_obs_core.cuh"
 #include "lux_tma.cuh"
+
+#define LUX_OBS_PRE_UNITS 32
+#define LUX_OBS_PRE_TILES 32
 
 struct LuxObsLayoutDev { LuxObsLayout L; int mbar; int total; };
 
@@ -20,13 +25,20 @@ __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_
     unsigned char* smem = lux_smem + (size_t)warp * D.total;
     const int ncell = b.size * b.size;
     LuxObsMatch M;
-    lux_obs_bind(M, smem, D.L, b.size);
+    lux_obs_bind(M, smem, D.L, b.size, b.cities + (size_t)m * b.c_cap);
     uint64_t* bar = (uint64_t*)(smem + D.mbar);
+    const LuxUnit* g_units = b.units + (size_t)m * b.u_cap;
+    const uint16_t* g_tiles = b.tiles + (size_t)m * b.t_cap;
+    const uint32_t pu = min(b.u_cap, LUX_OBS_PRE_UNITS), pt = min(b.t_cap, LUX_OBS_PRE_TILES);
     if (lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
-        mbar_expect_tx(bar, LUX_HDR_BYTES);
+        mbar_expect_tx(bar, LUX_HDR_BYTES + ncell * 8 + b.r_cap * 2 + pu * 16 + pt * 2);
         tma_g2s(M.hdr, b.hdr + m, LUX_HDR_BYTES, bar);
+        tma_g2s(M.cells, b.cells + (size_t)m * ncell, ncell * 8, bar);
+        tma_g2s(M.res, b.res + (size_t)m * b.r_cap, b.r_cap * 2, bar);
+        tma_g2s(M.units, g_units, pu * 16, bar);
+        tma_g2s(M.tiles, g_tiles, pt * 2, bar);
     }
     __syncwarp();
     mbar_wait(bar, 0);
@@ -39,19 +51,17 @@ __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_
         if (row_offsets) for (int i = lane; i < room; i += 32) ent_slot[row0 + i] = -1;
         return;
     }
-    const uint32_t nu = M.hdr->n_units, nc = M.hdr->n_cities, nt = M.hdr->n_tiles, nr = M.hdr->n_res;
-    const uint32_t b_cells = ncell * 8, b_units = nu * 16, b_cities = nc * 16;
-    const uint32_t b_tiles = (nt * 2 + 15) & ~15u, b_res = (nr * 2 + 15) & ~15u;
-    if (lane == 0) {
-        mbar_expect_tx(bar, b_cells + b_units + b_cities + b_tiles + b_res);
-        tma_g2s(M.cells, b.cells + (size_t)m * ncell, b_cells, bar);
-        if (b_units) tma_g2s(M.units, b.units + (size_t)m * b.u_cap, b_units, bar);
-        if (b_cities) tma_g2s(M.cities, b.cities + (size_t)m * b.c_cap, b_cities, bar);
-        if (b_tiles) tma_g2s(M.tiles, b.tiles + (size_t)m * b.t_cap, b_tiles, bar);
-        if (b_res) tma_g2s(M.res, b.res + (size_t)m * b.r_cap, b_res, bar);
+    const uint32_t nu = M.hdr->n_units, nt = M.hdr->n_tiles;
+    if (nu > pu || nt > pt) {
+        const uint32_t ru = nu > pu ? nu - pu : 0, rt2 = nt > pt ? ((nt - pt) * 2 + 15) & ~15u : 0;
+        if (lane == 0) {
+            mbar_expect_tx(bar, ru * 16 + rt2);
+            if (ru) tma_g2s(M.units + pu, g_units + pu, ru * 16, bar);
+            if (rt2) tma_g2s(M.tiles + pt, g_tiles + pt, rt2, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 1);
     }
-    __syncwarp();
-    mbar_wait(bar, 1);
     int n = lux_observe(M, team_sel[m] & 1, obs + row0 * LUX_OBS_DIM, ent_slot + row0, room);
     if (n > room) n = room;
     if (lane == 0) ent_count[m] = n;
@@ -71,12 +81,10 @@ extern "C" int lux_b200_observe(const LuxBatch* b, const uint8_t* team_sel, floa
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
     LuxObsLayoutDev D;
-    D.L = lux_obs_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    D.L = lux_obs_layout(b->size, b->u_cap, b->t_cap, b->r_cap);
     D.mbar = D.L.total;
     D.total = D.L.total + 16;
-    int wpc = (96 * 1024) / D.total;
-    if (wpc < 1) wpc = 1;
-    if (wpc > 4) wpc = 4;
+    int wpc = D.total >= 8 * 1024 ? 1 : 2;
     size_t smem = (size_t)D.total * wpc;
     if (smem > 227 * 1024) return LUX_E_CAPACITY;
     cudaError_t e = cudaFuncSetAttribute(lux_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

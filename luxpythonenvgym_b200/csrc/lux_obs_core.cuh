@@ -11,8 +11,9 @@
 //     (distance, index) minimum, second minimum, maximum and second maximum -- that gives both the
 //     closest and the furthest node with numpy's first-index tie-break, with and without the
 //     np.delete(closest) self-exclusion (:328-336);
-//   * rows are assembled in a shared-memory staging tile of 32 entities and written with 16-byte
-//     coalesced stores.
+//   * a row is ~70 % zeros: the warp first zero-fills the rows of the 32 entities in flight with
+//     coalesced 16-byte stores, then every lane drops its ~25 non-zero features into its own row.
+//     No staging tile is needed, which keeps the shared-memory footprint at the staged match itself.
 // Values are computed in float64 exactly as the reference's Python expressions and rounded once.
 #pragma once
 #include "lux_step_core.cuh"
@@ -20,7 +21,7 @@
 #define LUX_OBS_DIM 85
 
 struct LuxObsLayout {
-    int hdr, cells, units, cities, tiles, res, nodes_res, nodes_tile, nodes_work, first, count, stage, total;
+    int hdr, cells, units, tiles, res, nodes_res, nodes_tile, nodes_work, total;
 };
 
 #ifdef LUX_EMULATE
@@ -28,7 +29,7 @@ static inline
 #else
 __host__ __device__ inline
 #endif
-LuxObsLayout lux_obs_layout(int size, int u_cap, int c_cap, int t_cap, int r_cap) {
+LuxObsLayout lux_obs_layout(int size, int u_cap, int t_cap, int r_cap) {
     LuxObsLayout L;
     int ncell = size * size;
     int o = 0;
@@ -36,35 +37,30 @@ LuxObsLayout lux_obs_layout(int size, int u_cap, int c_cap, int t_cap, int r_cap
     LUX_TAKE(hdr, LUX_HDR_BYTES)
     LUX_TAKE(cells, ncell * 8)
     LUX_TAKE(units, u_cap * 16)
-    LUX_TAKE(cities, c_cap * 16)
     LUX_TAKE(tiles, t_cap * 2)
     LUX_TAKE(res, r_cap * 2)
     LUX_TAKE(nodes_res, r_cap * 2)      // wood | coal | uranium node positions (x | y << 8)
     LUX_TAKE(nodes_tile, t_cap * 2)
     LUX_TAKE(nodes_work, u_cap * 2)
-    LUX_TAKE(first, ncell * 4)          // lowest unit slot standing on the cell (0xFFFFFFFF none)
-    LUX_TAKE(count, ncell)              // units standing on the cell
-    LUX_TAKE(stage, 32 * LUX_OBS_DIM * 4)
 #undef LUX_TAKE
     L.total = o;
     return L;
 }
 
 struct LuxObsMatch {
-    LuxHeader* hdr; LuxCell* cells; LuxUnit* units; LuxCity* cities; uint16_t* tiles; uint16_t* res;
+    LuxHeader* hdr; LuxCell* cells; LuxUnit* units; uint16_t* tiles; uint16_t* res;
     uint16_t* nodes_res; uint16_t* nodes_tile; uint16_t* nodes_work;
-    unsigned* first; uint8_t* count; float* stage;
+    const LuxCity* g_cities;     // cities stay in global memory: two lookups per entity
     int S, ncell;
 };
 
-LUX_DEV void lux_obs_bind(LuxObsMatch& M, unsigned char* smem, const LuxObsLayout& L, int size) {
+LUX_DEV void lux_obs_bind(LuxObsMatch& M, unsigned char* smem, const LuxObsLayout& L, int size, const LuxCity* g_cities) {
     M.hdr = (LuxHeader*)(smem + L.hdr); M.cells = (LuxCell*)(smem + L.cells);
-    M.units = (LuxUnit*)(smem + L.units); M.cities = (LuxCity*)(smem + L.cities);
+    M.units = (LuxUnit*)(smem + L.units);
     M.tiles = (uint16_t*)(smem + L.tiles); M.res = (uint16_t*)(smem + L.res);
     M.nodes_res = (uint16_t*)(smem + L.nodes_res); M.nodes_tile = (uint16_t*)(smem + L.nodes_tile);
     M.nodes_work = (uint16_t*)(smem + L.nodes_work);
-    M.first = (unsigned*)(smem + L.first); M.count = (uint8_t*)(smem + L.count);
-    M.stage = (float*)(smem + L.stage);
+    M.g_cities = g_cities;
     M.S = size; M.ncell = size * size;
 }
 
@@ -79,19 +75,12 @@ LUX_DEV void lux_arg_max2(LuxArg& a1, LuxArg& a2, int d, int i) {
     else if (d > a2.d) { a2.d = d; a2.i = i; }
 }
 
-LUX_DEV unsigned lux_atomic_min_u32(unsigned* p, unsigned v) {
-#ifdef LUX_EMULATE
-    unsigned o = *p; if (v < o) *p = v; return o;
-#else
-    return atomicMin(p, v);
-#endif
-}
-
-// one (closest|furthest, key) block of 7 floats (agent_policy.py:327-385)
+// one (closest|furthest, key) block of 7 floats (agent_policy.py:327-385), written into the (zeroed) row
 LUX_DEV void lux_obs_block(const LuxObsMatch& M, float* o, const uint16_t* nodes, int n, int px, int py,
-                           int exclude, int furthest, int key) {
+                           int exclude, int furthest, int key, int n_units) {
     if (n == 0) return;                                   // key not in object_nodes
     LuxArg mn1 = {0x7fffffff, -1}, mn2 = {0x7fffffff, -1}, mx1 = {-1, -1}, mx2 = {-1, -1};
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
         int xy = nodes[i];
         int dx = (xy & 0xff) - px, dy = (xy >> 8) - py;
@@ -119,44 +108,60 @@ LUX_DEV void lux_obs_block(const LuxObsMatch& M, float* o, const uint16_t* nodes
     const LuxCell& T = M.cells[ty * M.S + tx];
     double v;
     if (key == 3) {
-        const LuxCity& city = M.cities[T.city_slot];
+        const LuxCity city = M.g_cities[T.city_slot];
         double upkeep = (double)((int)city.ntiles * LUX_UPKEEP_CITY - (int)city.adjsum * LUX_ADJ_BONUS);
         v = (double)city.fuel / (upkeep * 200.0);
     } else if (key < 3) {
         v = (double)T.amount / 500.0;
     } else {
-        const LuxUnit& F = M.units[M.first[ty * M.S + tx]];
-        v = (double)unit_space(F) / 100.0;
+        // first unit in that cell's dict (:380-381): every unit standing on a cell gives the same value in
+        // reachable states; the first in slot order is taken
+        int f = 0;
+#pragma unroll 1
+        for (int i = 0; i < n_units; i++)
+            if (M.units[i].x == tx && M.units[i].y == ty) { f = i; break; }
+        v = (double)unit_space(M.units[f]) / 100.0;
     }
     o[6] = (float)(v < 1.0 ? v : 1.0);
 }
 
-// Shared memory holds the match (hdr, cells, units, cities, tiles, res).  Writes obs rows, entity
-// codes and the entity count for `team`.  Returns the number of entities (clamped to e_cap).
-LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, int e_cap) {
+// zero-fill `count` floats starting at p: scalar head/tail, 16-byte body
+LUX_DEV void lux_zero_floats(float* p, int count) {
+    const int lane = lux_lane();
+    int head = (int)((16 - ((uintptr_t)p & 15)) & 15) / 4;
+    if (head > count) head = count;
+    if (lane < head) p[lane] = 0.0f;
+    float* q = p + head;
+    int body = (count - head) / 4;
+#ifdef LUX_EMULATE
+    for (int i = lane; i < body * 4; i += 32) q[i] = 0.0f;
+#else
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* q4 = (float4*)q;
+#pragma unroll 1
+    for (int i = lane; i < body; i += 32) q4[i] = z;
+#endif
+    int done = head + body * 4;
+    if (lane < count - done) p[done + lane] = 0.0f;
+}
+
+// Shared memory holds the match (hdr, cells, units, tiles, res).  Writes obs rows, entity codes and
+// returns the number of entities (rows beyond `room` are dropped).
+LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, int room) {
     const int lane = lux_lane();
     const unsigned lt = lux_lanemask_lt();
     const LuxHeader* h = M.hdr;
     const int S = M.S;
     const int n_units = h->n_units, n_tiles = h->n_tiles, n_res = h->n_res;
 
-    // ---- per-cell unit count and lowest slot
-    for (int i = lane; i < M.ncell; i += 32) M.first[i] = 0xFFFFFFFFu;
-    lux_zero16(M.count, lux_align16(M.ncell));
-    lux_sync();
-    for (int u = lane; u < n_units; u += 32) {
-        int c = M.units[u].y * S + M.units[u].x;
-        lux_atomic_min_u32(&M.first[c], (unsigned)u);
-        unsigned* w = (unsigned*)(M.count + (c & ~3));
-        lux_atomic_add((int*)w, 1 << ((c & 3) * 8));
-    }
-
     // ---- node lists (agent_policy.py:197-247), order-preserving ballot compaction
     int n_type[3] = {0, 0, 0};
     {
         int base_out = 0;
+#pragma unroll 1
         for (int t = 1; t <= 3; t++) {
             int cnt = 0;
+#pragma unroll 1
             for (int base = 0; base < n_res; base += 32) {
                 int r = base + lane;
                 int cell = r < n_res ? M.res[r] : 0;
@@ -170,6 +175,7 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
         }
     }
     int own_tiles = 0, opp_tiles = 0;
+#pragma unroll 1
     for (int base = 0; base < n_tiles; base += 32) {
         int p = base + lane;
         int cell = p < n_tiles ? M.tiles[p] : 0;
@@ -180,6 +186,7 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
         opp_tiles += lux_popc(lux_ballot(p < n_tiles && !own));
     }
     int own_workers = 0, own_carts = 0;
+#pragma unroll 1
     for (int base = 0; base < n_units; base += 32) {
         int u = base + lane;
         int mine = u < n_units && unit_team(M.units[u]) == team;
@@ -197,22 +204,19 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
     const float f_workers = (float)((double)own_workers / 30.0), f_carts = (float)((double)own_carts / 30.0);
     const int rp = h->research[team];
     const float f_rp = (float)((double)rp / 200.0);
-    const uint16_t* nodes_key[5] = {M.nodes_res, M.nodes_res + n_type[0], M.nodes_res + n_type[0] + n_type[1],
-                                    M.nodes_tile, M.nodes_work};
-    const int n_key[5] = {n_type[0], n_type[1], n_type[2], own_tiles, own_workers};
 
     // ---- entities: the team's units with can_act, then its tiles with can_act, 32 per pass
     int n_ent = 0;
     const int total = n_units + n_tiles;
+#pragma unroll 1
     for (int base = 0; base < total; base += 32) {
         int e = base + lane;
         int is_unit = e < n_units;
-        int px = 0, py = 0, kind = 0, code = 0, valid = 0, alone = 0;
+        int px = 0, py = 0, kind = 0, code = 0, valid = 0;
         if (is_unit) {
             const LuxUnit& U = M.units[e];
             valid = unit_team(U) == team && U.cd_q < 4;
             px = U.x; py = U.y; kind = unit_is_cart(U) ? 1 : 0; code = e;
-            alone = M.count[py * S + px] <= 1;
         } else if (e < total) {
             int p = e - n_units;
             int cell = M.tiles[p];
@@ -223,18 +227,33 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
         unsigned vm = lux_ballot(valid);
         int nv = lux_popc(vm);
         if (nv == 0) continue;
-        int row = lux_popc(vm & lt);
-        // zero the staging rows that will be used
-        for (int i = lane; i < nv * LUX_OBS_DIM; i += 32) M.stage[i] = 0.0f;
+        int row = n_ent + lux_popc(vm & lt);
+        int rows_out = n_ent + nv <= room ? nv : (room > n_ent ? room - n_ent : 0);
+        // the rows of this pass are zero-filled by the whole warp (coalesced, 16-byte stores) ...
+        lux_zero_floats(g_obs + (size_t)n_ent * LUX_OBS_DIM, rows_out * LUX_OBS_DIM);
         lux_sync();
-        if (valid) {
-            float* o = M.stage + row * LUX_OBS_DIM;
+        // ... then every lane writes the non-zero features of its own row
+        if (valid && row < room) {
+            float* o = g_obs + (size_t)row * LUX_OBS_DIM;
             o[kind] = 1.0f;
+            int alone = 1;
+            if (kind == 0) {                       // len(cell.units) <= 1 (agent_policy.py:330)
+                int cnt = 0;
+#pragma unroll 1
+                for (int i = 0; i < n_units; i++) cnt += M.units[i].x == px && M.units[i].y == py;
+                alone = cnt <= 1;
+            }
             int at = 3;
+#pragma unroll 1
             for (int furthest = 0; furthest < 2; furthest++)
+#pragma unroll 1
                 for (int key = 0; key < 5; key++, at += 7) {
                     int exclude = (key == 3 && kind == 2) || (key == 4 && kind == 0 && alone);
-                    lux_obs_block(M, o + at, nodes_key[key], n_key[key], px, py, exclude, furthest, key);
+                    const uint16_t* nodes = key == 0 ? M.nodes_res : key == 1 ? M.nodes_res + n_type[0]
+                                          : key == 2 ? M.nodes_res + n_type[0] + n_type[1]
+                                          : key == 3 ? M.nodes_tile : M.nodes_work;
+                    int n = key < 3 ? n_type[key] : key == 3 ? own_tiles : own_workers;
+                    lux_obs_block(M, o + at, nodes, n, px, py, exclude, furthest, key, n_units);
                 }
             if (kind != 2) o[73] = (float)((double)unit_space(M.units[e]) / 100.0);
             o[74] = night ? 1.0f : 0.0f;
@@ -245,14 +264,8 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
             o[82] = f_rp;
             o[83] = rp >= LUX_RESEARCH_COAL ? 1.0f : 0.0f;
             o[84] = rp >= LUX_RESEARCH_URANIUM ? 1.0f : 0.0f;
-            if (n_ent + row < e_cap) g_ent[n_ent + row] = (int16_t)code;
+            g_ent[row] = (int16_t)code;
         }
-        lux_sync();
-        // coalesced copy of nv rows to obs[n_ent .. n_ent+nv)
-        int room = e_cap - n_ent;
-        int rows_out = nv < room ? nv : (room > 0 ? room : 0);
-        float* dst = g_obs + (size_t)n_ent * LUX_OBS_DIM;
-        for (int i = lane; i < rows_out * LUX_OBS_DIM; i += 32) dst[i] = M.stage[i];
         n_ent += nv;
         lux_sync();
     }

@@ -79,13 +79,12 @@ static void emu_obs_lane(void* p) {
     const LuxBatch* b = a->b;
     int m = a->m, ncell = b->size * b->size;
     LuxObsMatch M;
-    lux_obs_bind(M, a->smem, a->L, b->size);
+    lux_obs_bind(M, a->smem, a->L, b->size, b->cities + (size_t)m * b->c_cap);
     lux_copy16(M.hdr, b->hdr + m, LUX_HDR_BYTES);
     lux_sync();
     if (M.hdr->done) { if (lux_lane() == 0) a->cnt[m] = 0; return; }
     lux_copy16(M.cells, b->cells + (size_t)m * ncell, ncell * 8);
     lux_copy16(M.units, b->units + (size_t)m * b->u_cap, M.hdr->n_units * 16);
-    lux_copy16(M.cities, b->cities + (size_t)m * b->c_cap, M.hdr->n_cities * 16);
     lux_copy16(M.tiles, b->tiles + (size_t)m * b->t_cap, M.hdr->n_tiles * 2);
     lux_copy16(M.res, b->res + (size_t)m * b->r_cap, M.hdr->n_res * 2);
     lux_sync();
@@ -97,7 +96,7 @@ extern "C" int lux_emu_observe(const LuxBatch* b, const uint8_t* team_sel, float
     if (!b || !team_sel || !obs || !ent || !cnt) return LUX_E_ARG;
     EmuObsArgs a;
     a.b = b; a.team_sel = team_sel; a.obs = obs; a.ent = ent; a.cnt = cnt; a.e_cap = e_cap;
-    a.L = lux_obs_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    a.L = lux_obs_layout(b->size, b->u_cap, b->t_cap, b->r_cap);
     a.smem = (unsigned char*)aligned_alloc(16, a.L.total);
     for (int m = 0; m < b->n_matches; m++) {
         memset(a.smem, 0xA5, a.L.total);
