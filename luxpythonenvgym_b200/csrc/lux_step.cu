@@ -464,6 +464,7 @@ extern "C" size_t lux_b200_step_smem_bytes(int size, int u_cap, int c_cap, int t
 static int g_use_tma = 1;
 static int g_warps_per_cta = 0;   // 0 = automatic
 static int g_two_class = -1;      // -1 automatic, 0 off, 1 always
+static int g_stage[3] = {96, 64, 96};   // small staging class (units, cities, tiles); tests shrink it to force spills
 static int g_heavy_first = 0;     // schedule the previous step's populous matches first (measured +-0: off)
 // tuning / fallback knobs (tests flip them to cover every launch path)
 extern "C" int lux_b200_set_option(const char* name, int value) {
@@ -472,6 +473,9 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "warps_per_cta")) { g_warps_per_cta = value; return LUX_OK; }
     if (!strcmp(name, "two_class")) { g_two_class = value; return LUX_OK; }
     if (!strcmp(name, "heavy_first")) { g_heavy_first = value != 0; return LUX_OK; }
+    if (!strcmp(name, "stage_units")) { g_stage[0] = value < 32 ? 32 : (value + 3) & ~3; return LUX_OK; }
+    if (!strcmp(name, "stage_cities")) { g_stage[1] = value < 16 ? 16 : value; return LUX_OK; }
+    if (!strcmp(name, "stage_tiles")) { g_stage[2] = value < 32 ? 32 : (value + 15) & ~15; return LUX_OK; }
     return LUX_E_ARG;
 }
 
@@ -550,7 +554,8 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
     }
 
     // 96 / 64 / 96 is the largest staging class that still puts 14 matches of a 32x32 map on an SM
-    LuxStage small = {96 < b->u_cap ? 96 : b->u_cap, 64 < b->c_cap ? 64 : b->c_cap, 96 < b->t_cap ? 96 : b->t_cap};
+    LuxStage small = {g_stage[0] < b->u_cap ? g_stage[0] : b->u_cap, g_stage[1] < b->c_cap ? g_stage[1] : b->c_cap,
+                      g_stage[2] < b->t_cap ? g_stage[2] : b->t_cap};
     LuxSmemLayout Ls = lux_smem_layout(b->size, small.u, small.c, small.t, b->r_cap);
     bool two = g_two_class != 0 && (g_two_class == 1 || (L.total >= 12 * 1024 && Ls.total * 4 <= L.total * 3));
     bool sched = g_heavy_first != 0;

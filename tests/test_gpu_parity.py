@@ -395,3 +395,48 @@ def test_packed_observations_equal_padded():
         codes = torch.randint(0, 9, (obs.shape[0],), dtype=torch.int32, device="cuda")
         (obs, ent, cnt, off), reward, done = env.step(codes)
     assert (env.game.headers()["status"] == 0).all()
+
+
+def test_spill_list_and_scheduling_paths_under_load():
+    """Force the rarely taken launch paths on a real batch: a tiny staging class (32/16/32) so that a large
+    share of a dense batch spills to the retry list every turn, with and without heavy-first scheduling,
+    forced two-class mode (no automatic fallback), and more batches than the library caches scratch for."""
+    lib = _lib.load()
+    z = G.npz("dense")
+    names = [nm for nm in G.dense_names() if int(z[nm + "/size"]) == 32]
+    caps = S.default_caps(32)
+    inits = [_recap(G.get_state(z, nm + "/init"), caps) for nm in names]
+    sparse = mapgen.generate_batch(np.arange(4000, 4096), 32)
+    try:
+        for heavy in (0, 1):
+            for k, v in ((b"stage_units", 32), (b"stage_cities", 16), (b"stage_tiles", 32), (b"two_class", 1), (b"heavy_first", heavy)):
+                assert lib.lux_b200_set_option(k, v) == 0
+            n = 384
+            g = _game(n, 32)
+            g.load_states([inits[i % len(inits)] for i in range(n - 96)])       # dense: spill
+            g.load_arrays(sparse, first=n - 96)                                   # fresh maps: fit
+            host = gpu_util.HostBatch(g)
+            for turn in range(45):
+                g.gen_actions(5150 + heavy, 0)
+                host.gen_actions(5150 + heavy, 0)
+                g.step()
+                host.step()
+                bad = gpu_util.diff_batches(host, g)
+                assert len(bad) == 0, "heavy=%d turn %d: %s" % (heavy, turn, gpu_util.explain(host, g, int(bad[0])))
+        # more live batches than cached scratch slots (8): eviction and re-creation stay correct
+        games = [_game(16, 12) for _ in range(11)]
+        hosts = []
+        for i, gm in enumerate(games):
+            gm.load_arrays(mapgen.generate_batch(np.arange(100 * i, 100 * i + 16), 12))
+            hosts.append(gpu_util.HostBatch(gm))
+        for turn in range(12):
+            for i, gm in enumerate(games):
+                gm.gen_actions(1 + i, 0)
+                hosts[i].gen_actions(1 + i, 0)
+                gm.step()
+                hosts[i].step()
+        for i, gm in enumerate(games):
+            assert len(gpu_util.diff_batches(hosts[i], gm)) == 0, i
+    finally:
+        for k, v in ((b"stage_units", 96), (b"stage_cities", 64), (b"stage_tiles", 96), (b"two_class", -1), (b"heavy_first", 0)):
+            lib.lux_b200_set_option(k, v)
