@@ -215,11 +215,16 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         int team = unit_team(U);
         if (!unit_is_cart(U) && (team ? researched1 : researched0)) {
             int k = 0;
-            unsigned minable = 0;
+            // one pass: count the minable cells and register them in the request list (the mark does not
+            // depend on the amount, which needs the count)
 #pragma unroll 1
             for (int j = 0; j < 5; j++) {
                 int c = lux_cell5(S, U.x, U.y, j);
-                if (c >= 0 && cell_res_type(M.cells[c]) == rtype && M.cells[c].amount > 0) { k++; minable |= 1u << j; }
+                if (c >= 0 && cell_res_type(M.cells[c]) == rtype && M.cells[c].amount > 0) {
+                    k++;
+                    unsigned old = lux_scratch_or(M.cells, c, 0, 0x80u);
+                    if (!(old & 0x80u)) M.reqlist[lux_atomic_add(M.reqcnt, 1)] = (uint16_t)c;
+                }
             }
             if (k > 0) {
                 int space = unit_space(U);
@@ -231,13 +236,6 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                     // requests from one city tile are de-duplicated by amount (:920-931, :964-966)
                     int t = M.cprefix[C.city_slot] + C.key;
                     lux_atomic_or(&M.tmask[t], 1u << mine);
-                }
-#pragma unroll 1
-                for (int j = 0; j < 5; j++) {
-                    if (!(minable & (1u << j))) continue;
-                    int c = lux_cell5(S, U.x, U.y, j);
-                    unsigned old = lux_scratch_or(M.cells, c, 0, 0x80u);
-                    if (!(old & 0x80u)) M.reqlist[lux_atomic_add(M.reqcnt, 1)] = (uint16_t)c;
                 }
             }
         }
@@ -256,6 +254,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         // histogram of request amounts 0..20, 3 bits each (at most one request per amount and source cell)
         uint64_t hist = 0;
         unsigned present = 0;                         // amounts that occur
+        unsigned tile_dirs = 0;                       // neighbours that are city tiles holding requests
         int n = 0, sum = 0;
 #pragma unroll 1
         for (int j = 0; j < 5; j++) {
@@ -264,6 +263,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
             const LuxCell& P = M.cells[p];
             if (cell_is_tile(P)) {
                 unsigned mask = M.tmask[M.cprefix[P.city_slot] + P.key];
+                if (mask) tile_dirs |= 1u << j;
                 while (mask) {
                     int a = lux_ffs(mask) - 1;
                     mask &= mask - 1;
@@ -302,11 +302,11 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
             // city-tile requests are credited here (game.py:988-990)
             if (level > 0) {
 #pragma unroll 1
-                for (int j = 0; j < 5; j++) {
+                while (tile_dirs) {
+                    int j = lux_ffs(tile_dirs) - 1;
+                    tile_dirs &= tile_dirs - 1;
                     int p = lux_cell5(S, x, y, j);
-                    if (p < 0) continue;
                     const LuxCell& P = M.cells[p];
-                    if (!cell_is_tile(P)) continue;
                     unsigned mask = M.tmask[M.cprefix[P.city_slot] + P.key];
                     int got = 0;
                     while (mask) {
@@ -447,7 +447,7 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
 // cells/header/cities(uncompacted)/units(uncompacted, ust says who died); the caller's
 // store routine (lux_store_match) compacts while writing.  Returns packed flags:
 //   bit0 tiles list must be rewritten, [31:16] n_units (incl. spawned), others via hdr.
-struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; };
+struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; int alive0; int alive1; };
 
 template <int kS>
 LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
@@ -635,6 +635,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 
     // ---- city tiles: spawn validation (game.py:696-718) + CityTile.turn (city.py:96-120)
     int n_units = n_units0;
+    int born0 = 0, born1 = 0, died0 = 0, died1 = 0;      // per-team population changes of this turn
     {
         int acc0 = 0, acc1 = 0, spawned = 0, rp0 = 0, rp1 = 0;
         int wb0 = 0, wb1 = 0, cb0 = 0, cb1 = 0;
@@ -688,6 +689,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         int made = spawned < room ? spawned : room;
         if (made < 0) made = 0;
         n_units = n_units0 + made;
+        born0 = wb0 + cb0; born1 = wb1 + cb1;
         if (lane == 0) {
             if (spawned > room) h->status |= LUX_ST_UNIT_OVERFLOW;
             h->unit_id_count = uid0 + made;
@@ -776,46 +778,42 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     n_cities = lux_shfl(n_cities, 0);
     n_tiles = lux_shfl(n_tiles, 0);
     if (n_tiles != n_tiles0) tiles_dirty = 1;
-    // cooldowns of the acting units, then the carts' automatic roads (unit.py:196-197, :257-269)
+    // cooldowns of the acting units, then the carts' automatic roads (unit.py:196-197, :257-269); the same
+    // pass leaves the occupant mark the collection stage reads (units spawned this turn stand on city
+    // tiles, which carry no mark, so the old units are all there is to mark)
     {
-        int rb0 = 0, rb1 = 0;
+        int rb0 = 0, rb1 = 0, bad = 0;
 #pragma unroll 1
         for (int u = lane; u < n_units0; u += 32) {
             unsigned st = M.ust[u];
             LuxUnit& U = M.units[u];
             int cart = unit_is_cart(U);
             if ((st & 7) != 0 && !(st & UST_FAILED)) U.cd_q = (uint8_t)(U.cd_q + (cart ? 12 : 8) * mult);
-            if (cart && !(st & UST_FAILED)) {
-                LuxCell& C = M.cells[U.y * S + U.x];
-                if (!cell_is_tile(C) && C.road_q < LUX_MAX_ROAD_Q) {
+            LuxCell& C = M.cells[U.y * S + U.x];
+            if (!cell_is_tile(C)) {
+                if (cart && !(st & UST_FAILED) && C.road_q < LUX_MAX_ROAD_Q) {
                     int r = C.road_q + LUX_ROAD_DEV_Q;
                     C.road_q = (uint8_t)(r > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : r);
                     if (unit_team(U)) rb1 += LUX_ROAD_DEV_Q; else rb0 += LUX_ROAD_DEV_Q;
                 }
+                if (C.city_slot) bad = 1;          // cannot happen in play: a non-city cell holds one unit
+                C.city_slot = (uint8_t)(u + 1);
             }
             M.ust[u] = 0;
         }
         rb0 = lux_reduce_add(rb0);
         rb1 = lux_reduce_add(rb1);
-        if (lane == 0) { h->roads_built_q[0] += rb0; h->roads_built_q[1] += rb1; }
+        bad = lux_any(bad);
+        if (lane == 0) {
+            h->roads_built_q[0] += rb0; h->roads_built_q[1] += rb1;
+            if (bad) h->status |= LUX_ST_BAD_STATE;
+        }
     }
     lux_sync();
 
     // ---- resource collection: uranium, coal, wood (distribute_all_resources game.py:868-880)
     {
         lux_city_prefix(M, n_cities);     // also syncs
-        int bad = 0;
-#pragma unroll 1
-        for (int u = lane; u < n_units; u += 32) {
-            const LuxUnit& U = M.units[u];
-            int c = U.y * S + U.x;
-            if (!cell_is_tile(M.cells[c])) {
-                if (M.cells[c].city_slot) bad = 1;     // cannot happen in play: a non-city cell holds one unit
-                M.cells[c].city_slot = (uint8_t)(u + 1);
-            }
-        }
-        if (lux_any(bad) && lane == 0) h->status |= LUX_ST_BAD_STATE;
-        lux_sync();
         int rp0 = h->research[0], rp1 = h->research[1];
 #pragma unroll 1
         for (int rtype = LUX_RES_URANIUM; rtype >= LUX_RES_WOOD; rtype--) {
@@ -823,14 +821,6 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             if (rp0 < need && rp1 < need) continue;           // nobody may mine this type yet
             lux_collect_type<kS>(M, rtype, n_units, rp0 >= need, rp1 >= need);
         }
-        // collection is over: drop the occupant marks again
-#pragma unroll 1
-        for (int u = lane; u < n_units; u += 32) {
-            const LuxUnit& U = M.units[u];
-            int c = U.y * S + U.x;
-            if (!cell_is_tile(M.cells[c])) M.cells[c].city_slot = 0;
-        }
-        lux_sync();
     }
 
     // ---- deposit (handle_resource_deposit game.py:1003-1023)
@@ -839,9 +829,11 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 #pragma unroll 1
         for (int u = lane; u < n_units; u += 32) {
             LuxUnit& U = M.units[u];
-            const LuxCell& C = M.cells[U.y * S + U.x];
+            LuxCell& C = M.cells[U.y * S + U.x];
             int team = unit_team(U);
-            if (cell_is_tile(C) && cell_tile_team(C) == team) {
+            if (!cell_is_tile(C)) {
+                C.city_slot = 0;                    // collection is over: drop the occupant mark again
+            } else if (cell_tile_team(C) == team) {
                 int fuel = U.wood + 10 * U.coal + 40 * U.uranium;
                 if (fuel) lux_atomic_add(&M.cities[C.city_slot].fuel, fuel);
                 if (team) fg1 += fuel; else fg0 += fuel;
@@ -901,8 +893,13 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 used = U.uranium < want ? U.uranium : want;
                 need -= used * 40; U.uranium = (uint16_t)(U.uranium - used);
             }
-            if (need > 0) M.ust[u] = UST_FAILED;                      // dead: dropped while storing
+            if (need > 0) {                                           // dead: dropped while storing
+                M.ust[u] = UST_FAILED;
+                if (unit_team(U)) died1++; else died0++;
+            }
         }
+        died0 = lux_reduce_add(died0);
+        died1 = lux_reduce_add(died1);
         lux_sync();
     }
 
@@ -924,6 +921,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 
     LuxTurnOut out;
     out.n_units = n_units; out.n_cities = n_cities; out.n_tiles = n_tiles; out.tiles_dirty = tiles_dirty;
+    out.alive0 = tu0 + born0 - died0; out.alive1 = tu1 + born1 - died1;
     return out;
 }
 
@@ -991,14 +989,7 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
     }
 
     // match_over (game.py:570-592) is evaluated before the turn counter moves (:515-517)
-    int alive0 = 0, alive1 = 0;
-#pragma unroll 1
-    for (int u = lane; u < T.n_units; u += 32) {
-        if (M.ust[u] & UST_FAILED) continue;
-        if (unit_team(M.units[u])) alive1++; else alive0++;
-    }
-    alive0 = lux_reduce_add(alive0);
-    alive1 = lux_reduce_add(alive1);
+    const int alive0 = T.alive0, alive1 = T.alive1;    // start-of-turn counts + spawns - night deaths
     int over = h->turn >= LUX_MAX_DAYS - 1 || (alive0 + nc0 == 0) || (alive1 + nc1 == 0);
 
     // run_cooldowns (game.py:560-568) and the stable partition team A | team B while storing
