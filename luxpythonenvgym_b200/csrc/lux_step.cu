@@ -49,8 +49,6 @@ __device__ __forceinline__ int lux_step_match(const LuxBatch& b, int m, const ui
     const int lane = threadIdx.x & 31;
     const int size = kS > 0 ? kS : b.size;
     const int ncell = size * size;
-    LuxMatch M;
-    lux_match_bind(M, smem, L, size, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
     LuxHeader* g_hdr = b.hdr + m;
     LuxCell* g_cells = b.cells + (size_t)m * ncell;
     LuxUnit* g_units = b.units + (size_t)m * b.u_cap;
@@ -59,21 +57,22 @@ __device__ __forceinline__ int lux_step_match(const LuxBatch& b, int m, const ui
     const uint16_t* g_res = b.res + (size_t)m * b.r_cap;
     const uint32_t* g_ua = unit_actions + (size_t)m * b.u_cap;
     const uint8_t* g_ta = tile_actions + (size_t)m * b.t_cap;
+    LuxMatch M;
+    lux_match_bind(M, smem, L, g_cells, size, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
 
     if (kTma) {
         uint64_t* bar = (uint64_t*)(smem + L.mbar);
         const uint32_t pu = min(stage.u, LUX_PRE_UNITS), pc = min(stage.c, LUX_PRE_CITIES), pt = min(stage.t, LUX_PRE_TILES);
-        const uint32_t b_cells = ncell * 8, b_res = b.r_cap * 2;
+        const uint32_t b_res = b.r_cap * 2;
         if (lane == 0) {
-            mbar_expect_tx(bar, LUX_HDR_BYTES + b_cells + b_res + pu * 16 + pc * 16 + pt * 2 + pu * 4 + pt);
+            mbar_expect_tx(bar, LUX_HDR_BYTES + b_res + pu * 16 + pc * 16 + pt * 2 + pu * 4 + pt);
             tma_g2s(M.hdr, g_hdr, LUX_HDR_BYTES, bar);
-            tma_g2s(M.cells, g_cells, b_cells, bar);
-            tma_g2s(M.res, g_res, b_res, bar);
             tma_g2s(M.units, g_units, pu * 16, bar);
+            tma_g2s(M.uact, g_ua, pu * 4, bar);
             tma_g2s(M.cities, g_cities, pc * 16, bar);
             tma_g2s(M.tiles, g_tiles, pt * 2, bar);
-            tma_g2s(M.uact, g_ua, pu * 4, bar);
             tma_g2s(M.tact, g_ta, pt, bar);
+            tma_g2s(M.res, g_res, b_res, bar);
         }
         __syncwarp();
         mbar_wait(bar, phase);
@@ -102,7 +101,6 @@ __device__ __forceinline__ int lux_step_match(const LuxBatch& b, int m, const ui
         lux_copy16(M.hdr, g_hdr, LUX_HDR_BYTES);
         __syncwarp();
         if (M.hdr->done) return LUX_M_DONE;
-        lux_copy16(M.cells, g_cells, ncell * 8);
         lux_copy16(M.units, g_units, M.hdr->n_units * 16);
         lux_copy16(M.cities, g_cities, M.hdr->n_cities * 16);
         lux_copy16(M.tiles, g_tiles, M.hdr->n_tiles * 2);
@@ -131,21 +129,7 @@ __device__ __forceinline__ int lux_step_match(const LuxBatch& b, int m, const ui
     }
 
     LuxTurnOut T = lux_turn<kS>(M, flags);
-
-    if (kTma) {
-        lux_finish_and_store<false, kS>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
-        // every lane orders its own shared-memory writes before the async proxy reads them
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            tma_s2g(g_cells, M.cells, ncell * 8);
-            tma_s2g(g_hdr, M.hdr, LUX_HDR_BYTES);
-            tma_commit();
-            tma_wait_read0();
-        }
-    } else {
-        lux_finish_and_store<true, kS>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
-    }
+    lux_finish_and_store<kS>(M, T, g_hdr, g_units, g_cities, g_tiles);
     return (!M.hdr->done && (int)M.hdr->n_units + (int)M.hdr->n_tiles > LUX_HEAVY_THRESHOLD) ? LUX_M_HEAVY : LUX_M_PLAYED;
 }
 
@@ -165,7 +149,7 @@ struct LuxSched {
 };
 
 template <bool kTma, int kS, int kMode>
-__global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions,
+__global__ void __launch_bounds__(64, kMode == kList ? 1 : 16) lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions,
                                 const uint8_t* __restrict__ tile_actions, LuxSmemLayout L, unsigned flags,
                                 LuxStage stage, LuxSched sc) {
     extern __shared__ __align__(128) unsigned char lux_smem[];
@@ -178,8 +162,13 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
             mbar_init((uint64_t*)(smem + L.mbar), 1);
             fence_mbar_init();
         }
-        __syncwarp();
     }
+    {   // the per-cell byte planes start clean; every turn leaves them clean again
+        const int ncell = (kS > 0 ? kS : b.size) * (kS > 0 ? kS : b.size);
+        lux_zero16(smem + L.p1, (ncell + 15) & ~15);
+        lux_zero16(smem + L.occ, (ncell + 15) & ~15);
+    }
+    __syncwarp();
     if (kMode == kList) {
         const int count = *sc.retry_cnt;
         for (int idx = blockIdx.x * wpc + warp; idx < count; idx += gridDim.x * wpc) {
@@ -221,6 +210,7 @@ __global__ void lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_ac
 // kernels this library has launched (all entry points of this translation unit); bench.py reports the
 // difference over its timed region as "gpu_launches"
 static unsigned long long g_launches = 0;
+static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
 
 template <bool kTma, int kS, int kMode>
@@ -229,6 +219,11 @@ static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta,
     size_t smem = (size_t)L.total * wpc;
     cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return LUX_E_CUDA;
+    if (g_carveout >= 0) {
+        // the grid is read in place through L1: leave part of the SM's 256 KB to the cache
+        e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode>, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
+        if (e != cudaSuccess) return LUX_E_CUDA;
+    }
     lux_step_kernel<kTma, kS, kMode><<<grid, 32 * wpc, smem, st>>>(*b, ua, ta, L, flags, stage, sc);
     g_launches++;
     return LUX_OK;
@@ -473,6 +468,7 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "warps_per_cta")) { g_warps_per_cta = value; return LUX_OK; }
     if (!strcmp(name, "two_class")) { g_two_class = value; return LUX_OK; }
     if (!strcmp(name, "heavy_first")) { g_heavy_first = value != 0; return LUX_OK; }
+    if (!strcmp(name, "carveout")) { g_carveout = value > 100 ? 100 : value; return LUX_OK; }
     if (!strcmp(name, "stage_units")) { g_stage[0] = value < 32 ? 32 : (value + 3) & ~3; return LUX_OK; }
     if (!strcmp(name, "stage_cities")) { g_stage[1] = value < 16 ? 16 : value; return LUX_OK; }
     if (!strcmp(name, "stage_tiles")) { g_stage[2] = value < 32 ? 32 : (value + 15) & ~15; return LUX_OK; }

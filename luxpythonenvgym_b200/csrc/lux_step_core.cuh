@@ -54,8 +54,12 @@
 #define UST_REVERTED 0x40u
 #define UST_FAILED 0x80u  // transfer raised KeyError in the reference: no cooldown, no cart road
 
+// per-unit cache uinfo (built once per turn, after moves and city building): what the unit stands on
+#define UI_TILE 0x01000000u   // a city tile; [15:0] = its index in canonical tile order, [23:16] = city slot
+#define UI_OWN  0x02000000u   // ... of the unit's own team
+
 struct LuxSmemLayout {
-    int hdr, cells, units, cities, tiles, res, uact, tact, utgt, ust, umine, tmask, cprefix, cremap, reqlist, mbar, total;
+    int hdr, units, cities, tiles, res, uact, tact, utgt, ust, umine, uinfo, umin, tmask, cprefix, cremap, reqlist, p1, occ, mbar, total;
 };
 
 LUX_DEV int lux_align16(int x) { return (x + 15) & ~15; }
@@ -71,7 +75,6 @@ LuxSmemLayout lux_smem_layout(int size, int u_cap, int c_cap, int t_cap, int r_c
     int o = 0;
 #define LUX_TAKE(field, bytes) L.field = o; o += (((bytes) + 15) & ~15);
     LUX_TAKE(hdr, LUX_HDR_BYTES)
-    LUX_TAKE(cells, ncell * 8)
     LUX_TAKE(units, u_cap * 16)
     LUX_TAKE(cities, c_cap * 16)
     LUX_TAKE(tiles, t_cap * 2)
@@ -81,19 +84,26 @@ LuxSmemLayout lux_smem_layout(int size, int u_cap, int c_cap, int t_cap, int r_c
     LUX_TAKE(utgt, u_cap * 2)
     LUX_TAKE(ust, u_cap)
     LUX_TAKE(umine, u_cap)
+    LUX_TAKE(uinfo, u_cap * 4)
+    LUX_TAKE(umin, u_cap * 2)
     LUX_TAKE(tmask, t_cap * 4)
     LUX_TAKE(cprefix, (c_cap + 1) * 2)
     LUX_TAKE(cremap, c_cap)
     LUX_TAKE(reqlist, r_cap * 2 + 16)   // cells requested this collection pass (+ counter)
+    LUX_TAKE(p1, ncell)                 // per-cell flag plane (movement flags, then collection mark / fill level)
+    LUX_TAKE(occ, ncell)                // per-cell occupant plane (unit index + 1 during collection)
     LUX_TAKE(mbar, 16)
 #undef LUX_TAKE
     L.total = o;
     return L;
 }
 
+// The cell grid is NOT staged: `cells` points at the match's grid in global memory and the engine
+// touches only the cells its entities stand on, aim at, mine from or own (a few dozen 32-byte
+// sectors per turn instead of the whole 8 KB grid).  Everything else lives in shared memory.
 struct LuxMatch {
     LuxHeader* hdr;
-    LuxCell* cells;
+    LuxCell* cells;      // global memory
     LuxUnit* units;
     LuxCity* cities;
     uint16_t* tiles;
@@ -103,18 +113,22 @@ struct LuxMatch {
     uint16_t* utgt;
     uint8_t* ust;
     uint8_t* umine;
+    uint32_t* uinfo;
+    uint16_t* umin;
     uint32_t* tmask;
     uint16_t* cprefix;
     uint8_t* cremap;
     uint16_t* reqlist;
     int* reqcnt;
+    uint8_t* p1;
+    uint8_t* occ;
     int S, ncell, u_cap, c_cap, t_cap, r_cap;
 };
 
-LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayout& L, int size, int u_cap,
-                            int c_cap, int t_cap, int r_cap) {
+LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayout& L, LuxCell* g_cells, int size,
+                            int u_cap, int c_cap, int t_cap, int r_cap) {
     M.hdr = (LuxHeader*)(smem + L.hdr);
-    M.cells = (LuxCell*)(smem + L.cells);
+    M.cells = g_cells;
     M.units = (LuxUnit*)(smem + L.units);
     M.cities = (LuxCity*)(smem + L.cities);
     M.tiles = (uint16_t*)(smem + L.tiles);
@@ -124,11 +138,15 @@ LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayou
     M.utgt = (uint16_t*)(smem + L.utgt);
     M.ust = (uint8_t*)(smem + L.ust);
     M.umine = (uint8_t*)(smem + L.umine);
+    M.uinfo = (uint32_t*)(smem + L.uinfo);
+    M.umin = (uint16_t*)(smem + L.umin);
     M.tmask = (uint32_t*)(smem + L.tmask);
     M.cprefix = (uint16_t*)(smem + L.cprefix);
     M.cremap = (uint8_t*)(smem + L.cremap);
     M.reqcnt = (int*)(smem + L.reqlist);
     M.reqlist = (uint16_t*)(smem + L.reqlist + 16);
+    M.p1 = smem + L.p1;
+    M.occ = smem + L.occ;
     M.S = size; M.ncell = size * size;
     M.u_cap = u_cap; M.c_cap = c_cap; M.t_cap = t_cap; M.r_cap = r_cap;
 }
@@ -139,9 +157,9 @@ LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayou
 #define LUX_NOINLINE __device__ __noinline__
 #endif
 
-// ---- staging a match into shared memory with plain 16-byte loads --------------------------
+// ---- staging with plain 16-byte loads ------------------------------------------------------
 // (the CUDA build normally uses cp.async.bulk instead, see lux_step.cu; this form is what the
-//  host emulation runs and the device falls back to when LUX_NO_TMA is defined)
+//  host emulation runs and the device uses when the "tma" option is off)
 LUX_DEV void lux_copy16(void* dst, const void* src, int bytes) {   // bytes rounded up to 16
     int lane = lux_lane();
     const uint64_t* s = (const uint64_t*)src;
@@ -157,6 +175,18 @@ LUX_DEV int cell_tile_team(const LuxCell& c) { return ((c.flags >> 2) & 3) - 1; 
 LUX_DEV int cell_res_type(const LuxCell& c) { return c.flags & 3; }
 LUX_DEV int cell_adj(const LuxCell& c) { return (c.flags >> 4) & 7; }
 
+// one 8-byte access per cell record
+LUX_DEV LuxCell lux_ldcell(const LuxCell* cells, int i) {
+    union { uint64_t w; LuxCell c; } v;
+    v.w = *(const uint64_t*)(cells + i);
+    return v.c;
+}
+LUX_DEV void lux_stcell(LuxCell* cells, int i, const LuxCell& c) {
+    union { uint64_t w; LuxCell c; } v;
+    v.c = c;
+    *(uint64_t*)(cells + i) = v.w;
+}
+
 LUX_DEV int unit_team(const LuxUnit& u) { return u.team_type & 1; }
 LUX_DEV int unit_is_cart(const LuxUnit& u) { return (u.team_type >> 1) & 1; }
 LUX_DEV int unit_space(const LuxUnit& u) {   // unit.py:43-52
@@ -164,18 +194,6 @@ LUX_DEV int unit_space(const LuxUnit& u) {   // unit.py:43-52
 }
 LUX_DEV int lux_dx(int dir) { return dir == LUX_DIR_EAST ? 1 : dir == LUX_DIR_WEST ? -1 : 0; }
 LUX_DEV int lux_dy(int dir) { return dir == LUX_DIR_SOUTH ? 1 : dir == LUX_DIR_NORTH ? -1 : 0; }
-
-// Per-cell scratch without extra planes: on a cell that is NOT a city tile the upper word of LuxCell
-// (tile_cd, city_slot, key) is unused, so the engine keeps its transient per-cell flags there --
-// byte 0 (tile_cd): movement flags P1_*, later the collection "requested / fill level" byte;
-// byte 1 (city_slot): index + 1 of the unit standing on the cell during collection.
-// Every such byte is cleared again before the grid is stored (canonical state has zeros there).
-LUX_DEV unsigned lux_scratch_or(LuxCell* cells, int c, int which, unsigned bits) {
-    unsigned* w = ((unsigned*)&cells[c]) + 1;
-    int sh = which * 8;
-    unsigned old = lux_atomic_or(w, bits << sh);
-    return (old >> sh) & 0xffu;
-}
 
 // the five cells a worker mines from: own, N, E, S, W (game.py:950-951, game_map.py:484-508)
 LUX_DEV int lux_cell5(int S, int x, int y, int k) {
@@ -192,9 +210,18 @@ LUX_DEV void lux_zero16(void* p, int bytes) {   // bytes multiple of 16, p 16-by
     for (int i = lane; i < bytes / 16; i += 32) { q[2 * i] = 0; q[2 * i + 1] = 0; }
 }
 
+// The two per-cell byte planes must be all-zero when a turn starts; the engine clears every byte it
+// sets before the turn ends, so a warp zeroes them once (here) and then plays any number of matches.
+LUX_DEV void lux_planes_init(LuxMatch& M) {
+    lux_zero16(M.p1, lux_align16(M.ncell));
+    lux_zero16(M.occ, lux_align16(M.ncell));
+}
+
 // ---- collection of one resource type (game.py:882-1001) -----------------------------------
 // One inlined copy inside a rolled loop over the resource types, inner loops rolled: the kernel is
 // instruction-fetch sensitive (flat, once-through code far larger than the instruction caches).
+// Works on shared memory only, except for the amount of each requested cell (one global load and one
+// store per cell): which neighbours a worker can mine was cached in umin[] by the unit pass.
 template <int kS>
 LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researched0, int researched1) {
     const int lane = lux_lane();
@@ -210,32 +237,29 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
     // and registers the cells it mines from in the request list
 #pragma unroll 1
     for (int u = lane; u < n_units; u += 32) {
-        LuxUnit& U = M.units[u];
+        const LuxUnit& U = M.units[u];
         int mine = 0xFF;
-        int team = unit_team(U);
-        if (!unit_is_cart(U) && (team ? researched1 : researched0)) {
+        unsigned mm = M.umin[u];                      // 0 for carts
+        if (mm && (unit_team(U) ? researched1 : researched0)) {
             int k = 0;
-            // one pass: count the minable cells and register them in the request list (the mark does not
-            // depend on the amount, which needs the count)
 #pragma unroll 1
             for (int j = 0; j < 5; j++) {
+                if ((int)((mm >> (2 * j)) & 3u) != rtype) continue;
                 int c = lux_cell5(S, U.x, U.y, j);
-                if (c >= 0 && cell_res_type(M.cells[c]) == rtype && M.cells[c].amount > 0) {
-                    k++;
-                    unsigned old = lux_scratch_or(M.cells, c, 0, 0x80u);
-                    if (!(old & 0x80u)) M.reqlist[lux_atomic_add(M.reqcnt, 1)] = (uint16_t)c;
-                }
+                k++;
+                unsigned old = lux_atomic_or_byte(M.p1, c, 0x80u);
+                if (!(old & 0x80u)) M.reqlist[lux_atomic_add(M.reqcnt, 1)] = (uint16_t)c;
             }
             if (k > 0) {
                 int space = unit_space(U);
                 mine = (space + k - 1) / k;
                 if (mine > rate) mine = rate;
-                int ucell = U.y * S + U.x;
-                const LuxCell& C = M.cells[ucell];
-                if (cell_is_tile(C)) {
-                    // requests from one city tile are de-duplicated by amount (:920-931, :964-966)
-                    int t = M.cprefix[C.city_slot] + C.key;
-                    lux_atomic_or(&M.tmask[t], 1u << mine);
+                unsigned info = M.uinfo[u];
+                if (info & UI_TILE) {
+                    // requests from one city tile are de-duplicated by amount (:920-931, :964-966); the
+                    // occupant plane names any one requester standing on the tile
+                    lux_atomic_or(&M.tmask[info & 0xFFFFu], 1u << mine);
+                    M.occ[U.y * S + U.x] = (uint8_t)(u + 1);
                 }
             }
         }
@@ -248,7 +272,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
 #pragma unroll 1
     for (int q = lane; q < n_req; q += 32) {
         int c = M.reqlist[q];
-        LuxCell& C = M.cells[c];
+        int left = M.cells[c].amount;                 // global; consumed after the gather below
         int level = 0;
         int x = c % S, y = c / S;
         // histogram of request amounts 0..20, 3 bits each (at most one request per amount and source cell)
@@ -260,9 +284,11 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         for (int j = 0; j < 5; j++) {
             int p = lux_cell5(S, x, y, j);
             if (p < 0) continue;
-            const LuxCell& P = M.cells[p];
-            if (cell_is_tile(P)) {
-                unsigned mask = M.tmask[M.cprefix[P.city_slot] + P.key];
+            int o = M.occ[p];
+            if (!o) continue;
+            unsigned info = M.uinfo[o - 1];
+            if (info & UI_TILE) {
+                unsigned mask = M.tmask[info & 0xFFFFu];
                 if (mask) tile_dirs |= 1u << j;
                 while (mask) {
                     int a = lux_ffs(mask) - 1;
@@ -272,15 +298,11 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                     n++; sum += a;
                 }
             } else {
-                int o = P.city_slot;                      // scratch: unit index + 1
-                if (o) {
-                    int a = M.umine[o - 1];
-                    if (a != 0xFF) { hist += (uint64_t)1 << (3 * a); present |= 1u << a; n++; sum += a; }
-                }
+                int a = M.umine[o - 1];
+                if (a != 0xFF) { hist += (uint64_t)1 << (3 * a); present |= 1u << a; n++; sum += a; }
             }
         }
         if (n > 0 && sum > 0) {
-            int left = C.amount;
 #pragma unroll 1
             while (present && n > 0 && left > 0) {        // ascending over the amounts that occur
                 int a = lux_ffs(present) - 1;
@@ -298,7 +320,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                     left = 0;
                 }
             }
-            C.amount = (uint16_t)left;
+            M.cells[c].amount = (uint16_t)left;
             // city-tile requests are credited here (game.py:988-990)
             if (level > 0) {
 #pragma unroll 1
@@ -306,8 +328,8 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                     int j = lux_ffs(tile_dirs) - 1;
                     tile_dirs &= tile_dirs - 1;
                     int p = lux_cell5(S, x, y, j);
-                    const LuxCell& P = M.cells[p];
-                    unsigned mask = M.tmask[M.cprefix[P.city_slot] + P.key];
+                    unsigned info = M.uinfo[M.occ[p] - 1];
+                    unsigned mask = M.tmask[info & 0xFFFFu];
                     int got = 0;
                     while (mask) {
                         int a = lux_ffs(mask) - 1;
@@ -315,14 +337,14 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                         got += a < level ? a : level;
                     }
                     if (got) {
-                        LuxCity& city = M.cities[P.city_slot];
+                        LuxCity& city = M.cities[(info >> 16) & 0xFFu];
                         lux_atomic_add(&city.fuel, got * fuel_rate);
                         lux_atomic_add(&h->collected[city.team][rtype - 1], got);
                     }
                 }
             }
         }
-        C.tile_cd = (uint8_t)level;                   // scratch: fill level (replaces the request mark)
+        M.p1[c] = (uint8_t)level;                     // fill level (replaces the request mark)
     }
     lux_sync();
 
@@ -330,23 +352,21 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
     int got0 = 0, got1 = 0;
 #pragma unroll 1
     for (int u = lane; u < n_units; u += 32) {
-        LuxUnit& U = M.units[u];
         int mine = M.umine[u];
         if (mine == 0xFF) continue;
-        int ucell = U.y * S + U.x;
-        const LuxCell& C = M.cells[ucell];
-        if (cell_is_tile(C)) {
-            M.tmask[M.cprefix[C.city_slot] + C.key] = 0;   // leave the mask plane clean for the next type
+        unsigned info = M.uinfo[u];
+        if (info & UI_TILE) {
+            M.tmask[info & 0xFFFFu] = 0;                   // leave the mask plane clean for the next type
             continue;
         }
+        LuxUnit& U = M.units[u];
+        unsigned mm = M.umin[u];
         int gain = 0;
 #pragma unroll 1
         for (int j = 0; j < 5; j++) {
-            int c = lux_cell5(S, U.x, U.y, j);
-            if (c >= 0 && cell_res_type(M.cells[c]) == rtype) {
-                int lv = M.cells[c].tile_cd & 0x7F;
-                gain += mine < lv ? mine : lv;
-            }
+            if ((int)((mm >> (2 * j)) & 3u) != rtype) continue;
+            int lv = M.p1[lux_cell5(S, U.x, U.y, j)] & 0x7F;
+            gain += mine < lv ? mine : lv;
         }
         int space = unit_space(U);
         if (gain > space) gain = space;
@@ -361,6 +381,8 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         h->collected[0][rtype - 1] += got0;
         h->collected[1][rtype - 1] += got1;
     }
+    // the levels of this pass stay in p1 until the regrowth pass clears them: the next type's cells are
+    // disjoint from these (a cell holds one resource type)
     lux_sync();
 }
 
@@ -389,14 +411,22 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
     const int S = kS > 0 ? kS : M.S;
     const int team = unit_team(U);
     const int idx = U.y * S + U.x;
-    LuxCell& C = M.cells[idx];
+    // the cell and its four neighbours: five independent global loads
+    int pos[5];
+    LuxCell nb[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        pos[j] = lux_cell5(S, U.x, U.y, j);
+        if (pos[j] >= 0) nb[j] = lux_ldcell(M.cells, pos[j]);
+    }
+    LuxCell C = nb[0];
     int same[4], nsame = 0, found[4], nfound = 0;
+#pragma unroll
     for (int j = 1; j < 5; j++) {
-        int p = lux_cell5(S, U.x, U.y, j);
-        if (p < 0) continue;
-        const LuxCell& P = M.cells[p];
+        if (pos[j] < 0) continue;
+        const LuxCell& P = nb[j];
         if (cell_is_tile(P) && cell_tile_team(P) == team) {
-            same[nsame++] = p;
+            same[nsame++] = j;
             int seen = 0;
             for (int f = 0; f < nfound; f++) seen |= (found[f] == P.city_slot);
             if (!seen) found[nfound++] = P.city_slot;
@@ -411,6 +441,7 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
         city.pad[0] = city.pad[1] = city.pad[2] = 0;
         C.flags = (uint8_t)((C.flags & 0x03) | ((team + 1) << 2));
         C.tile_cd = 0; C.city_slot = (uint8_t)n_cities; C.key = 0;
+        lux_stcell(M.cells, idx, C);
         M.tiles[n_tiles++] = (uint16_t)idx;
         n_cities++;
         return;
@@ -419,7 +450,8 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
     LuxCity& city = M.cities[cid];
     C.flags = (uint8_t)((C.flags & 0x03) | ((team + 1) << 2) | (nsame << 4));
     C.tile_cd = 0; C.city_slot = (uint8_t)cid; C.key = city.ntiles;
-    for (int k = 0; k < nsame; k++) M.cells[same[k]].flags = (uint8_t)(M.cells[same[k]].flags + 0x10);
+    lux_stcell(M.cells, idx, C);
+    for (int k = 0; k < nsame; k++) M.cells[pos[same[k]]].flags = (uint8_t)(nb[same[k]].flags + 0x10);
     city.ntiles = (uint16_t)(city.ntiles + 1);
     city.adjsum = (uint16_t)(city.adjsum + 2 * nsame);
     M.tiles[n_tiles++] = (uint16_t)idx;
@@ -428,10 +460,12 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
         int base = city.ntiles;
 #pragma unroll 1
         for (int t = 0; t < n_tiles; t++) {
-            LuxCell& T = M.cells[M.tiles[t]];
+            int tc = M.tiles[t];
+            LuxCell T = lux_ldcell(M.cells, tc);
             if (cell_is_tile(T) && T.city_slot == found[f]) {
                 T.city_slot = (uint8_t)cid;
                 T.key = (uint16_t)(T.key + base);
+                lux_stcell(M.cells, tc, T);
             }
         }
         city.ntiles = (uint16_t)(city.ntiles + old.ntiles);
@@ -442,12 +476,16 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
 }
 
 // ---- the turn ------------------------------------------------------------------------------
-// On entry the match is staged in shared memory (M.hdr, cells, units[0..n_units), cities,
-// tiles, res, uact, tact) and hdr.done == 0.  On exit shared memory holds the post-turn
-// cells/header/cities(uncompacted)/units(uncompacted, ust says who died); the caller's
-// store routine (lux_store_match) compacts while writing.  Returns packed flags:
-//   bit0 tiles list must be rewritten, [31:16] n_units (incl. spawned), others via hdr.
+// On entry the match's lists are staged in shared memory (M.hdr, units[0..n_units), cities, tiles,
+// res, uact, tact), the two byte planes are all-zero, M.cells points at the grid in global memory
+// and hdr.done == 0.  On exit the grid holds the post-turn cells, shared memory the post-turn
+// header / cities (uncompacted) / units (uncompacted, ust says who died); lux_finish_and_store
+// compacts while writing.
 struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; int alive0; int alive1; };
+
+// utgt[u]: [9:0] target cell of the unit's validated move (own cell otherwise), bit 14 = the target is a city tile
+#define UTGT_TILE 0x4000u
+#define UTGT_CELL 0x03FFu
 
 template <int kS>
 LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
@@ -481,19 +519,21 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     const int tu0 = h->n_team_units[0], tu1 = h->n_team_units[1];
 
     int any_move = 0;
-    // ---- unit action validation (validate_command game.py:646-695), lanes over units
+    // ---- unit action validation (validate_command game.py:646-695), lanes over units; at most one
+    // global cell load per unit (its own cell for a build, the target cell for a move)
 #pragma unroll 1
     for (int u = lane; u < n_units0; u += 32) {
         const LuxUnit& U = M.units[u];
         unsigned w = M.uact[u];
         int kind = w & 7;
         int ucell = U.y * S + U.x;
-        const LuxCell& C = M.cells[ucell];
         unsigned st = 0;
-        int tgt = ucell;
+        unsigned tgt = ucell;
         if (kind == LUX_UA_BCITY) {
-            if (!cell_is_tile(C) && C.amount == 0 && U.cd_q < 4 &&
-                (int)U.wood + (int)U.coal + (int)U.uranium >= LUX_CITY_BUILD_COST) st = kind;
+            if (U.cd_q < 4 && (int)U.wood + (int)U.coal + (int)U.uranium >= LUX_CITY_BUILD_COST) {
+                LuxCell C = lux_ldcell(M.cells, ucell);
+                if (!cell_is_tile(C) && C.amount == 0) st = kind;
+            }
         } else if (kind == LUX_UA_MOVE) {
             int dir = (w >> 3) & 7;
             if (U.cd_q < 4 && dir <= 4) {
@@ -503,11 +543,19 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                     if (nx < 0 || ny < 0 || nx >= S || ny >= S) ok = 0;
                     else {
                         tgt = ny * S + nx;
-                        const LuxCell& T = M.cells[tgt];
-                        if (cell_is_tile(T) && cell_tile_team(T) != unit_team(U)) ok = 0;
+                        LuxCell T = lux_ldcell(M.cells, tgt);
+                        if (cell_is_tile(T)) {
+                            if (cell_tile_team(T) != unit_team(U)) ok = 0;
+                            tgt |= UTGT_TILE;
+                        }
                     }
+                } else {
+                    // a CENTER move targets the unit's own cell: its tile-ness decides whether it collides
+                    LuxCell C = lux_ldcell(M.cells, ucell);
+                    if (cell_is_tile(C)) tgt |= UTGT_TILE;
                 }
                 if (ok) st = kind | (dir << 3);
+                else tgt = ucell;
             }
         } else if (kind == LUX_UA_PILLAGE || kind == LUX_UA_TRANSFER) {
             st = kind;                                             // game.py:721-723: no check
@@ -546,23 +594,25 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             unsigned st = u < n_units0 ? M.ust[u] : 0;
             int is_move = (st & 7) == LUX_UA_MOVE;
             int center = is_move && ((st >> 3) & 7) == LUX_DIR_CENTER;
-            int t = is_move ? M.utgt[u] : 0;
+            unsigned tg = is_move ? M.utgt[u] : 0;
+            int t = tg & UTGT_CELL;
             int team = is_move ? unit_team(M.units[u]) : 0;
-            int cand = is_move && !center && !cell_is_tile(M.cells[t]);
+            int cand = is_move && !center && !(tg & UTGT_TILE);
             unsigned peers = lux_match_any(cand ? ((t << 1) | team) : (int)(0x40000000 | lane));
             if (center) M.ust[u] = 0;
             if (cand) {
                 unsigned bit = team ? P1_CLAIM1 : P1_CLAIM0;
                 int first = lux_ffs(peers) - 1 == lane;
-                if (!first || (M.cells[t].tile_cd & bit)) M.ust[u] = 0;
+                if (!first || (M.p1[t] & bit)) M.ust[u] = 0;
             }
             lux_sync();
-            if (cand && M.ust[u]) lux_scratch_or(M.cells, t, 0, team ? P1_CLAIM1 : P1_CLAIM0);
+            if (cand && M.ust[u]) lux_atomic_or_byte(M.p1, t, team ? P1_CLAIM1 : P1_CLAIM0);
             lux_sync();
         }
     }
 
-    // ---- collision pruning (handle_movement_actions game.py:1104-1195)
+    // ---- collision pruning (handle_movement_actions game.py:1104-1195); shared memory only.
+    // Flags are set on every cell (city tiles too) but only ever read on non-city target cells.
     if (any_move) {
 #pragma unroll 1
     for (int u = lane; u < n_units0; u += 32) {
@@ -570,16 +620,14 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         int ucell = U.y * S + U.x;
         unsigned st = M.ust[u];
         int moving = (st & 7) == LUX_UA_MOVE;
-        // flags are only ever read on non-city cells, and only those have the scratch byte
-        if (!cell_is_tile(M.cells[ucell])) {
-            unsigned old = lux_scratch_or(M.cells, ucell, 0, P1_HAS1 | (moving ? 0u : P1_STILL));
-            if (old & P1_HAS1) lux_scratch_or(M.cells, ucell, 0, P1_HAS2);
-        }
+        unsigned old = lux_atomic_or_byte(M.p1, ucell, P1_HAS1 | (moving ? 0u : P1_STILL));
+        if (old & P1_HAS1) lux_atomic_or_byte(M.p1, ucell, P1_HAS2);
         if (moving) {
-            int t = M.utgt[u];
-            if (!cell_is_tile(M.cells[t])) {
-                unsigned old = lux_scratch_or(M.cells, t, 0, P1_IN1);
-                if (old & P1_IN1) lux_scratch_or(M.cells, t, 0, P1_IN2);
+            unsigned tg = M.utgt[u];
+            if (!(tg & UTGT_TILE)) {
+                int t = tg & UTGT_CELL;
+                unsigned o2 = lux_atomic_or_byte(M.p1, t, P1_IN1);
+                if (o2 & P1_IN1) lux_atomic_or_byte(M.p1, t, P1_IN2);
             }
         }
     }
@@ -590,14 +638,13 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     for (int u = lane; u < n_units0; u += 32) {
         unsigned st = M.ust[u];
         if ((st & 7) != LUX_UA_MOVE) continue;
-        int t = M.utgt[u];
-        if (cell_is_tile(M.cells[t])) continue;
-        unsigned f = M.cells[t].tile_cd;
+        unsigned tg = M.utgt[u];
+        if (tg & UTGT_TILE) continue;
+        unsigned f = M.p1[tg & UTGT_CELL];
         if ((f & P1_IN2) || ((f & P1_HAS1) && !(f & P1_HAS2) && (f & P1_STILL))) {
             M.ust[u] = (uint8_t)(st | UST_REVERTED);
             const LuxUnit& U = M.units[u];
-            int o = U.y * S + U.x;
-            if (!cell_is_tile(M.cells[o])) lux_scratch_or(M.cells, o, 0, P1_BLOCKED);
+            lux_atomic_or_byte(M.p1, U.y * S + U.x, P1_BLOCKED);
         }
     }
     lux_sync();
@@ -609,26 +656,24 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         for (int u = lane; u < n_units0; u += 32) {
             unsigned st = M.ust[u];
             if ((st & 7) != LUX_UA_MOVE || (st & UST_REVERTED)) continue;
-            int t = M.utgt[u];
-            if (cell_is_tile(M.cells[t])) continue;
-            if (M.cells[t].tile_cd & P1_BLOCKED) {
+            unsigned tg = M.utgt[u];
+            if (tg & UTGT_TILE) continue;
+            if (M.p1[tg & UTGT_CELL] & P1_BLOCKED) {
                 M.ust[u] = (uint8_t)(st | UST_REVERTED);
                 const LuxUnit& U = M.units[u];
-                int o = U.y * S + U.x;
-                if (!cell_is_tile(M.cells[o])) lux_scratch_or(M.cells, o, 0, P1_BLOCKED);
+                lux_atomic_or_byte(M.p1, U.y * S + U.x, P1_BLOCKED);
                 changed = 1;
             }
         }
         lux_sync();
         if (!lux_any(changed)) break;
     }
-    // the movement flags have served: clear the scratch byte of every cell a unit stands on or aimed at
+    // the movement flags have served: clear the byte of every cell a unit stands on or aimed at
 #pragma unroll 1
     for (int u = lane; u < n_units0; u += 32) {
         const LuxUnit& U = M.units[u];
-        int ucell = U.y * S + U.x, t = M.utgt[u];
-        if (!cell_is_tile(M.cells[ucell])) M.cells[ucell].tile_cd = 0;
-        if (!cell_is_tile(M.cells[t])) M.cells[t].tile_cd = 0;
+        M.p1[U.y * S + U.x] = 0;
+        M.p1[M.utgt[u] & UTGT_CELL] = 0;
     }
     lux_sync();
     }   // any_move
@@ -647,7 +692,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             int valid = p < n_tiles0;
             int code = valid ? M.tact[p] : 0;
             int cell = valid ? M.tiles[p] : 0;
-            LuxCell& C = M.cells[cell];
+            LuxCell C = lux_ldcell(M.cells, cell);
             int team = valid ? cell_tile_team(C) : 0;
             int cd = C.tile_cd;
             int cand = valid && (code == LUX_TA_BUILD_WORKER || code == LUX_TA_BUILD_CART) && cd < 1;
@@ -681,9 +726,10 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             rp0 += lux_popc(lux_ballot(research && team == 0));
             rp1 += lux_popc(lux_ballot(research && team == 1));
             if (valid) {
+                int cd0 = cd;
                 if (acted) cd = LUX_CITY_ACTION_COOLDOWN;
                 if (cd > 0) cd -= 1;
-                C.tile_cd = (uint8_t)cd;
+                if (cd != cd0) M.cells[cell].tile_cd = (uint8_t)cd;
             }
         }
         int made = spawned < room ? spawned : room;
@@ -767,8 +813,9 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                             *cg[r] = 0;
                         }
                     } else {                                          // pillage unit.py:188-192
-                        LuxCell& C = M.cells[U.y * S + U.x];
-                        C.road_q = (uint8_t)(C.road_q > LUX_PILLAGE_Q ? C.road_q - LUX_PILLAGE_Q : 0);
+                        int pc = U.y * S + U.x;
+                        int rq = M.cells[pc].road_q;
+                        M.cells[pc].road_q = (uint8_t)(rq > LUX_PILLAGE_Q ? rq - LUX_PILLAGE_Q : 0);
                     }
                 }
             }
@@ -778,27 +825,55 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     n_cities = lux_shfl(n_cities, 0);
     n_tiles = lux_shfl(n_tiles, 0);
     if (n_tiles != n_tiles0) tiles_dirty = 1;
-    // cooldowns of the acting units, then the carts' automatic roads (unit.py:196-197, :257-269); the same
-    // pass leaves the occupant mark the collection stage reads (units spawned this turn stand on city
-    // tiles, which carry no mark, so the old units are all there is to mark)
+    lux_city_prefix(M, n_cities);     // also syncs
+
+    // ---- the unit pass: cooldowns of the acting units, the carts' automatic roads (unit.py:196-197,
+    // :257-269), and the per-unit caches the rest of the turn works from -- what the unit stands on
+    // (uinfo), which of its five cells it can mine (umin, 2 bits of resource type per direction) and the
+    // occupant mark of its cell.  This is the one place a unit reads the grid: five independent loads.
     {
         int rb0 = 0, rb1 = 0, bad = 0;
 #pragma unroll 1
-        for (int u = lane; u < n_units0; u += 32) {
-            unsigned st = M.ust[u];
+        for (int u = lane; u < n_units; u += 32) {
             LuxUnit& U = M.units[u];
-            int cart = unit_is_cart(U);
+            const int isold = u < n_units0;
+            unsigned st = isold ? M.ust[u] : 0u;
+            const int cart = unit_is_cart(U);
+            const int ucell = U.y * S + U.x;
+            int pos[5];
+            LuxCell nb[5];
+            pos[0] = ucell;
+            nb[0] = lux_ldcell(M.cells, ucell);
+            if (!cart) {
+#pragma unroll
+                for (int j = 1; j < 5; j++) {
+                    pos[j] = lux_cell5(S, U.x, U.y, j);
+                    if (pos[j] >= 0) nb[j] = lux_ldcell(M.cells, pos[j]);
+                }
+            }
             if ((st & 7) != 0 && !(st & UST_FAILED)) U.cd_q = (uint8_t)(U.cd_q + (cart ? 12 : 8) * mult);
-            LuxCell& C = M.cells[U.y * S + U.x];
-            if (!cell_is_tile(C)) {
+            const LuxCell& C = nb[0];
+            unsigned info = 0xFFFFu;
+            if (cell_is_tile(C)) {
+                info = (unsigned)(M.cprefix[C.city_slot] + C.key) | ((unsigned)C.city_slot << 16) | UI_TILE |
+                       (cell_tile_team(C) == unit_team(U) ? UI_OWN : 0u);
+            } else {
                 if (cart && !(st & UST_FAILED) && C.road_q < LUX_MAX_ROAD_Q) {
                     int r = C.road_q + LUX_ROAD_DEV_Q;
-                    C.road_q = (uint8_t)(r > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : r);
+                    M.cells[ucell].road_q = (uint8_t)(r > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : r);
                     if (unit_team(U)) rb1 += LUX_ROAD_DEV_Q; else rb0 += LUX_ROAD_DEV_Q;
                 }
-                if (C.city_slot) bad = 1;          // cannot happen in play: a non-city cell holds one unit
-                C.city_slot = (uint8_t)(u + 1);
+                // a non-city cell holds one unit in play; a stack (left behind by a destroyed city) is flagged
+                if (lux_atomic_or_byte(M.occ, ucell, (unsigned)(u + 1))) bad = 1;
             }
+            unsigned mm = 0;
+            if (!cart) {
+#pragma unroll
+                for (int j = 0; j < 5; j++)
+                    if (pos[j] >= 0 && nb[j].amount > 0) mm |= (unsigned)cell_res_type(nb[j]) << (2 * j);
+            }
+            M.uinfo[u] = info;
+            M.umin[u] = (uint16_t)mm;
             M.ust[u] = 0;
         }
         rb0 = lux_reduce_add(rb0);
@@ -813,7 +888,6 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 
     // ---- resource collection: uranium, coal, wood (distribute_all_resources game.py:868-880)
     {
-        lux_city_prefix(M, n_cities);     // also syncs
         int rp0 = h->research[0], rp1 = h->research[1];
 #pragma unroll 1
         for (int rtype = LUX_RES_URANIUM; rtype >= LUX_RES_WOOD; rtype--) {
@@ -829,14 +903,12 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 #pragma unroll 1
         for (int u = lane; u < n_units; u += 32) {
             LuxUnit& U = M.units[u];
-            LuxCell& C = M.cells[U.y * S + U.x];
-            int team = unit_team(U);
-            if (!cell_is_tile(C)) {
-                C.city_slot = 0;                    // collection is over: drop the occupant mark again
-            } else if (cell_tile_team(C) == team) {
+            unsigned info = M.uinfo[u];
+            M.occ[U.y * S + U.x] = 0;               // collection is over: drop the occupant mark again
+            if (info & UI_OWN) {
                 int fuel = U.wood + 10 * U.coal + 40 * U.uranium;
-                if (fuel) lux_atomic_add(&M.cities[C.city_slot].fuel, fuel);
-                if (team) fg1 += fuel; else fg0 += fuel;
+                if (fuel) lux_atomic_add(&M.cities[(info >> 16) & 0xFFu].fuel, fuel);
+                if (unit_team(U)) fg1 += fuel; else fg0 += fuel;
                 U.wood = 0; U.coal = 0; U.uranium = 0;
             }
         }
@@ -859,27 +931,29 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             else city.fuel -= upkeep;
         }
         lux_sync();
-        if (lux_any(died)) {
+        died = lux_any(died);
+        if (died) {
             tiles_dirty = 1;
 #pragma unroll 1
             for (int t = lane; t < n_tiles; t += 32) {                // destroy_city :1059-1070
-                LuxCell& C = M.cells[M.tiles[t]];
+                int tc = M.tiles[t];
+                LuxCell C = lux_ldcell(M.cells, tc);
                 if (cell_is_tile(C) && M.cremap[C.city_slot]) {
                     C.flags &= 0x03;
                     C.tile_cd = 0; C.city_slot = 0; C.key = 0;
                     C.road_q = 0;
+                    lux_stcell(M.cells, tc, C);
                 }
             }
-            lux_sync();
-#pragma unroll 1
-            for (int s = lane; s < n_cities; s += 32)
-                if (M.cremap[s]) { M.cities[s].ntiles = 0; M.cities[s].fuel = 0; M.cities[s].adjsum = 0; }
-            lux_sync();
         }
 #pragma unroll 1
         for (int u = lane; u < n_units; u += 32) {                    // spend_fuel_to_survive unit.py:64-98
             LuxUnit& U = M.units[u];
-            if (cell_is_tile(M.cells[U.y * S + U.x])) continue;
+            unsigned info = M.uinfo[u];
+            if (info & UI_TILE) {
+                if (!died || !M.cremap[(info >> 16) & 0xFFu]) continue;
+                M.uinfo[u] = 0xFFFFu;                                  // its city fell: it stands in the open now
+            }
             int need = unit_is_cart(U) ? LUX_UPKEEP_CART : LUX_UPKEEP_WORKER;
             int used = U.wood < need ? U.wood : need;
             need -= used; U.wood = (uint16_t)(U.wood - used);
@@ -901,19 +975,38 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         died0 = lux_reduce_add(died0);
         died1 = lux_reduce_add(died1);
         lux_sync();
+        if (died) {
+#pragma unroll 1
+            for (int s = lane; s < n_cities; s += 32)
+                if (M.cremap[s]) { M.cities[s].ntiles = 0; M.cities[s].fuel = 0; M.cities[s].adjsum = 0; }
+            lux_sync();
+        }
     }
 
-    // ---- depleted cells leave the list (game.py:498-510), trees regrow (:1081-1102)
+    // ---- depleted cells leave the list (game.py:498-510), trees regrow (:1081-1102): four resource
+    // cells per lane and round, loads first
     {
-        int n_res = h->n_res;
+        const int n_res = h->n_res;
 #pragma unroll 1
-        for (int r = lane; r < n_res; r += 32) {
-            LuxCell& C = M.cells[M.res[r]];
-            if (!cell_is_tile(C)) C.tile_cd = 0;                          // collection scratch (fill level)
-            if (C.amount == 0) { C.flags &= 0xFC; continue; }
-            if (cell_res_type(C) == LUX_RES_WOOD && C.amount < LUX_MAX_WOOD) {
-                int a = (41 * (int)C.amount + 39) / 40;               // == ceil(min(a*1.025, 500)), tests/test_oracle_golden.py
-                C.amount = (uint16_t)(a > LUX_MAX_WOOD ? LUX_MAX_WOOD : a);
+        for (int base = 0; base < n_res; base += 128) {
+            int idx[4];
+            LuxCell c[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int r = base + 32 * k + lane;
+                idx[k] = r < n_res ? (int)M.res[r] : -1;
+                if (idx[k] >= 0) c[k] = lux_ldcell(M.cells, idx[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (idx[k] < 0) continue;
+                M.p1[idx[k]] = 0;                                          // collection scratch (fill level)
+                if (c[k].amount == 0) {
+                    if (c[k].flags & 0x03) M.cells[idx[k]].flags = (uint8_t)(c[k].flags & 0xFC);
+                } else if (cell_res_type(c[k]) == LUX_RES_WOOD && c[k].amount < LUX_MAX_WOOD) {
+                    int a = (41 * (int)c[k].amount + 39) / 40;            // == ceil(min(a*1.025, 500)), tests/test_oracle_golden.py
+                    M.cells[idx[k]].amount = (uint16_t)(a > LUX_MAX_WOOD ? LUX_MAX_WOOD : a);
+                }
             }
         }
     }
@@ -926,11 +1019,10 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 }
 
 // ---- epilogue: compaction, match_over, cooldowns, canonical tile order, store ---------------
-// g_* are the match's sections in global memory.
-// With kStoreGrid == false the caller moves the cell grid and the header itself (bulk copy).
-template <bool kStoreGrid, int kS>
-LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g_hdr, LuxCell* g_cells,
-                                  LuxUnit* g_units, LuxCity* g_cities, uint16_t* g_tiles) {
+// g_* are the match's sections in global memory (the grid is already up to date there).
+template <int kS>
+LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g_hdr, LuxUnit* g_units,
+                                  LuxCity* g_cities, uint16_t* g_tiles) {
     const int lane = lux_lane();
     const unsigned lt = lux_lanemask_lt();
     LuxHeader* h = M.hdr;
@@ -953,20 +1045,14 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
     tl0 = lux_reduce_add(tl0); tl1 = lux_reduce_add(tl1);
     lux_sync();
     const int cities_moved = n_alive != T.n_cities;
-    if (cities_moved) {
-#pragma unroll 1
-        for (int t = lane; t < T.n_tiles; t += 32) {
-            LuxCell& C = M.cells[M.tiles[t]];
-            if (cell_is_tile(C)) C.city_slot = M.cremap[C.city_slot];
-        }
-    }
     // store cities compacted
 #pragma unroll 1
     for (int s = lane; s < T.n_cities; s += 32) {
         int ns = M.cremap[s];
         if (ns != 0xFF) g_cities[ns] = M.cities[s];
     }
-    // canonical tile list: position = prefix[new slot] + key
+    // canonical tile list: position = prefix[new slot] + key; surviving tiles of moved cities get their
+    // new slot written into the grid in the same pass
     int n_tiles_live = tl0 + tl1;
     if (T.tiles_dirty || cities_moved) {
         int run = 0;
@@ -983,8 +1069,12 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
 #pragma unroll 1
         for (int t = lane; t < T.n_tiles; t += 32) {
             int cell = M.tiles[t];
-            const LuxCell& C = M.cells[cell];
-            if (cell_is_tile(C)) g_tiles[M.cprefix[C.city_slot] + C.key] = (uint16_t)cell;
+            LuxCell C = lux_ldcell(M.cells, cell);
+            if (cell_is_tile(C)) {
+                int ns = M.cremap[C.city_slot];
+                if (ns != C.city_slot) M.cells[cell].city_slot = (uint8_t)ns;
+                g_tiles[M.cprefix[ns] + C.key] = (uint16_t)cell;
+            }
         }
     }
 
@@ -1002,8 +1092,7 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
         unsigned m0 = lux_ballot(valid && team == 0), m1 = lux_ballot(valid && team == 1);
         if (valid) {
             LuxUnit U = M.units[u];
-            const LuxCell& C = M.cells[U.y * S + U.x];
-            int road = cell_is_tile(C) ? LUX_MAX_ROAD_Q : C.road_q;    // cell.py:77-85
+            int road = (M.uinfo[u] & UI_TILE) ? LUX_MAX_ROAD_Q : (int)M.cells[U.y * S + U.x].road_q;    // cell.py:77-85
             int cd = (int)U.cd_q - road - 4;
             U.cd_q = (uint8_t)(cd > 0 ? cd : 0);
             U.pad = 0;
@@ -1034,14 +1123,11 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
         }
     }
     lux_sync();
-    // cells and header: straight copies
-    if (kStoreGrid) {
-        const uint64_t* s = (const uint64_t*)M.cells;
-        uint64_t* d = (uint64_t*)g_cells;
-#pragma unroll 1
-        for (int i = lane; i < M.ncell; i += 32) d[i] = s[i];
+    // header: a straight copy (8 lanes x 16 bytes)
+    if (lane < LUX_HDR_BYTES / 16) {
         const uint64_t* hs = (const uint64_t*)M.hdr;
         uint64_t* hd = (uint64_t*)g_hdr;
-        if (lane < LUX_HDR_BYTES / 8) hd[lane] = hs[lane];
+        uint64_t a = hs[2 * lane], b = hs[2 * lane + 1];
+        hd[2 * lane] = a; hd[2 * lane + 1] = b;
     }
 }

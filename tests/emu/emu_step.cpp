@@ -17,6 +17,7 @@ struct EmuArgs {
     unsigned char* smem;
     LuxSmemLayout L;
     unsigned flags;
+    int dirty;
 };
 
 static void emu_lane(void* p) {
@@ -24,18 +25,18 @@ static void emu_lane(void* p) {
     const LuxBatch* b = a->b;
     int m = a->m;
     int ncell = b->size * b->size;
-    LuxMatch M;
-    lux_match_bind(M, a->smem, a->L, b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
     LuxHeader* g_hdr = b->hdr + m;
     LuxCell* g_cells = b->cells + (size_t)m * ncell;
     LuxUnit* g_units = b->units + (size_t)m * b->u_cap;
     LuxCity* g_cities = b->cities + (size_t)m * b->c_cap;
     uint16_t* g_tiles = b->tiles + (size_t)m * b->t_cap;
     uint16_t* g_res = b->res + (size_t)m * b->r_cap;
+    LuxMatch M;
+    lux_match_bind(M, a->smem, a->L, g_cells, b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    lux_planes_init(M);
     lux_copy16(M.hdr, g_hdr, LUX_HDR_BYTES);
     lux_sync();
     if (M.hdr->done) return;
-    lux_copy16(M.cells, g_cells, ncell * 8);
     lux_copy16(M.units, g_units, M.hdr->n_units * 16);
     lux_copy16(M.cities, g_cities, M.hdr->n_cities * 16);
     lux_copy16(M.tiles, g_tiles, M.hdr->n_tiles * 2);
@@ -44,7 +45,11 @@ static void emu_lane(void* p) {
     lux_copy16(M.tact, a->ta + (size_t)m * b->t_cap, M.hdr->n_tiles);
     lux_sync();
     LuxTurnOut T = b->size == 32 ? lux_turn<32>(M, a->flags) : lux_turn<0>(M, a->flags);
-    lux_finish_and_store<true, 0>(M, T, g_hdr, g_cells, g_units, g_cities, g_tiles);
+    lux_finish_and_store<0>(M, T, g_hdr, g_units, g_cities, g_tiles);
+    lux_sync();
+    // the engine's contract: both byte planes are clean again after the turn
+    for (int i = lux_lane(); i < ncell; i += 32)
+        if (M.p1[i] || M.occ[i]) a->dirty = 1;
 }
 
 extern "C" size_t lux_emu_smem_bytes(int size, int u_cap, int c_cap, int t_cap, int r_cap) {
@@ -54,7 +59,7 @@ extern "C" size_t lux_emu_smem_bytes(int size, int u_cap, int c_cap, int t_cap, 
 extern "C" int lux_emu_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions, unsigned flags) {
     if (!b || !unit_actions || !tile_actions) return LUX_E_ARG;
     EmuArgs a;
-    a.b = b; a.ua = unit_actions; a.ta = tile_actions; a.flags = flags;
+    a.b = b; a.ua = unit_actions; a.ta = tile_actions; a.flags = flags; a.dirty = 0;
     a.L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
     a.smem = (unsigned char*)aligned_alloc(16, a.L.total);
     for (int m = 0; m < b->n_matches; m++) {
@@ -63,7 +68,7 @@ extern "C" int lux_emu_step(const LuxBatch* b, const uint32_t* unit_actions, con
         warp_emu::run_warp(emu_lane, &a);
     }
     free(a.smem);
-    return 0;
+    return a.dirty ? -100 : 0;
 }
 
 // ---- observations through the emulated warp ------------------------------------------------
