@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--matches", type=int, default=MATCHES_PER_GPU)
     ap.add_argument("--size", type=int, default=SIZE)
-    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = as many as --steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -267,26 +267,32 @@ def run_b200(args):
     step_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / K
     live_turns, alg_bytes = [int(x) for x in counters.cpu().tolist()]
 
-    # ---- end to end through the host entry point: pinned host action LIST in, done flags + summary out
-    E = min(args.e2e_steps, K)
+    # ---- end to end through the host entry point: pinned host action LIST in, done flags + summary out.
+    # The device path above is replayed from a snapshot: the action lists of W_e + E turns are recorded on the
+    # host first (untimed), then the same turns run through lux_b200_step_host_sparse -- W_e untimed calls
+    # (first-call allocations, pinned-page faults) and E timed ones.
+    E = min(args.e2e_steps, K) if args.e2e_steps > 0 else K
+    W_e = 5
     snap = {k: t.clone() for k, t in game.sections().items()}
     epoch0 = epoch[0]
-    ent_cap = n * 24
-    ent_h = torch.zeros((E, ent_cap, 2), dtype=torch.int32).pin_memory()
-    ent_k = []
-    for k in range(E):                       # untimed: record the action LISTS of E turns on the host
+    ent_dev, ent_k = [], []
+    for k in range(W_e + E):
         game.unit_actions.zero_()
         game.tile_actions.zero_()
         game.gen_actions(STREAM_SEED, base)
         ent = game.pack_entries()
-        assert ent.shape[0] <= ent_cap
-        ent_h[k, : ent.shape[0]].copy_(ent)
+        ent_dev.append(ent)
         ent_k.append(int(ent.shape[0]))
         game.step()
         game.reset_done(pool, epoch[0], resets)
         epoch[0] += 1
     torch.cuda.synchronize()
     final_hdr_device_path = game.hdr.clone()
+    ent_off = np.concatenate([[0], np.cumsum(ent_k)]).astype(np.int64)
+    ent_h = torch.empty((max(int(ent_off[-1]), 1), 2), dtype=torch.int32).pin_memory()     # ragged: one slice per turn
+    for k, ent in enumerate(ent_dev):
+        ent_h[ent_off[k]: ent_off[k + 1]].copy_(ent)
+    del ent_dev
     for k, t in game.sections().items():     # rewind
         t.copy_(snap[k])
     epoch[0] = epoch0
@@ -294,13 +300,16 @@ def run_b200(args):
     game.tile_actions.zero_()
     done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
     summ_h = torch.zeros(4, dtype=torch.int32).pin_memory()
-    barrier()
-    w0 = time.perf_counter()
     h2d_total = 0
-    for k in range(E):
+    e2e_s = 0.0
+    for k in range(W_e + E):
+        if k == W_e:
+            barrier()
+            w0 = time.perf_counter()
         # H2D: this turn's action list (8 bytes per action); step; D2H: done flags + summary; sync
-        game.step_host_sparse(ent_h[k], ent_k[k], done_h, summ_h)
-        h2d_total += 8 * ent_k[k]
+        game.step_host_sparse(ent_h[ent_off[k]: ent_off[k + 1]], ent_k[k], done_h, summ_h)
+        if k >= W_e:
+            h2d_total += 8 * ent_k[k]
         game.reset_done(pool, epoch[0], resets)
         epoch[0] += 1
     torch.cuda.synchronize()
@@ -340,11 +349,11 @@ def run_b200(args):
                 "gpu_launches": int(launches) * world,
                 "kernel_ms": {"lux_step_kernel": step_ms, "whole_step": total_ms / K},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "lux_step_kernel<true>",
+                             "traffic": None, "peak_source": peak_src, "kernel": "lux_step_kernel (small-class launch + retry-list launch = one step)",
                              "algorithmic_bytes_per_launch": bytes_all / world / K,
                              "live_match_turns_per_launch": live_all / world / K},
                 "e2e": {"value": e2e_turns / e2e_s, "unit": "match-turns/s", "h2d_bytes_per_step": h2d * world,
-                        "d2h_bytes_per_step": d2h * world, "steps": E,
+                        "d2h_bytes_per_step": d2h * world, "steps": E, "warmup": 5,
                         "note": "lux_b200_step_host_sparse: pinned host action LIST (8 B per action) -> device, scatter, "
                                 "step, done flags + summary -> host, sync every step; counts resident matches per step "
                                 "(finished ones are reset the same step)"},

@@ -41,14 +41,17 @@ struct LuxStage { int u, c, t; };      // shared-memory staging capacities (unit
 enum { LUX_M_DONE = 0, LUX_M_SPILL = 1, LUX_M_PLAYED = 2, LUX_M_HEAVY = 3 };
 #define LUX_HEAVY_THRESHOLD 28     // units + tiles
 
-template <bool kTma, int kS>
-__device__ __forceinline__ int lux_step_match(const LuxBatch& b, int m, const uint32_t* __restrict__ unit_actions,
+// One lane group plays match `m` (or, with valid == 0, walks along on an empty match: the groups of a
+// warp run in lockstep and every collective needs all 32 lanes).
+template <bool kTma, int kS, int G>
+__device__ __forceinline__ int lux_step_match(const LuxBatch& b, int m, int valid, const uint32_t* __restrict__ unit_actions,
                                                const uint8_t* __restrict__ tile_actions, const LuxSmemLayout& L,
                                                unsigned char* smem, unsigned flags, const LuxStage& stage,
                                                bool check_fit, uint32_t& phase) {
-    const int lane = threadIdx.x & 31;
+    const int lane = lux_lane<G>();
     const int size = kS > 0 ? kS : b.size;
     const int ncell = size * size;
+    if (!valid) m = 0;
     LuxHeader* g_hdr = b.hdr + m;
     LuxCell* g_cells = b.cells + (size_t)m * ncell;
     LuxUnit* g_units = b.units + (size_t)m * b.u_cap;
@@ -59,12 +62,13 @@ __device__ __forceinline__ int lux_step_match(const LuxBatch& b, int m, const ui
     const uint8_t* g_ta = tile_actions + (size_t)m * b.t_cap;
     LuxMatch M;
     lux_match_bind(M, smem, L, g_cells, size, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
+    int active = valid, result = LUX_M_DONE;
 
     if (kTma) {
         uint64_t* bar = (uint64_t*)(smem + L.mbar);
         const uint32_t pu = min(stage.u, LUX_PRE_UNITS), pc = min(stage.c, LUX_PRE_CITIES), pt = min(stage.t, LUX_PRE_TILES);
         const uint32_t b_res = b.r_cap * 2;
-        if (lane == 0) {
+        if (active && lane == 0) {
             mbar_expect_tx(bar, LUX_HDR_BYTES + b_res + pu * 16 + pc * 16 + pt * 2 + pu * 4 + pt);
             tma_g2s(M.hdr, g_hdr, LUX_HDR_BYTES, bar);
             tma_g2s(M.units, g_units, pu * 16, bar);
@@ -74,62 +78,71 @@ __device__ __forceinline__ int lux_step_match(const LuxBatch& b, int m, const ui
             tma_g2s(M.tact, g_ta, pt, bar);
             tma_g2s(M.res, g_res, b_res, bar);
         }
-        __syncwarp();
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        if (M.hdr->done) return LUX_M_DONE;
-        const uint32_t nu = M.hdr->n_units, nc = M.hdr->n_cities, nt = M.hdr->n_tiles;
+        lux_sync<G>();
+        if (active) { mbar_wait(bar, phase); phase ^= 1; }
+        uint32_t nu = 0, nc = 0, nt = 0;
+        if (active) {
+            if (M.hdr->done) active = 0;
+            nu = M.hdr->n_units; nc = M.hdr->n_cities; nt = M.hdr->n_tiles;
+        }
         // the live lists themselves must fit the staging arrays before anything more is loaded
-        if (check_fit && (nu > (uint32_t)stage.u || nc > (uint32_t)stage.c || nt > (uint32_t)stage.t)) return LUX_M_SPILL;
-        if (nu > pu || nc > pc || nt > pt) {                      // warp-uniform
+        if (active && check_fit && (nu > (uint32_t)stage.u || nc > (uint32_t)stage.c || nt > (uint32_t)stage.t)) {
+            active = 0; result = LUX_M_SPILL;
+        }
+        const int more = active && (nu > pu || nc > pc || nt > pt);   // group-uniform
+        if (more && lane == 0) {
             const uint32_t ru = nu > pu ? nu - pu : 0, rc = nc > pc ? nc - pc : 0;
             const uint32_t rt2 = nt > pt ? ((nt - pt) * 2 + 15) & ~15u : 0;
             const uint32_t rua = nu > pu ? ((nu - pu) * 4 + 15) & ~15u : 0, rta = nt > pt ? ((nt - pt) + 15) & ~15u : 0;
-            if (lane == 0) {
-                mbar_expect_tx(bar, ru * 16 + rc * 16 + rt2 + rua + rta);
-                if (ru) tma_g2s(M.units + pu, g_units + pu, ru * 16, bar);
-                if (rc) tma_g2s(M.cities + pc, g_cities + pc, rc * 16, bar);
-                if (rt2) tma_g2s(M.tiles + pt, g_tiles + pt, rt2, bar);
-                if (rua) tma_g2s(M.uact + pu, g_ua + pu, rua, bar);
-                if (rta) tma_g2s(M.tact + pt, g_ta + pt, rta, bar);
-            }
-            __syncwarp();
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            mbar_expect_tx(bar, ru * 16 + rc * 16 + rt2 + rua + rta);
+            if (ru) tma_g2s(M.units + pu, g_units + pu, ru * 16, bar);
+            if (rc) tma_g2s(M.cities + pc, g_cities + pc, rc * 16, bar);
+            if (rt2) tma_g2s(M.tiles + pt, g_tiles + pt, rt2, bar);
+            if (rua) tma_g2s(M.uact + pu, g_ua + pu, rua, bar);
+            if (rta) tma_g2s(M.tact + pt, g_ta + pt, rta, bar);
         }
+        lux_sync<G>();        // also: every lane has read the header before an idle group clears it
+        if (more) { mbar_wait(bar, phase); phase ^= 1; }
     } else {
-        lux_copy16(M.hdr, g_hdr, LUX_HDR_BYTES);
-        __syncwarp();
-        if (M.hdr->done) return LUX_M_DONE;
-        lux_copy16(M.units, g_units, M.hdr->n_units * 16);
-        lux_copy16(M.cities, g_cities, M.hdr->n_cities * 16);
-        lux_copy16(M.tiles, g_tiles, M.hdr->n_tiles * 2);
-        lux_copy16(M.res, g_res, M.hdr->n_res * 2);
-        lux_copy16(M.uact, g_ua, M.hdr->n_units * 4);
-        lux_copy16(M.tact, g_ta, M.hdr->n_tiles);
-        __syncwarp();
+        if (active) lux_copy16<G>(M.hdr, g_hdr, LUX_HDR_BYTES);
+        lux_sync<G>();
+        if (active && M.hdr->done) active = 0;
+        lux_sync<G>();
+        if (active) {
+            lux_copy16<G>(M.units, g_units, M.hdr->n_units * 16);
+            lux_copy16<G>(M.cities, g_cities, M.hdr->n_cities * 16);
+            lux_copy16<G>(M.tiles, g_tiles, M.hdr->n_tiles * 2);
+            lux_copy16<G>(M.res, g_res, M.hdr->n_res * 2);
+            lux_copy16<G>(M.uact, g_ua, M.hdr->n_units * 4);
+            lux_copy16<G>(M.tact, g_ta, M.hdr->n_tiles);
+        }
+        lux_sync<G>();
     }
 
     if (check_fit) {
         // growth inside this turn is bounded by the actions actually present: every spawn action may add
         // a unit, every build-city action a tile and a city
         int spawns = 0, builds = 0;
-        const int nu = M.hdr->n_units, nt = M.hdr->n_tiles, nc = M.hdr->n_cities;
-        for (int base = 0; base < nt; base += 32) {
+        const int nu = active ? M.hdr->n_units : 0, nt = active ? M.hdr->n_tiles : 0, nc = active ? M.hdr->n_cities : 0;
+        const int nt_max = lux_wmax<G>(nt), nu_max = lux_wmax<G>(nu);
+        for (int base = 0; base < nt_max; base += G) {
             int p = base + lane;
             int code = p < nt ? M.tact[p] : 0;
-            spawns += __popc(__ballot_sync(0xffffffffu, code == LUX_TA_BUILD_WORKER || code == LUX_TA_BUILD_CART));
+            spawns += __popc(lux_ballot<G>(code == LUX_TA_BUILD_WORKER || code == LUX_TA_BUILD_CART));
         }
-        for (int base = 0; base < nu; base += 32) {
+        for (int base = 0; base < nu_max; base += G) {
             int u = base + lane;
             int kind = u < nu ? (int)(M.uact[u] & 7) : 0;
-            builds += __popc(__ballot_sync(0xffffffffu, kind == LUX_UA_BCITY));
+            builds += __popc(lux_ballot<G>(kind == LUX_UA_BCITY));
         }
-        if (nu + spawns > stage.u || nc + builds > stage.c || nt + builds > stage.t) return LUX_M_SPILL;
+        if (active && (nu + spawns > stage.u || nc + builds > stage.c || nt + builds > stage.t)) { active = 0; result = LUX_M_SPILL; }
     }
+    if (!active) lux_idle_header<G>(M);
+    lux_sync<G>();
 
-    LuxTurnOut T = lux_turn<kS>(M, flags);
-    lux_finish_and_store<kS>(M, T, g_hdr, g_units, g_cities, g_tiles);
+    LuxTurnOut T = lux_turn<kS, G>(M, flags);
+    lux_finish_and_store<kS, G>(M, T, g_hdr, g_units, g_cities, g_tiles, active);
+    if (!active) return result;
     return (!M.hdr->done && (int)M.hdr->n_units + (int)M.hdr->n_tiles > LUX_HEAVY_THRESHOLD) ? LUX_M_HEAVY : LUX_M_PLAYED;
 }
 
@@ -148,14 +161,15 @@ struct LuxSched {
     int hcap;                                        // 0 = scheduling off
 };
 
-template <bool kTma, int kS, int kMode>
-__global__ void __launch_bounds__(64, kMode == kList ? 1 : 16) lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions,
-                                const uint8_t* __restrict__ tile_actions, LuxSmemLayout L, unsigned flags,
-                                LuxStage stage, LuxSched sc) {
+template <bool kTma, int kS, int kMode, int G>
+__global__ void __launch_bounds__((G == 32 && kMode != kList) ? 1024 : 64, 1)
+lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uint8_t* __restrict__ tile_actions,
+                LuxSmemLayout L, unsigned flags, LuxStage stage, LuxSched sc) {
     extern __shared__ __align__(128) unsigned char lux_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpc = blockDim.x >> 5;
-    unsigned char* smem = lux_smem + (size_t)warp * L.total;
+    // a group of G lanes plays one match; 32 / G matches share a warp
+    const int grp = threadIdx.x / G, lane = lux_lane<G>();
+    const int gpc = blockDim.x / G;
+    unsigned char* smem = lux_smem + (size_t)grp * L.total;
     uint32_t phase = 0;
     if (kTma) {
         if (lane == 0) {
@@ -165,36 +179,39 @@ __global__ void __launch_bounds__(64, kMode == kList ? 1 : 16) lux_step_kernel(L
     }
     {   // the per-cell byte planes start clean; every turn leaves them clean again
         const int ncell = (kS > 0 ? kS : b.size) * (kS > 0 ? kS : b.size);
-        lux_zero16(smem + L.p1, (ncell + 15) & ~15);
-        lux_zero16(smem + L.occ, (ncell + 15) & ~15);
+        lux_zero16<G>(smem + L.p1, (ncell + 15) & ~15);
+        lux_zero16<G>(smem + L.occ, (ncell + 15) & ~15);
     }
-    __syncwarp();
+    lux_sync<G>();
     if (kMode == kList) {
         const int count = *sc.retry_cnt;
-        for (int idx = blockIdx.x * wpc + warp; idx < count; idx += gridDim.x * wpc) {
-            lux_step_match<kTma, kS>(b, sc.retry_list[idx], unit_actions, tile_actions, L, smem, flags, stage, false, phase);
-            __syncwarp();
+        for (int idx = blockIdx.x * gpc + grp; lux_wany<G>(idx < count); idx += gridDim.x * gpc) {
+            const int valid = idx < count;
+            lux_step_match<kTma, kS, G>(b, valid ? sc.retry_list[idx] : 0, valid, unit_actions, tile_actions, L, smem, flags, stage,
+                                        false, phase);
+            lux_sync<G>();
         }
         return;
     }
-    const int gidx = blockIdx.x * wpc + warp;
-    int m;
+    const int gidx = blockIdx.x * gpc + grp;
+    int m = 0, valid = 1;
     if (sc.zero_a && gidx == 0 && lane == 0) { *sc.zero_a = 0; *sc.zero_b = 0; }
     if (sc.hcap > 0) {
         if (gidx < sc.hcap) {
             int cnt = *sc.heavy_cnt;
-            if (gidx >= (cnt < sc.hcap ? cnt : sc.hcap)) return;
-            m = sc.heavy_list[gidx];
+            if (gidx >= (cnt < sc.hcap ? cnt : sc.hcap)) valid = 0;
+            else m = sc.heavy_list[gidx];
         } else {
             m = gidx - sc.hcap;
-            if (m >= b.n_matches || sc.hint_cur[m]) return;
+            if (m >= b.n_matches || sc.hint_cur[m]) valid = 0;
         }
     } else {
         m = gidx;
     }
-    if (m < 0 || m >= b.n_matches) return;
-    int r = lux_step_match<kTma, kS>(b, m, unit_actions, tile_actions, L, smem, flags, stage, kMode == kSmall, phase);
-    if (lane == 0) {
+    if (m < 0 || m >= b.n_matches) valid = 0;
+    if (!lux_wany<G>(valid)) return;
+    int r = lux_step_match<kTma, kS, G>(b, m, valid, unit_actions, tile_actions, L, smem, flags, stage, kMode == kSmall, phase);
+    if (valid && lane == 0) {
         if (r == LUX_M_SPILL) sc.retry_list[atomicAdd(sc.retry_cnt, 1)] = m;
         if (sc.hcap > 0) {
             uint8_t heavy = 0;
@@ -213,32 +230,45 @@ static unsigned long long g_launches = 0;
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
 
-template <bool kTma, int kS, int kMode>
+// `gpc` = matches (lane groups) per CTA; the CTA has gpc * G threads
+template <bool kTma, int kS, int kMode, int G>
 static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L, unsigned flags,
-                       LuxStage stage, const LuxSched& sc, int grid, int wpc, cudaStream_t st) {
-    size_t smem = (size_t)L.total * wpc;
-    cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                       LuxStage stage, const LuxSched& sc, int n_groups, int wpc, cudaStream_t st) {
+    const int gpc = wpc * (32 / G);
+    size_t smem = (size_t)L.total * gpc;
+    cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return LUX_E_CUDA;
     if (g_carveout >= 0) {
         // the grid is read in place through L1: leave part of the SM's 256 KB to the cache
-        e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode>, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
+        e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G>, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
         if (e != cudaSuccess) return LUX_E_CUDA;
     }
-    lux_step_kernel<kTma, kS, kMode><<<grid, 32 * wpc, smem, st>>>(*b, ua, ta, L, flags, stage, sc);
+    lux_step_kernel<kTma, kS, kMode, G><<<(n_groups + gpc - 1) / gpc, 32 * wpc, smem, st>>>(*b, ua, ta, L, flags, stage, sc);
     g_launches++;
     return LUX_OK;
 }
 
-template <bool kTma, int kMode>
+template <bool kTma, int kMode, int G>
 static int launch_step_size(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L, unsigned flags,
-                            LuxStage stage, const LuxSched& sc, int grid, int wpc, cudaStream_t st) {
+                            LuxStage stage, const LuxSched& sc, int n_groups, int wpc, cudaStream_t st) {
     switch (kTma ? b->size : 0) {
-        case 12: return launch_step<kTma, 12, kMode>(b, ua, ta, L, flags, stage, sc, grid, wpc, st);
-        case 16: return launch_step<kTma, 16, kMode>(b, ua, ta, L, flags, stage, sc, grid, wpc, st);
-        case 24: return launch_step<kTma, 24, kMode>(b, ua, ta, L, flags, stage, sc, grid, wpc, st);
-        case 32: return launch_step<kTma, 32, kMode>(b, ua, ta, L, flags, stage, sc, grid, wpc, st);
-        default: return launch_step<kTma, 0, kMode>(b, ua, ta, L, flags, stage, sc, grid, wpc, st);
+        case 12: return launch_step<kTma, 12, kMode, G>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
+        case 16: return launch_step<kTma, 16, kMode, G>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
+        case 24: return launch_step<kTma, 24, kMode, G>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
+        case 32: return launch_step<kTma, 32, kMode, G>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
+        default: return launch_step<kTma, 0, kMode, G>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
     }
+}
+
+// lane-group width: 8, 16 or 32 lanes per match (kList, the dense class, always plays with a full warp)
+template <bool kTma, int kMode>
+static int launch_step_group(int group, const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L,
+                             unsigned flags, LuxStage stage, const LuxSched& sc, int n_groups, int wpc, cudaStream_t st) {
+    if constexpr (kTma && kMode != kList) {
+        if (group == 8) return launch_step_size<kTma, kMode, 8>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
+        if (group == 16) return launch_step_size<kTma, kMode, 16>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
+    }
+    return launch_step_size<kTma, kMode, 32>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
 }
 
 // ---------------------------------------------------------------- canonical action stream
@@ -460,6 +490,7 @@ static int g_use_tma = 1;
 static int g_warps_per_cta = 0;   // 0 = automatic
 static int g_two_class = -1;      // -1 automatic, 0 off, 1 always
 static int g_stage[3] = {96, 64, 96};   // small staging class (units, cities, tiles); tests shrink it to force spills
+static int g_group = 0;           // lanes per match: 0 automatic, else 8 / 16 / 32
 static int g_heavy_first = 0;     // schedule the previous step's populous matches first (measured +-0: off)
 // tuning / fallback knobs (tests flip them to cover every launch path)
 extern "C" int lux_b200_set_option(const char* name, int value) {
@@ -468,6 +499,7 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "warps_per_cta")) { g_warps_per_cta = value; return LUX_OK; }
     if (!strcmp(name, "two_class")) { g_two_class = value; return LUX_OK; }
     if (!strcmp(name, "heavy_first")) { g_heavy_first = value != 0; return LUX_OK; }
+    if (!strcmp(name, "group")) { g_group = value; return LUX_OK; }
     if (!strcmp(name, "carveout")) { g_carveout = value > 100 ? 100 : value; return LUX_OK; }
     if (!strcmp(name, "stage_units")) { g_stage[0] = value < 32 ? 32 : (value + 3) & ~3; return LUX_OK; }
     if (!strcmp(name, "stage_cities")) { g_stage[1] = value < 16 ? 16 : value; return LUX_OK; }
@@ -537,23 +569,32 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
     LuxSmemLayout L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
     LuxStage full = {b->u_cap, b->c_cap, b->t_cap};
     if ((size_t)L.total > 227 * 1024) return LUX_E_CAPACITY;
-    // one match per CTA measured fastest for staged footprints of 8 KB and more; pair small matches to
-    // lift the 32-CTA-per-SM limit
-    int wpc = g_warps_per_cta > 0 ? g_warps_per_cta : (L.total >= 8 * 1024 ? 1 : 2);
-    if ((size_t)L.total * wpc > 227 * 1024) wpc = 1;
+    // CTA shape: `wpc` warps, each holding 32 / group matches.  Automatic: one warp per CTA unless the
+    // per-CTA footprint is so small that the 32-CTA-per-SM limit would bind.
+    auto pick_wpc = [&](const LuxSmemLayout& lay, int group) {
+        size_t per_warp = (size_t)lay.total * (32 / group);
+        int w = g_warps_per_cta > 0 ? g_warps_per_cta : (per_warp >= 7 * 1024 ? 1 : 2);
+        while (w > 1 && per_warp * w > 227 * 1024) w--;
+        return w;
+    };
+    auto pick_group = [&](const LuxSmemLayout& lay) {
+        int g = g_group == 8 || g_group == 16 || g_group == 32 ? g_group : 32;   // automatic: measured fastest
+        while (g < 32 && (size_t)lay.total * (32 / g) > 227 * 1024) g *= 2;
+        return g;
+    };
     LuxSched sc;
     memset(&sc, 0, sizeof sc);
     if (!g_use_tma) {
-        rc = launch_step_size<false, kAll>(b, unit_actions, tile_actions, L, flags, full, sc, (b->n_matches + wpc - 1) / wpc, wpc, st);
+        int wpc = pick_wpc(L, 32);
+        rc = launch_step_group<false, kAll>(32, b, unit_actions, tile_actions, L, flags, full, sc, b->n_matches, wpc, st);
         if (rc) return rc;
         return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
     }
 
-    // 96 / 64 / 96 is the largest staging class that still puts 14 matches of a 32x32 map on an SM
     LuxStage small = {g_stage[0] < b->u_cap ? g_stage[0] : b->u_cap, g_stage[1] < b->c_cap ? g_stage[1] : b->c_cap,
                       g_stage[2] < b->t_cap ? g_stage[2] : b->t_cap};
     LuxSmemLayout Ls = lux_smem_layout(b->size, small.u, small.c, small.t, b->r_cap);
-    bool two = g_two_class != 0 && (g_two_class == 1 || (L.total >= 12 * 1024 && Ls.total * 4 <= L.total * 3));
+    bool two = g_two_class != 0 && (g_two_class == 1 || (L.total >= 10 * 1024 && Ls.total * 4 <= L.total * 3));
     bool sched = g_heavy_first != 0;
     StepScratch* S = (two || sched) ? scratch_get(b, st) : nullptr;
     if ((two || sched) && !S) return LUX_E_CUDA;
@@ -580,19 +621,20 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
     }
     if (!two) {
         // single full-capacity launch (small maps, dense batches); spills cannot happen
-        int grid = (b->n_matches + hcap + wpc - 1) / wpc;
-        rc = launch_step_size<true, kAll>(b, unit_actions, tile_actions, L, flags, full, sc, grid, wpc, st);
+        int group = g_group == 8 || g_group == 16 ? pick_group(L) : 32;
+        rc = launch_step_group<true, kAll>(group, b, unit_actions, tile_actions, L, flags, full, sc, b->n_matches + hcap,
+                                           pick_wpc(L, group), st);
         if (rc) return rc;
         return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
     }
-    int wpc_s = g_warps_per_cta > 0 ? g_warps_per_cta : (Ls.total >= 8 * 1024 ? 1 : 2);
-    rc = launch_step_size<true, kSmall>(b, unit_actions, tile_actions, Ls, flags, small, sc,
-                                        (b->n_matches + hcap + wpc_s - 1) / wpc_s, wpc_s, st);
+    int group = pick_group(Ls);
+    rc = launch_step_group<true, kSmall>(group, b, unit_actions, tile_actions, Ls, flags, small, sc, b->n_matches + hcap,
+                                         pick_wpc(Ls, group), st);
     if (rc) return rc;
     rc = cuda_ok(cudaGetLastError(), "lux_step_kernel (small class) launch");
     if (rc) return rc;
     int grid_l = b->n_matches < 148 * 8 ? b->n_matches : 148 * 8;
-    rc = launch_step_size<true, kList>(b, unit_actions, tile_actions, L, flags, full, sc, grid_l, 1, st);
+    rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, L, flags, full, sc, grid_l, 1, st);
     if (rc) return rc;
     rc = cuda_ok(cudaGetLastError(), "lux_step_kernel (retry list) launch");
     if (rc) return rc;

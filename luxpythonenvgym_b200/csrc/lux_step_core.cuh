@@ -160,13 +160,14 @@ LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayou
 // ---- staging with plain 16-byte loads ------------------------------------------------------
 // (the CUDA build normally uses cp.async.bulk instead, see lux_step.cu; this form is what the
 //  host emulation runs and the device uses when the "tma" option is off)
+template <int G = 32>
 LUX_DEV void lux_copy16(void* dst, const void* src, int bytes) {   // bytes rounded up to 16
-    int lane = lux_lane();
+    int lane = lux_lane<G>();
     const uint64_t* s = (const uint64_t*)src;
     uint64_t* d = (uint64_t*)dst;
     int n = (bytes + 15) / 16;
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) { uint64_t a = s[2 * i], b = s[2 * i + 1]; d[2 * i] = a; d[2 * i + 1] = b; }
+    for (int i = lane; i < n; i += G) { uint64_t a = s[2 * i], b = s[2 * i + 1]; d[2 * i] = a; d[2 * i + 1] = b; }
 }
 
 // ---- cell accessors ----------------------------------------------------------------------
@@ -203,40 +204,47 @@ LUX_DEV int lux_cell5(int S, int x, int y, int k) {
     return ((unsigned)nx < (unsigned)S && (unsigned)ny < (unsigned)S) ? ny * S + nx : -1;
 }
 
+template <int G = 32>
 LUX_DEV void lux_zero16(void* p, int bytes) {   // bytes multiple of 16, p 16-byte aligned
-    int lane = lux_lane();
+    int lane = lux_lane<G>();
     uint64_t* q = (uint64_t*)p;
 #pragma unroll 1
-    for (int i = lane; i < bytes / 16; i += 32) { q[2 * i] = 0; q[2 * i + 1] = 0; }
+    for (int i = lane; i < bytes / 16; i += G) { q[2 * i] = 0; q[2 * i + 1] = 0; }
 }
 
 // The two per-cell byte planes must be all-zero when a turn starts; the engine clears every byte it
 // sets before the turn ends, so a warp zeroes them once (here) and then plays any number of matches.
+template <int G = 32>
 LUX_DEV void lux_planes_init(LuxMatch& M) {
-    lux_zero16(M.p1, lux_align16(M.ncell));
-    lux_zero16(M.occ, lux_align16(M.ncell));
+    lux_zero16<G>(M.p1, lux_align16(M.ncell));
+    lux_zero16<G>(M.occ, lux_align16(M.ncell));
 }
+
+// A group without a match to play (past the end of the batch, finished, does not fit the staging class)
+// walks through the turn in lockstep with the other groups of its warp on an empty match: all counts zero.
+template <int G = 32>
+LUX_DEV void lux_idle_header(LuxMatch& M) { lux_zero16<G>(M.hdr, LUX_HDR_BYTES); }
 
 // ---- collection of one resource type (game.py:882-1001) -----------------------------------
 // One inlined copy inside a rolled loop over the resource types, inner loops rolled: the kernel is
 // instruction-fetch sensitive (flat, once-through code far larger than the instruction caches).
 // Works on shared memory only, except for the amount of each requested cell (one global load and one
 // store per cell): which neighbours a worker can mine was cached in umin[] by the unit pass.
-template <int kS>
+template <int kS, int G>
 LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researched0, int researched1) {
-    const int lane = lux_lane();
+    const int lane = lux_lane<G>();
     const int S = kS > 0 ? kS : M.S;
     LuxHeader* h = M.hdr;
     const int rate = rtype == LUX_RES_WOOD ? 20 : rtype == LUX_RES_COAL ? 5 : 2;
     const int fuel_rate = rtype == LUX_RES_WOOD ? 1 : rtype == LUX_RES_COAL ? 10 : 40;
 
     if (lane == 0) *M.reqcnt = 0;
-    lux_sync();
+    lux_sync<G>();
 
     // W1: every eligible worker computes its request amount (create_resource_requests :933-967)
     // and registers the cells it mines from in the request list
 #pragma unroll 1
-    for (int u = lane; u < n_units; u += 32) {
+    for (int u = lane; u < n_units; u += G) {
         const LuxUnit& U = M.units[u];
         int mine = 0xFF;
         unsigned mm = M.umin[u];                      // 0 for carts
@@ -265,12 +273,12 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         }
         M.umine[u] = (uint8_t)mine;
     }
-    lux_sync();
+    lux_sync<G>();
 
     // C: every requested cell resolves its requests (resolve_resource_requests :969-1001)
     const int n_req = *M.reqcnt;
 #pragma unroll 1
-    for (int q = lane; q < n_req; q += 32) {
+    for (int q = lane; q < n_req; q += G) {
         int c = M.reqlist[q];
         int left = M.cells[c].amount;                 // global; consumed after the gather below
         int level = 0;
@@ -346,12 +354,12 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         }
         M.p1[c] = (uint8_t)level;                     // fill level (replaces the request mark)
     }
-    lux_sync();
+    lux_sync<G>();
 
     // W2: workers off city tiles take min(request, level) from each cell, capped by cargo space
     int got0 = 0, got1 = 0;
 #pragma unroll 1
-    for (int u = lane; u < n_units; u += 32) {
+    for (int u = lane; u < n_units; u += G) {
         int mine = M.umine[u];
         if (mine == 0xFF) continue;
         unsigned info = M.uinfo[u];
@@ -375,36 +383,38 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         else U.uranium = (uint16_t)(U.uranium + gain);
         if (unit_team(U)) got1 += gain; else got0 += gain;
     }
-    got0 = lux_reduce_add(got0);
-    got1 = lux_reduce_add(got1);
+    got0 = lux_reduce_add<G>(got0);
+    got1 = lux_reduce_add<G>(got1);
     if (lane == 0) {
         h->collected[0][rtype - 1] += got0;
         h->collected[1][rtype - 1] += got1;
     }
     // the levels of this pass stay in p1 until the regrowth pass clears them: the next type's cells are
     // disjoint from these (a cell holds one resource type)
-    lux_sync();
+    lux_sync<G>();
 }
 
 // exclusive prefix of city tile counts -> M.cprefix[0..n_cities]
+template <int G = 32>
 LUX_DEV void lux_city_prefix(LuxMatch& M, int n_cities) {
-    const int lane = lux_lane();
+    const int lane = lux_lane<G>();
+    const int nc_max = lux_wmax<G>(n_cities);
     int run = 0;
 #pragma unroll 1
-    for (int base = 0; base < n_cities; base += 32) {
+    for (int base = 0; base < nc_max; base += G) {
         int s = base + lane;
         int v = s < n_cities ? M.cities[s].ntiles : 0;
         int tot;
-        int ex = lux_exscan_add(v, &tot);
+        int ex = lux_exscan_add<G>(v, &tot);
         if (s < n_cities) M.cprefix[s] = (uint16_t)(run + ex);
         run += tot;
     }
     if (lane == 0) M.cprefix[n_cities] = (uint16_t)run;
-    lux_sync();
+    lux_sync<G>();
 }
 
 // ---- build a city tile under unit `u` (spawn_city_tile game.py:798-854); lane 0 only ---------
-template <int kS>
+template <int kS, int G>
 LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tiles) {
     LuxHeader* h = M.hdr;
     LuxUnit& U = M.units[u];
@@ -487,10 +497,10 @@ struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; int
 #define UTGT_TILE 0x4000u
 #define UTGT_CELL 0x03FFu
 
-template <int kS>
+template <int kS, int G>
 LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
-    const int lane = lux_lane();
-    const unsigned lt = lux_lanemask_lt();
+    const int lane = lux_lane<G>();
+    const unsigned lt = lux_lanemask_lt<G>();
     LuxHeader* h = M.hdr;
     const int S = kS > 0 ? kS : M.S;
     const int n_units0 = h->n_units;
@@ -505,24 +515,24 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     {
         int nt = n_tiles0 + n_units0;                 // tile indices that can exist during this turn
         if (nt > M.t_cap) nt = M.t_cap;
-        lux_zero16(M.tmask, lux_align16(nt * 4));
+        lux_zero16<G>(M.tmask, lux_align16(nt * 4));
     }
 
     // ---- team city-tile counts (worker_unit_cap_reached game.py:725-735)
     int tt0 = 0, tt1 = 0;
 #pragma unroll 1
-    for (int s = lane; s < n_cities; s += 32) {
+    for (int s = lane; s < n_cities; s += G) {
         if (M.cities[s].team) tt1 += M.cities[s].ntiles; else tt0 += M.cities[s].ntiles;
     }
-    tt0 = lux_reduce_add(tt0);
-    tt1 = lux_reduce_add(tt1);
+    tt0 = lux_reduce_add<G>(tt0);
+    tt1 = lux_reduce_add<G>(tt1);
     const int tu0 = h->n_team_units[0], tu1 = h->n_team_units[1];
 
     int any_move = 0;
     // ---- unit action validation (validate_command game.py:646-695), lanes over units; at most one
     // global cell load per unit (its own cell for a build, the target cell for a move)
 #pragma unroll 1
-    for (int u = lane; u < n_units0; u += 32) {
+    for (int u = lane; u < n_units0; u += G) {
         const LuxUnit& U = M.units[u];
         unsigned w = M.uact[u];
         int kind = w & 7;
@@ -581,15 +591,18 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         M.utgt[u] = (uint16_t)tgt;
         any_move |= (st & 7) == LUX_UA_MOVE;
     }
-    lux_sync();
-    any_move = lux_any(any_move);      // no validated move anywhere: the whole collision stage is a no-op
+    lux_sync<G>();
+    // no validated move anywhere in the warp: the whole collision stage is a no-op (a group without moves
+    // that walks through it with its neighbours sets and clears a few flags, nothing else)
+    const int any_move_w = lux_any_warp(any_move);
+    const int nu0_max = lux_wmax<G>(n_units0);
 
     // ---- MatchController pre-validation of moves (MoveAction.is_valid actions.py:58-116): of the
     // same-team moves into one non-city cell only the first in unit order is buffered; a CENTER
     // move is the do-nothing action and never changes the outcome, so it is dropped here
-    if ((flags & LUX_STEP_PREVALIDATE) && any_move) {
+    if ((flags & LUX_STEP_PREVALIDATE) && any_move_w) {
 #pragma unroll 1
-        for (int base = 0; base < n_units0; base += 32) {
+        for (int base = 0; base < nu0_max; base += G) {
             int u = base + lane;
             unsigned st = u < n_units0 ? M.ust[u] : 0;
             int is_move = (st & 7) == LUX_UA_MOVE;
@@ -598,24 +611,24 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             int t = tg & UTGT_CELL;
             int team = is_move ? unit_team(M.units[u]) : 0;
             int cand = is_move && !center && !(tg & UTGT_TILE);
-            unsigned peers = lux_match_any(cand ? ((t << 1) | team) : (int)(0x40000000 | lane));
+            unsigned peers = lux_match_any<G>(cand ? ((t << 1) | team) : (int)(0x1000 | lane));
             if (center) M.ust[u] = 0;
             if (cand) {
                 unsigned bit = team ? P1_CLAIM1 : P1_CLAIM0;
                 int first = lux_ffs(peers) - 1 == lane;
                 if (!first || (M.p1[t] & bit)) M.ust[u] = 0;
             }
-            lux_sync();
+            lux_sync<G>();
             if (cand && M.ust[u]) lux_atomic_or_byte(M.p1, t, team ? P1_CLAIM1 : P1_CLAIM0);
-            lux_sync();
+            lux_sync<G>();
         }
     }
 
     // ---- collision pruning (handle_movement_actions game.py:1104-1195); shared memory only.
     // Flags are set on every cell (city tiles too) but only ever read on non-city target cells.
-    if (any_move) {
+    if (any_move_w) {
 #pragma unroll 1
-    for (int u = lane; u < n_units0; u += 32) {
+    for (int u = lane; u < n_units0; u += G) {
         const LuxUnit& U = M.units[u];
         int ucell = U.y * S + U.x;
         unsigned st = M.ust[u];
@@ -631,11 +644,11 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             }
         }
     }
-    lux_sync();
+    lux_sync<G>();
     // seeds: >= 2 moves into a non-city cell, or one move into a non-city cell whose single
     // occupant is not moving (:1164-1179)
 #pragma unroll 1
-    for (int u = lane; u < n_units0; u += 32) {
+    for (int u = lane; u < n_units0; u += G) {
         unsigned st = M.ust[u];
         if ((st & 7) != LUX_UA_MOVE) continue;
         unsigned tg = M.utgt[u];
@@ -647,13 +660,13 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             lux_atomic_or_byte(M.p1, U.y * S + U.x, P1_BLOCKED);
         }
     }
-    lux_sync();
+    lux_sync<G>();
     // cascade (revert_action :1138-1156): a reverted mover blocks its own non-city cell
 #pragma unroll 1
     for (;;) {
         int changed = 0;
 #pragma unroll 1
-        for (int u = lane; u < n_units0; u += 32) {
+        for (int u = lane; u < n_units0; u += G) {
             unsigned st = M.ust[u];
             if ((st & 7) != LUX_UA_MOVE || (st & UST_REVERTED)) continue;
             unsigned tg = M.utgt[u];
@@ -665,18 +678,18 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 changed = 1;
             }
         }
-        lux_sync();
-        if (!lux_any(changed)) break;
+        lux_sync<G>();
+        if (!lux_any_warp(changed)) break;
     }
     // the movement flags have served: clear the byte of every cell a unit stands on or aimed at
 #pragma unroll 1
-    for (int u = lane; u < n_units0; u += 32) {
+    for (int u = lane; u < n_units0; u += G) {
         const LuxUnit& U = M.units[u];
         M.p1[U.y * S + U.x] = 0;
         M.p1[M.utgt[u] & UTGT_CELL] = 0;
     }
-    lux_sync();
-    }   // any_move
+    lux_sync<G>();
+    }   // any_move_w
 
     // ---- city tiles: spawn validation (game.py:696-718) + CityTile.turn (city.py:96-120)
     int n_units = n_units0;
@@ -686,21 +699,24 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         int wb0 = 0, wb1 = 0, cb0 = 0, cb1 = 0;
         const int uid0 = h->unit_id_count;
         const int room = M.u_cap - n_units0;
+        const int nt0_max = lux_wmax<G>(n_tiles0);
 #pragma unroll 1
-        for (int base = 0; base < n_tiles0; base += 32) {
+        for (int base = 0; base < nt0_max; base += G) {
             int p = base + lane;
             int valid = p < n_tiles0;
             int code = valid ? M.tact[p] : 0;
             int cell = valid ? M.tiles[p] : 0;
-            LuxCell C = lux_ldcell(M.cells, cell);
+            LuxCell C;
+            C.flags = 0; C.tile_cd = 0;
+            if (valid) C = lux_ldcell(M.cells, cell);
             int team = valid ? cell_tile_team(C) : 0;
             int cd = C.tile_cd;
             int cand = valid && (code == LUX_TA_BUILD_WORKER || code == LUX_TA_BUILD_CART) && cd < 1;
-            unsigned m0 = lux_ballot(cand && team == 0), m1 = lux_ballot(cand && team == 1);
+            unsigned m0 = lux_ballot<G>(cand && team == 0), m1 = lux_ballot<G>(cand && team == 1);
             int rank = team ? acc1 + lux_popc(m1 & lt) : acc0 + lux_popc(m0 & lt);
             int ok = cand && ((team ? tu1 : tu0) + rank < (team ? tt1 : tt0));
             acc0 += lux_popc(m0); acc1 += lux_popc(m1);
-            unsigned mok = lux_ballot(ok);
+            unsigned mok = lux_ballot<G>(ok);
             int srank = spawned + lux_popc(mok & lt);
             spawned += lux_popc(mok);
             int research = valid && code == LUX_TA_RESEARCH &&
@@ -719,12 +735,12 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 acted = 1;
             }
             int okroom = ok && srank < room;
-            wb0 += lux_popc(lux_ballot(okroom && team == 0 && code == LUX_TA_BUILD_WORKER));
-            wb1 += lux_popc(lux_ballot(okroom && team == 1 && code == LUX_TA_BUILD_WORKER));
-            cb0 += lux_popc(lux_ballot(okroom && team == 0 && code == LUX_TA_BUILD_CART));
-            cb1 += lux_popc(lux_ballot(okroom && team == 1 && code == LUX_TA_BUILD_CART));
-            rp0 += lux_popc(lux_ballot(research && team == 0));
-            rp1 += lux_popc(lux_ballot(research && team == 1));
+            wb0 += lux_popc(lux_ballot<G>(okroom && team == 0 && code == LUX_TA_BUILD_WORKER));
+            wb1 += lux_popc(lux_ballot<G>(okroom && team == 1 && code == LUX_TA_BUILD_WORKER));
+            cb0 += lux_popc(lux_ballot<G>(okroom && team == 0 && code == LUX_TA_BUILD_CART));
+            cb1 += lux_popc(lux_ballot<G>(okroom && team == 1 && code == LUX_TA_BUILD_CART));
+            rp0 += lux_popc(lux_ballot<G>(research && team == 0));
+            rp1 += lux_popc(lux_ballot<G>(research && team == 1));
             if (valid) {
                 int cd0 = cd;
                 if (acted) cd = LUX_CITY_ACTION_COOLDOWN;
@@ -744,12 +760,12 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             h->research[0] += rp0; h->research[1] += rp1;
         }
     }
-    lux_sync();
+    lux_sync<G>();
 
     // ---- unit turns (Worker.turn unit.py:162-197, Cart.turn :234-269)
     // moves are conflict-free after pruning: lane-parallel
 #pragma unroll 1
-    for (int u = lane; u < n_units0; u += 32) {
+    for (int u = lane; u < n_units0; u += G) {
         unsigned st = M.ust[u];
         if ((st & 7) != LUX_UA_MOVE) continue;
         int dir = (st >> 3) & 7;
@@ -758,31 +774,37 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         U.x = (uint8_t)(U.x + lux_dx(dir));
         U.y = (uint8_t)(U.y + lux_dy(dir));
     }
-    lux_sync();
-    // transfer / build city / pillage depend on unit order (team A then B == slot order)
+    lux_sync<G>();
+    // transfer / build city / pillage depend on unit order (team A then B == slot order): one pending
+    // action per group and round, the groups of the warp in lockstep
+    const int nu_max = lux_wmax<G>(n_units);
 #pragma unroll 1
-    for (int base = 0; base < n_units0; base += 32) {
+    for (int base = 0; base < nu0_max; base += G) {
         int u = base + lane;
         int k = u < n_units0 ? (M.ust[u] & 7) : 0;
-        unsigned pend = lux_ballot(k == LUX_UA_TRANSFER || k == LUX_UA_BCITY || k == LUX_UA_PILLAGE);
-        while (pend) {
-            int j = lux_ffs(pend) - 1;
-            pend &= pend - 1;
-            int su = base + j;
-            int kind = M.ust[su] & 7;
-            if (kind == LUX_UA_TRANSFER) {                           // transfer_resources game.py:1039-1057
-                unsigned w = M.uact[su];
+        unsigned pend = lux_ballot<G>(k == LUX_UA_TRANSFER || k == LUX_UA_BCITY || k == LUX_UA_PILLAGE);
+#pragma unroll 1
+        while (lux_wany<G>(pend != 0)) {
+            int su = 0, kind = 0;
+            if (pend) {
+                su = base + lux_ffs(pend) - 1;
+                pend &= pend - 1;
+                kind = M.ust[su] & 7;
+            }
+            if (lux_wany<G>(kind == LUX_UA_TRANSFER)) {             // transfer_resources game.py:1039-1057
+                const int xfer = kind == LUX_UA_TRANSFER;
+                unsigned w = xfer ? M.uact[su] : 0u;
                 int dest_id = (int)(w >> 17);
-                int steam = unit_team(M.units[su]);
+                int steam = xfer ? unit_team(M.units[su]) : 0;
                 int dest = -1;
 #pragma unroll 1
-                for (int cb = 0; cb < n_units; cb += 32) {
+                for (int cb = 0; cb < nu_max; cb += G) {
                     int v = cb + lane;
-                    int hit = v < n_units && M.units[v].id == dest_id && unit_team(M.units[v]) == steam;
-                    unsigned hm = lux_ballot(hit);
-                    if (hm) { dest = cb + lux_ffs(hm) - 1; break; }
+                    int hit = xfer && v < n_units && M.units[v].id == dest_id && unit_team(M.units[v]) == steam;
+                    unsigned hm = lux_ballot<G>(hit);
+                    if (hm && dest < 0) dest = cb + lux_ffs(hm) - 1;
                 }
-                if (lane == 0) {
+                if (xfer && lane == 0) {
                     int r = (int)((w >> 3) & 3);
                     if (dest < 0 || r > 2) {
                         M.ust[su] = (uint8_t)(kind | UST_FAILED);
@@ -799,11 +821,12 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                         *cbp = (uint16_t)(*cbp + amt);
                     }
                 }
-            } else if (lane == 0) {
+            }
+            if ((kind == LUX_UA_BCITY || kind == LUX_UA_PILLAGE) && lane == 0) {
                 LuxUnit& U = M.units[su];
                 if (!unit_is_cart(U)) {
                     if (kind == LUX_UA_BCITY) {
-                        lux_build_city_lane0<kS>(M, su, n_cities, n_tiles);
+                        lux_build_city_lane0<kS, G>(M, su, n_cities, n_tiles);
                         int spent = 0;                                // expend_resources_for_city unit.py:146-160
                         uint16_t* cg[3] = {&U.wood, &U.coal, &U.uranium};
 #pragma unroll 1
@@ -819,13 +842,13 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                     }
                 }
             }
-            lux_sync();
+            lux_sync<G>();
         }
     }
-    n_cities = lux_shfl(n_cities, 0);
-    n_tiles = lux_shfl(n_tiles, 0);
+    n_cities = lux_shfl<G>(n_cities, 0);
+    n_tiles = lux_shfl<G>(n_tiles, 0);
     if (n_tiles != n_tiles0) tiles_dirty = 1;
-    lux_city_prefix(M, n_cities);     // also syncs
+    lux_city_prefix<G>(M, n_cities);     // also syncs
 
     // ---- the unit pass: cooldowns of the acting units, the carts' automatic roads (unit.py:196-197,
     // :257-269), and the per-unit caches the rest of the turn works from -- what the unit stands on
@@ -834,7 +857,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     {
         int rb0 = 0, rb1 = 0, bad = 0;
 #pragma unroll 1
-        for (int u = lane; u < n_units; u += 32) {
+        for (int u = lane; u < n_units; u += G) {
             LuxUnit& U = M.units[u];
             const int isold = u < n_units0;
             unsigned st = isold ? M.ust[u] : 0u;
@@ -876,15 +899,15 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             M.umin[u] = (uint16_t)mm;
             M.ust[u] = 0;
         }
-        rb0 = lux_reduce_add(rb0);
-        rb1 = lux_reduce_add(rb1);
-        bad = lux_any(bad);
+        rb0 = lux_reduce_add<G>(rb0);
+        rb1 = lux_reduce_add<G>(rb1);
+        bad = lux_any<G>(bad);
         if (lane == 0) {
             h->roads_built_q[0] += rb0; h->roads_built_q[1] += rb1;
             if (bad) h->status |= LUX_ST_BAD_STATE;
         }
     }
-    lux_sync();
+    lux_sync<G>();
 
     // ---- resource collection: uranium, coal, wood (distribute_all_resources game.py:868-880)
     {
@@ -892,8 +915,8 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 #pragma unroll 1
         for (int rtype = LUX_RES_URANIUM; rtype >= LUX_RES_WOOD; rtype--) {
             int need = rtype == LUX_RES_WOOD ? 0 : rtype == LUX_RES_COAL ? LUX_RESEARCH_COAL : LUX_RESEARCH_URANIUM;
-            if (rp0 < need && rp1 < need) continue;           // nobody may mine this type yet
-            lux_collect_type<kS>(M, rtype, n_units, rp0 >= need, rp1 >= need);
+                    if (!lux_wany<G>(rp0 >= need || rp1 >= need)) continue;   // nobody in the warp may mine this type yet
+            lux_collect_type<kS, G>(M, rtype, n_units, rp0 >= need, rp1 >= need);
         }
     }
 
@@ -901,7 +924,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     {
         int fg0 = 0, fg1 = 0;
 #pragma unroll 1
-        for (int u = lane; u < n_units; u += 32) {
+        for (int u = lane; u < n_units; u += G) {
             LuxUnit& U = M.units[u];
             unsigned info = M.uinfo[u];
             M.occ[U.y * S + U.x] = 0;               // collection is over: drop the occupant mark again
@@ -912,17 +935,19 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 U.wood = 0; U.coal = 0; U.uranium = 0;
             }
         }
-        fg0 = lux_reduce_add(fg0);
-        fg1 = lux_reduce_add(fg1);
+        fg0 = lux_reduce_add<G>(fg0);
+        fg1 = lux_reduce_add<G>(fg1);
         if (lane == 0) { h->fuel_generated[0] += fg0; h->fuel_generated[1] += fg1; }
     }
-    lux_sync();
+    lux_sync<G>();
 
-    // ---- night (handle_night game.py:537-558)
-    if (night) {
+    // ---- night (handle_night game.py:537-558); matches of one warp differ in their turn counters, so
+    // the phase runs when any of them has night and the others walk through it with empty lists
+    if (lux_wany<G>(night)) {
+        const int nc_n = night ? n_cities : 0, nu_n = night ? n_units : 0;
         int died = 0;
 #pragma unroll 1
-        for (int s = lane; s < n_cities; s += 32) {
+        for (int s = lane; s < nc_n; s += G) {
             LuxCity& city = M.cities[s];
             M.cremap[s] = 0;
             if (city.ntiles == 0) continue;
@@ -930,12 +955,12 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             if (city.fuel < upkeep) { M.cremap[s] = 1; died = 1; }
             else city.fuel -= upkeep;
         }
-        lux_sync();
-        died = lux_any(died);
+        lux_sync<G>();
+        died = lux_any<G>(died);
         if (died) {
             tiles_dirty = 1;
 #pragma unroll 1
-            for (int t = lane; t < n_tiles; t += 32) {                // destroy_city :1059-1070
+            for (int t = lane; t < n_tiles; t += G) {                // destroy_city :1059-1070
                 int tc = M.tiles[t];
                 LuxCell C = lux_ldcell(M.cells, tc);
                 if (cell_is_tile(C) && M.cremap[C.city_slot]) {
@@ -947,7 +972,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             }
         }
 #pragma unroll 1
-        for (int u = lane; u < n_units; u += 32) {                    // spend_fuel_to_survive unit.py:64-98
+        for (int u = lane; u < nu_n; u += G) {                        // spend_fuel_to_survive unit.py:64-98
             LuxUnit& U = M.units[u];
             unsigned info = M.uinfo[u];
             if (info & UI_TILE) {
@@ -972,15 +997,15 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 if (unit_team(U)) died1++; else died0++;
             }
         }
-        died0 = lux_reduce_add(died0);
-        died1 = lux_reduce_add(died1);
-        lux_sync();
+        died0 = lux_reduce_add<G>(died0);
+        died1 = lux_reduce_add<G>(died1);
+        lux_sync<G>();
         if (died) {
 #pragma unroll 1
-            for (int s = lane; s < n_cities; s += 32)
+            for (int s = lane; s < n_cities; s += G)
                 if (M.cremap[s]) { M.cities[s].ntiles = 0; M.cities[s].fuel = 0; M.cities[s].adjsum = 0; }
-            lux_sync();
         }
+        lux_sync<G>();
     }
 
     // ---- depleted cells leave the list (game.py:498-510), trees regrow (:1081-1102): four resource
@@ -988,12 +1013,12 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     {
         const int n_res = h->n_res;
 #pragma unroll 1
-        for (int base = 0; base < n_res; base += 128) {
+        for (int base = 0; base < n_res; base += 4 * G) {
             int idx[4];
             LuxCell c[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                int r = base + 32 * k + lane;
+                int r = base + G * k + lane;
                 idx[k] = r < n_res ? (int)M.res[r] : -1;
                 if (idx[k] >= 0) c[k] = lux_ldcell(M.cells, idx[k]);
             }
@@ -1010,7 +1035,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             }
         }
     }
-    lux_sync();
+    lux_sync<G>();
 
     LuxTurnOut out;
     out.n_units = n_units; out.n_cities = n_cities; out.n_tiles = n_tiles; out.tiles_dirty = tiles_dirty;
@@ -1020,54 +1045,57 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 
 // ---- epilogue: compaction, match_over, cooldowns, canonical tile order, store ---------------
 // g_* are the match's sections in global memory (the grid is already up to date there).
-template <int kS>
+template <int kS, int G>
 LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g_hdr, LuxUnit* g_units,
-                                  LuxCity* g_cities, uint16_t* g_tiles) {
-    const int lane = lux_lane();
-    const unsigned lt = lux_lanemask_lt();
+                                  LuxCity* g_cities, uint16_t* g_tiles, int active) {
+    const int lane = lux_lane<G>();
+    const unsigned lt = lux_lanemask_lt<G>();
     LuxHeader* h = M.hdr;
     const int S = kS > 0 ? kS : M.S;
 
     // cities: drop the dead (ntiles == 0), keep order
     int n_alive = 0, nc0 = 0, nc1 = 0, tl0 = 0, tl1 = 0;
+    const int nc_max = lux_wmax<G>(T.n_cities);
 #pragma unroll 1
-    for (int base = 0; base < T.n_cities; base += 32) {
+    for (int base = 0; base < nc_max; base += G) {
         int s = base + lane;
         int alive = s < T.n_cities && M.cities[s].ntiles > 0;
-        unsigned m = lux_ballot(alive);
+        unsigned m = lux_ballot<G>(alive);
         if (s < T.n_cities) M.cremap[s] = (uint8_t)(alive ? n_alive + lux_popc(m & lt) : 0xFF);
         n_alive += lux_popc(m);
         int team = alive ? M.cities[s].team : 0;
         nc0 += alive && team == 0; nc1 += alive && team == 1;
         if (alive) { if (team) tl1 += M.cities[s].ntiles; else tl0 += M.cities[s].ntiles; }
     }
-    nc0 = lux_reduce_add(nc0); nc1 = lux_reduce_add(nc1);
-    tl0 = lux_reduce_add(tl0); tl1 = lux_reduce_add(tl1);
-    lux_sync();
+    nc0 = lux_reduce_add<G>(nc0); nc1 = lux_reduce_add<G>(nc1);
+    tl0 = lux_reduce_add<G>(tl0); tl1 = lux_reduce_add<G>(tl1);
+    lux_sync<G>();
     const int cities_moved = n_alive != T.n_cities;
     // store cities compacted
 #pragma unroll 1
-    for (int s = lane; s < T.n_cities; s += 32) {
+    for (int s = lane; s < T.n_cities; s += G) {
         int ns = M.cremap[s];
         if (ns != 0xFF) g_cities[ns] = M.cities[s];
     }
     // canonical tile list: position = prefix[new slot] + key; surviving tiles of moved cities get their
     // new slot written into the grid in the same pass
     int n_tiles_live = tl0 + tl1;
-    if (T.tiles_dirty || cities_moved) {
+    const int relist = T.tiles_dirty || cities_moved;
+    if (lux_wany<G>(relist)) {
+        const int nt_r = relist ? T.n_tiles : 0;
         int run = 0;
 #pragma unroll 1
-        for (int base = 0; base < T.n_cities; base += 32) {
+        for (int base = 0; base < nc_max; base += G) {
             int s = base + lane;
             int v = (s < T.n_cities) ? M.cities[s].ntiles : 0;   // dead cities have 0 tiles
             int tot;
-            int ex = lux_exscan_add(v, &tot);
-            if (s < T.n_cities && v > 0) M.cprefix[M.cremap[s]] = (uint16_t)(run + ex);
+            int ex = lux_exscan_add<G>(v, &tot);
+            if (relist && s < T.n_cities && v > 0) M.cprefix[M.cremap[s]] = (uint16_t)(run + ex);
             run += tot;
         }
-        lux_sync();
+        lux_sync<G>();
 #pragma unroll 1
-        for (int t = lane; t < T.n_tiles; t += 32) {
+        for (int t = lane; t < nt_r; t += G) {
             int cell = M.tiles[t];
             LuxCell C = lux_ldcell(M.cells, cell);
             if (cell_is_tile(C)) {
@@ -1084,12 +1112,13 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
 
     // run_cooldowns (game.py:560-568) and the stable partition team A | team B while storing
     int run0 = 0, run1 = 0;
+    const int nu_max = lux_wmax<G>(T.n_units);
 #pragma unroll 1
-    for (int base = 0; base < T.n_units; base += 32) {
+    for (int base = 0; base < nu_max; base += G) {
         int u = base + lane;
         int valid = u < T.n_units && !(M.ust[u] & UST_FAILED);
         int team = valid ? unit_team(M.units[u]) : 0;
-        unsigned m0 = lux_ballot(valid && team == 0), m1 = lux_ballot(valid && team == 1);
+        unsigned m0 = lux_ballot<G>(valid && team == 0), m1 = lux_ballot<G>(valid && team == 1);
         if (valid) {
             LuxUnit U = M.units[u];
             int road = (M.uinfo[u] & UI_TILE) ? LUX_MAX_ROAD_Q : (int)M.cells[U.y * S + U.x].road_q;    // cell.py:77-85
@@ -1122,12 +1151,7 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
             h->winner = (uint8_t)w;
         }
     }
-    lux_sync();
-    // header: a straight copy (8 lanes x 16 bytes)
-    if (lane < LUX_HDR_BYTES / 16) {
-        const uint64_t* hs = (const uint64_t*)M.hdr;
-        uint64_t* hd = (uint64_t*)g_hdr;
-        uint64_t a = hs[2 * lane], b = hs[2 * lane + 1];
-        hd[2 * lane] = a; hd[2 * lane + 1] = b;
-    }
+    lux_sync<G>();
+    // header: a straight copy
+    if (active) lux_copy16<G>(g_hdr, M.hdr, LUX_HDR_BYTES);
 }

@@ -15,6 +15,7 @@ from oracle.coracle import LuxBatchC, _p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = None
+GROUP = 32     # lane-group width the emulated step runs with (8 / 16 / 32); tests sweep it
 
 
 def lib():
@@ -33,7 +34,7 @@ def lib():
     return _LIB
 
 
-def step(ms, unit_words, tile_bytes, flags=0):
+def step(ms, unit_words, tile_bytes, flags=0, group=None):
     """One turn of one MatchState in place through the emulated kernel."""
     L = lib()
     hdr = ms.hdr.reshape(1)
@@ -46,11 +47,36 @@ def step(ms, unit_words, tile_bytes, flags=0):
     b = LuxBatchC(1, ms.size, len(ms.units), len(ms.cities), len(ms.tiles), len(ms.res),
                   hdr.ctypes.data, ms.cells.ctypes.data, ms.units.ctypes.data, ms.cities.ctypes.data,
                   ms.tiles.ctypes.data, ms.res.ctypes.data)
-    rc = L.lux_emu_step(ctypes.byref(b), _p(uw), _p(tb), int(flags))
+    rc = L.lux_emu_step_group(ctypes.byref(b), _p(uw), _p(tb), int(flags), int(group or GROUP))
     ms.hdr = hdr[0]
     if rc != 0:
         raise RuntimeError("lux_emu_step -> %d" % rc)
     return bool(ms.hdr["done"])
+
+
+def step_many(states, unit_words, tile_bytes, flags=0, group=None):
+    """One turn of several same-size MatchStates in place as ONE batch: with group < 32 they share
+    warps (32 / group lane groups in lockstep), which is what the multi-match kernel runs."""
+    L = lib()
+    n, ms0 = len(states), states[0]
+    arr = {k: np.ascontiguousarray(np.stack([getattr(ms, k).view(np.uint8).reshape(-1) for ms in states]))
+           for k in ("cells", "units", "cities", "tiles", "res")}
+    arr["hdr"] = np.ascontiguousarray(np.stack([ms.hdr.reshape(1).view(np.uint8).reshape(-1) for ms in states]))
+    uw = np.zeros((n, len(ms0.units)), dtype=np.uint32)
+    tb = np.zeros((n, len(ms0.tiles)), dtype=np.uint8)
+    for i in range(n):
+        uw[i] = unit_words[i][: uw.shape[1]]
+        tb[i] = tile_bytes[i][: tb.shape[1]]
+    b = LuxBatchC(n, ms0.size, len(ms0.units), len(ms0.cities), len(ms0.tiles), len(ms0.res),
+                  *[arr[k].ctypes.data for k in ("hdr", "cells", "units", "cities", "tiles", "res")])
+    rc = L.lux_emu_step_group(ctypes.byref(b), _p(uw), _p(tb), int(flags), int(group or GROUP))
+    if rc != 0:
+        raise RuntimeError("lux_emu_step_group -> %d" % rc)
+    for i, ms in enumerate(states):
+        ms.hdr = arr["hdr"][i].view(ms.hdr.dtype)[0].copy()
+        for k in ("cells", "units", "cities", "tiles", "res"):
+            dst = getattr(ms, k)
+            dst[...] = arr[k][i].view(dst.dtype).reshape(dst.shape)
 
 
 def observe(ms, team, e_cap=640):

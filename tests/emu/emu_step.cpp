@@ -18,12 +18,17 @@ struct EmuArgs {
     LuxSmemLayout L;
     unsigned flags;
     int dirty;
+    int group;
 };
 
+template <int G>
 static void emu_lane(void* p) {
     EmuArgs* a = (EmuArgs*)p;
     const LuxBatch* b = a->b;
-    int m = a->m;
+    const int grp = lux_lane32() / G;
+    int m = a->m + grp;                       // 32 / G matches per warp, one lane group each
+    int active = m < b->n_matches;
+    if (!active) m = 0;
     int ncell = b->size * b->size;
     LuxHeader* g_hdr = b->hdr + m;
     LuxCell* g_cells = b->cells + (size_t)m * ncell;
@@ -32,23 +37,28 @@ static void emu_lane(void* p) {
     uint16_t* g_tiles = b->tiles + (size_t)m * b->t_cap;
     uint16_t* g_res = b->res + (size_t)m * b->r_cap;
     LuxMatch M;
-    lux_match_bind(M, a->smem, a->L, g_cells, b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
-    lux_planes_init(M);
-    lux_copy16(M.hdr, g_hdr, LUX_HDR_BYTES);
-    lux_sync();
-    if (M.hdr->done) return;
-    lux_copy16(M.units, g_units, M.hdr->n_units * 16);
-    lux_copy16(M.cities, g_cities, M.hdr->n_cities * 16);
-    lux_copy16(M.tiles, g_tiles, M.hdr->n_tiles * 2);
-    lux_copy16(M.res, g_res, M.hdr->n_res * 2);
-    lux_copy16(M.uact, a->ua + (size_t)m * b->u_cap, M.hdr->n_units * 4);
-    lux_copy16(M.tact, a->ta + (size_t)m * b->t_cap, M.hdr->n_tiles);
-    lux_sync();
-    LuxTurnOut T = b->size == 32 ? lux_turn<32>(M, a->flags) : lux_turn<0>(M, a->flags);
-    lux_finish_and_store<0>(M, T, g_hdr, g_units, g_cities, g_tiles);
-    lux_sync();
+    lux_match_bind(M, a->smem + (size_t)grp * a->L.total, a->L, g_cells, b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    lux_planes_init<G>(M);
+    if (active) lux_copy16<G>(M.hdr, g_hdr, LUX_HDR_BYTES);
+    lux_sync<G>();
+    if (active && M.hdr->done) active = 0;
+    lux_sync<G>();                            // every lane has read the header before an idle group clears it
+    if (active) {
+        lux_copy16<G>(M.units, g_units, M.hdr->n_units * 16);
+        lux_copy16<G>(M.cities, g_cities, M.hdr->n_cities * 16);
+        lux_copy16<G>(M.tiles, g_tiles, M.hdr->n_tiles * 2);
+        lux_copy16<G>(M.res, g_res, M.hdr->n_res * 2);
+        lux_copy16<G>(M.uact, a->ua + (size_t)m * b->u_cap, M.hdr->n_units * 4);
+        lux_copy16<G>(M.tact, a->ta + (size_t)m * b->t_cap, M.hdr->n_tiles);
+    } else {
+        lux_idle_header<G>(M);
+    }
+    lux_sync<G>();
+    LuxTurnOut T = b->size == 32 ? lux_turn<32, G>(M, a->flags) : lux_turn<0, G>(M, a->flags);
+    lux_finish_and_store<0, G>(M, T, g_hdr, g_units, g_cities, g_tiles, active);
+    lux_sync<G>();
     // the engine's contract: both byte planes are clean again after the turn
-    for (int i = lux_lane(); i < ncell; i += 32)
+    for (int i = lux_lane<G>(); i < ncell; i += G)
         if (M.p1[i] || M.occ[i]) a->dirty = 1;
 }
 
@@ -56,19 +66,26 @@ extern "C" size_t lux_emu_smem_bytes(int size, int u_cap, int c_cap, int t_cap, 
     return (size_t)lux_smem_layout(size, u_cap, c_cap, t_cap, r_cap).total;
 }
 
-extern "C" int lux_emu_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions, unsigned flags) {
+extern "C" int lux_emu_step_group(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions, unsigned flags,
+                                  int group) {
     if (!b || !unit_actions || !tile_actions) return LUX_E_ARG;
+    if (group != 8 && group != 16 && group != 32) return LUX_E_ARG;
     EmuArgs a;
-    a.b = b; a.ua = unit_actions; a.ta = tile_actions; a.flags = flags; a.dirty = 0;
+    a.b = b; a.ua = unit_actions; a.ta = tile_actions; a.flags = flags; a.dirty = 0; a.group = group;
     a.L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
-    a.smem = (unsigned char*)aligned_alloc(16, a.L.total);
-    for (int m = 0; m < b->n_matches; m++) {
-        memset(a.smem, 0xA5, a.L.total);   // shared memory is not zero-initialised on the device either
+    const int gpw = 32 / group;
+    a.smem = (unsigned char*)aligned_alloc(16, (size_t)a.L.total * gpw);
+    for (int m = 0; m < b->n_matches; m += gpw) {
+        memset(a.smem, 0xA5, (size_t)a.L.total * gpw);   // shared memory is not zero-initialised on the device either
         a.m = m;
-        warp_emu::run_warp(emu_lane, &a);
+        warp_emu::run_warp(group == 8 ? emu_lane<8> : group == 16 ? emu_lane<16> : emu_lane<32>, &a, 32);
     }
     free(a.smem);
     return a.dirty ? -100 : 0;
+}
+
+extern "C" int lux_emu_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions, unsigned flags) {
+    return lux_emu_step_group(b, unit_actions, tile_actions, flags, 32);
 }
 
 // ---- observations through the emulated warp ------------------------------------------------

@@ -62,6 +62,33 @@ def test_emulated_step_random(k):
         assert ms.digest() == int(digests[turn]), "match %d turn %d" % (k, turn)
 
 
+@pytest.mark.parametrize("group", [8, 16])
+def test_emulated_step_lockstep_groups(group):
+    """Several different matches share one warp (32 / group lane groups in lockstep): dense late-game
+    states next to fresh sparse ones, different turn counters (day and night in one warp), a finished
+    match and an odd batch size so that idle groups walk along."""
+    zd, zr = G.npz("dense"), G.npz("random")
+    names = [nm for nm in G.dense_names() if int(zd[nm + "/size"]) == 32][:3]
+    a = [recap(G.get_state(zd, nm + "/init")) for nm in names]
+    ids = [int(nm.split("@")[1]) for nm in names]
+    for k in range(int(zr["n"])):
+        ms = recap(G.get_state(zr, "%d/init" % k))
+        if ms.size == 32 and len(a) < 9:
+            a.append(ms)
+            ids.append(k)
+    assert len(a) >= 6
+    b = [ms.copy() for ms in a]
+    seed = int(zd["stream_seed"])
+    for turn in range(70):
+        acts = [coracle.gen_actions(ms, seed, i) for ms, i in zip(a, ids)]
+        for ms, (uw, tb) in zip(a, acts):
+            if not ms.hdr["done"]:
+                coracle.step(ms, uw, tb)
+        emu.step_many(b, [x[0] for x in acts], [x[1] for x in acts], group=group)
+        for i, (x, y) in enumerate(zip(a, b)):
+            assert x.diff(y) == [], "group %d turn %d match %d" % (group, turn, i)
+
+
 @pytest.mark.parametrize("name", G.obs_names())
 def test_emulated_observations(name):
     z = G.npz("obs")

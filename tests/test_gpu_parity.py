@@ -32,11 +32,14 @@ def _recap(ms, caps):
     return o
 
 
-@pytest.mark.parametrize("tma,two_class,heavy_first", [(1, -1, 1), (1, 1, 0), (1, 0, 1), (1, 0, 0), (0, -1, 1)])
-def test_replays_bit_exact(tma, two_class, heavy_first):
+@pytest.mark.parametrize("tma,two_class,heavy_first,group", [(1, -1, 1, 0), (1, 1, 0, 16), (1, 0, 1, 32), (1, 0, 0, 8),
+                                                              (1, 1, 0, 32), (0, -1, 1, 0)])
+def test_replays_bit_exact(tma, two_class, heavy_first, group):
     """The 7 Kaggle episodes of the reference's test_replay.py, 360 turns each, through every launch
-    path: TMA staging with the automatic / forced / disabled two-class launch, and plain loads."""
+    path: TMA staging with the automatic / forced / disabled two-class launch, 8 / 16 / 32 lanes per match,
+    and plain loads."""
     lib = _lib.load()
+    lib.lux_b200_set_option(b"group", group)
     lib.lux_b200_set_option(b"tma", tma)
     lib.lux_b200_set_option(b"two_class", two_class)
     lib.lux_b200_set_option(b"heavy_first", heavy_first)
@@ -57,6 +60,7 @@ def test_replays_bit_exact(tma, two_class, heavy_first):
                     assert ms.digest() == int(digests[turn]), "replay %s turn %d" % (rid, turn)
             assert g.headers()["done"][0] == 1
     finally:
+        lib.lux_b200_set_option(b"group", 0)
         lib.lux_b200_set_option(b"tma", 1)
         lib.lux_b200_set_option(b"two_class", -1)
         lib.lux_b200_set_option(b"heavy_first", 1)
@@ -409,7 +413,8 @@ def test_spill_list_and_scheduling_paths_under_load():
     sparse = mapgen.generate_batch(np.arange(4000, 4096), 32)
     try:
         for heavy in (0, 1):
-            for k, v in ((b"stage_units", 32), (b"stage_cities", 16), (b"stage_tiles", 32), (b"two_class", 1), (b"heavy_first", heavy)):
+            for k, v in ((b"stage_units", 32), (b"stage_cities", 16), (b"stage_tiles", 32), (b"two_class", 1), (b"heavy_first", heavy),
+                         (b"group", 16 if heavy else 8)):
                 assert lib.lux_b200_set_option(k, v) == 0
             n = 384
             g = _game(n, 32)
@@ -438,5 +443,6 @@ def test_spill_list_and_scheduling_paths_under_load():
         for i, gm in enumerate(games):
             assert len(gpu_util.diff_batches(hosts[i], gm)) == 0, i
     finally:
-        for k, v in ((b"stage_units", 96), (b"stage_cities", 64), (b"stage_tiles", 96), (b"two_class", -1), (b"heavy_first", 0)):
+        for k, v in ((b"stage_units", 96), (b"stage_cities", 64), (b"stage_tiles", 96), (b"two_class", -1), (b"heavy_first", 0),
+                     (b"group", 0)):
             lib.lux_b200_set_option(k, v)
