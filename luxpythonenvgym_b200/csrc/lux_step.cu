@@ -18,224 +18,170 @@
 #define LUX_B200_VERSION 100
 
 // ---------------------------------------------------------------- the step kernel
-// Speculative first batch: these many leading records of each list travel together with the header
-// and the cell grid, so a typical (sparse) match needs ONE global->shared round trip; only matches
-// with more entities issue a second batch for the remainder.
-#define LUX_PRE_UNITS 32
-#define LUX_PRE_CITIES 16
-#define LUX_PRE_TILES 32
-
-// Launch modes.  The staged footprint of a match is dominated by capacity, not by content: with the
-// default 32x32 capacities (252 units / 255 cities / 384 tiles) a match needs 25 KB of shared memory and
-// only 8 warps fit on an SM, although a typical match holds a dozen entities.  So a step is two launches:
-//   kSmall : every match; shared memory is sized for `stage` capacities (e.g. 64/64/96); a match whose
-//            populations could outgrow them during this turn is appended to a retry list instead;
-//   kList  : the retry list, full capacities, grid-stride over the list.
+// Launch modes.  A match's shared-memory slice is laid out for what THIS turn can touch (LuxNeed: live lists
+// + worst-case growth, ~3 KB for a typical match), not for the batch capacities (252 units / 255 cities /
+// 384 tiles = 18 KB at 32x32).  A step is therefore
+//   classify : one thread per match reads the header, marks the matches whose turn does not fit the small
+//              slice (cls[m] = 1) and appends them to the big list;
+//   kList    : the big list, slices sized for the full capacities, grid-stride over the list;
+//   kSmall   : every other match, `slice` bytes each (default 4.5 KB: 32 resident matches leave room for the
+//              L1 cache the in-place grid accesses run through).  Launched as a programmatic dependent of
+//              kList (griddepcontrol), so the two run CONCURRENTLY: a dense match is a long single-warp job
+//              (30-45 us) and as a separate serialized launch it added that much to every step.
 // kAll is the single full-capacity launch (small maps, dense batches, the non-TMA path).
 enum { kAll = 0, kSmall = 1, kList = 2 };
-
-struct LuxStage { int u, c, t; };      // shared-memory staging capacities (units, cities, tiles)
-
-// result of one match: skipped because finished, did not fit the staging class, or played
-// (LUX_M_HEAVY: its end-of-turn population is above the "schedule first next step" threshold)
-enum { LUX_M_DONE = 0, LUX_M_SPILL = 1, LUX_M_PLAYED = 2, LUX_M_HEAVY = 3 };
-#define LUX_HEAVY_THRESHOLD 28     // units + tiles
 
 // One lane group plays match `m` (or, with valid == 0, walks along on an empty match: the groups of a
 // warp run in lockstep and every collective needs all 32 lanes).
 template <bool kTma, int kS, int G>
-__device__ __forceinline__ int lux_step_match(const LuxBatch& b, int m, int valid, const uint32_t* __restrict__ unit_actions,
-                                               const uint8_t* __restrict__ tile_actions, const LuxSmemLayout& L,
-                                               unsigned char* smem, unsigned flags, const LuxStage& stage,
-                                               bool check_fit, uint32_t& phase) {
+__device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int valid, const uint32_t* __restrict__ unit_actions,
+                                               const uint8_t* __restrict__ tile_actions, unsigned char* smem, unsigned flags,
+                                               int slice, uint32_t& phase) {
     const int lane = lux_lane<G>();
     const int size = kS > 0 ? kS : b.size;
     const int ncell = size * size;
     if (!valid) m = 0;
-    LuxHeader* g_hdr = b.hdr + m;
-    LuxCell* g_cells = b.cells + (size_t)m * ncell;
-    LuxUnit* g_units = b.units + (size_t)m * b.u_cap;
-    LuxCity* g_cities = b.cities + (size_t)m * b.c_cap;
-    uint16_t* g_tiles = b.tiles + (size_t)m * b.t_cap;
-    const uint16_t* g_res = b.res + (size_t)m * b.r_cap;
-    const uint32_t* g_ua = unit_actions + (size_t)m * b.u_cap;
-    const uint8_t* g_ta = tile_actions + (size_t)m * b.t_cap;
+    LuxGlobalMatch g;
+    g.hdr = b.hdr + m;
+    g.cells = b.cells + (size_t)m * ncell;
+    g.units = b.units + (size_t)m * b.u_cap;
+    g.cities = b.cities + (size_t)m * b.c_cap;
+    g.tiles = b.tiles + (size_t)m * b.t_cap;
+    g.res = b.res + (size_t)m * b.r_cap;
+    g.uact = unit_actions + (size_t)m * b.u_cap;
+    g.tact = tile_actions + (size_t)m * b.t_cap;
     LuxMatch M;
-    lux_match_bind(M, smem, L, g_cells, size, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
-    int active = valid, result = LUX_M_DONE;
+    int active, result;
 
     if (kTma) {
-        uint64_t* bar = (uint64_t*)(smem + L.mbar);
-        const uint32_t pu = min(stage.u, LUX_PRE_UNITS), pc = min(stage.c, LUX_PRE_CITIES), pt = min(stage.t, LUX_PRE_TILES);
-        const uint32_t b_res = b.r_cap * 2;
+        const LuxNeed none = lux_need_turn(0, 0, 0, 0, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
+        const LuxSmemLayout L0 = lux_smem_layout_need(size, none);         // fixed part: planes, barrier, header
+        uint64_t* bar = (uint64_t*)(smem + L0.mbar);
+        LuxHeader* sh = (LuxHeader*)(smem + L0.hdr);
+        active = valid; result = LUX_M_DONE;
+        // trip 1: the header
         if (active && lane == 0) {
-            mbar_expect_tx(bar, LUX_HDR_BYTES + b_res + pu * 16 + pc * 16 + pt * 2 + pu * 4 + pt);
-            tma_g2s(M.hdr, g_hdr, LUX_HDR_BYTES, bar);
-            tma_g2s(M.units, g_units, pu * 16, bar);
-            tma_g2s(M.uact, g_ua, pu * 4, bar);
-            tma_g2s(M.cities, g_cities, pc * 16, bar);
-            tma_g2s(M.tiles, g_tiles, pt * 2, bar);
-            tma_g2s(M.tact, g_ta, pt, bar);
-            tma_g2s(M.res, g_res, b_res, bar);
+            mbar_expect_tx(bar, LUX_HDR_BYTES);
+            tma_g2s(sh, g.hdr, LUX_HDR_BYTES, bar);
         }
         lux_sync<G>();
         if (active) { mbar_wait(bar, phase); phase ^= 1; }
-        uint32_t nu = 0, nc = 0, nt = 0;
+        if (active && sh->done) active = 0;
+        LuxNeed need = none;
+        uint32_t nu = 0, nc = 0, nt = 0, nr = 0;
         if (active) {
-            if (M.hdr->done) active = 0;
-            nu = M.hdr->n_units; nc = M.hdr->n_cities; nt = M.hdr->n_tiles;
+            nu = sh->n_units; nc = sh->n_cities; nt = sh->n_tiles; nr = sh->n_res;
+            need = lux_need_turn(nu, nc, nt, nr, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
         }
-        // the live lists themselves must fit the staging arrays before anything more is loaded
-        if (active && check_fit && (nu > (uint32_t)stage.u || nc > (uint32_t)stage.c || nt > (uint32_t)stage.t)) {
+        LuxSmemLayout L = lux_smem_layout_need(size, need);
+        if (active && L.total > slice) {
             active = 0; result = LUX_M_SPILL;
+            need = none;
+            L = L0;
         }
-        const int more = active && (nu > pu || nc > pc || nt > pt);   // group-uniform
-        if (more && lane == 0) {
-            const uint32_t ru = nu > pu ? nu - pu : 0, rc = nc > pc ? nc - pc : 0;
-            const uint32_t rt2 = nt > pt ? ((nt - pt) * 2 + 15) & ~15u : 0;
-            const uint32_t rua = nu > pu ? ((nu - pu) * 4 + 15) & ~15u : 0, rta = nt > pt ? ((nt - pt) + 15) & ~15u : 0;
-            mbar_expect_tx(bar, ru * 16 + rc * 16 + rt2 + rua + rta);
-            if (ru) tma_g2s(M.units + pu, g_units + pu, ru * 16, bar);
-            if (rc) tma_g2s(M.cities + pc, g_cities + pc, rc * 16, bar);
-            if (rt2) tma_g2s(M.tiles + pt, g_tiles + pt, rt2, bar);
-            if (rua) tma_g2s(M.uact + pu, g_ua + pu, rua, bar);
-            if (rta) tma_g2s(M.tact + pt, g_ta + pt, rta, bar);
+        lux_match_bind(M, smem, L, g.cells, size, need);
+        // trip 2: the live lists and this turn's action words, one bulk-copy batch
+        if (active && lane == 0) {
+            const uint32_t bu = nu * 16, bua = (nu * 4 + 15) & ~15u, bc = nc * 16, bt = (nt * 2 + 15) & ~15u,
+                           bta = (nt + 15) & ~15u, br = (nr * 2 + 15) & ~15u;
+            mbar_expect_tx(bar, bu + bua + bc + bt + bta + br);
+            if (bu) { tma_g2s(M.units, g.units, bu, bar); tma_g2s(M.uact, g.uact, bua, bar); }
+            if (bc) tma_g2s(M.cities, g.cities, bc, bar);
+            if (bt) { tma_g2s(M.tiles, g.tiles, bt, bar); tma_g2s(M.tact, g.tact, bta, bar); }
+            if (br) tma_g2s(M.res, g.res, br, bar);
         }
         lux_sync<G>();        // also: every lane has read the header before an idle group clears it
-        if (more) { mbar_wait(bar, phase); phase ^= 1; }
+        if (active) { mbar_wait(bar, phase); phase ^= 1; }
+        else lux_idle_header<G>(M);
+        lux_sync<G>();
     } else {
-        if (active) lux_copy16<G>(M.hdr, g_hdr, LUX_HDR_BYTES);
-        lux_sync<G>();
-        if (active && M.hdr->done) active = 0;
-        lux_sync<G>();
-        if (active) {
-            lux_copy16<G>(M.units, g_units, M.hdr->n_units * 16);
-            lux_copy16<G>(M.cities, g_cities, M.hdr->n_cities * 16);
-            lux_copy16<G>(M.tiles, g_tiles, M.hdr->n_tiles * 2);
-            lux_copy16<G>(M.res, g_res, M.hdr->n_res * 2);
-            lux_copy16<G>(M.uact, g_ua, M.hdr->n_units * 4);
-            lux_copy16<G>(M.tact, g_ta, M.hdr->n_tiles);
-        }
-        lux_sync<G>();
+        active = lux_stage_plain<G>(M, smem, g, valid, size, b.u_cap, b.c_cap, b.t_cap, b.r_cap, slice, &result);
     }
-
-    if (check_fit) {
-        // growth inside this turn is bounded by the actions actually present: every spawn action may add
-        // a unit, every build-city action a tile and a city
-        int spawns = 0, builds = 0;
-        const int nu = active ? M.hdr->n_units : 0, nt = active ? M.hdr->n_tiles : 0, nc = active ? M.hdr->n_cities : 0;
-        const int nt_max = lux_wmax<G>(nt), nu_max = lux_wmax<G>(nu);
-        for (int base = 0; base < nt_max; base += G) {
-            int p = base + lane;
-            int code = p < nt ? M.tact[p] : 0;
-            spawns += __popc(lux_ballot<G>(code == LUX_TA_BUILD_WORKER || code == LUX_TA_BUILD_CART));
-        }
-        for (int base = 0; base < nu_max; base += G) {
-            int u = base + lane;
-            int kind = u < nu ? (int)(M.uact[u] & 7) : 0;
-            builds += __popc(lux_ballot<G>(kind == LUX_UA_BCITY));
-        }
-        if (active && (nu + spawns > stage.u || nc + builds > stage.c || nt + builds > stage.t)) { active = 0; result = LUX_M_SPILL; }
-    }
-    if (!active) lux_idle_header<G>(M);
-    lux_sync<G>();
 
     LuxTurnOut T = lux_turn<kS, G>(M, flags);
-    lux_finish_and_store<kS, G>(M, T, g_hdr, g_units, g_cities, g_tiles, active);
-    if (!active) return result;
-    return (!M.hdr->done && (int)M.hdr->n_units + (int)M.hdr->n_tiles > LUX_HEAVY_THRESHOLD) ? LUX_M_HEAVY : LUX_M_PLAYED;
+    lux_finish_and_store<kS, G>(M, T, g.hdr, g.units, g.cities, g.tiles, active);
+    // cannot happen (the classification pass routes such a match to the big class); visible if it ever does
+    if (valid && result == LUX_M_SPILL && lane == 0) atomicOr((unsigned*)&g.hdr->done, (unsigned)LUX_ST_BAD_STATE << 16);   // done | winner | status | size
 }
 
-// Scheduling scratch (device pointers, owned by the library, see StepScratch below).
-//  * retry list: matches the small staging class could not hold this step (consumed by kList);
-//  * heavy list: matches whose population was above LUX_HEAVY_THRESHOLD at the end of the previous step.
-//    The first `hcap` CTAs of a launch take their match from this list, the remaining CTAs walk the
-//    matches in index order and skip the ones flagged in `hint_cur`: long jobs start first, which removes
-//    the tail a late-starting dense match would otherwise add to the launch (LPT scheduling).
-//    Lists and hints are hints only: a stale or empty list just means index order.
+// Classification of one step (device pointers, owned by the library, see StepScratch below).
 struct LuxSched {
-    int* retry_cnt; int* retry_list;                 // this step
-    const int* heavy_cnt; const int* heavy_list; const uint8_t* hint_cur;   // built during the previous step
-    int* heavy_next_cnt; int* heavy_next; uint8_t* hint_next;               // built now
-    int* zero_a; int* zero_b;                        // counters to clear for the step after
-    int hcap;                                        // 0 = scheduling off
+    int* big_cnt; int* big_list;      // matches of the big class (written by classify, read by kList)
+    uint8_t* cls;                     // [n] 1 = big class (kSmall skips it)
+    int* zero;                        // the previous step's counter: trailed to the host, then cleared for reuse
+    int* seen_host;                   // pinned, mapped host word
 };
+
+__global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m == 0) { *sc.seen_host = *sc.zero; *sc.zero = 0; }     // a stale value only delays the host's mode switch
+    if (m >= b.n_matches) return;
+    const LuxHeader* h = b.hdr + m;
+    int big = 0;
+    if (!h->done) {
+        LuxNeed need = lux_need_turn(h->n_units, h->n_cities, h->n_tiles, h->n_res, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
+        big = lux_smem_layout_need(b.size, need).total > slice;
+    }
+    sc.cls[m] = (uint8_t)big;
+    if (big) sc.big_list[atomicAdd(sc.big_cnt, 1)] = m;
+}
 
 template <bool kTma, int kS, int kMode, int G>
 __global__ void __launch_bounds__((G == 32 && kMode != kList) ? 1024 : 64, 1)
 lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uint8_t* __restrict__ tile_actions,
-                LuxSmemLayout L, unsigned flags, LuxStage stage, LuxSched sc) {
+                int slice, unsigned flags, LuxSched sc) {
     extern __shared__ __align__(128) unsigned char lux_smem[];
+    // the small class may start while this (big) class is still running: the two touch disjoint matches
+    if (kMode == kList) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // a group of G lanes plays one match; 32 / G matches share a warp
     const int grp = threadIdx.x / G, lane = lux_lane<G>();
     const int gpc = blockDim.x / G;
-    unsigned char* smem = lux_smem + (size_t)grp * L.total;
+    unsigned char* smem = lux_smem + (size_t)grp * slice;
     uint32_t phase = 0;
-    if (kTma) {
-        if (lane == 0) {
-            mbar_init((uint64_t*)(smem + L.mbar), 1);
+    if (kMode == kList && (int)(blockIdx.x * gpc) >= *sc.big_cnt) return;      // past the end of the big list
+    {   // fixed part of the slice: the per-cell byte planes start clean (every turn leaves them clean again)
+        const int size = kS > 0 ? kS : b.size;
+        const LuxSmemLayout L0 = lux_smem_layout_need(size, lux_need_turn(0, 0, 0, 0, b.u_cap, b.c_cap, b.t_cap, b.r_cap));
+        if (kTma && lane == 0) {
+            mbar_init((uint64_t*)(smem + L0.mbar), 1);
             fence_mbar_init();
         }
-    }
-    {   // the per-cell byte planes start clean; every turn leaves them clean again
-        const int ncell = (kS > 0 ? kS : b.size) * (kS > 0 ? kS : b.size);
-        lux_zero16<G>(smem + L.p1, (ncell + 15) & ~15);
-        lux_zero16<G>(smem + L.occ, (ncell + 15) & ~15);
+        lux_zero16<G>(smem + L0.p1, (size * size + 15) & ~15);
+        lux_zero16<G>(smem + L0.occ, (size * size + 15) & ~15);
     }
     lux_sync<G>();
     if (kMode == kList) {
-        const int count = *sc.retry_cnt;
+        const int count = *sc.big_cnt;
         for (int idx = blockIdx.x * gpc + grp; lux_wany<G>(idx < count); idx += gridDim.x * gpc) {
             const int valid = idx < count;
-            lux_step_match<kTma, kS, G>(b, valid ? sc.retry_list[idx] : 0, valid, unit_actions, tile_actions, L, smem, flags, stage,
-                                        false, phase);
+            lux_step_match<kTma, kS, G>(b, valid ? sc.big_list[idx] : 0, valid, unit_actions, tile_actions, smem, flags, slice, phase);
             lux_sync<G>();
         }
         return;
     }
-    const int gidx = blockIdx.x * gpc + grp;
-    int m = 0, valid = 1;
-    if (sc.zero_a && gidx == 0 && lane == 0) { *sc.zero_a = 0; *sc.zero_b = 0; }
-    if (sc.hcap > 0) {
-        if (gidx < sc.hcap) {
-            int cnt = *sc.heavy_cnt;
-            if (gidx >= (cnt < sc.hcap ? cnt : sc.hcap)) valid = 0;
-            else m = sc.heavy_list[gidx];
-        } else {
-            m = gidx - sc.hcap;
-            if (m >= b.n_matches || sc.hint_cur[m]) valid = 0;
-        }
-    } else {
-        m = gidx;
-    }
-    if (m < 0 || m >= b.n_matches) valid = 0;
-    if (!lux_wany<G>(valid)) return;
-    int r = lux_step_match<kTma, kS, G>(b, m, valid, unit_actions, tile_actions, L, smem, flags, stage, kMode == kSmall, phase);
-    if (valid && lane == 0) {
-        if (r == LUX_M_SPILL) sc.retry_list[atomicAdd(sc.retry_cnt, 1)] = m;
-        if (sc.hcap > 0) {
-            uint8_t heavy = 0;
-            if (r == LUX_M_SPILL || r == LUX_M_HEAVY) {
-                int i = atomicAdd(sc.heavy_next_cnt, 1);
-                if (i < sc.hcap) { sc.heavy_next[i] = m; heavy = 1; }
-            }
-            sc.hint_next[m] = heavy;
-        }
-    }
+    const int m = blockIdx.x * gpc + grp;
+    int valid = m < b.n_matches;
+    if (kMode == kSmall && valid && sc.cls[m]) valid = 0;          // the big class plays it
+    if (lux_wany<G>(valid))
+        lux_step_match<kTma, kS, G>(b, m, valid, unit_actions, tile_actions, smem, flags, slice, phase);
+    // a programmatic dependent may not finish before its primary: later work on the stream waits for this grid
+    if (kMode == kSmall) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // kernels this library has launched (all entry points of this translation unit); bench.py reports the
 // difference over its timed region as "gpu_launches"
 static unsigned long long g_launches = 0;
+static int g_list_grid = 0;       // CTAs of the big-class launch (0 = automatic)
+static int g_overlap = 1;         // 1 = the small class is a programmatic dependent of the big class (they overlap)
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
 
-// `gpc` = matches (lane groups) per CTA; the CTA has gpc * G threads
+// `gpc` = matches (lane groups) per CTA; the CTA has gpc * G threads and gpc slices of `slice` bytes
 template <bool kTma, int kS, int kMode, int G>
-static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L, unsigned flags,
-                       LuxStage stage, const LuxSched& sc, int n_groups, int wpc, cudaStream_t st) {
+static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, int slice, unsigned flags, const LuxSched& sc,
+                       int n_groups, int wpc, cudaStream_t st) {
     const int gpc = wpc * (32 / G);
-    size_t smem = (size_t)L.total * gpc;
+    size_t smem = (size_t)slice * gpc;
     cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return LUX_E_CUDA;
     if (g_carveout >= 0) {
@@ -243,32 +189,50 @@ static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta,
         e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G>, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
         if (e != cudaSuccess) return LUX_E_CUDA;
     }
-    lux_step_kernel<kTma, kS, kMode, G><<<(n_groups + gpc - 1) / gpc, 32 * wpc, smem, st>>>(*b, ua, ta, L, flags, stage, sc);
+    if (kMode == kSmall && g_overlap) {
+        // programmatic dependent launch: may start as soon as every CTA of the preceding big-class kernel has
+        // issued griddepcontrol.launch_dependents (its first instruction)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((n_groups + gpc - 1) / gpc);
+        cfg.blockDim = dim3(32 * wpc);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, lux_step_kernel<kTma, kS, kMode, G>, *b, ua, ta, slice, flags, sc);
+        if (e != cudaSuccess) return LUX_E_CUDA;
+    } else {
+        lux_step_kernel<kTma, kS, kMode, G><<<(n_groups + gpc - 1) / gpc, 32 * wpc, smem, st>>>(*b, ua, ta, slice, flags, sc);
+    }
     g_launches++;
     return LUX_OK;
 }
 
 template <bool kTma, int kMode, int G>
-static int launch_step_size(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L, unsigned flags,
-                            LuxStage stage, const LuxSched& sc, int n_groups, int wpc, cudaStream_t st) {
+static int launch_step_size(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, int slice, unsigned flags, const LuxSched& sc,
+                            int n_groups, int wpc, cudaStream_t st) {
     switch (kTma ? b->size : 0) {
-        case 12: return launch_step<kTma, 12, kMode, G>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
-        case 16: return launch_step<kTma, 16, kMode, G>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
-        case 24: return launch_step<kTma, 24, kMode, G>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
-        case 32: return launch_step<kTma, 32, kMode, G>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
-        default: return launch_step<kTma, 0, kMode, G>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
+        case 12: return launch_step<kTma, 12, kMode, G>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
+        case 16: return launch_step<kTma, 16, kMode, G>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
+        case 24: return launch_step<kTma, 24, kMode, G>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
+        case 32: return launch_step<kTma, 32, kMode, G>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
+        default: return launch_step<kTma, 0, kMode, G>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
     }
 }
 
 // lane-group width: 8, 16 or 32 lanes per match (kList, the dense class, always plays with a full warp)
 template <bool kTma, int kMode>
-static int launch_step_group(int group, const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, const LuxSmemLayout& L,
-                             unsigned flags, LuxStage stage, const LuxSched& sc, int n_groups, int wpc, cudaStream_t st) {
+static int launch_step_group(int group, const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, int slice, unsigned flags,
+                             const LuxSched& sc, int n_groups, int wpc, cudaStream_t st) {
     if constexpr (kTma && kMode != kList) {
-        if (group == 8) return launch_step_size<kTma, kMode, 8>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
-        if (group == 16) return launch_step_size<kTma, kMode, 16>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
+        if (group == 8) return launch_step_size<kTma, kMode, 8>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
+        if (group == 16) return launch_step_size<kTma, kMode, 16>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
     }
-    return launch_step_size<kTma, kMode, 32>(b, ua, ta, L, flags, stage, sc, n_groups, wpc, st);
+    return launch_step_size<kTma, kMode, 32>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
 }
 
 // ---------------------------------------------------------------- canonical action stream
@@ -317,8 +281,8 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
     }
     const uint64_t mid = match_id_base + (uint64_t)m;
     // only the live prefix (rounded up to the staging granule) is written: the step kernel never looks further
-    const int nu_w = done ? 0 : min(b.u_cap, max((nu + 3) & ~3, LUX_PRE_UNITS));
-    const int nt_w = done ? 0 : min(b.t_cap, max((nt + 15) & ~15, LUX_PRE_TILES));
+    const int nu_w = done ? 0 : min(b.u_cap, (nu + 3) & ~3);
+    const int nt_w = done ? 0 : min(b.t_cap, (nt + 15) & ~15);
     for (int i = lane; i < nu_w; i += 32) {
         uint32_t w = 0;
         if (!done && i < nu) {
@@ -489,32 +453,30 @@ extern "C" size_t lux_b200_step_smem_bytes(int size, int u_cap, int c_cap, int t
 static int g_use_tma = 1;
 static int g_warps_per_cta = 0;   // 0 = automatic
 static int g_two_class = -1;      // -1 automatic, 0 off, 1 always
-static int g_stage[3] = {96, 64, 96};   // small staging class (units, cities, tiles); tests shrink it to force spills
+static int g_slice = 0;           // shared-memory bytes per match of the small class (0 = default); tests shrink it to force spills
 static int g_group = 0;           // lanes per match: 0 automatic, else 8 / 16 / 32
-static int g_heavy_first = 0;     // schedule the previous step's populous matches first (measured +-0: off)
 // tuning / fallback knobs (tests flip them to cover every launch path)
 extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!name) return LUX_E_ARG;
     if (!strcmp(name, "tma")) { g_use_tma = value != 0; return LUX_OK; }
     if (!strcmp(name, "warps_per_cta")) { g_warps_per_cta = value; return LUX_OK; }
     if (!strcmp(name, "two_class")) { g_two_class = value; return LUX_OK; }
-    if (!strcmp(name, "heavy_first")) { g_heavy_first = value != 0; return LUX_OK; }
+    if (!strcmp(name, "list_grid")) { g_list_grid = value; return LUX_OK; }
+    if (!strcmp(name, "overlap")) { g_overlap = value != 0; return LUX_OK; }
     if (!strcmp(name, "group")) { g_group = value; return LUX_OK; }
     if (!strcmp(name, "carveout")) { g_carveout = value > 100 ? 100 : value; return LUX_OK; }
-    if (!strcmp(name, "stage_units")) { g_stage[0] = value < 32 ? 32 : (value + 3) & ~3; return LUX_OK; }
-    if (!strcmp(name, "stage_cities")) { g_stage[1] = value < 16 ? 16 : value; return LUX_OK; }
-    if (!strcmp(name, "stage_tiles")) { g_stage[2] = value < 32 ? 32 : (value + 15) & ~15; return LUX_OK; }
+    if (!strcmp(name, "slice")) { g_slice = value; return LUX_OK; }
     return LUX_E_ARG;
 }
 
-// Scheduling scratch of one batch (keyed by its header pointer; a few batches are cached so that
-// interleaved batches -- mixed map sizes, a pool -- each keep their own lists).
+// Per-batch scratch (keyed by its header pointer; a few batches are cached so that interleaved batches --
+// mixed map sizes, a pool -- each keep their own lists).
 struct StepScratch {
     const void* key; int n; int dev;
-    int* counts;                 // [0..2] heavy counts (3-way rotation), [3..5] retry counts
-    int* lists;                  // heavy[2][n] then retry[n]
-    unsigned char* hints;        // [2][n]
-    int* seen;                   // pinned host copy of a recent retry count (may be stale)
+    int* counts;                 // [0..2] big-class counts (3-way rotation: this step, next, being cleared)
+    int* list;                   // [n] big-class matches of this step
+    unsigned char* cls;          // [n] 1 = big class
+    int* seen;                   // pinned host copy of a recent big-class count (may be stale)
     uint2* entries[2];           // sparse host actions of this / the previous call (device copies)
     int entries_cap, entries_prev_n, entries_flip;
     uint8_t* done_dev;           // compact done flags for the host path
@@ -527,8 +489,8 @@ static unsigned g_scratch_clock = 0;
 
 static void scratch_free(StepScratch& s) {
     if (s.counts) cudaFree(s.counts);
-    if (s.lists) cudaFree(s.lists);
-    if (s.hints) cudaFree(s.hints);
+    if (s.list) cudaFree(s.list);
+    if (s.cls) cudaFree(s.cls);
     if (s.seen) cudaFreeHost(s.seen);
     for (int k = 0; k < 2; k++) if (s.entries[k]) cudaFree(s.entries[k]);
     if (s.done_dev) cudaFree(s.done_dev);
@@ -546,12 +508,11 @@ static StepScratch* scratch_get(const LuxBatch* b, cudaStream_t st) {
         if (!s.key) { slot = &s; break; }
     if (!slot) { slot = &g_scratch[g_scratch_clock++ % 8]; cudaStreamSynchronize(st); scratch_free(*slot); }
     size_t n = (size_t)b->n_matches;
-    if (cudaMalloc(&slot->counts, 8 * sizeof(int)) != cudaSuccess) return nullptr;
-    if (cudaMalloc(&slot->lists, 3 * n * sizeof(int)) != cudaSuccess) return nullptr;
-    if (cudaMalloc(&slot->hints, 2 * n) != cudaSuccess) return nullptr;
-    if (cudaMallocHost(&slot->seen, sizeof(int)) != cudaSuccess) return nullptr;
-    if (cudaMemsetAsync(slot->counts, 0, 8 * sizeof(int), st) != cudaSuccess) return nullptr;
-    if (cudaMemsetAsync(slot->hints, 0, 2 * n, st) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&slot->counts, 4 * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&slot->list, n * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&slot->cls, n) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&slot->seen, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    if (cudaMemsetAsync(slot->counts, 0, 4 * sizeof(int), st) != cudaSuccess) return nullptr;
     *slot->seen = 0;
     slot->key = b->hdr; slot->n = b->n_matches; slot->dev = dev; slot->step = 0; slot->dense_hold = 0;
     return slot;
@@ -566,80 +527,72 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    LuxSmemLayout L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
-    LuxStage full = {b->u_cap, b->c_cap, b->t_cap};
-    if ((size_t)L.total > 227 * 1024) return LUX_E_CAPACITY;
+    const int full = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap).total;   // slice for the batch capacities
+    if ((size_t)full > 227 * 1024) return LUX_E_CAPACITY;
     // CTA shape: `wpc` warps, each holding 32 / group matches.  Automatic: one warp per CTA unless the
     // per-CTA footprint is so small that the 32-CTA-per-SM limit would bind.
-    auto pick_wpc = [&](const LuxSmemLayout& lay, int group) {
-        size_t per_warp = (size_t)lay.total * (32 / group);
+    auto pick_wpc = [&](int slice, int group) {
+        size_t per_warp = (size_t)slice * (32 / group);
         int w = g_warps_per_cta > 0 ? g_warps_per_cta : (per_warp >= 7 * 1024 ? 1 : 2);
         while (w > 1 && per_warp * w > 227 * 1024) w--;
         return w;
     };
-    auto pick_group = [&](const LuxSmemLayout& lay) {
+    auto pick_group = [&](int slice) {
         int g = g_group == 8 || g_group == 16 || g_group == 32 ? g_group : 32;   // automatic: measured fastest
-        while (g < 32 && (size_t)lay.total * (32 / g) > 227 * 1024) g *= 2;
+        while (g < 32 && (size_t)slice * (32 / g) > 227 * 1024) g *= 2;
         return g;
     };
     LuxSched sc;
     memset(&sc, 0, sizeof sc);
     if (!g_use_tma) {
-        int wpc = pick_wpc(L, 32);
-        rc = launch_step_group<false, kAll>(32, b, unit_actions, tile_actions, L, flags, full, sc, b->n_matches, wpc, st);
+        rc = launch_step_group<false, kAll>(32, b, unit_actions, tile_actions, full, flags, sc, b->n_matches, pick_wpc(full, 32), st);
         if (rc) return rc;
         return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
     }
 
-    LuxStage small = {g_stage[0] < b->u_cap ? g_stage[0] : b->u_cap, g_stage[1] < b->c_cap ? g_stage[1] : b->c_cap,
-                      g_stage[2] < b->t_cap ? g_stage[2] : b->t_cap};
-    LuxSmemLayout Ls = lux_smem_layout(b->size, small.u, small.c, small.t, b->r_cap);
-    bool two = g_two_class != 0 && (g_two_class == 1 || (L.total >= 10 * 1024 && Ls.total * 4 <= L.total * 3));
-    bool sched = g_heavy_first != 0;
-    StepScratch* S = (two || sched) ? scratch_get(b, st) : nullptr;
-    if ((two || sched) && !S) return LUX_E_CUDA;
+    // the small class: every match whose turn fits `small` bytes (the empty-match floor is planes + header)
+    const int floor_bytes = lux_smem_layout_need(b->size, lux_need_turn(0, 0, 0, 0, b->u_cap, b->c_cap, b->t_cap, b->r_cap)).total;
+    int small = (g_slice > 0 ? g_slice : 4608);
+    if (small < floor_bytes + 256) small = floor_bytes + 256;
+    small = (small + 127) & ~127;
+    bool two = g_two_class != 0 && (g_two_class == 1 || small * 2 <= full);
+    if (small > full) { small = full; two = false; }
+    StepScratch* S = two ? scratch_get(b, st) : nullptr;
+    if (two && !S) return LUX_E_CUDA;
     if (two && g_two_class < 0) {
+        // when most of the batch is in the big class (dense batches) one full-capacity launch is the better shape
         if (S->dense_hold > 0) { S->dense_hold--; two = false; }
         else if (*S->seen * 2 > b->n_matches) { S->dense_hold = 64; *S->seen = 0; two = false; }
     }
-    int hcap = 0;
-    if (S) {
-        const size_t n = (size_t)b->n_matches;
-        const unsigned t = S->step++;
-        sc.retry_cnt = S->counts + 3 + t % 3;
-        sc.retry_list = S->lists + 2 * n;
-        sc.heavy_cnt = S->counts + t % 3;
-        sc.heavy_list = S->lists + (t & 1) * n;
-        sc.hint_cur = S->hints + (t & 1) * n;
-        sc.heavy_next_cnt = S->counts + (t + 1) % 3;
-        sc.heavy_next = S->lists + ((t + 1) & 1) * n;
-        sc.hint_next = S->hints + ((t + 1) & 1) * n;
-        sc.zero_a = S->counts + (t + 2) % 3;
-        sc.zero_b = S->counts + 3 + (t + 1) % 3;
-        hcap = sched ? (b->n_matches / 4 + 64) : 0;
-        sc.hcap = hcap;
-    }
     if (!two) {
-        // single full-capacity launch (small maps, dense batches); spills cannot happen
-        int group = g_group == 8 || g_group == 16 ? pick_group(L) : 32;
-        rc = launch_step_group<true, kAll>(group, b, unit_actions, tile_actions, L, flags, full, sc, b->n_matches + hcap,
-                                           pick_wpc(L, group), st);
+        // single full-capacity launch (small maps, dense batches)
+        int group = g_group == 8 || g_group == 16 ? pick_group(full) : 32;
+        rc = launch_step_group<true, kAll>(group, b, unit_actions, tile_actions, full, flags, sc, b->n_matches, pick_wpc(full, group), st);
         if (rc) return rc;
         return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
     }
-    int group = pick_group(Ls);
-    rc = launch_step_group<true, kSmall>(group, b, unit_actions, tile_actions, Ls, flags, small, sc, b->n_matches + hcap,
-                                         pick_wpc(Ls, group), st);
+    const unsigned t = S->step++;
+    sc.big_cnt = S->counts + t % 3;
+    sc.big_list = S->list;
+    sc.cls = S->cls;
+    sc.zero = S->counts + (t + 2) % 3;
+    sc.seen_host = S->seen;
+    lux_classify_kernel<<<(b->n_matches + 255) / 256, 256, 0, st>>>(*b, small, sc);
+    g_launches++;
+    rc = cuda_ok(cudaGetLastError(), "lux_classify_kernel launch");
     if (rc) return rc;
-    rc = cuda_ok(cudaGetLastError(), "lux_step_kernel (small class) launch");
+    // one CTA per big match up to a quarter of the batch (grid-stride beyond); CTAs past the list leave at once
+    int grid_l = b->n_matches / 4 > 148 * 4 ? b->n_matches / 4 : 148 * 4;
+    if (g_list_grid > 0) grid_l = g_list_grid;
+    if (grid_l > b->n_matches) grid_l = b->n_matches;
+    rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, full, flags, sc, grid_l, 1, st);
     if (rc) return rc;
-    int grid_l = b->n_matches < 148 * 8 ? b->n_matches : 148 * 8;
-    rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, L, flags, full, sc, grid_l, 1, st);
+    rc = cuda_ok(cudaGetLastError(), "lux_step_kernel (big class) launch");
     if (rc) return rc;
-    rc = cuda_ok(cudaGetLastError(), "lux_step_kernel (retry list) launch");
+    int group = pick_group(small);
+    rc = launch_step_group<true, kSmall>(group, b, unit_actions, tile_actions, small, flags, sc, b->n_matches, pick_wpc(small, group), st);
     if (rc) return rc;
-    // trail the retry count to the host without synchronising; a stale value only delays the mode switch
-    return cuda_ok(cudaMemcpyAsync(S->seen, sc.retry_cnt, sizeof(int), cudaMemcpyDeviceToHost, st), "retry count copy");
+    return cuda_ok(cudaGetLastError(), "lux_step_kernel (small class) launch");
 }
 
 extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,

@@ -59,43 +59,72 @@
 #define UI_OWN  0x02000000u   // ... of the unit's own team
 
 struct LuxSmemLayout {
-    int hdr, units, cities, tiles, res, uact, tact, utgt, ust, umine, uinfo, umin, tmask, cprefix, cremap, reqlist, p1, occ, mbar, total;
+    int p1, occ, mbar, hdr, units, cities, tiles, res, uact, tact, utgt, ust, umine, uinfo, umin, tmask, cprefix, cremap, reqlist, total;
 };
 
 LUX_DEV int lux_align16(int x) { return (x + 15) & ~15; }
 
+// What one turn of a match can touch: its live lists plus the most they can grow before the turn ends
+// (every city tile may spawn a unit, every unit may found a city with one tile), its resource list and the
+// request list of a collection pass.  The shared-memory slice of a match is laid out for exactly this, so a
+// typical match (a dozen entities) takes ~3 KB although the batch capacities are 252 / 255 / 384.
+struct LuxNeed { int u, c, t, r, q; };
+
 #ifdef LUX_EMULATE
-static inline
+#define LUX_HD static inline
 #else
-__host__ __device__ inline
+#define LUX_HD __host__ __device__ inline
 #endif
-LuxSmemLayout lux_smem_layout(int size, int u_cap, int c_cap, int t_cap, int r_cap) {
+
+LUX_HD LuxNeed lux_need_caps(int u_cap, int c_cap, int t_cap, int r_cap) {
+    LuxNeed n; n.u = u_cap; n.c = c_cap; n.t = t_cap; n.r = r_cap; n.q = r_cap;
+    return n;
+}
+
+LUX_HD LuxNeed lux_need_turn(int n_units, int n_cities, int n_tiles, int n_res, int u_cap, int c_cap, int t_cap, int r_cap) {
+    LuxNeed n;
+    n.u = (n_units + n_tiles + 3) & ~3;    if (n.u > u_cap) n.u = u_cap;     // spawns: at most one per city tile
+    n.c = n_cities + n_units;              if (n.c > c_cap) n.c = c_cap;     // new cities: at most one per unit
+    if (n.c < 1) n.c = 1;
+    n.t = (n_tiles + n_units + 15) & ~15;  if (n.t > t_cap) n.t = t_cap;     // new tiles: at most one per unit
+    n.r = (n_res + 7) & ~7;                if (n.r > r_cap) n.r = r_cap;
+    n.q = 5 * n.u < n.r ? 5 * n.u : n.r;                                     // requested cells: five per worker at most
+    return n;
+}
+
+// The byte planes, the barrier and the header sit at fixed offsets (they are needed before the match's
+// sizes are known); the lists follow.
+LUX_HD LuxSmemLayout lux_smem_layout_need(int size, LuxNeed n) {
     LuxSmemLayout L;
     int ncell = size * size;
     int o = 0;
 #define LUX_TAKE(field, bytes) L.field = o; o += (((bytes) + 15) & ~15);
-    LUX_TAKE(hdr, LUX_HDR_BYTES)
-    LUX_TAKE(units, u_cap * 16)
-    LUX_TAKE(cities, c_cap * 16)
-    LUX_TAKE(tiles, t_cap * 2)
-    LUX_TAKE(res, r_cap * 2)
-    LUX_TAKE(uact, u_cap * 4)
-    LUX_TAKE(tact, t_cap)
-    LUX_TAKE(utgt, u_cap * 2)
-    LUX_TAKE(ust, u_cap)
-    LUX_TAKE(umine, u_cap)
-    LUX_TAKE(uinfo, u_cap * 4)
-    LUX_TAKE(umin, u_cap * 2)
-    LUX_TAKE(tmask, t_cap * 4)
-    LUX_TAKE(cprefix, (c_cap + 1) * 2)
-    LUX_TAKE(cremap, c_cap)
-    LUX_TAKE(reqlist, r_cap * 2 + 16)   // cells requested this collection pass (+ counter)
     LUX_TAKE(p1, ncell)                 // per-cell flag plane (movement flags, then collection mark / fill level)
     LUX_TAKE(occ, ncell)                // per-cell occupant plane (unit index + 1 during collection)
     LUX_TAKE(mbar, 16)
+    LUX_TAKE(hdr, LUX_HDR_BYTES)
+    LUX_TAKE(units, n.u * 16)
+    LUX_TAKE(uact, n.u * 4)
+    LUX_TAKE(cities, n.c * 16)
+    LUX_TAKE(tiles, n.t * 2)
+    LUX_TAKE(tact, n.t)
+    LUX_TAKE(res, n.r * 2)
+    LUX_TAKE(utgt, n.u * 2)
+    LUX_TAKE(ust, n.u)
+    LUX_TAKE(umine, n.u)
+    LUX_TAKE(uinfo, n.u * 4)
+    LUX_TAKE(umin, n.u * 2)
+    LUX_TAKE(tmask, n.t * 4)
+    LUX_TAKE(cprefix, (n.c + 1) * 2)
+    LUX_TAKE(cremap, n.c)
+    LUX_TAKE(reqlist, n.q * 2 + 16)     // cells requested this collection pass (+ counter)
 #undef LUX_TAKE
     L.total = o;
     return L;
+}
+
+LUX_HD LuxSmemLayout lux_smem_layout(int size, int u_cap, int c_cap, int t_cap, int r_cap) {
+    return lux_smem_layout_need(size, lux_need_caps(u_cap, c_cap, t_cap, r_cap));
 }
 
 // The cell grid is NOT staged: `cells` points at the match's grid in global memory and the engine
@@ -126,7 +155,7 @@ struct LuxMatch {
 };
 
 LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayout& L, LuxCell* g_cells, int size,
-                            int u_cap, int c_cap, int t_cap, int r_cap) {
+                            const LuxNeed& need) {
     M.hdr = (LuxHeader*)(smem + L.hdr);
     M.cells = g_cells;
     M.units = (LuxUnit*)(smem + L.units);
@@ -148,7 +177,9 @@ LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayou
     M.p1 = smem + L.p1;
     M.occ = smem + L.occ;
     M.S = size; M.ncell = size * size;
-    M.u_cap = u_cap; M.c_cap = c_cap; M.t_cap = t_cap; M.r_cap = r_cap;
+    // the capacities the turn checks overflow against: the batch capacities wherever they bind, otherwise
+    // more than the turn can reach
+    M.u_cap = need.u; M.c_cap = need.c; M.t_cap = need.t; M.r_cap = need.r;
 }
 
 #ifdef LUX_EMULATE
@@ -224,6 +255,51 @@ LUX_DEV void lux_planes_init(LuxMatch& M) {
 // walks through the turn in lockstep with the other groups of its warp on an empty match: all counts zero.
 template <int G = 32>
 LUX_DEV void lux_idle_header(LuxMatch& M) { lux_zero16<G>(M.hdr, LUX_HDR_BYTES); }
+
+// ---- staging with plain loads: header first, then the lists at the sizes the header names --------------
+// Pointers into one match's sections in global memory.
+struct LuxGlobalMatch {
+    LuxHeader* hdr; LuxCell* cells; LuxUnit* units; LuxCity* cities; uint16_t* tiles; const uint16_t* res;
+    const uint32_t* uact; const uint8_t* tact;
+};
+enum { LUX_M_DONE = 0, LUX_M_SPILL = 1, LUX_M_PLAYED = 2, LUX_M_HEAVY = 3 };
+
+// Returns the group's `active` flag (0: nothing to play -- invalid, finished, or the turn's footprint does not
+// fit `slice` bytes, in which case *result says which) with M bound and, when active, staged.  An inactive
+// group is bound to an empty match.  Warp-uniform control flow: every lane of the warp must call this.
+template <int G>
+LUX_DEV int lux_stage_plain(LuxMatch& M, unsigned char* smem, const LuxGlobalMatch& g, int valid, int size, int u_cap, int c_cap,
+                            int t_cap, int r_cap, int slice, int* result) {
+    const LuxSmemLayout L0 = lux_smem_layout_need(size, lux_need_turn(0, 0, 0, 0, u_cap, c_cap, t_cap, r_cap));
+    LuxHeader* sh = (LuxHeader*)(smem + L0.hdr);
+    int active = valid;
+    *result = LUX_M_DONE;
+    if (active) lux_copy16<G>(sh, g.hdr, LUX_HDR_BYTES);
+    lux_sync<G>();
+    if (active && sh->done) active = 0;
+    LuxNeed need = lux_need_turn(0, 0, 0, 0, u_cap, c_cap, t_cap, r_cap);
+    if (active) need = lux_need_turn(sh->n_units, sh->n_cities, sh->n_tiles, sh->n_res, u_cap, c_cap, t_cap, r_cap);
+    LuxSmemLayout L = lux_smem_layout_need(size, need);
+    if (active && L.total > slice) {
+        active = 0; *result = LUX_M_SPILL;
+        need = lux_need_turn(0, 0, 0, 0, u_cap, c_cap, t_cap, r_cap);
+        L = lux_smem_layout_need(size, need);
+    }
+    lux_match_bind(M, smem, L, g.cells, size, need);
+    lux_sync<G>();                            // every lane has read the header before an idle group clears it
+    if (active) {
+        lux_copy16<G>(M.units, g.units, M.hdr->n_units * 16);
+        lux_copy16<G>(M.cities, g.cities, M.hdr->n_cities * 16);
+        lux_copy16<G>(M.tiles, g.tiles, M.hdr->n_tiles * 2);
+        lux_copy16<G>(M.res, g.res, M.hdr->n_res * 2);
+        lux_copy16<G>(M.uact, g.uact, M.hdr->n_units * 4);
+        lux_copy16<G>(M.tact, g.tact, M.hdr->n_tiles);
+    } else {
+        lux_idle_header<G>(M);
+    }
+    lux_sync<G>();
+    return active;
+}
 
 // ---- collection of one resource type (game.py:882-1001) -----------------------------------
 // One inlined copy inside a rolled loop over the resource types, inner loops rolled: the kernel is

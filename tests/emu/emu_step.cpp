@@ -27,35 +27,26 @@ static void emu_lane(void* p) {
     const LuxBatch* b = a->b;
     const int grp = lux_lane32() / G;
     int m = a->m + grp;                       // 32 / G matches per warp, one lane group each
-    int active = m < b->n_matches;
-    if (!active) m = 0;
+    int valid = m < b->n_matches;
+    if (!valid) m = 0;
     int ncell = b->size * b->size;
-    LuxHeader* g_hdr = b->hdr + m;
-    LuxCell* g_cells = b->cells + (size_t)m * ncell;
-    LuxUnit* g_units = b->units + (size_t)m * b->u_cap;
-    LuxCity* g_cities = b->cities + (size_t)m * b->c_cap;
-    uint16_t* g_tiles = b->tiles + (size_t)m * b->t_cap;
-    uint16_t* g_res = b->res + (size_t)m * b->r_cap;
+    LuxGlobalMatch g;
+    g.hdr = b->hdr + m;
+    g.cells = b->cells + (size_t)m * ncell;
+    g.units = b->units + (size_t)m * b->u_cap;
+    g.cities = b->cities + (size_t)m * b->c_cap;
+    g.tiles = b->tiles + (size_t)m * b->t_cap;
+    g.res = b->res + (size_t)m * b->r_cap;
+    g.uact = a->ua + (size_t)m * b->u_cap;
+    g.tact = a->ta + (size_t)m * b->t_cap;
+    unsigned char* smem = a->smem + (size_t)grp * a->L.total;
+    lux_zero16<G>(smem + a->L.p1, (ncell + 15) & ~15);
+    lux_zero16<G>(smem + a->L.occ, (ncell + 15) & ~15);
     LuxMatch M;
-    lux_match_bind(M, a->smem + (size_t)grp * a->L.total, a->L, g_cells, b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
-    lux_planes_init<G>(M);
-    if (active) lux_copy16<G>(M.hdr, g_hdr, LUX_HDR_BYTES);
-    lux_sync<G>();
-    if (active && M.hdr->done) active = 0;
-    lux_sync<G>();                            // every lane has read the header before an idle group clears it
-    if (active) {
-        lux_copy16<G>(M.units, g_units, M.hdr->n_units * 16);
-        lux_copy16<G>(M.cities, g_cities, M.hdr->n_cities * 16);
-        lux_copy16<G>(M.tiles, g_tiles, M.hdr->n_tiles * 2);
-        lux_copy16<G>(M.res, g_res, M.hdr->n_res * 2);
-        lux_copy16<G>(M.uact, a->ua + (size_t)m * b->u_cap, M.hdr->n_units * 4);
-        lux_copy16<G>(M.tact, a->ta + (size_t)m * b->t_cap, M.hdr->n_tiles);
-    } else {
-        lux_idle_header<G>(M);
-    }
-    lux_sync<G>();
+    int result;
+    int active = lux_stage_plain<G>(M, smem, g, valid, b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap, a->L.total, &result);
     LuxTurnOut T = b->size == 32 ? lux_turn<32, G>(M, a->flags) : lux_turn<0, G>(M, a->flags);
-    lux_finish_and_store<0, G>(M, T, g_hdr, g_units, g_cities, g_tiles, active);
+    lux_finish_and_store<0, G>(M, T, g.hdr, g.units, g.cities, g.tiles, active);
     lux_sync<G>();
     // the engine's contract: both byte planes are clean again after the turn
     for (int i = lux_lane<G>(); i < ncell; i += G)

@@ -32,9 +32,9 @@ def _recap(ms, caps):
     return o
 
 
-@pytest.mark.parametrize("tma,two_class,heavy_first,group", [(1, -1, 1, 0), (1, 1, 0, 16), (1, 0, 1, 32), (1, 0, 0, 8),
-                                                              (1, 1, 0, 32), (0, -1, 1, 0)])
-def test_replays_bit_exact(tma, two_class, heavy_first, group):
+@pytest.mark.parametrize("tma,two_class,overlap,group", [(1, -1, 1, 0), (1, 1, 0, 16), (1, 0, 1, 32), (1, 0, 0, 8),
+                                                          (1, 1, 1, 32), (1, 1, 1, 8), (0, -1, 1, 0)])
+def test_replays_bit_exact(tma, two_class, overlap, group):
     """The 7 Kaggle episodes of the reference's test_replay.py, 360 turns each, through every launch
     path: TMA staging with the automatic / forced / disabled two-class launch, 8 / 16 / 32 lanes per match,
     and plain loads."""
@@ -42,7 +42,7 @@ def test_replays_bit_exact(tma, two_class, heavy_first, group):
     lib.lux_b200_set_option(b"group", group)
     lib.lux_b200_set_option(b"tma", tma)
     lib.lux_b200_set_option(b"two_class", two_class)
-    lib.lux_b200_set_option(b"heavy_first", heavy_first)
+    lib.lux_b200_set_option(b"overlap", overlap)
     try:
         z = G.npz("replays")
         for rid in G.replay_ids():
@@ -63,7 +63,7 @@ def test_replays_bit_exact(tma, two_class, heavy_first, group):
         lib.lux_b200_set_option(b"group", 0)
         lib.lux_b200_set_option(b"tma", 1)
         lib.lux_b200_set_option(b"two_class", -1)
-        lib.lux_b200_set_option(b"heavy_first", 1)
+        lib.lux_b200_set_option(b"overlap", 1)
 
 
 def test_random_and_dense_fixtures():
@@ -402,8 +402,8 @@ def test_packed_observations_equal_padded():
 
 
 def test_spill_list_and_scheduling_paths_under_load():
-    """Force the rarely taken launch paths on a real batch: a tiny staging class (32/16/32) so that a large
-    share of a dense batch spills to the retry list every turn, with and without heavy-first scheduling,
+    """Force the rarely taken launch paths on a real batch: a tiny small-class slice (3200 B) so that a large
+    share of a dense batch goes to the big class every turn, with and without overlapping the two classes,
     forced two-class mode (no automatic fallback), and more batches than the library caches scratch for."""
     lib = _lib.load()
     z = G.npz("dense")
@@ -412,8 +412,8 @@ def test_spill_list_and_scheduling_paths_under_load():
     inits = [_recap(G.get_state(z, nm + "/init"), caps) for nm in names]
     sparse = mapgen.generate_batch(np.arange(4000, 4096), 32)
     try:
-        for heavy in (0, 1):
-            for k, v in ((b"stage_units", 32), (b"stage_cities", 16), (b"stage_tiles", 32), (b"two_class", 1), (b"heavy_first", heavy),
+        for heavy in (0, 1):          # here: overlap off / on
+            for k, v in ((b"slice", 3200), (b"two_class", 1), (b"overlap", heavy),
                          (b"group", 16 if heavy else 8)):
                 assert lib.lux_b200_set_option(k, v) == 0
             n = 384
@@ -443,6 +443,6 @@ def test_spill_list_and_scheduling_paths_under_load():
         for i, gm in enumerate(games):
             assert len(gpu_util.diff_batches(hosts[i], gm)) == 0, i
     finally:
-        for k, v in ((b"stage_units", 96), (b"stage_cities", 64), (b"stage_tiles", 96), (b"two_class", -1), (b"heavy_first", 0),
+        for k, v in ((b"slice", 0), (b"two_class", -1), (b"overlap", 1),
                      (b"group", 0)):
             lib.lux_b200_set_option(k, v)
