@@ -54,7 +54,7 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
     int active, result;
 
     if (kTma) {
-        const LuxNeed none = lux_need_turn(0, 0, 0, 0, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
+        const LuxNeed none = lux_need_none(b.u_cap, b.c_cap, b.t_cap, b.r_cap);
         const LuxSmemLayout L0 = lux_smem_layout_need(size, none);         // fixed part: planes, barrier, header
         uint64_t* bar = (uint64_t*)(smem + L0.mbar);
         LuxHeader* sh = (LuxHeader*)(smem + L0.hdr);
@@ -71,7 +71,7 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
         uint32_t nu = 0, nc = 0, nt = 0, nr = 0;
         if (active) {
             nu = sh->n_units; nc = sh->n_cities; nt = sh->n_tiles; nr = sh->n_res;
-            need = lux_need_turn(nu, nc, nt, nr, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
+            need = lux_need_header(sh, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
         }
         LuxSmemLayout L = lux_smem_layout_need(size, need);
         if (active && L.total > slice) {
@@ -119,7 +119,7 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
     const LuxHeader* h = b.hdr + m;
     int big = 0;
     if (!h->done) {
-        LuxNeed need = lux_need_turn(h->n_units, h->n_cities, h->n_tiles, h->n_res, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
+        LuxNeed need = lux_need_header(h, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
         big = lux_smem_layout_need(b.size, need).total > slice;
     }
     sc.cls[m] = (uint8_t)big;
@@ -141,7 +141,7 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
     if (kMode == kList && (int)(blockIdx.x * gpc) >= *sc.big_cnt) return;      // past the end of the big list
     {   // fixed part of the slice: the per-cell byte planes start clean (every turn leaves them clean again)
         const int size = kS > 0 ? kS : b.size;
-        const LuxSmemLayout L0 = lux_smem_layout_need(size, lux_need_turn(0, 0, 0, 0, b.u_cap, b.c_cap, b.t_cap, b.r_cap));
+        const LuxSmemLayout L0 = lux_smem_layout_need(size, lux_need_none(b.u_cap, b.c_cap, b.t_cap, b.r_cap));
         if (kTma && lane == 0) {
             mbar_init((uint64_t*)(smem + L0.mbar), 1);
             fence_mbar_init();
@@ -551,7 +551,7 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
     }
 
     // the small class: every match whose turn fits `small` bytes (the empty-match floor is planes + header)
-    const int floor_bytes = lux_smem_layout_need(b->size, lux_need_turn(0, 0, 0, 0, b->u_cap, b->c_cap, b->t_cap, b->r_cap)).total;
+    const int floor_bytes = lux_smem_layout_need(b->size, lux_need_none(b->u_cap, b->c_cap, b->t_cap, b->r_cap)).total;
     int small = (g_slice > 0 ? g_slice : 4608);
     if (small < floor_bytes + 256) small = floor_bytes + 256;
     small = (small + 127) & ~127;

@@ -81,15 +81,28 @@ LUX_HD LuxNeed lux_need_caps(int u_cap, int c_cap, int t_cap, int r_cap) {
     return n;
 }
 
-LUX_HD LuxNeed lux_need_turn(int n_units, int n_cities, int n_tiles, int n_res, int u_cap, int c_cap, int t_cap, int r_cap) {
+// `spawns` = the most units the turn can add: a team spawns only while it has fewer units than city tiles
+// (game.py:725-735), and never more than one unit per tile.
+LUX_HD LuxNeed lux_need_turn(int n_units, int n_cities, int n_tiles, int n_res, int spawns, int u_cap, int c_cap, int t_cap,
+                             int r_cap) {
     LuxNeed n;
-    n.u = (n_units + n_tiles + 3) & ~3;    if (n.u > u_cap) n.u = u_cap;     // spawns: at most one per city tile
+    if (spawns > n_tiles) spawns = n_tiles;
+    n.u = (n_units + spawns + 3) & ~3;     if (n.u > u_cap) n.u = u_cap;
     n.c = n_cities + n_units;              if (n.c > c_cap) n.c = c_cap;     // new cities: at most one per unit
     if (n.c < 1) n.c = 1;
     n.t = (n_tiles + n_units + 15) & ~15;  if (n.t > t_cap) n.t = t_cap;     // new tiles: at most one per unit
     n.r = (n_res + 7) & ~7;                if (n.r > r_cap) n.r = r_cap;
     n.q = 5 * n.u < n.r ? 5 * n.u : n.r;                                     // requested cells: five per worker at most
     return n;
+}
+LUX_HD LuxNeed lux_need_none(int u_cap, int c_cap, int t_cap, int r_cap) { return lux_need_turn(0, 0, 0, 0, 0, u_cap, c_cap, t_cap, r_cap); }
+// from a header (a header whose per-team counts do not add up gets the safe bound: one spawn per tile)
+LUX_HD LuxNeed lux_need_header(const LuxHeader* h, int u_cap, int c_cap, int t_cap, int r_cap) {
+    int s0 = (int)h->n_team_tiles[0] - (int)h->n_team_units[0], s1 = (int)h->n_team_tiles[1] - (int)h->n_team_units[1];
+    int spawns = (s0 > 0 ? s0 : 0) + (s1 > 0 ? s1 : 0);
+    if ((int)h->n_team_tiles[0] + h->n_team_tiles[1] != h->n_tiles || (int)h->n_team_units[0] + h->n_team_units[1] != h->n_units)
+        spawns = h->n_tiles;
+    return lux_need_turn(h->n_units, h->n_cities, h->n_tiles, h->n_res, spawns, u_cap, c_cap, t_cap, r_cap);
 }
 
 // The byte planes, the barrier and the header sit at fixed offsets (they are needed before the match's
@@ -270,19 +283,19 @@ enum { LUX_M_DONE = 0, LUX_M_SPILL = 1, LUX_M_PLAYED = 2, LUX_M_HEAVY = 3 };
 template <int G>
 LUX_DEV int lux_stage_plain(LuxMatch& M, unsigned char* smem, const LuxGlobalMatch& g, int valid, int size, int u_cap, int c_cap,
                             int t_cap, int r_cap, int slice, int* result) {
-    const LuxSmemLayout L0 = lux_smem_layout_need(size, lux_need_turn(0, 0, 0, 0, u_cap, c_cap, t_cap, r_cap));
+    const LuxSmemLayout L0 = lux_smem_layout_need(size, lux_need_none(u_cap, c_cap, t_cap, r_cap));
     LuxHeader* sh = (LuxHeader*)(smem + L0.hdr);
     int active = valid;
     *result = LUX_M_DONE;
     if (active) lux_copy16<G>(sh, g.hdr, LUX_HDR_BYTES);
     lux_sync<G>();
     if (active && sh->done) active = 0;
-    LuxNeed need = lux_need_turn(0, 0, 0, 0, u_cap, c_cap, t_cap, r_cap);
-    if (active) need = lux_need_turn(sh->n_units, sh->n_cities, sh->n_tiles, sh->n_res, u_cap, c_cap, t_cap, r_cap);
+    LuxNeed need = lux_need_none(u_cap, c_cap, t_cap, r_cap);
+    if (active) need = lux_need_header(sh, u_cap, c_cap, t_cap, r_cap);
     LuxSmemLayout L = lux_smem_layout_need(size, need);
     if (active && L.total > slice) {
         active = 0; *result = LUX_M_SPILL;
-        need = lux_need_turn(0, 0, 0, 0, u_cap, c_cap, t_cap, r_cap);
+        need = lux_need_none(u_cap, c_cap, t_cap, r_cap);
         L = lux_smem_layout_need(size, need);
     }
     lux_match_bind(M, smem, L, g.cells, size, need);
