@@ -256,6 +256,13 @@ LUX_DEV void lux_zero16(void* p, int bytes) {   // bytes multiple of 16, p 16-by
     for (int i = lane; i < bytes / 16; i += G) { q[2 * i] = 0; q[2 * i + 1] = 0; }
 }
 
+// umin[] holds 2 bits of resource type for each of a worker's five cells; bit 2j of the result is set where
+// field j equals `rtype` (1..3)
+LUX_DEV unsigned lux_fields_equal(unsigned mm, int rtype) {
+    unsigned x = mm ^ ((unsigned)rtype * 0x155u);
+    return ~(x | (x >> 1)) & 0x155u;
+}
+
 // The two per-cell byte planes must be all-zero when a turn starts; the engine clears every byte it
 // sets before the turn ends, so a warp zeroes them once (here) and then plays any number of matches.
 template <int G = 32>
@@ -336,20 +343,22 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
     for (int u = lane; u < n_units; u += G) {
         const LuxUnit& U = M.units[u];
         int mine = 0xFF;
-        unsigned mm = M.umin[u];                      // 0 for carts
-        if (mm && (unit_team(U) ? researched1 : researched0)) {
-            int k = 0;
+        unsigned z = lux_fields_equal(M.umin[u], rtype);     // the cells of this type it can mine (none for carts)
+        if (z && (unit_team(U) ? researched1 : researched0)) {
+            const int k = lux_popc(z);
 #pragma unroll 1
-            for (int j = 0; j < 5; j++) {
-                if ((int)((mm >> (2 * j)) & 3u) != rtype) continue;
+            while (z) {
+                int j = (lux_ffs(z) - 1) >> 1;
+                z &= z - 1;
                 int c = lux_cell5(S, U.x, U.y, j);
-                k++;
                 unsigned old = lux_atomic_or_byte(M.p1, c, 0x80u);
                 if (!(old & 0x80u)) M.reqlist[lux_atomic_add(M.reqcnt, 1)] = (uint16_t)c;
             }
-            if (k > 0) {
+            {
                 int space = unit_space(U);
-                mine = (space + k - 1) / k;
+                // ceil(space / k), k = 1..5, space <= 2000: multiply by ceil(2^16 / k) instead of dividing
+                unsigned inv = k == 1 ? 65536u : k == 2 ? 32768u : k == 3 ? 21846u : k == 4 ? 16384u : 13108u;
+                mine = (int)(((unsigned)(space + k - 1) * inv) >> 16);
                 if (mine > rate) mine = rate;
                 unsigned info = M.uinfo[u];
                 if (info & UI_TILE) {
@@ -377,12 +386,18 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         unsigned present = 0;                         // amounts that occur
         unsigned tile_dirs = 0;                       // neighbours that are city tiles holding requests
         int n = 0, sum = 0;
-#pragma unroll 1
+        // the occupants of the five source cells, one byte each (most are empty)
+        uint64_t occ5 = 0;
+#pragma unroll
         for (int j = 0; j < 5; j++) {
             int p = lux_cell5(S, x, y, j);
-            if (p < 0) continue;
-            int o = M.occ[p];
-            if (!o) continue;
+            if (p >= 0) occ5 |= (uint64_t)M.occ[p] << (8 * j);
+        }
+#pragma unroll 1
+        while (occ5) {
+            int j = ((occ5 & 0xFFFFFFFFull) ? lux_ffs((unsigned)occ5) - 1 : 32 + lux_ffs((unsigned)(occ5 >> 32)) - 1) >> 3;
+            int o = (int)((occ5 >> (8 * j)) & 0xFFu);
+            occ5 &= ~((uint64_t)0xFF << (8 * j));
             unsigned info = M.uinfo[o - 1];
             if (info & UI_TILE) {
                 unsigned mask = M.tmask[info & 0xFFFFu];
@@ -457,11 +472,12 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
             continue;
         }
         LuxUnit& U = M.units[u];
-        unsigned mm = M.umin[u];
+        unsigned z = lux_fields_equal(M.umin[u], rtype);
         int gain = 0;
 #pragma unroll 1
-        for (int j = 0; j < 5; j++) {
-            if ((int)((mm >> (2 * j)) & 3u) != rtype) continue;
+        while (z) {
+            int j = (lux_ffs(z) - 1) >> 1;
+            z &= z - 1;
             int lv = M.p1[lux_cell5(S, U.x, U.y, j)] & 0x7F;
             gain += mine < lv ? mine : lv;
         }

@@ -1,10 +1,11 @@
 """Aggregate an ncu source page (ncu -i X.ncu-rep --page source --csv --print-source sass,cuda) per
-source line and per engine phase: instructions executed and stall samples.  usage: ncu_lines.py REP [top]"""
+source line and per engine phase: instructions executed and stall samples.  usage: ncu_lines.py REP [top [kernel-name-substring]]"""
 import csv, subprocess, sys, collections, re, io
 def I(x):
     try: return int(x)
     except ValueError: return 0
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+fn_filter = sys.argv[3] if len(sys.argv) > 3 else None   # substring of the kernel name to keep
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
 lines = list(csv.reader(io.StringIO(out)))
 cur_file = None; cols = None
@@ -15,8 +16,10 @@ for r in lines:
     if not r: continue
     if r[0] == "File Path": cur_file = r[1].split("/")[-1]; continue
     if r[0] == "Function Name":
-        if first_fn is None: first_fn = r[1]
-        kernel = 1 if r[1] == first_fn else 2
+        if fn_filter is not None: kernel = 1 if fn_filter in r[1] else 2
+        else:
+            if first_fn is None: first_fn = r[1]
+            kernel = 1 if r[1] == first_fn else 2
         continue
     if r[0] == "Line No": cols = {c: i for i, c in enumerate(r)}; continue
     if cols is None or kernel > 1: continue
