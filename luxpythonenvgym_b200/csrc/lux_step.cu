@@ -108,25 +108,32 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
 }
 
 // Classification of one step (device pointers, owned by the library, see StepScratch below).
+#define LUX_N_CAND 4     // candidate slice sizes the classification pass keeps statistics for
 struct LuxSched {
     int* big_cnt; int* big_list;      // matches of the big class (written by classify, read by kList)
     uint8_t* cls;                     // [n] 1 = big class (kSmall skips it)
-    int* zero;                        // the previous step's counter: trailed to the host, then cleared for reuse
-    int* seen_host;                   // pinned, mapped host word
+    int* zero;                        // the previous step's counters: trailed to the host, then cleared for reuse
+    int* seen_host;                   // pinned, mapped host words
+    int cand[LUX_N_CAND];             // big_cnt[1 + i] += matches whose need exceeds cand[i]
 };
 
 __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m == 0) { *sc.seen_host = *sc.zero; *sc.zero = 0; }     // a stale value only delays the host's mode switch
-    if (m >= b.n_matches) return;
-    const LuxHeader* h = b.hdr + m;
-    int big = 0;
-    if (!h->done) {
-        LuxNeed need = lux_need_header(h, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
-        big = lux_smem_layout_need(b.size, need).total > slice;
+    // the previous step's statistics go to the host (stale values only delay its choice of slice), then clear
+    if (m <= LUX_N_CAND) { sc.seen_host[m] = sc.zero[m]; sc.zero[m] = 0; }
+    int total = 0;
+    if (m < b.n_matches) {
+        const LuxHeader* h = b.hdr + m;
+        if (!h->done) total = lux_smem_layout_need(b.size, lux_need_header(h, b.u_cap, b.c_cap, b.t_cap, b.r_cap)).total;
+        const int big = total > slice;
+        sc.cls[m] = (uint8_t)big;
+        if (big) sc.big_list[atomicAdd(sc.big_cnt, 1)] = m;
     }
-    sc.cls[m] = (uint8_t)big;
-    if (big) sc.big_list[atomicAdd(sc.big_cnt, 1)] = m;
+#pragma unroll
+    for (int i = 0; i < LUX_N_CAND; i++) {
+        unsigned over = __ballot_sync(0xffffffffu, total > sc.cand[i]);
+        if ((threadIdx.x & 31) == 0 && over) atomicAdd(sc.big_cnt + 1 + i, __popc(over));
+    }
 }
 
 template <bool kTma, int kS, int kMode, int G>
@@ -478,16 +485,15 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
 // mixed map sizes, a pool -- each keep their own lists).
 struct StepScratch {
     const void* key; int n; int dev;
-    int* counts;                 // [0..2] big-class counts (3-way rotation: this step, next, being cleared)
+    int* counts;                 // 3 x (1 + LUX_N_CAND): big-class count + statistics (rotation: this step, next, being cleared)
     int* list;                   // [n] big-class matches of this step
     unsigned char* cls;          // [n] 1 = big class
-    int* seen;                   // pinned host copy of a recent big-class count (may be stale)
+    int* seen;                   // pinned host copy of a recent step's counters (may be stale)
     uint2* entries[2];           // sparse host actions of this / the previous call (device copies)
     int entries_cap, entries_prev_n, entries_flip;
     uint8_t* done_dev;           // compact done flags for the host path
     int* summary_dev;            // [0] max n_units, [1] max n_tiles, [2] live matches, [3] finished
     unsigned step;
-    int dense_hold;              // steps left in single-launch mode after a dense observation
 };
 static StepScratch g_scratch[8];
 static unsigned g_scratch_clock = 0;
@@ -513,13 +519,13 @@ static StepScratch* scratch_get(const LuxBatch* b, cudaStream_t st) {
         if (!s.key) { slot = &s; break; }
     if (!slot) { slot = &g_scratch[g_scratch_clock++ % 8]; cudaStreamSynchronize(st); scratch_free(*slot); }
     size_t n = (size_t)b->n_matches;
-    if (cudaMalloc(&slot->counts, 4 * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&slot->counts, 3 * (1 + LUX_N_CAND) * sizeof(int)) != cudaSuccess) return nullptr;
     if (cudaMalloc(&slot->list, n * sizeof(int)) != cudaSuccess) return nullptr;
     if (cudaMalloc(&slot->cls, n) != cudaSuccess) return nullptr;
-    if (cudaHostAlloc(&slot->seen, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
-    if (cudaMemsetAsync(slot->counts, 0, 4 * sizeof(int), st) != cudaSuccess) return nullptr;
-    *slot->seen = 0;
-    slot->key = b->hdr; slot->n = b->n_matches; slot->dev = dev; slot->step = 0; slot->dense_hold = 0;
+    if (cudaHostAlloc(&slot->seen, (1 + LUX_N_CAND) * sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    if (cudaMemsetAsync(slot->counts, 0, 3 * (1 + LUX_N_CAND) * sizeof(int), st) != cudaSuccess) return nullptr;
+    for (int i = 0; i <= LUX_N_CAND; i++) slot->seen[i] = 0;
+    slot->key = b->hdr; slot->n = b->n_matches; slot->dev = dev; slot->step = 0;
     return slot;
 }
 
@@ -555,33 +561,52 @@ extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, co
         return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
     }
 
-    // the small class: every match whose turn fits `small` bytes (the empty-match floor is planes + header)
+    // The small class: every match whose turn fits `small` bytes (the empty-match floor is planes + header).
+    // Automatic choice: the smallest candidate slice that at most 1/12 of the batch exceeded a step or two ago
+    // (sparse batches: 4.5 KB; dense late-game batches: 8-12 KB), the single full-capacity launch when even the
+    // largest candidate leaves most of the batch to the big class.
     const int floor_bytes = lux_smem_layout_need(b->size, lux_need_none(b->u_cap, b->c_cap, b->t_cap, b->r_cap)).total;
-    int small = (g_slice > 0 ? g_slice : 4608);
-    if (small < floor_bytes + 256) small = floor_bytes + 256;
-    small = (small + 127) & ~127;
-    bool two = g_two_class != 0 && (g_two_class == 1 || small * 2 <= full);
-    if (small > full) { small = full; two = false; }
+    const int cand[LUX_N_CAND] = {4608, 6144, 8192, 12288};
+    bool two = g_two_class != 0 && (g_two_class == 1 || cand[0] * 2 <= full);
     StepScratch* S = two ? scratch_get(b, st) : nullptr;
     if (two && !S) return LUX_E_CUDA;
-    if (two && g_two_class < 0) {
-        // when most of the batch is in the big class (dense batches) one full-capacity launch is the better shape
-        if (S->dense_hold > 0) { S->dense_hold--; two = false; }
-        else if (*S->seen * 2 > b->n_matches) { S->dense_hold = 64; *S->seen = 0; two = false; }
+    int small = g_slice > 0 ? g_slice : cand[0];
+    if (two && g_slice <= 0) {
+        int pick = LUX_N_CAND - 1;
+        for (int i = LUX_N_CAND - 1; i >= 0; i--)
+            if (S->seen[1 + i] * 12 <= b->n_matches) pick = i;
+        small = cand[pick];
+        if (g_two_class < 0 && (S->seen[1 + pick] * 2 > b->n_matches || small * 4 > full * 3)) two = false;
     }
+    if (small < floor_bytes + 256) small = floor_bytes + 256;
+    small = (small + 127) & ~127;
+    if (small >= full) two = false;
     if (!two) {
-        // single full-capacity launch (small maps, dense batches)
+        // single full-capacity launch (small maps, very dense batches).  The statistics still have to move, or
+        // the host would never see the batch thin out again: classify runs with the current choice.
+        if (S) {
+            const unsigned t = S->step++;
+            sc.big_cnt = S->counts + (t % 3) * (1 + LUX_N_CAND);
+            sc.big_list = S->list;
+            sc.cls = S->cls;
+            sc.zero = S->counts + ((t + 2) % 3) * (1 + LUX_N_CAND);
+            sc.seen_host = S->seen;
+            for (int i = 0; i < LUX_N_CAND; i++) sc.cand[i] = cand[i];
+            lux_classify_kernel<<<(b->n_matches + 255) / 256, 256, 0, st>>>(*b, full, sc);
+            g_launches++;
+        }
         int group = g_group == 8 || g_group == 16 ? pick_group(full) : 32;
         rc = launch_step_group<true, kAll>(group, b, unit_actions, tile_actions, full, flags, sc, b->n_matches, pick_wpc(full, group), st);
         if (rc) return rc;
         return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
     }
     const unsigned t = S->step++;
-    sc.big_cnt = S->counts + t % 3;
+    sc.big_cnt = S->counts + (t % 3) * (1 + LUX_N_CAND);
     sc.big_list = S->list;
     sc.cls = S->cls;
-    sc.zero = S->counts + (t + 2) % 3;
+    sc.zero = S->counts + ((t + 2) % 3) * (1 + LUX_N_CAND);
     sc.seen_host = S->seen;
+    for (int i = 0; i < LUX_N_CAND; i++) sc.cand[i] = cand[i];
     lux_classify_kernel<<<(b->n_matches + 255) / 256, 256, 0, st>>>(*b, small, sc);
     g_launches++;
     rc = cuda_ok(cudaGetLastError(), "lux_classify_kernel launch");
