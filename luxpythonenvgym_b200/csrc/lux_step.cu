@@ -1,12 +1,11 @@
 // lux_step.cu -- sm_100a kernels and the C ABI (include/lux_b200.h) of the batched turn engine.
 //
-// lux_step_kernel: one warp per match.  The warp's slice of dynamic shared memory holds the
-// whole match; it is filled by the TMA unit (cp.async.bulk global->shared, completion on a
-// per-warp mbarrier: 128-byte header first, then the live prefixes of every section), the
-// turn runs in shared memory (lux_step_core.cuh), and the cell grid + header go back with
-// cp.async.bulk shared->global while the compacted unit/city/tile lists are written with
-// plain vector stores.  No CPU fallback exists: without a device the entry points return
-// LUX_E_NO_DEVICE.
+// lux_step_kernel: one lane group (a warp by default) per match.  The group's slice of dynamic shared
+// memory holds the match's lists; it is filled by the TMA unit (cp.async.bulk global->shared, completion on
+// a per-match mbarrier: the 128-byte header first, then the live prefixes of every list at the sizes the
+// header names), the turn runs on them with the cell grid read in place from global memory
+// (lux_step_core.cuh), and the compacted unit / city / tile lists and the header are written back with
+// plain vector stores.  No CPU fallback exists: without a device the entry points return LUX_E_NO_DEVICE.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

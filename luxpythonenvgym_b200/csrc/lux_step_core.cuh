@@ -1,16 +1,17 @@
-// lux_step_core.cuh -- one Lux AI 2021 turn for one match, executed by one warp.
+// lux_step_core.cuh -- one Lux AI 2021 turn for one match, executed by one lane group (a warp by default).
 //
-// The match's whole state (header, cell grid, units, cities, tile and resource lists,
-// action words) is staged in the warp's slice of shared memory, every phase of
-// Game.run_turn_with_actions (reference: luxai2021/game/game.py:390-535) runs there with
-// lanes striding over units / city tiles / resource cells, and the result is written back.
-// There is no block-level synchronisation: warps (matches) of a CTA are independent.
+// The match's lists (header, units, cities, tile and resource lists, action words) are staged in the
+// group's slice of shared memory, laid out for what this turn can touch (LuxNeed); the cell grid stays in
+// global memory and is read in place, a cell at most once per phase; every phase of
+// Game.run_turn_with_actions (reference: luxai2021/game/game.py:390-535) runs with lanes striding over
+// units / city tiles / resource cells, and the lists are written back in canonical order.
+// There is no block-level synchronisation: groups (matches) of a CTA are independent.
 //
 // This is a parallel re-derivation, not a transcription, of the reference's sequential
 // algorithm; oracle/lux_oracle.c keeps the sequential form and the tests compare the two:
 //   * spawn-cap validation (game.py:696-718) = per-team ordered prefix via ballots;
-//   * collision pruning (game.py:1104-1195)  = static seeds + fixpoint over per-cell flags;
-//   * collection (game.py:868-1001)          = per-resource-cell water-filling on a packed
+//   * collision pruning (game.py:1104-1195)  = static seeds + fixpoint over a per-cell flag plane;
+//   * collection (game.py:868-1001)          = per-requested-cell water-filling on a packed
 //     histogram of request amounts, then per-worker gather (the iterative equal split is
 //     closed-form: request i receives min(amount_i, final level));
 //   * order-dependent actions (transfer, build city, pillage; unit.py:162-197) run in unit
