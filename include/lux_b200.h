@@ -173,10 +173,12 @@ int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_actions_host,
  * The turn for a host caller that holds an action LIST, as Game.run_turn_with_actions(actions) takes it
  * (game.py:390): k entries of two uint32 { tile flag (bit 31) | match index (bits 30:10) | slot (bits 9:0),
  * action word (units) or action byte (tiles) }.  The entries are uploaded and scattered into the device
- * action tensors (the previous call's entries are cleared first, so the tensors must not be written by
- * anything else between calls), the step runs, then done flags (n_matches bytes) and a 4-int summary
- * { max n_units, max n_tiles, live matches, finished matches } are copied to the host buffers (either may
- * be NULL) and the stream is synchronised.  8*k bytes travel up and n + 16 bytes down per turn.
+ * action tensors -- which must be all-zero before the first call and must not be written by anything else
+ * between calls: the step zeroes the action words of every match it plays, and entries that name a finished
+ * match or a slot beyond the live lists are dropped, so the tensors are clean again after every call --
+ * the step runs, then done flags (n_matches bytes) and a 4-int summary { max n_units, max n_tiles, live
+ * matches, finished matches } arrive in the host buffers (either may be NULL; they travel through mapped pinned
+ * memory) and the stream is synchronised.  8*k bytes travel up and n + 16 bytes down per turn.
  */
 int lux_b200_step_host_sparse(const LuxBatch* b, const void* entries_host, int k, uint32_t* unit_actions_dev,
                               uint8_t* tile_actions_dev, uint8_t* done_host, int32_t* summary_host,

@@ -29,6 +29,10 @@
 //              (30-45 us) and as a separate serialized launch it added that much to every step.
 // kAll is the single full-capacity launch (small maps, dense batches, the non-TMA path).
 enum { kAll = 0, kSmall = 1, kList = 2 };
+// internal step flag (upper half of `flags`; the public half is masked at the ABI): the kernel zeroes the
+// action words of every match it plays once they are staged, so a caller that scatters a sparse action list
+// into the tensors (lux_b200_step_host_sparse) never has to clear the previous turn's entries
+#define LUX_STEP_CONSUME (1u << 16)
 #ifndef LUX_SMALL_MIN_CTAS
 #define LUX_SMALL_MIN_CTAS 16      // 2-warp CTAs per SM the small-class kernel is compiled for: 64 registers (48 / 40 measured slower)
 #endif
@@ -100,7 +104,14 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
         active = lux_stage_plain<G>(M, smem, g, valid, size, b.u_cap, b.c_cap, b.t_cap, b.r_cap, slice, &result);
     }
 
-    LuxTurnOut T = lux_turn<kS, G>(M, flags);
+    if ((flags & LUX_STEP_CONSUME) && active) {
+        const int nu4 = (M.hdr->n_units + 3) >> 2, nt16 = (M.hdr->n_tiles + 15) >> 4;
+        uint4* ua4 = (uint4*)const_cast<uint32_t*>(g.uact);
+        uint4* ta4 = (uint4*)const_cast<uint8_t*>(g.tact);
+        for (int i = lane; i < nu4; i += G) ua4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = lane; i < nt16; i += G) ta4[i] = make_uint4(0, 0, 0, 0);
+    }
+    LuxTurnOut T = lux_turn<kS, G>(M, flags & 0xFFFFu);
     lux_finish_and_store<kS, G>(M, T, g.hdr, g.units, g.cities, g.tiles, active);
     // cannot happen (the classification pass routes such a match to the big class); visible if it ever does
     if (valid && result == LUX_M_SPILL && lane == 0) atomicOr((unsigned*)&g.hdr->done, (unsigned)LUX_ST_BAD_STATE << 16);   // done | winner | status | size
@@ -488,10 +499,11 @@ struct StepScratch {
     int* list;                   // [n] big-class matches of this step
     unsigned char* cls;          // [n] 1 = big class
     int* seen;                   // pinned host copy of a recent step's counters (may be stale)
-    uint2* entries[2];           // sparse host actions of this / the previous call (device copies)
-    int entries_cap, entries_prev_n, entries_flip;
-    uint8_t* done_dev;           // compact done flags for the host path
-    int* summary_dev;            // [0] max n_units, [1] max n_tiles, [2] live matches, [3] finished
+    uint2* entries;              // sparse host actions of the current call (device copy)
+    int entries_cap;
+    uint8_t* done_pinned;        // mapped pinned: compact done flags for the host path, followed by
+    int* summary_pinned;         // [0] max n_units, [1] max n_tiles, [2] live matches, [3] finished
+    int* summary_acc;            // device accumulators of the summary kernel (+ its CTA ticket)
     unsigned step;
 };
 static StepScratch g_scratch[8];
@@ -502,9 +514,9 @@ static void scratch_free(StepScratch& s) {
     if (s.list) cudaFree(s.list);
     if (s.cls) cudaFree(s.cls);
     if (s.seen) cudaFreeHost(s.seen);
-    for (int k = 0; k < 2; k++) if (s.entries[k]) cudaFree(s.entries[k]);
-    if (s.done_dev) cudaFree(s.done_dev);
-    if (s.summary_dev) cudaFree(s.summary_dev);
+    if (s.entries) cudaFree(s.entries);
+    if (s.done_pinned) cudaFreeHost(s.done_pinned);
+    if (s.summary_acc) cudaFree(s.summary_acc);
     memset(&s, 0, sizeof s);
 }
 
@@ -528,8 +540,16 @@ static StepScratch* scratch_get(const LuxBatch* b, cudaStream_t st) {
     return slot;
 }
 
+static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions, uint32_t flags,
+                         void* cuda_stream);
+
 extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions,
                              uint32_t flags, void* cuda_stream) {
+    return lux_step_impl(b, unit_actions, tile_actions, flags & 0xFFFFu, cuda_stream);
+}
+
+static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions, uint32_t flags,
+                         void* cuda_stream) {
     int rc = check_batch(b);
     if (rc) return rc;
     if (!unit_actions || !tile_actions) return LUX_E_ARG;
@@ -662,42 +682,68 @@ extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_action
 }
 
 // ---------------------------------------------------------------- sparse host actions
-// entry.x = tile flag (bit 31) | match index (bits 30:10) | slot (bits 9:0), entry.y = action word / byte
-__global__ void lux_apply_entries_kernel(const uint2* __restrict__ entries, int k, int clear, uint32_t* __restrict__ ua,
-                                         uint8_t* __restrict__ ta, int u_cap, int t_cap, int n_matches) {
+// entry.x = tile flag (bit 31) | match index (bits 30:10) | slot (bits 9:0), entry.y = action word / byte.
+// Entries for finished matches or for slots beyond the live lists are dropped: the step kernel consumes
+// (zeroes) exactly the live action words of the matches it plays, so nothing stale is left behind.
+__global__ void lux_apply_entries_kernel(LuxBatch b, const uint2* __restrict__ entries, int k, uint32_t* __restrict__ ua,
+                                         uint8_t* __restrict__ ta) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k) return;
     uint2 e = entries[i];
     unsigned m = (e.x >> 10) & 0x1FFFFFu, slot = e.x & 1023u;
-    if ((int)m >= n_matches) return;
-    if (e.x >> 31) { if ((int)slot < t_cap) ta[(size_t)m * t_cap + slot] = clear ? 0 : (uint8_t)e.y; }
-    else if ((int)slot < u_cap) ua[(size_t)m * u_cap + slot] = clear ? 0u : e.y;
+    if ((int)m >= b.n_matches) return;
+    const LuxHeader* h = b.hdr + m;
+    if (h->done) return;
+    if (e.x >> 31) { if (slot < h->n_tiles) ta[(size_t)m * b.t_cap + slot] = (uint8_t)e.y; }
+    else if (slot < h->n_units) ua[(size_t)m * b.u_cap + slot] = e.y;
 }
 
-__global__ void lux_summary_kernel(LuxBatch b, uint8_t* __restrict__ done, int* __restrict__ summary) {
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
+// done flags and the 4-int summary straight into mapped pinned host memory: every thread packs the flags of
+// four matches into one word (coalesced 128-byte rows over the bus), CTAs accumulate into device scratch and
+// the last one to finish publishes the summary and clears the scratch for the next call.
+__global__ void lux_summary_kernel(LuxBatch b, uint32_t* __restrict__ done4, int* __restrict__ summary, int* __restrict__ acc) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;      // matches 4q .. 4q+3
     int nu = 0, nt = 0, live = 0, fin = 0;
-    if (m < b.n_matches) {
-        const LuxHeader* h = b.hdr + m;
-        int d = h->done;
-        done[m] = (uint8_t)d;
-        nu = h->n_units; nt = h->n_tiles; live = !d; fin = d;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int m = 4 * q + j;
+        if (m < b.n_matches) {
+            const LuxHeader* h = b.hdr + m;
+            const int d = h->done != 0;
+            packed |= (uint32_t)h->done << (8 * j);
+            nu = max(nu, (int)h->n_units); nt = max(nt, (int)h->n_tiles); live += !d; fin += d;
+        }
     }
+    if (4 * q < b.n_matches) done4[q] = packed;
     nu = __reduce_max_sync(0xffffffffu, nu);
     nt = __reduce_max_sync(0xffffffffu, nt);
     live = __reduce_add_sync(0xffffffffu, live);
     fin = __reduce_add_sync(0xffffffffu, fin);
+    __shared__ int last;
     if ((threadIdx.x & 31) == 0) {
-        atomicMax(summary, nu); atomicMax(summary + 1, nt);
-        if (live) atomicAdd(summary + 2, live);
-        if (fin) atomicAdd(summary + 3, fin);
+        atomicMax(acc, nu); atomicMax(acc + 1, nt);
+        if (live) atomicAdd(acc + 2, live);
+        if (fin) atomicAdd(acc + 3, fin);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(acc + 4, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 5) {
+        __threadfence();
+        if (threadIdx.x < 4) summary[threadIdx.x] = atomicExch(acc + threadIdx.x, 0);
+        else acc[4] = 0;
     }
 }
 
 // The turn for a HOST caller that holds an action LIST (what Game.run_turn_with_actions takes): k entries
-// are uploaded, scattered into the device action tensors (the previous call's entries are cleared first),
-// the step runs, and done flags (n bytes) + a 4-int summary come back.  Per step this moves 8*k bytes up
-// and n + 16 bytes down instead of dense action tensors and full headers.
+// are uploaded and scattered into the device action tensors (which must be all-zero before the first call and
+// not written by anything else: the step consumes the words it plays), the step runs, and done flags
+// (n bytes) + a 4-int summary come back through mapped pinned memory.  Per step this moves 8*k bytes up
+// and n + 16 bytes down instead of dense action tensors and full headers: four launches and one copy.
 extern "C" int lux_b200_step_host_sparse(const LuxBatch* b, const void* entries_host, int k, uint32_t* unit_actions_dev,
                                          uint8_t* tile_actions_dev, uint8_t* done_host, int32_t* summary_host,
                                          uint32_t flags, void* cuda_stream) {
@@ -709,55 +755,36 @@ extern "C" int lux_b200_step_host_sparse(const LuxBatch* b, const void* entries_
     cudaStream_t st = (cudaStream_t)cuda_stream;
     StepScratch* S = scratch_get(b, st);
     if (!S) return LUX_E_CUDA;
-    if (!S->done_dev) {
-        if (cudaMalloc(&S->done_dev, (size_t)b->n_matches) != cudaSuccess) return LUX_E_CUDA;
-        if (cudaMalloc(&S->summary_dev, 4 * sizeof(int)) != cudaSuccess) return LUX_E_CUDA;
+    if (!S->done_pinned) {
+        if (cudaHostAlloc(&S->done_pinned, (size_t)b->n_matches + 64, cudaHostAllocMapped) != cudaSuccess) return LUX_E_CUDA;
+        S->summary_pinned = (int*)(S->done_pinned + (((size_t)b->n_matches + 15) & ~(size_t)15));
+        if (cudaMalloc(&S->summary_acc, 8 * sizeof(int)) != cudaSuccess) return LUX_E_CUDA;
+        if (cudaMemsetAsync(S->summary_acc, 0, 8 * sizeof(int), st) != cudaSuccess) return LUX_E_CUDA;
     }
     if (k > S->entries_cap) {
         cudaStreamSynchronize(st);
         int cap = k * 2 + 1024;
-        for (int j = 0; j < 2; j++) {
-            uint2* fresh = nullptr;
-            if (cudaMalloc(&fresh, (size_t)cap * sizeof(uint2)) != cudaSuccess) return LUX_E_CUDA;
-            if (S->entries[j]) {
-                cudaMemcpy(fresh, S->entries[j], (size_t)S->entries_cap * sizeof(uint2), cudaMemcpyDeviceToDevice);
-                cudaFree(S->entries[j]);
-            }
-            S->entries[j] = fresh;
-        }
+        uint2* fresh = nullptr;
+        if (cudaMalloc(&fresh, (size_t)cap * sizeof(uint2)) != cudaSuccess) return LUX_E_CUDA;
+        if (S->entries) cudaFree(S->entries);
+        S->entries = fresh;
         S->entries_cap = cap;
     }
-    uint2* prev = S->entries[S->entries_flip];
-    uint2* cur = S->entries[S->entries_flip ^ 1];
-    if (S->entries_prev_n > 0) {
-        lux_apply_entries_kernel<<<(S->entries_prev_n + 255) / 256, 256, 0, st>>>(prev, S->entries_prev_n, 1, unit_actions_dev,
-                                                                                  tile_actions_dev, b->u_cap, b->t_cap, b->n_matches);
-        g_launches++;
-    }
     if (k > 0) {
-        rc = cuda_ok(cudaMemcpyAsync(cur, entries_host, (size_t)k * sizeof(uint2), cudaMemcpyHostToDevice, st), "h2d action entries");
+        rc = cuda_ok(cudaMemcpyAsync(S->entries, entries_host, (size_t)k * sizeof(uint2), cudaMemcpyHostToDevice, st), "h2d action entries");
         if (rc) return rc;
-        lux_apply_entries_kernel<<<(k + 255) / 256, 256, 0, st>>>(cur, k, 0, unit_actions_dev, tile_actions_dev, b->u_cap,
-                                                                  b->t_cap, b->n_matches);
+        lux_apply_entries_kernel<<<(k + 255) / 256, 256, 0, st>>>(*b, S->entries, k, unit_actions_dev, tile_actions_dev);
         g_launches++;
     }
-    S->entries_flip ^= 1;
-    S->entries_prev_n = k;
-    rc = lux_b200_step(b, unit_actions_dev, tile_actions_dev, flags, cuda_stream);
+    rc = lux_step_impl(b, unit_actions_dev, tile_actions_dev, (flags & 0xFFFFu) | LUX_STEP_CONSUME, cuda_stream);
     if (rc) return rc;
-    rc = cuda_ok(cudaMemsetAsync(S->summary_dev, 0, 4 * sizeof(int), st), "summary memset");
-    if (rc) return rc;
-    lux_summary_kernel<<<(b->n_matches + 255) / 256, 256, 0, st>>>(*b, S->done_dev, S->summary_dev);
+    lux_summary_kernel<<<(b->n_matches + 1023) / 1024, 256, 0, st>>>(*b, (uint32_t*)S->done_pinned, S->summary_pinned, S->summary_acc);
     g_launches++;
-    if (done_host) {
-        rc = cuda_ok(cudaMemcpyAsync(done_host, S->done_dev, (size_t)b->n_matches, cudaMemcpyDeviceToHost, st), "d2h done flags");
-        if (rc) return rc;
-    }
-    if (summary_host) {
-        rc = cuda_ok(cudaMemcpyAsync(summary_host, S->summary_dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, st), "d2h summary");
-        if (rc) return rc;
-    }
-    return cuda_ok(cudaStreamSynchronize(st), "step sync");
+    rc = cuda_ok(cudaStreamSynchronize(st), "step sync");
+    if (rc) return rc;
+    if (done_host) memcpy(done_host, S->done_pinned, (size_t)b->n_matches);
+    if (summary_host) memcpy(summary_host, S->summary_pinned, 4 * sizeof(int));
+    return LUX_OK;
 }
 
 extern "C" int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t match_id_base,

@@ -191,7 +191,7 @@ def test_step_host_sparse_matches_device_step():
     arr = mapgen.generate_batch(np.arange(900, 948), size)
     for g in (a, b):
         g.load_arrays(arr)
-    ent_h = torch.zeros((48 * 64, 2), dtype=torch.int32).pin_memory()
+    ent_h = torch.zeros((48 * 64 + 8, 2), dtype=torch.int32).pin_memory()
     done_h = torch.zeros(48, dtype=torch.uint8).pin_memory()
     summ_h = torch.zeros(4, dtype=torch.int32).pin_memory()
     for turn in range(60):
@@ -201,8 +201,18 @@ def test_step_host_sparse_matches_device_step():
         ent = a.pack_entries()
         k = ent.shape[0]
         ent_h[:k].copy_(ent)
+        # entries that name no live entity (slot beyond the live lists, a finished match) must be dropped
+        ent_h[k, 0], ent_h[k, 1] = (5 << 10) | 200, 1
+        ent_h[k + 1, 0], ent_h[k + 1, 1] = -(1 << 31) + ((7 << 10) | 300), 3
+        k += 2
+        fin = np.nonzero(a.headers()["done"])[0]
+        if len(fin):
+            ent_h[k, 0], ent_h[k, 1] = (int(fin[0]) << 10) | 0, 1 | (1 << 3)
+            k += 1
         a.step(prevalidate=True)
         b.step_host_sparse(ent_h, k, done_h, summ_h, prevalidate=True)
+        # the step consumed every action word it played: the tensors are clean for the next list
+        assert not bool(b.unit_actions.any()) and not bool(b.tile_actions.any()), turn
         hh = a.headers()
         assert torch.equal(b.hdr, a.hdr), turn
         assert np.array_equal(done_h.numpy(), hh["done"])
