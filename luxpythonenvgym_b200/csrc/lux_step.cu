@@ -61,7 +61,7 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
 
     if (kTma) {
         const LuxNeed none = lux_need_none(b.u_cap, b.c_cap, b.t_cap, b.r_cap);
-        const LuxSmemLayout L0 = lux_smem_layout_need(size, none);         // fixed part: planes, barrier, header
+        const LuxSmemFixed L0 = lux_smem_fixed(size);                     // fixed part: planes, barrier, header
         uint64_t* bar = (uint64_t*)(smem + L0.mbar);
         LuxHeader* sh = (LuxHeader*)(smem + L0.hdr);
         active = valid; result = LUX_M_DONE;
@@ -83,7 +83,7 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
         if (active && L.total > slice) {
             active = 0; result = LUX_M_SPILL;
             need = none;
-            L = L0;
+            L = lux_smem_layout_need(size, none);
         }
         lux_match_bind(M, smem, L, g.cells, size, need);
         // trip 2: the live lists and this turn's action words, one bulk-copy batch
@@ -161,7 +161,7 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
     if (kMode == kList && (int)(blockIdx.x * gpc) >= *sc.big_cnt) return;      // past the end of the big list
     {   // fixed part of the slice: the per-cell byte planes start clean (every turn leaves them clean again)
         const int size = kS > 0 ? kS : b.size;
-        const LuxSmemLayout L0 = lux_smem_layout_need(size, lux_need_none(b.u_cap, b.c_cap, b.t_cap, b.r_cap));
+        const LuxSmemFixed L0 = lux_smem_fixed(size);
         if (kTma && lane == 0) {
             mbar_init((uint64_t*)(smem + L0.mbar), 1);
             fence_mbar_init();

@@ -137,6 +137,15 @@ LUX_HD LuxSmemLayout lux_smem_layout_need(int size, LuxNeed n) {
     return L;
 }
 
+// the fixed head of every slice (same offsets as lux_smem_layout_need gives them)
+struct LuxSmemFixed { int p1, occ, mbar, hdr; };
+LUX_HD LuxSmemFixed lux_smem_fixed(int size) {
+    LuxSmemFixed F;
+    const int plane = (size * size + 15) & ~15;
+    F.p1 = 0; F.occ = plane; F.mbar = 2 * plane; F.hdr = 2 * plane + 16;
+    return F;
+}
+
 LUX_HD LuxSmemLayout lux_smem_layout(int size, int u_cap, int c_cap, int t_cap, int r_cap) {
     return lux_smem_layout_need(size, lux_need_caps(u_cap, c_cap, t_cap, r_cap));
 }
@@ -291,7 +300,7 @@ enum { LUX_M_DONE = 0, LUX_M_SPILL = 1, LUX_M_PLAYED = 2, LUX_M_HEAVY = 3 };
 template <int G>
 LUX_DEV int lux_stage_plain(LuxMatch& M, unsigned char* smem, const LuxGlobalMatch& g, int valid, int size, int u_cap, int c_cap,
                             int t_cap, int r_cap, int slice, int* result) {
-    const LuxSmemLayout L0 = lux_smem_layout_need(size, lux_need_none(u_cap, c_cap, t_cap, r_cap));
+    const LuxSmemFixed L0 = lux_smem_fixed(size);
     LuxHeader* sh = (LuxHeader*)(smem + L0.hdr);
     int active = valid;
     *result = LUX_M_DONE;
@@ -489,8 +498,10 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         else U.uranium = (uint16_t)(U.uranium + gain);
         if (unit_team(U)) got1 += gain; else got0 += gain;
     }
-    got0 = lux_reduce_add<G>(got0);
-    got1 = lux_reduce_add<G>(got1);
+    {   // one reduction: a team gains at most 5 cells x 20 x 252 workers < 2^16 per pass
+        unsigned packed = (unsigned)lux_reduce_add<G>(got0 | (got1 << 16));
+        got0 = (int)(packed & 0xFFFFu); got1 = (int)(packed >> 16);
+    }
     if (lane == 0) {
         h->collected[0][rtype - 1] += got0;
         h->collected[1][rtype - 1] += got1;
@@ -625,13 +636,19 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     }
 
     // ---- team city-tile counts (worker_unit_cap_reached game.py:725-735)
-    int tt0 = 0, tt1 = 0;
+    // the header carries them (lux_finish_and_store, the host map generator); a header whose per-team counts
+    // do not add up is recounted from the cities
+    int tt0 = h->n_team_tiles[0], tt1 = h->n_team_tiles[1];
+    if (lux_wany<G>(tt0 + tt1 != n_tiles0)) {
+        int c0 = 0, c1 = 0;
 #pragma unroll 1
-    for (int s = lane; s < n_cities; s += G) {
-        if (M.cities[s].team) tt1 += M.cities[s].ntiles; else tt0 += M.cities[s].ntiles;
+        for (int s = lane; s < n_cities; s += G) {
+            if (M.cities[s].team) c1 += M.cities[s].ntiles; else c0 += M.cities[s].ntiles;
+        }
+        c0 = lux_reduce_add<G>(c0);
+        c1 = lux_reduce_add<G>(c1);
+        if (tt0 + tt1 != n_tiles0) { tt0 = c0; tt1 = c1; }
     }
-    tt0 = lux_reduce_add<G>(tt0);
-    tt1 = lux_reduce_add<G>(tt1);
     const int tu0 = h->n_team_units[0], tu1 = h->n_team_units[1];
 
     int any_move = 0;
@@ -817,6 +834,11 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             if (valid) C = lux_ldcell(M.cells, cell);
             int team = valid ? cell_tile_team(C) : 0;
             int cd = C.tile_cd;
+            if (!lux_wany<G>(lux_any<G>(code != 0))) {
+                // no tile of this chunk acts (the common case: a tile rests ten turns after every action)
+                if (valid && cd > 0) M.cells[cell].tile_cd = (uint8_t)(cd - 1);
+                continue;
+            }
             int cand = valid && (code == LUX_TA_BUILD_WORKER || code == LUX_TA_BUILD_CART) && cd < 1;
             unsigned m0 = lux_ballot<G>(cand && team == 0), m1 = lux_ballot<G>(cand && team == 1);
             int rank = team ? acc1 + lux_popc(m1 & lt) : acc0 + lux_popc(m0 & lt);
@@ -1005,9 +1027,10 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             M.umin[u] = (uint16_t)mm;
             M.ust[u] = 0;
         }
-        rb0 = lux_reduce_add<G>(rb0);
-        rb1 = lux_reduce_add<G>(rb1);
-        bad = lux_any<G>(bad);
+        {   // one reduction: road steps are < 2^12 per team (3 per cart), stacks < 2^8
+            int packed = lux_reduce_add<G>(rb0 | (rb1 << 12) | (bad << 24));
+            rb0 = packed & 0xFFF; rb1 = (packed >> 12) & 0xFFF; bad = packed >> 24;
+        }
         if (lane == 0) {
             h->roads_built_q[0] += rb0; h->roads_built_q[1] += rb1;
             if (bad) h->status |= LUX_ST_BAD_STATE;
@@ -1173,8 +1196,10 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
         nc0 += alive && team == 0; nc1 += alive && team == 1;
         if (alive) { if (team) tl1 += M.cities[s].ntiles; else tl0 += M.cities[s].ntiles; }
     }
-    nc0 = lux_reduce_add<G>(nc0); nc1 = lux_reduce_add<G>(nc1);
-    tl0 = lux_reduce_add<G>(tl0); tl1 = lux_reduce_add<G>(tl1);
+    {   // two reductions instead of four (cities <= 255, tiles <= 1024 per team)
+        unsigned pc = (unsigned)lux_reduce_add<G>(nc0 | (nc1 << 16)), pt = (unsigned)lux_reduce_add<G>(tl0 | (tl1 << 16));
+        nc0 = (int)(pc & 0xFFFFu); nc1 = (int)(pc >> 16); tl0 = (int)(pt & 0xFFFFu); tl1 = (int)(pt >> 16);
+    }
     lux_sync<G>();
     const int cities_moved = n_alive != T.n_cities;
     // store cities compacted
