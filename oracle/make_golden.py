@@ -12,6 +12,7 @@ imported through oracle/refshim.py); the packed encoding is oracle/flatten.py.
   random.npz   seeded random-action matches on 12/16/24/32 maps (canonical stream,
                oracle/stream.py): initial state, per-turn digests, final state.
   dense.npz    replay states imported at turns 80/200/300 (process_updates, game.py:159-262)
+  wire.npz     the update lines those imports consumed (input of luxpythonenvgym_b200/wire.py)
                continued for 45 turns with the canonical stream: digests + final state.
 """
 import glob
@@ -157,6 +158,25 @@ def make_dense(ref, stream_seed=31337):
     store["names"] = np.array(names)
     store["stream_seed"] = np.array(stream_seed)
     np.savez_compressed(os.path.join(OUT, "dense.npz"), **store)
+
+
+def make_wire():
+    """Update lines of the replay observations the dense fixtures were imported from (the expected packed
+    states are dense.npz <name>/init, produced by the reference's own process_updates)."""
+    store = {}
+    names = []
+    files = sorted(glob.glob(os.path.join(refshim.REFERENCE_ROOT, "luxai2021/tests/replays_for_test/*[0-9].json")))
+    for f in files:
+        rid = os.path.basename(f)[:-5]
+        rep = json.load(open(f))
+        for start in (80, 200, 300):
+            obs = rep["steps"][start][0]["observation"]
+            name = "%s@%d" % (rid, start)
+            store[name + "/updates"] = np.array("\n".join(obs["updates"][2:]))
+            store[name + "/meta"] = np.array([obs["width"], obs["step"], obs["globalUnitIDCount"], obs["globalCityIDCount"]])
+            names.append(name)
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "wire.npz"), **store)
 
 
 def make_obs(ref, stream_seed=4711):
@@ -356,6 +376,7 @@ def main():
     make_dense(ref)
     make_obs(ref)
     make_env(ref)
+    make_wire()
 
 
 if __name__ == "__main__":
