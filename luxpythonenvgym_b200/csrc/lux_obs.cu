@@ -1,8 +1,8 @@
 // lux_obs.cu -- lux_b200_observe: per-entity observation tensors (see lux_obs_core.cuh).
-// One warp per match; header, cell grid, resource list and the leading unit / tile records are staged
-// in shared memory by one cp.async.bulk (TMA) batch exactly like the step kernel (a second batch only
-// for populous matches); cities are read in place; rows are zero-filled with coalesced 16-byte stores
-// and the non-zero features written by the owning lanes.
+// One warp per match; header, resource list and the leading unit / tile records are staged in shared
+// memory by one cp.async.bulk (TMA) batch (a second batch only for populous matches); the cell grid and the
+// cities are read in place; rows are zero-filled with coalesced 16-byte stores and the non-zero features
+// written by the owning lanes.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -25,7 +25,7 @@ __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_
     unsigned char* smem = lux_smem + (size_t)warp * D.total;
     const int ncell = b.size * b.size;
     LuxObsMatch M;
-    lux_obs_bind(M, smem, D.L, b.size, b.cities + (size_t)m * b.c_cap);
+    lux_obs_bind(M, smem, D.L, b.size, b.cells + (size_t)m * ncell, b.cities + (size_t)m * b.c_cap);
     uint64_t* bar = (uint64_t*)(smem + D.mbar);
     const LuxUnit* g_units = b.units + (size_t)m * b.u_cap;
     const uint16_t* g_tiles = b.tiles + (size_t)m * b.t_cap;
@@ -33,9 +33,8 @@ __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_
     if (lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
-        mbar_expect_tx(bar, LUX_HDR_BYTES + ncell * 8 + b.r_cap * 2 + pu * 16 + pt * 2);
+        mbar_expect_tx(bar, LUX_HDR_BYTES + b.r_cap * 2 + pu * 16 + pt * 2);
         tma_g2s(M.hdr, b.hdr + m, LUX_HDR_BYTES, bar);
-        tma_g2s(M.cells, b.cells + (size_t)m * ncell, ncell * 8, bar);
         tma_g2s(M.res, b.res + (size_t)m * b.r_cap, b.r_cap * 2, bar);
         tma_g2s(M.units, g_units, pu * 16, bar);
         tma_g2s(M.tiles, g_tiles, pt * 2, bar);

@@ -13,7 +13,10 @@
 //     np.delete(closest) self-exclusion (:328-336);
 //   * a row is ~70 % zeros: the warp first zero-fills the rows of the 32 entities in flight with
 //     coalesced 16-byte stores, then every lane drops its ~25 non-zero features into its own row.
-//     No staging tile is needed, which keeps the shared-memory footprint at the staged match itself.
+//     No staging tile is needed.
+//   * the cell grid is read in place (like the step kernel): one global load per resource cell and per
+//     city tile while the node lists are built; what the feature blocks need from a cell (amount, city
+//     slot, tile team / cooldown) rides in the node entries, so nothing else touches the grid.
 // Values are computed in float64 exactly as the reference's Python expressions and rounded once.
 #pragma once
 #include "lux_step_core.cuh"
@@ -21,7 +24,7 @@
 #define LUX_OBS_DIM 85
 
 struct LuxObsLayout {
-    int hdr, cells, units, tiles, res, nodes_res, nodes_tile, nodes_work, total;
+    int hdr, units, tiles, res, nodes_res, nodes_tile, nodes_work, tinfo, r_cap, total;
 };
 
 #ifdef LUX_EMULATE
@@ -34,34 +37,40 @@ LuxObsLayout lux_obs_layout(int size, int u_cap, int t_cap, int r_cap) {
     int ncell = size * size;
     int o = 0;
 #define LUX_TAKE(field, bytes) L.field = o; o += (((bytes) + 15) & ~15);
+    (void)ncell;
     LUX_TAKE(hdr, LUX_HDR_BYTES)
-    LUX_TAKE(cells, ncell * 8)
     LUX_TAKE(units, u_cap * 16)
     LUX_TAKE(tiles, t_cap * 2)
     LUX_TAKE(res, r_cap * 2)
-    LUX_TAKE(nodes_res, r_cap * 2)      // wood | coal | uranium node positions (x | y << 8)
-    LUX_TAKE(nodes_tile, t_cap * 2)
-    LUX_TAKE(nodes_work, u_cap * 2)
+    LUX_TAKE(nodes_res, 3 * r_cap * 4)  // wood, coal, uranium nodes: x | y << 8 | amount << 16, r_cap entries each
+    LUX_TAKE(nodes_tile, t_cap * 4)     // own city tiles: x | y << 8 | city slot << 16
+    LUX_TAKE(nodes_work, u_cap * 4)     // own workers: x | y << 8
+    LUX_TAKE(tinfo, t_cap)              // per tile: team | can_act << 1
 #undef LUX_TAKE
+    L.r_cap = r_cap;
     L.total = o;
     return L;
 }
 
 struct LuxObsMatch {
-    LuxHeader* hdr; LuxCell* cells; LuxUnit* units; uint16_t* tiles; uint16_t* res;
-    uint16_t* nodes_res; uint16_t* nodes_tile; uint16_t* nodes_work;
+    LuxHeader* hdr; LuxUnit* units; uint16_t* tiles; uint16_t* res;
+    uint32_t* nodes_res; uint32_t* nodes_tile; uint32_t* nodes_work; uint8_t* tinfo;
+    const LuxCell* cells;        // the grid stays in global memory, read once per resource cell / city tile
     const LuxCity* g_cities;     // cities stay in global memory: two lookups per entity
-    int S, ncell;
+    int S, ncell, r_cap;
 };
 
-LUX_DEV void lux_obs_bind(LuxObsMatch& M, unsigned char* smem, const LuxObsLayout& L, int size, const LuxCity* g_cities) {
-    M.hdr = (LuxHeader*)(smem + L.hdr); M.cells = (LuxCell*)(smem + L.cells);
+LUX_DEV void lux_obs_bind(LuxObsMatch& M, unsigned char* smem, const LuxObsLayout& L, int size, const LuxCell* g_cells,
+                          const LuxCity* g_cities) {
+    M.hdr = (LuxHeader*)(smem + L.hdr);
     M.units = (LuxUnit*)(smem + L.units);
     M.tiles = (uint16_t*)(smem + L.tiles); M.res = (uint16_t*)(smem + L.res);
-    M.nodes_res = (uint16_t*)(smem + L.nodes_res); M.nodes_tile = (uint16_t*)(smem + L.nodes_tile);
-    M.nodes_work = (uint16_t*)(smem + L.nodes_work);
+    M.nodes_res = (uint32_t*)(smem + L.nodes_res); M.nodes_tile = (uint32_t*)(smem + L.nodes_tile);
+    M.nodes_work = (uint32_t*)(smem + L.nodes_work);
+    M.tinfo = smem + L.tinfo;
+    M.cells = g_cells;
     M.g_cities = g_cities;
-    M.S = size; M.ncell = size * size;
+    M.S = size; M.ncell = size * size; M.r_cap = L.r_cap;
 }
 
 // lexicographic trackers over (squared distance, list index)
@@ -76,13 +85,13 @@ LUX_DEV void lux_arg_max2(LuxArg& a1, LuxArg& a2, int d, int i) {
 }
 
 // one (closest|furthest, key) block of 7 floats (agent_policy.py:327-385), written into the (zeroed) row
-LUX_DEV void lux_obs_block(const LuxObsMatch& M, float* o, const uint16_t* nodes, int n, int px, int py,
+LUX_DEV void lux_obs_block(const LuxObsMatch& M, float* o, const uint32_t* nodes, int n, int px, int py,
                            int exclude, int furthest, int key, int n_units) {
     if (n == 0) return;                                   // key not in object_nodes
     LuxArg mn1 = {0x7fffffff, -1}, mn2 = {0x7fffffff, -1}, mx1 = {-1, -1}, mx2 = {-1, -1};
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        int xy = nodes[i];
+        int xy = (int)(nodes[i] & 0xffffu);
         int dx = (xy & 0xff) - px, dy = (xy >> 8) - py;
         int d = dx * dx + dy * dy;
         lux_arg_min2(mn1, mn2, d, i);
@@ -96,8 +105,8 @@ LUX_DEV void lux_obs_block(const LuxObsMatch& M, float* o, const uint16_t* nodes
     } else {
         pick = furthest ? mx1.i : mn1.i;
     }
-    int xy = nodes[pick];
-    int tx = xy & 0xff, ty = xy >> 8;
+    const unsigned node = nodes[pick];
+    int tx = node & 0xff, ty = (node >> 8) & 0xff;
     // Position.direction_to (position.py:48-66): N, E, S, W, first strict improvement; slots c,n,w,s,e
     int slot = 0;
     if (ty < py) slot = 1; else if (tx > px) slot = 4; else if (ty > py) slot = 3; else if (tx < px) slot = 2;
@@ -105,14 +114,13 @@ LUX_DEV void lux_obs_block(const LuxObsMatch& M, float* o, const uint16_t* nodes
     int man = (tx > px ? tx - px : px - tx) + (ty > py ? ty - py : py - ty);
     double dist = (double)man / 20.0;
     o[5] = (float)(dist < 1.0 ? dist : 1.0);
-    const LuxCell& T = M.cells[ty * M.S + tx];
     double v;
     if (key == 3) {
-        const LuxCity city = M.g_cities[T.city_slot];
+        const LuxCity city = M.g_cities[node >> 16];
         double upkeep = (double)((int)city.ntiles * LUX_UPKEEP_CITY - (int)city.adjsum * LUX_ADJ_BONUS);
         v = (double)city.fuel / (upkeep * 200.0);
     } else if (key < 3) {
-        v = (double)T.amount / 500.0;
+        v = (double)(node >> 16) / 500.0;
     } else {
         // first unit in that cell's dict (:380-381): every unit standing on a cell gives the same value in
         // reachable states; the first in slot order is taken
@@ -145,7 +153,7 @@ LUX_DEV void lux_zero_floats(float* p, int count) {
     if (lane < count - done) p[done + lane] = 0.0f;
 }
 
-// Shared memory holds the match (hdr, cells, units, tiles, res).  Writes obs rows, entity codes and
+// Shared memory holds the match's lists (hdr, units, tiles, res); the grid is read in place.  Writes obs rows, entity codes and
 // returns the number of entities (rows beyond `room` are dropped).
 LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, int room) {
     const int lane = lux_lane();
@@ -154,24 +162,23 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
     const int S = M.S;
     const int n_units = h->n_units, n_tiles = h->n_tiles, n_res = h->n_res;
 
-    // ---- node lists (agent_policy.py:197-247), order-preserving ballot compaction
+    // ---- node lists (agent_policy.py:197-247), order-preserving ballot compaction; the one pass that reads
+    // the grid: a global load per resource cell and per city tile, what later stages need rides in the entry
     int n_type[3] = {0, 0, 0};
-    {
-        int base_out = 0;
 #pragma unroll 1
-        for (int t = 1; t <= 3; t++) {
-            int cnt = 0;
-#pragma unroll 1
-            for (int base = 0; base < n_res; base += 32) {
-                int r = base + lane;
-                int cell = r < n_res ? M.res[r] : 0;
-                int ok = r < n_res && M.cells[cell].amount > 0 && cell_res_type(M.cells[cell]) == t;
-                unsigned m = lux_ballot(ok);
-                if (ok) M.nodes_res[base_out + cnt + lux_popc(m & lt)] = (uint16_t)((cell % S) | ((cell / S) << 8));
-                cnt += lux_popc(m);
-            }
-            n_type[t - 1] = cnt;
-            base_out += cnt;
+    for (int base = 0; base < n_res; base += 32) {
+        int r = base + lane;
+        int cell = r < n_res ? M.res[r] : 0;
+        LuxCell C;
+        C.amount = 0; C.flags = 0;
+        if (r < n_res) C = lux_ldcell(M.cells, cell);
+        const int t = C.amount > 0 ? cell_res_type(C) : 0;
+        const unsigned node = (unsigned)(cell % S) | ((unsigned)(cell / S) << 8) | ((unsigned)C.amount << 16);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            unsigned m = lux_ballot(t == k + 1);
+            if (t == k + 1) M.nodes_res[k * M.r_cap + n_type[k] + lux_popc(m & lt)] = node;
+            n_type[k] += lux_popc(m);
         }
     }
     int own_tiles = 0, opp_tiles = 0;
@@ -179,9 +186,13 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
     for (int base = 0; base < n_tiles; base += 32) {
         int p = base + lane;
         int cell = p < n_tiles ? M.tiles[p] : 0;
-        int own = p < n_tiles && cell_tile_team(M.cells[cell]) == team;
+        LuxCell C;
+        C.flags = 0; C.tile_cd = 0; C.city_slot = 0;
+        if (p < n_tiles) C = lux_ldcell(M.cells, cell);
+        int own = p < n_tiles && cell_tile_team(C) == team;
+        if (p < n_tiles) M.tinfo[p] = (uint8_t)((cell_tile_team(C) & 1) | ((C.tile_cd < 1) << 1));
         unsigned m = lux_ballot(own);
-        if (own) M.nodes_tile[own_tiles + lux_popc(m & lt)] = (uint16_t)((cell % S) | ((cell / S) << 8));
+        if (own) M.nodes_tile[own_tiles + lux_popc(m & lt)] = (unsigned)(cell % S) | ((unsigned)(cell / S) << 8) | ((unsigned)C.city_slot << 16);
         own_tiles += lux_popc(m);
         opp_tiles += lux_popc(lux_ballot(p < n_tiles && !own));
     }
@@ -192,7 +203,7 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
         int mine = u < n_units && unit_team(M.units[u]) == team;
         int worker = mine && !unit_is_cart(M.units[u]);
         unsigned m = lux_ballot(worker);
-        if (worker) M.nodes_work[own_workers + lux_popc(m & lt)] = (uint16_t)(M.units[u].x | (M.units[u].y << 8));
+        if (worker) M.nodes_work[own_workers + lux_popc(m & lt)] = (unsigned)M.units[u].x | ((unsigned)M.units[u].y << 8);
         own_workers += lux_popc(m);
         own_carts += lux_popc(lux_ballot(mine && !worker));
     }
@@ -220,8 +231,8 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
         } else if (e < total) {
             int p = e - n_units;
             int cell = M.tiles[p];
-            const LuxCell& C = M.cells[cell];
-            valid = cell_tile_team(C) == team && C.tile_cd < 1;
+            const int ti = M.tinfo[p];
+            valid = (ti & 1) == team && (ti & 2) != 0;
             px = cell % S; py = cell / S; kind = 2; code = 0x4000 | p;
         }
         unsigned vm = lux_ballot(valid);
@@ -249,9 +260,7 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
 #pragma unroll 1
                 for (int key = 0; key < 5; key++, at += 7) {
                     int exclude = (key == 3 && kind == 2) || (key == 4 && kind == 0 && alone);
-                    const uint16_t* nodes = key == 0 ? M.nodes_res : key == 1 ? M.nodes_res + n_type[0]
-                                          : key == 2 ? M.nodes_res + n_type[0] + n_type[1]
-                                          : key == 3 ? M.nodes_tile : M.nodes_work;
+                    const uint32_t* nodes = key < 3 ? M.nodes_res + key * M.r_cap : key == 3 ? M.nodes_tile : M.nodes_work;
                     int n = key < 3 ? n_type[key] : key == 3 ? own_tiles : own_workers;
                     lux_obs_block(M, o + at, nodes, n, px, py, exclude, furthest, key, n_units);
                 }

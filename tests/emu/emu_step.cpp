@@ -92,11 +92,10 @@ static void emu_obs_lane(void* p) {
     const LuxBatch* b = a->b;
     int m = a->m, ncell = b->size * b->size;
     LuxObsMatch M;
-    lux_obs_bind(M, a->smem, a->L, b->size, b->cities + (size_t)m * b->c_cap);
+    lux_obs_bind(M, a->smem, a->L, b->size, b->cells + (size_t)m * ncell, b->cities + (size_t)m * b->c_cap);
     lux_copy16(M.hdr, b->hdr + m, LUX_HDR_BYTES);
     lux_sync();
     if (M.hdr->done) { if (lux_lane() == 0) a->cnt[m] = 0; return; }
-    lux_copy16(M.cells, b->cells + (size_t)m * ncell, ncell * 8);
     lux_copy16(M.units, b->units + (size_t)m * b->u_cap, M.hdr->n_units * 16);
     lux_copy16(M.tiles, b->tiles + (size_t)m * b->t_cap, M.hdr->n_tiles * 2);
     lux_copy16(M.res, b->res + (size_t)m * b->r_cap, M.hdr->n_res * 2);
