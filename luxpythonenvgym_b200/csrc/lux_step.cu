@@ -191,6 +191,7 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
 // kernels this library has launched (all entry points of this translation unit); bench.py reports the
 // difference over its timed region as "gpu_launches"
 static unsigned long long g_launches = 0;
+static int g_gen_wpc = 8;         // warps (matches) per CTA of the action-stream kernel
 static int g_list_grid = 0;       // CTAs of the big-class launch (0 = automatic)
 static int g_overlap = 1;         // 1 = the small class is a programmatic dependent of the big class (they overlap)
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
@@ -305,58 +306,68 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
     // only the live prefix (rounded up to the staging granule) is written: the step kernel never looks further
     const int nu_w = done ? 0 : min(b.u_cap, (nu + 3) & ~3);
     const int nt_w = done ? 0 : min(b.t_cap, (nt + 15) & ~15);
-    for (int i = lane; i < nu_w; i += 32) {
-        uint32_t w = 0;
-        if (!done && i < nu) {
-            const LuxUnit U = units[i];
-            uint64_t r = lux_hash(seed, mid, (uint64_t)turn, 0, (uint64_t)U.id);
-            int can_act = U.cd_q < 4;
-            if (can_act || ((r >> 32) & 15) == 0) {
-                unsigned p = lux_mod64(r, 100);
-                const LuxCell C = cells[U.y * S + U.x];
-                int cargo = U.wood + U.coal + U.uranium;
-                int night = (turn % 40) >= 30;
-                int on_tile = (C.flags & 0x0C) != 0;
-                int can_build = !(U.team_type & 2) && cargo >= 100 && !on_tile && C.amount == 0;
-                if (can_build && ((r >> 40) & 3) != 0) w = LUX_UA_BCITY;
-                else if (night && on_tile && ((r >> 42) & 7) != 0) w = 0;
-                else if (p < 40) w = 0;
-                else if (p < 80) w = LUX_UA_MOVE | ((1 + ((r >> 8) & 3)) << 3);
-                else if (p < 85) w = LUX_UA_BCITY;
-                else if (p < 88) w = LUX_UA_PILLAGE;
-                else {
-                    int best_id = 0x7fffffff;
-                    for (int j = 0; j < nu; j++) {
-                        const LuxUnit V = units[j];
-                        if (j == i || ((V.team_type ^ U.team_type) & 1)) continue;
-                        int d = abs((int)V.x - (int)U.x) + abs((int)V.y - (int)U.y);
-                        if (d <= 1 && V.id < best_id) best_id = V.id;
-                    }
-                    if (best_id != 0x7fffffff) {
-                        uint32_t res = lux_mod64(r >> 8, 3), amount = 1 + lux_mod64(r >> 16, 100);
-                        w = LUX_UA_TRANSFER | (res << 3) | (amount << 6) | ((uint32_t)best_id << 17);
+    // units and city tiles share one pass (entity e < nu_w: unit slot e, else tile position e - nu_w): the
+    // 64-bit hash is most of the work and a typical match has fewer than 32 entities of both kinds together
+    for (int e = lane; e < nu_w + nt_w; e += 32) {
+        const int is_unit = e < nu_w;
+        const int i = is_unit ? e : e - nu_w;
+        const int live = !done && i < (is_unit ? nu : nt);
+        LuxUnit U;
+        int cell = 0;
+        uint64_t r = 0;
+        if (live) {
+            if (is_unit) { U = units[i]; cell = U.y * S + U.x; }
+            else cell = tiles[i];
+            r = lux_hash(seed, mid, (uint64_t)turn, is_unit ? 0 : 1, is_unit ? (uint64_t)U.id : (uint64_t)cell);
+        }
+        if (is_unit) {
+            uint32_t w = 0;
+            if (live) {
+                int can_act = U.cd_q < 4;
+                if (can_act || ((r >> 32) & 15) == 0) {
+                    unsigned p = lux_mod64(r, 100);
+                    const LuxCell C = cells[cell];
+                    int cargo = U.wood + U.coal + U.uranium;
+                    int night = (turn % 40) >= 30;
+                    int on_tile = (C.flags & 0x0C) != 0;
+                    int can_build = !(U.team_type & 2) && cargo >= 100 && !on_tile && C.amount == 0;
+                    if (can_build && ((r >> 40) & 3) != 0) w = LUX_UA_BCITY;
+                    else if (night && on_tile && ((r >> 42) & 7) != 0) w = 0;
+                    else if (p < 40) w = 0;
+                    else if (p < 80) w = LUX_UA_MOVE | ((1 + ((r >> 8) & 3)) << 3);
+                    else if (p < 85) w = LUX_UA_BCITY;
+                    else if (p < 88) w = LUX_UA_PILLAGE;
+                    else {
+                        int best_id = 0x7fffffff;
+                        for (int j = 0; j < nu; j++) {
+                            const LuxUnit V = units[j];
+                            if (j == i || ((V.team_type ^ U.team_type) & 1)) continue;
+                            int d = abs((int)V.x - (int)U.x) + abs((int)V.y - (int)U.y);
+                            if (d <= 1 && V.id < best_id) best_id = V.id;
+                        }
+                        if (best_id != 0x7fffffff) {
+                            uint32_t res = lux_mod64(r >> 8, 3), amount = 1 + lux_mod64(r >> 16, 100);
+                            w = LUX_UA_TRANSFER | (res << 3) | (amount << 6) | ((uint32_t)best_id << 17);
+                        }
                     }
                 }
             }
-        }
-        ua[i] = w;
-    }
-    for (int p = lane; p < nt_w; p += 32) {
-        uint8_t code = 0;
-        if (!done && p < nt) {
-            int cell = tiles[p];
-            uint64_t r = lux_hash(seed, mid, (uint64_t)turn, 1, (uint64_t)cell);
-            int can_act = cells[cell].tile_cd < 1;
-            if (can_act || ((r >> 32) & 15) == 0) {
-                unsigned q = lux_mod64(r, 100);
-                code = q < 45 ? LUX_TA_BUILD_WORKER : q < 50 ? LUX_TA_BUILD_CART : q < 90 ? LUX_TA_RESEARCH : LUX_TA_NONE;
+            ua[i] = w;
+        } else {
+            uint8_t code = 0;
+            if (live) {
+                int can_act = cells[cell].tile_cd < 1;
+                if (can_act || ((r >> 32) & 15) == 0) {
+                    unsigned q = lux_mod64(r, 100);
+                    code = q < 45 ? LUX_TA_BUILD_WORKER : q < 50 ? LUX_TA_BUILD_CART : q < 90 ? LUX_TA_RESEARCH : LUX_TA_NONE;
+                }
             }
+            ta[i] = code;
         }
-        ta[p] = code;
     }
 }
 
-__global__ void lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match_id_base,
+__global__ void __launch_bounds__(1024, 2) lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match_id_base,
                                        uint32_t* __restrict__ unit_actions, uint8_t* __restrict__ tile_actions,
                                        unsigned long long* counters) {
     __shared__ unsigned long long cta_counters[2];
@@ -483,6 +494,7 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "tma")) { g_use_tma = value != 0; return LUX_OK; }
     if (!strcmp(name, "warps_per_cta")) { g_warps_per_cta = value; return LUX_OK; }
     if (!strcmp(name, "two_class")) { g_two_class = value; return LUX_OK; }
+    if (!strcmp(name, "gen_wpc")) { g_gen_wpc = value < 1 ? 1 : value > 32 ? 32 : value; return LUX_OK; }
     if (!strcmp(name, "list_grid")) { g_list_grid = value; return LUX_OK; }
     if (!strcmp(name, "overlap")) { g_overlap = value != 0; return LUX_OK; }
     if (!strcmp(name, "group")) { g_group = value; return LUX_OK; }
@@ -795,7 +807,7 @@ extern "C" int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t m
     if (!unit_actions || !tile_actions) return LUX_E_ARG;
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
-    const int wpc = 8;
+    const int wpc = g_gen_wpc;
     lux_gen_actions_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, 0, (cudaStream_t)cuda_stream>>>(
         *b, seed, match_id_base, unit_actions, tile_actions, (unsigned long long*)counters);
     g_launches++;
