@@ -78,12 +78,13 @@ class BatchedLuxEnvironment:
         self.team = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
         self.reward_state = torch.zeros((self.n, 4), dtype=torch.int32, device=self.device)
         self.resets = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._gen = torch.Generator(device="cpu").manual_seed(team_seed)
+        self._gen = torch.Generator(device=self.device).manual_seed(team_seed)
         self._epoch = 0
 
     def _draw_teams(self, mask=None):
-        # learning team = coin flip per reset (MatchController.reset, match_controller.py:118-122)
-        flips = torch.randint(0, 2, (self.n,), generator=self._gen, dtype=torch.uint8).to(self.device)
+        # learning team = coin flip per reset (MatchController.reset, match_controller.py:118-122); drawn on the
+        # device so that a step never waits for the host
+        flips = torch.randint(0, 2, (self.n,), generator=self._gen, dtype=torch.uint8, device=self.device)
         self.team = flips if mask is None else torch.where(mask, flips, self.team)
 
     def reset(self):
@@ -116,10 +117,10 @@ class BatchedLuxEnvironment:
         g.step(prevalidate=True)
         reward = g.reward(self.team, self.reward_state)
         done = g.hdr[:, 24] != 0
-        if bool(done.any()):
-            g.reset_done(self.pool, self._epoch, self.resets)
-            self.reward_state[done] = 0
-            self._draw_teams(done)
+        # no host decision here: the reset kernel skips live matches, the other two are masked updates
+        g.reset_done(self.pool, self._epoch, self.resets)
+        self.reward_state.masked_fill_(done[:, None], 0)
+        self._draw_teams(done)
         self._epoch += 1
         return self._observe(), reward, done
 
