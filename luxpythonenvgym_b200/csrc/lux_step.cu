@@ -286,7 +286,7 @@ __device__ __forceinline__ unsigned lux_mod64(uint64_t r, unsigned m) {
 // one warp per match, state read in place from global memory (harness kernel, not the hot path)
 __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, uint64_t seed, uint64_t match_id_base,
                                                       uint32_t* __restrict__ unit_actions,
-                                                      uint8_t* __restrict__ tile_actions, unsigned long long* counters) {
+                                                      uint8_t* __restrict__ tile_actions, unsigned* counters) {
     const int lane = threadIdx.x & 31;
     const int ncell = b.size * b.size, S = b.size;
     const LuxHeader* h = b.hdr + m;
@@ -299,8 +299,8 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
     if (counters && lane == 0 && !done) {
         // live match-turns and their algorithmic bytes for the turn about to run
         // (`counters` is the CTA's shared-memory pair here; one global add per CTA follows)
-        atomicAdd(counters, 1ULL);
-        atomicAdd(counters + 1, (unsigned long long)(2 * (8 * ncell + 16 * nu + 16 * (int)h->n_cities + 64) + 4 * (nu + nt)));
+        atomicAdd(counters, 1u);
+        atomicAdd(counters + 1, (unsigned)(2 * (8 * ncell + 16 * nu + 16 * (int)h->n_cities + 64) + 4 * (nu + nt)));
     }
     const uint64_t mid = match_id_base + (uint64_t)m;
     // only the live prefix (rounded up to the staging granule) is written: the step kernel never looks further
@@ -370,13 +370,25 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
 __global__ void __launch_bounds__(1024, 2) lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match_id_base,
                                        uint32_t* __restrict__ unit_actions, uint8_t* __restrict__ tile_actions,
                                        unsigned long long* counters) {
-    __shared__ unsigned long long cta_counters[2];
-    if (threadIdx.x < 2) cta_counters[threadIdx.x] = 0;
-    __syncthreads();
+    // per-CTA accumulation of the two counters; the last warp to finish publishes them (no barrier at the end:
+    // the warps of a CTA have very different amounts of work)
+    __shared__ unsigned cta_counters[2];
+    __shared__ unsigned cta_ticket;
+    if (counters) {
+        if (threadIdx.x < 2) cta_counters[threadIdx.x] = 0;
+        if (threadIdx.x == 2) cta_ticket = 0;
+        __syncthreads();
+    }
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m < b.n_matches) lux_gen_actions_match(b, m, seed, match_id_base, unit_actions, tile_actions, counters ? cta_counters : nullptr);
-    __syncthreads();
-    if (counters && threadIdx.x < 2 && cta_counters[threadIdx.x]) atomicAdd(counters + threadIdx.x, cta_counters[threadIdx.x]);
+    if (counters && (threadIdx.x & 31) == 0) {
+        __threadfence_block();
+        if (atomicAdd(&cta_ticket, 1u) == (blockDim.x >> 5) - 1) {
+            __threadfence_block();
+            unsigned live = atomicAdd(&cta_counters[0], 0u), bytes = atomicAdd(&cta_counters[1], 0u);
+            if (live) { atomicAdd(counters, (unsigned long long)live); atomicAdd(counters + 1, (unsigned long long)bytes); }
+        }
+    }
 }
 
 // ---------------------------------------------------------------- episode statistics

@@ -79,6 +79,34 @@ def step_many(states, unit_words, tile_bytes, flags=0, group=None):
             dst[...] = arr[k][i].view(dst.dtype).reshape(dst.shape)
 
 
+def need(ms):
+    """(LuxNeed fields u, c, t, r, q, slice bytes) the kernel computes from this state's header."""
+    L = lib()
+    hdr = ms.hdr.reshape(1)
+    out = np.zeros(5, dtype=np.int32)
+    total = L.lux_emu_need(hdr.ctypes.data_as(ctypes.c_void_p), ms.size, len(ms.units), len(ms.cities), len(ms.tiles), len(ms.res), _p(out))
+    return tuple(int(x) for x in out) + (int(total),)
+
+
+def step_slice(ms, unit_words, tile_bytes, slice_bytes, flags=0):
+    """One turn with a `slice_bytes` shared-memory slice: returns True when the turn did not fit (state untouched).
+    A canary behind the slice catches any write past it."""
+    L = lib()
+    hdr = ms.hdr.reshape(1)
+    uw = np.zeros(len(ms.units), dtype=np.uint32)
+    tb = np.zeros(len(ms.tiles), dtype=np.uint8)
+    uw[:] = unit_words[: len(uw)]
+    tb[:] = tile_bytes[: len(tb)]
+    b = LuxBatchC(1, ms.size, len(ms.units), len(ms.cities), len(ms.tiles), len(ms.res),
+                  hdr.ctypes.data, ms.cells.ctypes.data, ms.units.ctypes.data, ms.cities.ctypes.data,
+                  ms.tiles.ctypes.data, ms.res.ctypes.data)
+    rc = L.lux_emu_step_slice(ctypes.byref(b), _p(uw), _p(tb), int(flags), int(slice_bytes))
+    ms.hdr = hdr[0]
+    if rc < 0:
+        raise RuntimeError("lux_emu_step_slice -> %d" % rc)
+    return rc > 0
+
+
 def observe(ms, team, e_cap=640):
     """Observation rows of one MatchState through the emulated kernel."""
     L = lib()

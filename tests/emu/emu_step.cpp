@@ -75,6 +75,40 @@ extern "C" int lux_emu_step_group(const LuxBatch* b, const uint32_t* unit_action
     return a.dirty ? -100 : 0;
 }
 
+// the per-turn shared-memory need of a header (lux_need_header + lux_smem_layout_need), for property tests
+extern "C" int lux_emu_need(const LuxHeader* h, int size, int u_cap, int c_cap, int t_cap, int r_cap, int* out5) {
+    LuxNeed n = lux_need_header(h, u_cap, c_cap, t_cap, r_cap);
+    out5[0] = n.u; out5[1] = n.c; out5[2] = n.t; out5[3] = n.r; out5[4] = n.q;
+    return lux_smem_layout_need(size, n).total;
+}
+
+// one turn with `slice` bytes per match: matches whose turn does not fit are left untouched (returns how many)
+extern "C" int lux_emu_step_slice(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions, unsigned flags,
+                                  int slice) {
+    if (!b || !unit_actions || !tile_actions) return LUX_E_ARG;
+    int skipped = 0;
+    unsigned char* smem = (unsigned char*)aligned_alloc(16, (size_t)slice + 64);
+    for (int m = 0; m < b->n_matches; m++) {
+        const LuxHeader* h = b->hdr + m;
+        if (!h->done && lux_smem_layout_need(b->size, lux_need_header(h, b->u_cap, b->c_cap, b->t_cap, b->r_cap)).total > slice) skipped++;
+    }
+    EmuArgs a;
+    a.b = b; a.ua = unit_actions; a.ta = tile_actions; a.flags = flags; a.dirty = 0; a.group = 32;
+    a.L = lux_smem_layout(b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap);
+    a.L.total = slice;                         // emu_lane sizes and limits the slice by L.total
+    a.smem = smem;
+    for (int m = 0; m < b->n_matches; m++) {
+        memset(smem, 0xA5, (size_t)slice);
+        memset(smem + slice, 0x5A, 64);        // canary behind the slice
+        a.m = m;
+        warp_emu::run_warp(emu_lane<32>, &a, 32);
+        for (int i = 0; i < 64; i++)
+            if (smem[slice + i] != 0x5A) { free(smem); return -101; }
+    }
+    free(smem);
+    return a.dirty ? -100 : skipped;
+}
+
 extern "C" int lux_emu_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions, unsigned flags) {
     return lux_emu_step_group(b, unit_actions, tile_actions, flags, 32);
 }

@@ -89,6 +89,31 @@ def test_emulated_step_lockstep_groups(group):
             assert x.diff(y) == [], "group %d turn %d match %d" % (group, turn, i)
 
 
+@pytest.mark.parametrize("name", G.dense_names()[::3])
+def test_turn_need_bounds_the_turn_and_slices_are_respected(name):
+    """The per-match shared-memory layout is sized by what the header says the turn can touch (LuxNeed).
+    Property, turn by turn on dense late-game states: (1) the populations after the turn never exceed the
+    need computed before it; (2) played with a slice of exactly that many bytes the emulated kernel matches
+    the oracle and never writes behind the slice (canary); (3) one byte less and the match is left untouched
+    for the big class."""
+    z = G.npz("dense")
+    seed, start = int(z["stream_seed"]), int(name.split("@")[1])
+    a = recap(G.get_state(z, name + "/init"))
+    b = a.copy()
+    for turn in range(30):
+        u, c, t, r, q, total = emu.need(a)
+        uw, tb = coracle.gen_actions(a, seed, start)
+        if turn % 7 == 3:
+            before = b.copy()
+            assert emu.step_slice(b, uw, tb, total - 16) is True
+            assert before.diff(b) == []
+        coracle.step(a, uw, tb)
+        assert emu.step_slice(b, uw, tb, total) is False
+        assert a.diff(b) == [], "turn %d" % turn
+        assert int(a.hdr["n_units"]) <= u and int(a.hdr["n_cities"]) <= c and int(a.hdr["n_tiles"]) <= t
+        assert int(a.hdr["status"]) == 0
+
+
 @pytest.mark.parametrize("name", G.obs_names())
 def test_emulated_observations(name):
     z = G.npz("obs")
