@@ -126,7 +126,8 @@ int lux_b200_device_count(void);
 /* Tuning knobs: "tma" (1 = cp.async.bulk staging, 0 = plain vector loads/stores),
  * "warps_per_cta" (0 = automatic), "two_class" (-1 automatic, 0 off, 1 always), "overlap" (1 = big and small class run concurrently),
  * "slice" (shared-memory bytes per match of the small class, 0 = default), "group" (lanes per match: 0 automatic,
- * 8 / 16 / 32), "carveout" (preferred shared-memory carve-out in percent, -1 = driver default).
+ * 8 / 16 / 32), "carveout" (preferred shared-memory carve-out in percent, -1 = automatic), "list_grid" (CTAs of
+ * the big-class launch, 0 = automatic), "gen_wpc" (matches per CTA of the action-stream kernel).
  * Returns LUX_E_ARG for an unknown name. */
 int lux_b200_set_option(const char* name, int value);
 
