@@ -146,10 +146,13 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
     }
 }
 
-template <bool kTma, int kS, int kMode, int G>
+// kPlain: compiled for flags == 0 (no pre-validation, no consumed action words): the common call, and a
+// shorter program for the instruction cache
+template <bool kTma, int kS, int kMode, int G, bool kPlain>
 __global__ void __launch_bounds__(64, (G == 32 && kMode == kSmall) ? LUX_SMALL_MIN_CTAS : 1)
 lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uint8_t* __restrict__ tile_actions,
-                int slice, unsigned flags, LuxSched sc) {
+                int slice, unsigned flags_in, LuxSched sc) {
+    const unsigned flags = kPlain ? 0u : flags_in;
     extern __shared__ __align__(128) unsigned char lux_smem[];
     // the small class may start while this (big) class is still running: the two touch disjoint matches
     if (kMode == kList) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -198,18 +201,18 @@ static int g_carveout = -1;       // preferred shared-memory carve-out in percen
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
 
 // `gpc` = matches (lane groups) per CTA; the CTA has gpc * G threads and gpc slices of `slice` bytes
-template <bool kTma, int kS, int kMode, int G>
-static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, int slice, unsigned flags, const LuxSched& sc,
+template <bool kTma, int kS, int kMode, int G, bool kPlain>
+static int launch_step_plain(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, int slice, unsigned flags, const LuxSched& sc,
                        int n_groups, int wpc, cudaStream_t st) {
     const int gpc = wpc * (32 / G);
     size_t smem = (size_t)slice * gpc;
-    cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G, kPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return LUX_E_CUDA;
     // Carve-out: the grid is read in place through L1, so part of the SM's 256 KB stays cache; and the big and
     // the small class only share an SM when both ask for the same split (measured: 72 % = 164 KB, 0.119 -> 0.110 ms)
     const int carve = g_carveout >= 0 ? g_carveout : (kMode != kAll ? 72 : -1);
     if (carve >= 0) {
-        e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G, kPlain>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return LUX_E_CUDA;
     }
     if (kMode == kSmall && g_overlap) {
@@ -226,13 +229,22 @@ static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta,
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, lux_step_kernel<kTma, kS, kMode, G>, *b, ua, ta, slice, flags, sc);
+        e = cudaLaunchKernelEx(&cfg, lux_step_kernel<kTma, kS, kMode, G, kPlain>, *b, ua, ta, slice, flags, sc);
         if (e != cudaSuccess) return LUX_E_CUDA;
     } else {
-        lux_step_kernel<kTma, kS, kMode, G><<<(n_groups + gpc - 1) / gpc, 32 * wpc, smem, st>>>(*b, ua, ta, slice, flags, sc);
+        lux_step_kernel<kTma, kS, kMode, G, kPlain><<<(n_groups + gpc - 1) / gpc, 32 * wpc, smem, st>>>(*b, ua, ta, slice, flags, sc);
     }
     g_launches++;
     return LUX_OK;
+}
+
+template <bool kTma, int kS, int kMode, int G>
+static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, int slice, unsigned flags, const LuxSched& sc,
+                       int n_groups, int wpc, cudaStream_t st) {
+    if constexpr (kTma && G == 32) {
+        if (flags == 0) return launch_step_plain<kTma, kS, kMode, G, true>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
+    }
+    return launch_step_plain<kTma, kS, kMode, G, false>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
 }
 
 template <bool kTma, int kMode, int G>
