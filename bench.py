@@ -349,7 +349,7 @@ def run_b200(args):
                 "gpu_launches": int(launches) * world,
                 "kernel_ms": {"lux_step_kernel": step_ms, "whole_step": total_ms / K},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "lux_step_kernel (small-class launch + retry-list launch = one step)",
+                             "traffic": None, "peak_source": peak_src, "kernel": "lux_step_kernel (classify + big-class launch overlapped with the small-class launch = one step)",
                              "algorithmic_bytes_per_launch": bytes_all / world / K,
                              "live_match_turns_per_launch": live_all / world / K},
                 "e2e": {"value": e2e_turns / e2e_s, "unit": "match-turns/s", "h2d_bytes_per_step": h2d * world,

@@ -281,7 +281,7 @@ LUX_DEV void lux_planes_init(LuxMatch& M) {
     lux_zero16<G>(M.occ, lux_align16(M.ncell));
 }
 
-// A group without a match to play (past the end of the batch, finished, does not fit the staging class)
+// A group without a match to play (past the end of the batch, finished, does not fit this launch's slice)
 // walks through the turn in lockstep with the other groups of its warp on an empty match: all counts zero.
 template <int G = 32>
 LUX_DEV void lux_idle_header(LuxMatch& M) { lux_zero16<G>(M.hdr, LUX_HDR_BYTES); }
@@ -292,7 +292,7 @@ struct LuxGlobalMatch {
     LuxHeader* hdr; LuxCell* cells; LuxUnit* units; LuxCity* cities; uint16_t* tiles; const uint16_t* res;
     const uint32_t* uact; const uint8_t* tact;
 };
-enum { LUX_M_DONE = 0, LUX_M_SPILL = 1, LUX_M_PLAYED = 2, LUX_M_HEAVY = 3 };
+enum { LUX_M_DONE = 0, LUX_M_SPILL = 1 };     // why a group is not playing: nothing to play / the turn does not fit the slice
 
 // Returns the group's `active` flag (0: nothing to play -- invalid, finished, or the turn's footprint does not
 // fit `slice` bytes, in which case *result says which) with M bound and, when active, staged.  An inactive

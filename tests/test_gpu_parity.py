@@ -422,7 +422,7 @@ def test_spill_list_and_scheduling_paths_under_load():
     inits = [_recap(G.get_state(z, nm + "/init"), caps) for nm in names]
     sparse = mapgen.generate_batch(np.arange(4000, 4096), 32)
     try:
-        for heavy in (0, 1):          # here: overlap off / on
+        for heavy in (0, 1):          # overlap of the two classes off / on
             for k, v in ((b"slice", 3200), (b"two_class", 1), (b"overlap", heavy),
                          (b"group", 16 if heavy else 8)):
                 assert lib.lux_b200_set_option(k, v) == 0
