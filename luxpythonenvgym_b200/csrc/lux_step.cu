@@ -320,11 +320,15 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
     const int nt_w = done ? 0 : min(b.t_cap, (nt + 15) & ~15);
     // units and city tiles share one pass (entity e < nu_w: unit slot e, else tile position e - nu_w): the
     // 64-bit hash is most of the work and a typical match has fewer than 32 entities of both kinds together
-    for (int e = lane; e < nu_w + nt_w; e += 32) {
+    const int total = nu_w + nt_w;
+    for (int base = 0; base < total; base += 32) {          // warp-uniform trip count (shuffles inside)
+        const int e = base + lane;
+        const int in_range = e < total;
         const int is_unit = e < nu_w;
         const int i = is_unit ? e : e - nu_w;
-        const int live = !done && i < (is_unit ? nu : nt);
+        const int live = in_range && !done && i < (is_unit ? nu : nt);
         LuxUnit U;
+        U.id = 0; U.x = 0; U.y = 0; U.team_type = 0; U.cd_q = 0; U.wood = U.coal = U.uranium = 0;
         int cell = 0;
         uint64_t r = 0;
         if (live) {
@@ -332,49 +336,60 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
             else cell = tiles[i];
             r = lux_hash(seed, mid, (uint64_t)turn, is_unit ? 0 : 1, is_unit ? (uint64_t)U.id : (uint64_t)cell);
         }
-        if (is_unit) {
-            uint32_t w = 0;
-            if (live) {
-                int can_act = U.cd_q < 4;
-                if (can_act || ((r >> 32) & 15) == 0) {
-                    unsigned p = lux_mod64(r, 100);
-                    const LuxCell C = cells[cell];
-                    int cargo = U.wood + U.coal + U.uranium;
-                    int night = (turn % 40) >= 30;
-                    int on_tile = (C.flags & 0x0C) != 0;
-                    int can_build = !(U.team_type & 2) && cargo >= 100 && !on_tile && C.amount == 0;
-                    if (can_build && ((r >> 40) & 3) != 0) w = LUX_UA_BCITY;
-                    else if (night && on_tile && ((r >> 42) & 7) != 0) w = 0;
-                    else if (p < 40) w = 0;
-                    else if (p < 80) w = LUX_UA_MOVE | ((1 + ((r >> 8) & 3)) << 3);
-                    else if (p < 85) w = LUX_UA_BCITY;
-                    else if (p < 88) w = LUX_UA_PILLAGE;
-                    else {
-                        int best_id = 0x7fffffff;
-                        for (int j = 0; j < nu; j++) {
-                            const LuxUnit V = units[j];
-                            if (j == i || ((V.team_type ^ U.team_type) & 1)) continue;
-                            int d = abs((int)V.x - (int)U.x) + abs((int)V.y - (int)U.y);
-                            if (d <= 1 && V.id < best_id) best_id = V.id;
-                        }
-                        if (best_id != 0x7fffffff) {
-                            uint32_t res = lux_mod64(r >> 8, 3), amount = 1 + lux_mod64(r >> 16, 100);
-                            w = LUX_UA_TRANSFER | (res << 3) | (amount << 6) | ((uint32_t)best_id << 17);
-                        }
-                    }
+        uint32_t w = 0;
+        uint8_t code = 0;
+        int want_target = 0;                       // a transfer: needs the lowest-id adjacent teammate
+        if (live && is_unit) {
+            int can_act = U.cd_q < 4;
+            if (can_act || ((r >> 32) & 15) == 0) {
+                unsigned p = lux_mod64(r, 100);
+                const LuxCell C = cells[cell];
+                int cargo = U.wood + U.coal + U.uranium;
+                int night = (turn % 40) >= 30;
+                int on_tile = (C.flags & 0x0C) != 0;
+                int can_build = !(U.team_type & 2) && cargo >= 100 && !on_tile && C.amount == 0;
+                if (can_build && ((r >> 40) & 3) != 0) w = LUX_UA_BCITY;
+                else if (night && on_tile && ((r >> 42) & 7) != 0) w = 0;
+                else if (p < 40) w = 0;
+                else if (p < 80) w = LUX_UA_MOVE | ((1 + ((r >> 8) & 3)) << 3);
+                else if (p < 85) w = LUX_UA_BCITY;
+                else if (p < 88) w = LUX_UA_PILLAGE;
+                else want_target = 1;
+            }
+        } else if (live) {
+            int can_act = cells[cell].tile_cd < 1;
+            if (can_act || ((r >> 32) & 15) == 0) {
+                unsigned q = lux_mod64(r, 100);
+                code = q < 45 ? LUX_TA_BUILD_WORKER : q < 50 ? LUX_TA_BUILD_CART : q < 90 ? LUX_TA_RESEARCH : LUX_TA_NONE;
+            }
+        }
+        if (__any_sync(0xffffffffu, want_target)) {
+            int best_id = 0x7fffffff;
+            if (base == 0 && nu <= 32) {
+                // every unit of the match sits in a lane of this pass: broadcast them one by one
+                const int mine = (int)U.x | ((int)U.y << 8) | ((int)(U.team_type & 1) << 16);
+                for (int j = 0; j < nu; j++) {
+                    const int other = __shfl_sync(0xffffffffu, mine, j), oid = __shfl_sync(0xffffffffu, U.id, j);
+                    if (j == i || ((other ^ mine) >> 16)) continue;
+                    int d = abs((other & 0xff) - (int)U.x) + abs(((other >> 8) & 0xff) - (int)U.y);
+                    if (d <= 1 && oid < best_id) best_id = oid;
+                }
+            } else if (want_target) {
+                for (int j = 0; j < nu; j++) {
+                    const LuxUnit V = units[j];
+                    if (j == i || ((V.team_type ^ U.team_type) & 1)) continue;
+                    int d = abs((int)V.x - (int)U.x) + abs((int)V.y - (int)U.y);
+                    if (d <= 1 && V.id < best_id) best_id = V.id;
                 }
             }
-            ua[i] = w;
-        } else {
-            uint8_t code = 0;
-            if (live) {
-                int can_act = cells[cell].tile_cd < 1;
-                if (can_act || ((r >> 32) & 15) == 0) {
-                    unsigned q = lux_mod64(r, 100);
-                    code = q < 45 ? LUX_TA_BUILD_WORKER : q < 50 ? LUX_TA_BUILD_CART : q < 90 ? LUX_TA_RESEARCH : LUX_TA_NONE;
-                }
+            if (want_target && best_id != 0x7fffffff) {
+                uint32_t res = lux_mod64(r >> 8, 3), amount = 1 + lux_mod64(r >> 16, 100);
+                w = LUX_UA_TRANSFER | (res << 3) | (amount << 6) | ((uint32_t)best_id << 17);
             }
-            ta[i] = code;
+        }
+        if (in_range) {
+            if (is_unit) ua[i] = w;
+            else ta[i] = code;
         }
     }
 }
