@@ -460,33 +460,39 @@ __global__ void lux_reset_done_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch,
     }
     src = __shfl_sync(0xffffffffu, src, 0);
     const int ncell = b.size * b.size;
-    // 8 independent 16-byte loads in flight per lane before the stores: the copy of one match is a
-    // single warp's latency chain otherwise (measured 17 us for 9 KB)
-    auto copy = [&](void* d, const void* s, size_t bytes) {
-        const uint4* sp = (const uint4*)s;
-        uint4* dp = (uint4*)d;
-        const size_t n16 = bytes / 16;
-        for (size_t base = 0; base < n16; base += 32 * 8) {
-            uint4 v[8];
+    // The pool header first (it names the live sizes), then every section as ONE flat run of 16-byte pieces
+    // with 8 independent loads in flight per lane: the copy of a match is a single warp's latency chain, so
+    // what counts is the number of dependent round trips (two here plus the stores), not the bytes.
+    const LuxHeader* ph = pool.hdr + src;
+    uint4 hv = make_uint4(0, 0, 0, 0);
+    if (lane < LUX_HDR_BYTES / 16) hv = ((const uint4*)ph)[lane];
+    // n_units, n_cities at byte 12 (lane 0, .w), n_tiles, n_res at byte 16 (lane 1, .x)
+    const unsigned w_uc = __shfl_sync(0xffffffffu, hv.w, 0), w_tr = __shfl_sync(0xffffffffu, hv.x, 1);
+    const int nu = w_uc & 0xffff, nc = w_uc >> 16, nt = w_tr & 0xffff, nr = w_tr >> 16;
+    const char* s0 = (const char*)(pool.cells + (size_t)src * ncell); char* d0 = (char*)(b.cells + (size_t)m * ncell);
+    const char* s1 = (const char*)(pool.units + (size_t)src * b.u_cap); char* d1 = (char*)(b.units + (size_t)m * b.u_cap);
+    const char* s2 = (const char*)(pool.cities + (size_t)src * b.c_cap); char* d2 = (char*)(b.cities + (size_t)m * b.c_cap);
+    const char* s3 = (const char*)(pool.tiles + (size_t)src * b.t_cap); char* d3 = (char*)(b.tiles + (size_t)m * b.t_cap);
+    const char* s4 = (const char*)(pool.res + (size_t)src * b.r_cap); char* d4 = (char*)(b.res + (size_t)m * b.r_cap);
+    // running end of each segment in the flat index space (16-byte pieces)
+    const int e0 = ncell / 2, e1 = e0 + nu, e2 = e1 + nc, e3 = e2 + (nt * 2 + 15) / 16, total = e3 + (nr * 2 + 15) / 16;
+    for (int base = 0; base < total; base += 32 * 8) {
+        uint4 v[8];
+        char* dst[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                size_t i = base + (size_t)k * 32 + lane;
-                if (i < n16) v[k] = sp[i];
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                size_t i = base + (size_t)k * 32 + lane;
-                if (i < n16) dp[i] = v[k];
-            }
+        for (int k = 0; k < 8; k++) {
+            const int f = base + k * 32 + lane;
+            const char* sb = f < e0 ? s0 : f < e1 ? s1 : f < e2 ? s2 : f < e3 ? s3 : s4;
+            char* db = f < e0 ? d0 : f < e1 ? d1 : f < e2 ? d2 : f < e3 ? d3 : d4;
+            const int o = f - (f < e0 ? 0 : f < e1 ? e0 : f < e2 ? e1 : f < e3 ? e2 : e3);
+            dst[k] = db + (size_t)o * 16;
+            if (f < total) v[k] = *(const uint4*)(sb + (size_t)o * 16);
         }
-    };
-    copy(b.cells + (size_t)m * ncell, pool.cells + (size_t)src * ncell, (size_t)ncell * 8);
-    copy(b.units + (size_t)m * b.u_cap, pool.units + (size_t)src * b.u_cap, (size_t)pool.hdr[src].n_units * 16);
-    copy(b.cities + (size_t)m * b.c_cap, pool.cities + (size_t)src * b.c_cap, (size_t)pool.hdr[src].n_cities * 16);
-    copy(b.tiles + (size_t)m * b.t_cap, pool.tiles + (size_t)src * b.t_cap, ((size_t)pool.hdr[src].n_tiles * 2 + 15) & ~(size_t)15);
-    copy(b.res + (size_t)m * b.r_cap, pool.res + (size_t)src * b.r_cap, ((size_t)pool.hdr[src].n_res * 2 + 15) & ~(size_t)15);
-    __syncwarp();
-    copy(b.hdr + m, pool.hdr + src, LUX_HDR_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (base + k * 32 + lane < total) *(uint4*)dst[k] = v[k];
+    }
+    if (lane < LUX_HDR_BYTES / 16) ((uint4*)(b.hdr + m))[lane] = hv;
 }
 
 // ---------------------------------------------------------------- C ABI
