@@ -16,6 +16,13 @@
 
 #define LUX_B200_VERSION 100
 
+// Programmatic dependent launch (griddepcontrol): every kernel of the per-step chain lets its successor be
+// scheduled early (LUX_PDL_TRIGGER, first thing) and waits for its predecessor's completion and memory before it
+// touches anything (LUX_PDL_WAIT).  The successor's launch latency and ramp then hide behind the predecessor's
+// tail.  Both are no-ops in a kernel that was launched the ordinary way.
+#define LUX_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define LUX_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
 // ---------------------------------------------------------------- the step kernel
 // Launch modes.  A match's shared-memory slice is laid out for what THIS turn can touch (LuxNeed: live lists
 // + worst-case growth, ~3 KB for a typical match), not for the batch capacities (252 units / 255 cities /
@@ -128,6 +135,8 @@ struct LuxSched {
 };
 
 __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     // the previous step's statistics go to the host (stale values only delay its choice of slice), then clear
     if (m <= LUX_N_CAND) { sc.seen_host[m] = sc.zero[m]; sc.zero[m] = 0; }
@@ -154,8 +163,12 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
                 int slice, unsigned flags_in, LuxSched sc) {
     const unsigned flags = kPlain ? 0u : flags_in;
     extern __shared__ __align__(128) unsigned char lux_smem[];
-    // the small class may start while this (big) class is still running: the two touch disjoint matches
-    if (kMode == kList) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // the big class needs the classification pass complete; after that the small class may start while this
+    // class is still running (the two touch disjoint matches).  The small class itself only lets its successor
+    // in early and waits for the big class at its END.
+    if (kMode == kList) LUX_PDL_WAIT();
+    if (kMode != kAll) LUX_PDL_TRIGGER();
+    if (kMode == kAll) { LUX_PDL_TRIGGER(); LUX_PDL_WAIT(); }
     // a group of G lanes plays one match; 32 / G matches share a warp
     const int grp = threadIdx.x / G, lane = lux_lane<G>();
     const int gpc = blockDim.x / G;
@@ -188,7 +201,7 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
     if (lux_wany<G>(valid))
         lux_step_match<kTma, kS, G>(b, m, valid, unit_actions, tile_actions, smem, flags, slice, phase);
     // a programmatic dependent may not finish before its primary: later work on the stream waits for this grid
-    if (kMode == kSmall) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (kMode == kSmall) LUX_PDL_WAIT();
 }
 
 // kernels this library has launched (all entry points of this translation unit); bench.py reports the
@@ -199,6 +212,24 @@ static int g_list_grid = 0;       // CTAs of the big-class launch (0 = automatic
 static int g_overlap = 1;         // 1 = the small class is a programmatic dependent of the big class (they overlap)
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
+
+// launch as a programmatic dependent of the preceding kernel on the stream ("overlap" option; ordinary launch
+// otherwise)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_overlap ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // `gpc` = matches (lane groups) per CTA; the CTA has gpc * G threads and gpc slices of `slice` bytes
 template <bool kTma, int kS, int kMode, int G, bool kPlain>
@@ -215,25 +246,9 @@ static int launch_step_plain(const LuxBatch* b, const uint32_t* ua, const uint8_
         e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G, kPlain>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return LUX_E_CUDA;
     }
-    if (kMode == kSmall && g_overlap) {
-        // programmatic dependent launch: may start as soon as every CTA of the preceding big-class kernel has
-        // issued griddepcontrol.launch_dependents (its first instruction)
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3((n_groups + gpc - 1) / gpc);
-        cfg.blockDim = dim3(32 * wpc);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, lux_step_kernel<kTma, kS, kMode, G, kPlain>, *b, ua, ta, slice, flags, sc);
-        if (e != cudaSuccess) return LUX_E_CUDA;
-    } else {
-        lux_step_kernel<kTma, kS, kMode, G, kPlain><<<(n_groups + gpc - 1) / gpc, 32 * wpc, smem, st>>>(*b, ua, ta, slice, flags, sc);
-    }
+    e = launch_chain(lux_step_kernel<kTma, kS, kMode, G, kPlain>, dim3((n_groups + gpc - 1) / gpc), dim3(32 * wpc), smem, st,
+                     *b, ua, ta, slice, flags, sc);
+    if (e != cudaSuccess) return LUX_E_CUDA;
     g_launches++;
     return LUX_OK;
 }
@@ -397,6 +412,8 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
 __global__ void __launch_bounds__(1024, 2) lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match_id_base,
                                        uint32_t* __restrict__ unit_actions, uint8_t* __restrict__ tile_actions,
                                        unsigned long long* counters) {
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
     // per-CTA accumulation of the two counters; the last warp to finish publishes them (no barrier at the end:
     // the warps of a CTA have very different amounts of work)
     __shared__ unsigned cta_counters[2];
@@ -446,6 +463,8 @@ __global__ void lux_stats_kernel(LuxBatch b, unsigned long long* out) {
 
 // ---------------------------------------------------------------- reset finished matches from a pool
 __global__ void lux_reset_done_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch, int* reset_count) {
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
     if (m >= b.n_matches) return;
@@ -668,7 +687,7 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
             sc.zero = S->counts + ((t + 2) % 3) * (1 + LUX_N_CAND);
             sc.seen_host = S->seen;
             for (int i = 0; i < LUX_N_CAND; i++) sc.cand[i] = cand[i];
-            lux_classify_kernel<<<(b->n_matches + 255) / 256, 256, 0, st>>>(*b, full, sc);
+            launch_chain(lux_classify_kernel, dim3((b->n_matches + 255) / 256), dim3(256), 0, st, *b, full, sc);
             g_launches++;
         }
         int group = g_group == 8 || g_group == 16 ? pick_group(full) : 32;
@@ -683,7 +702,7 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     sc.zero = S->counts + ((t + 2) % 3) * (1 + LUX_N_CAND);
     sc.seen_host = S->seen;
     for (int i = 0; i < LUX_N_CAND; i++) sc.cand[i] = cand[i];
-    lux_classify_kernel<<<(b->n_matches + 255) / 256, 256, 0, st>>>(*b, small, sc);
+    launch_chain(lux_classify_kernel, dim3((b->n_matches + 255) / 256), dim3(256), 0, st, *b, small, sc);
     g_launches++;
     rc = cuda_ok(cudaGetLastError(), "lux_classify_kernel launch");
     if (rc) return rc;
@@ -853,8 +872,8 @@ extern "C" int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t m
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
     const int wpc = g_gen_wpc;
-    lux_gen_actions_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, 0, (cudaStream_t)cuda_stream>>>(
-        *b, seed, match_id_base, unit_actions, tile_actions, (unsigned long long*)counters);
+    launch_chain(lux_gen_actions_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), 0, (cudaStream_t)cuda_stream,
+                 *b, seed, match_id_base, unit_actions, tile_actions, (unsigned long long*)counters);
     g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_gen_actions_kernel launch");
 }
@@ -872,8 +891,8 @@ extern "C" int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, uint
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
     const int wpc = 4;
-    lux_reset_done_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, 0, (cudaStream_t)cuda_stream>>>(
-        *b, *pool, epoch, reset_count);
+    launch_chain(lux_reset_done_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), 0, (cudaStream_t)cuda_stream,
+                 *b, *pool, epoch, (int*)reset_count);
     g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_reset_done_kernel launch");
 }
