@@ -8,6 +8,7 @@
 #include <stdio.h>
 
 #include "../../include/lux_b200.h"
+#include "lux_launch.cuh"
 
 #define ENV_CAP_WORKER 100
 #define ENV_CAP_CART 2000
@@ -51,6 +52,8 @@ __global__ void lux_encode_actions_kernel(LuxBatch b, const int16_t* __restrict_
                                           const int32_t* __restrict__ ent_count, const int32_t* __restrict__ codes,
                                           int e_cap, const int64_t* __restrict__ row_offsets,
                                           uint32_t* __restrict__ unit_actions, uint8_t* __restrict__ tile_actions) {
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
     if (m >= b.n_matches) return;
@@ -92,6 +95,8 @@ __global__ void lux_encode_actions_kernel(LuxBatch b, const int16_t* __restrict_
 
 __global__ void lux_reward_kernel(LuxBatch b, const uint8_t* __restrict__ team_sel, int32_t* __restrict__ last,
                                   double* __restrict__ reward) {
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= b.n_matches) return;
     const LuxHeader* h = b.hdr + m;
@@ -125,9 +130,10 @@ extern "C" int lux_b200_encode_actions(const LuxBatch* b, const int16_t* ent_slo
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
     const int wpc = 4;
-    lux_encode_actions_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, 0, (cudaStream_t)cuda_stream>>>(
-        *b, ent_slot, ent_count, codes, e_cap, row_offsets, unit_actions, tile_actions);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = lux_launch_chain(lux_encode_actions_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), 0,
+                                     (cudaStream_t)cuda_stream, *b, ent_slot, ent_count, codes, e_cap, row_offsets, unit_actions,
+                                     tile_actions);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { fprintf(stderr, "lux_b200: encode launch: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
     return LUX_OK;
 }
@@ -139,8 +145,9 @@ extern "C" int lux_b200_reward(const LuxBatch* b, const uint8_t* team_sel, int32
     if (!team_sel || !reward_state || !reward) return LUX_E_ARG;
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
-    lux_reward_kernel<<<(b->n_matches + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(*b, team_sel, reward_state, reward);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = lux_launch_chain(lux_reward_kernel, dim3((b->n_matches + 127) / 128), dim3(128), 0, (cudaStream_t)cuda_stream,
+                                     *b, team_sel, reward_state, reward);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { fprintf(stderr, "lux_b200: reward launch: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
     return LUX_OK;
 }

@@ -9,6 +9,7 @@
 
 #include "lux_obs_core.cuh"
 #include "lux_tma.cuh"
+#include "lux_launch.cuh"
 
 #define LUX_OBS_PRE_UNITS 32
 #define LUX_OBS_PRE_TILES 32
@@ -19,6 +20,8 @@ __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_
                                    int16_t* __restrict__ ent_slot, int32_t* __restrict__ ent_count, int e_cap,
                                    const int64_t* __restrict__ row_offsets, LuxObsLayoutDev D) {
     extern __shared__ __align__(128) unsigned char lux_smem[];
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
     if (m >= b.n_matches) return;
@@ -88,9 +91,9 @@ extern "C" int lux_b200_observe(const LuxBatch* b, const uint8_t* team_sel, floa
     if (smem > 227 * 1024) return LUX_E_CAPACITY;
     cudaError_t e = cudaFuncSetAttribute(lux_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { fprintf(stderr, "lux_b200: observe smem attr: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
-    lux_observe_kernel<<<(b->n_matches + wpc - 1) / wpc, 32 * wpc, smem, (cudaStream_t)cuda_stream>>>(
-        *b, team_sel, obs, ent_slot, ent_count, e_cap, row_offsets, D);
-    e = cudaGetLastError();
+    e = lux_launch_chain(lux_observe_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), smem, (cudaStream_t)cuda_stream,
+                         *b, team_sel, obs, ent_slot, ent_count, e_cap, row_offsets, D);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { fprintf(stderr, "lux_b200: lux_observe_kernel launch: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
     return LUX_OK;
 }

@@ -13,15 +13,10 @@
 
 #include "lux_step_core.cuh"
 #include "lux_tma.cuh"
+#include "lux_launch.cuh"
 
 #define LUX_B200_VERSION 100
 
-// Programmatic dependent launch (griddepcontrol): every kernel of the per-step chain lets its successor be
-// scheduled early (LUX_PDL_TRIGGER, first thing) and waits for its predecessor's completion and memory before it
-// touches anything (LUX_PDL_WAIT).  The successor's launch latency and ramp then hide behind the predecessor's
-// tail.  Both are no-ops in a kernel that was launched the ordinary way.
-#define LUX_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
-#define LUX_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 
 // ---------------------------------------------------------------- the step kernel
 // Launch modes.  A match's shared-memory slice is laid out for what THIS turn can touch (LuxNeed: live lists
@@ -209,27 +204,10 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
 static unsigned long long g_launches = 0;
 static int g_gen_wpc = 8;         // warps (matches) per CTA of the action-stream kernel
 static int g_list_grid = 0;       // CTAs of the big-class launch (0 = automatic)
-static int g_overlap = 1;         // 1 = the small class is a programmatic dependent of the big class (they overlap)
+static int g_overlap = 1;         // 1 = programmatic dependent launches: the two step classes overlap, launch gaps hide
+extern "C" int lux_b200_overlap_enabled(void) { return g_overlap; }
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
-
-// launch as a programmatic dependent of the preceding kernel on the stream ("overlap" option; ordinary launch
-// otherwise)
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g_overlap ? 1 : 0;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
 
 // `gpc` = matches (lane groups) per CTA; the CTA has gpc * G threads and gpc slices of `slice` bytes
 template <bool kTma, int kS, int kMode, int G, bool kPlain>
@@ -246,7 +224,7 @@ static int launch_step_plain(const LuxBatch* b, const uint32_t* ua, const uint8_
         e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G, kPlain>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return LUX_E_CUDA;
     }
-    e = launch_chain(lux_step_kernel<kTma, kS, kMode, G, kPlain>, dim3((n_groups + gpc - 1) / gpc), dim3(32 * wpc), smem, st,
+    e = lux_launch_chain(lux_step_kernel<kTma, kS, kMode, G, kPlain>, dim3((n_groups + gpc - 1) / gpc), dim3(32 * wpc), smem, st,
                      *b, ua, ta, slice, flags, sc);
     if (e != cudaSuccess) return LUX_E_CUDA;
     g_launches++;
@@ -437,6 +415,8 @@ __global__ void __launch_bounds__(1024, 2) lux_gen_actions_kernel(LuxBatch b, ui
 
 // ---------------------------------------------------------------- episode statistics
 __global__ void lux_stats_kernel(LuxBatch b, unsigned long long* out) {
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     long long v[12];
 #pragma unroll
@@ -687,7 +667,7 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
             sc.zero = S->counts + ((t + 2) % 3) * (1 + LUX_N_CAND);
             sc.seen_host = S->seen;
             for (int i = 0; i < LUX_N_CAND; i++) sc.cand[i] = cand[i];
-            launch_chain(lux_classify_kernel, dim3((b->n_matches + 255) / 256), dim3(256), 0, st, *b, full, sc);
+            lux_launch_chain(lux_classify_kernel, dim3((b->n_matches + 255) / 256), dim3(256), 0, st, *b, full, sc);
             g_launches++;
         }
         int group = g_group == 8 || g_group == 16 ? pick_group(full) : 32;
@@ -702,7 +682,7 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     sc.zero = S->counts + ((t + 2) % 3) * (1 + LUX_N_CAND);
     sc.seen_host = S->seen;
     for (int i = 0; i < LUX_N_CAND; i++) sc.cand[i] = cand[i];
-    launch_chain(lux_classify_kernel, dim3((b->n_matches + 255) / 256), dim3(256), 0, st, *b, small, sc);
+    lux_launch_chain(lux_classify_kernel, dim3((b->n_matches + 255) / 256), dim3(256), 0, st, *b, small, sc);
     g_launches++;
     rc = cuda_ok(cudaGetLastError(), "lux_classify_kernel launch");
     if (rc) return rc;
@@ -763,6 +743,8 @@ extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_action
 // (zeroes) exactly the live action words of the matches it plays, so nothing stale is left behind.
 __global__ void lux_apply_entries_kernel(LuxBatch b, const uint2* __restrict__ entries, int k, uint32_t* __restrict__ ua,
                                          uint8_t* __restrict__ ta) {
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k) return;
     uint2 e = entries[i];
@@ -778,6 +760,8 @@ __global__ void lux_apply_entries_kernel(LuxBatch b, const uint2* __restrict__ e
 // four matches into one word (coalesced 128-byte rows over the bus), CTAs accumulate into device scratch and
 // the last one to finish publishes the summary and clears the scratch for the next call.
 __global__ void lux_summary_kernel(LuxBatch b, uint32_t* __restrict__ done4, int* __restrict__ summary, int* __restrict__ acc) {
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;      // matches 4q .. 4q+3
     int nu = 0, nt = 0, live = 0, fin = 0;
     uint32_t packed = 0;
@@ -849,12 +833,14 @@ extern "C" int lux_b200_step_host_sparse(const LuxBatch* b, const void* entries_
     if (k > 0) {
         rc = cuda_ok(cudaMemcpyAsync(S->entries, entries_host, (size_t)k * sizeof(uint2), cudaMemcpyHostToDevice, st), "h2d action entries");
         if (rc) return rc;
-        lux_apply_entries_kernel<<<(k + 255) / 256, 256, 0, st>>>(*b, S->entries, k, unit_actions_dev, tile_actions_dev);
+        lux_launch_chain(lux_apply_entries_kernel, dim3((k + 255) / 256), dim3(256), 0, st, *b, (const uint2*)S->entries, k,
+                         unit_actions_dev, tile_actions_dev);
         g_launches++;
     }
     rc = lux_step_impl(b, unit_actions_dev, tile_actions_dev, (flags & 0xFFFFu) | LUX_STEP_CONSUME, cuda_stream);
     if (rc) return rc;
-    lux_summary_kernel<<<(b->n_matches + 1023) / 1024, 256, 0, st>>>(*b, (uint32_t*)S->done_pinned, S->summary_pinned, S->summary_acc);
+    lux_launch_chain(lux_summary_kernel, dim3((b->n_matches + 1023) / 1024), dim3(256), 0, st, *b, (uint32_t*)S->done_pinned,
+                     S->summary_pinned, S->summary_acc);
     g_launches++;
     rc = cuda_ok(cudaStreamSynchronize(st), "step sync");
     if (rc) return rc;
@@ -872,7 +858,7 @@ extern "C" int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t m
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
     const int wpc = g_gen_wpc;
-    launch_chain(lux_gen_actions_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), 0, (cudaStream_t)cuda_stream,
+    lux_launch_chain(lux_gen_actions_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), 0, (cudaStream_t)cuda_stream,
                  *b, seed, match_id_base, unit_actions, tile_actions, (unsigned long long*)counters);
     g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_gen_actions_kernel launch");
@@ -891,7 +877,7 @@ extern "C" int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, uint
     if (b->n_matches == 0) return LUX_OK;
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
     const int wpc = 4;
-    launch_chain(lux_reset_done_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), 0, (cudaStream_t)cuda_stream,
+    lux_launch_chain(lux_reset_done_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), 0, (cudaStream_t)cuda_stream,
                  *b, *pool, epoch, (int*)reset_count);
     g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_reset_done_kernel launch");
@@ -906,7 +892,7 @@ extern "C" int lux_b200_stats(const LuxBatch* b, int64_t* out16, void* cuda_stre
     rc = cuda_ok(cudaMemsetAsync(out16, 0, 16 * sizeof(int64_t), st), "stats memset");
     if (rc) return rc;
     if (b->n_matches == 0) return LUX_OK;
-    lux_stats_kernel<<<(b->n_matches + 127) / 128, 128, 0, st>>>(*b, (unsigned long long*)out16);
+    lux_launch_chain(lux_stats_kernel, dim3((b->n_matches + 127) / 128), dim3(128), 0, st, *b, (unsigned long long*)out16);
     g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_stats_kernel launch");
 }
