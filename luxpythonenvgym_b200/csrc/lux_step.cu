@@ -81,9 +81,17 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
             nu = sh->n_units; nc = sh->n_cities; nt = sh->n_tiles; nr = sh->n_res;
             need = lux_need_header(sh, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
         }
+        // one group per warp: a group with nothing to play has nobody to keep in step with and leaves at once
+        // (finished matches of a draining batch then cost a header load, not a walk through an empty turn)
+        if (G == 32 && !active) return;
         LuxSmemLayout L = lux_smem_layout_need(size, need);
         if (active && L.total > slice) {
             active = 0; result = LUX_M_SPILL;
+            if (G == 32) {
+                // cannot happen (the classification pass routes such a match to the big class); visible if it ever does
+                if (lane == 0) atomicOr((unsigned*)&g.hdr->done, (unsigned)LUX_ST_BAD_STATE << 16);   // done | winner | status | size
+                return;
+            }
             need = none;
             L = lux_smem_layout_need(size, none);
         }
