@@ -5,9 +5,9 @@ Contract (see DESIGN.md "Measurement"):
   python bench.py --gpus N --steps K --warmup W          our arm (one rank per GPU under torchrun for N>1)
   python bench.py --impl reference --gpus N ...          CPU arm: the oracle port on the host cores
 
-A "step" is one turn of every resident match: canonical seeded action stream
-(lux_b200_gen_actions) -> lux_b200_step -> lux_b200_reset_done (finished matches are
-replaced from a pool of pre-generated maps).  `value` counts only LIVE match-turns.
+A "step" is one turn of every resident match: lux_b200_step on this turn's canonical seeded
+actions, then lux_b200_reset_gen (finished matches are replaced from a pool of pre-generated
+maps and the next turn's actions generated, one fused pass).  `value` counts only LIVE match-turns.
 Workload: BASELINE.json config 5's per-GPU shape -- 32x32 maps, 16384 resident matches per
 GPU (state 230+ MB > the 126 MB L2, so no L2 flush is needed between steps), seeded random
 actions.  Matches shard independently over ranks (weak scaling); the only collective is
@@ -224,12 +224,14 @@ def run_b200(args):
     resets = torch.zeros(1, dtype=torch.int32, device=dev)
     epoch = [0]
 
+    # one step = this turn's canonical actions (generated by the fused reset + action-stream pass that closed
+    # the previous step) -> lux_b200_step -> finished matches replaced and the next turn's actions generated
     def one_step(count=None):
-        game.gen_actions(STREAM_SEED, base, counters=count)
         game.step()
-        game.reset_done(pool, epoch[0], resets)
+        game.reset_gen(pool, epoch[0], STREAM_SEED, base, reset_count=resets, counters=count)
         epoch[0] += 1
 
+    game.gen_actions(STREAM_SEED, base)
     for _ in range(BURN_IN_TURNS):
         one_step()
     for _ in range(max(args.warmup, 3)):
@@ -246,18 +248,21 @@ def run_b200(args):
     ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # counters: live match-turns and algorithmic bytes of the K timed turns.  The actions of the first timed turn
+    # exist already (generated by the pass that closed the last warm-up step): they are regenerated here, untimed,
+    # only to count that turn; every later turn is counted by the pass that generates its actions.
     counters.zero_()
+    game.gen_actions(STREAM_SEED, base, counters=counters)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     launches0 = game.lib.lux_b200_launch_count()
     t_start.record()
     for k in range(K):
-        game.gen_actions(STREAM_SEED, base, counters=counters)
         ev_a[k].record()
         game.step()
         ev_b[k].record()
-        game.reset_done(pool, epoch[0], resets)
+        game.reset_gen(pool, epoch[0], STREAM_SEED, base, reset_count=resets, counters=counters if k < K - 1 else None)
         epoch[0] += 1
     t_end.record()
     launches = game.lib.lux_b200_launch_count() - launches0

@@ -244,6 +244,15 @@ int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, uint32_t epoch,
                         int32_t* reset_count, void* cuda_stream);
 
 /*
+ * lux_b200_reset_done followed by lux_b200_gen_actions in one pass over the batch (the per-turn harness loop
+ * of benchmarks and stress tests: one launch and one read of the headers instead of two).  Same arguments and
+ * the same results as the two calls in that order.
+ */
+int lux_b200_reset_gen(const LuxBatch* b, const LuxBatch* pool, uint32_t epoch, int32_t* reset_count, uint64_t seed,
+                       uint64_t match_id_base, uint32_t* unit_actions, uint8_t* tile_actions, uint64_t* counters,
+                       void* cuda_stream);
+
+/*
  * Episode statistics summed over the batch into out[16] (device int64):
  * [0] live matches, [1] finished, [2] wins A, [3] wins B, [4] ties, [5] sum turn,
  * [6] sum fuelGenerated, [7] sum units, [8] sum city tiles, [9] sum cities,

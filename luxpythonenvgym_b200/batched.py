@@ -151,6 +151,17 @@ class BatchedGame:
                                                 reset_count.data_ptr() if reset_count is not None else None,
                                                 self._stream()), "lux_b200_reset_done")
 
+    def reset_gen(self, pool, epoch, seed, match_id_base=0, reset_count=None, counters=None, unit_actions=None,
+                  tile_actions=None):
+        """reset_done(pool, epoch) followed by gen_actions(seed, match_id_base) in one kernel (harness loops)."""
+        ua = self.unit_actions if unit_actions is None else unit_actions
+        ta = self.tile_actions if tile_actions is None else tile_actions
+        _lib.check(self.lib.lux_b200_reset_gen(ctypes.byref(self._desc), ctypes.byref(pool._desc), int(epoch) & 0xFFFFFFFF,
+                                               reset_count.data_ptr() if reset_count is not None else None,
+                                               seed, match_id_base, ua.data_ptr(), ta.data_ptr(),
+                                               counters.data_ptr() if counters is not None else None, self._stream()),
+                   "lux_b200_reset_gen")
+
     def observe(self, team_sel, e_cap=None):
         """Per-entity observation rows for team `team_sel[m]` of every match.
 

@@ -450,13 +450,9 @@ __global__ void lux_stats_kernel(LuxBatch b, unsigned long long* out) {
 }
 
 // ---------------------------------------------------------------- reset finished matches from a pool
-__global__ void lux_reset_done_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch, int* reset_count) {
-    LUX_PDL_TRIGGER();
-    LUX_PDL_WAIT();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (m >= b.n_matches) return;
-    if (!b.hdr[m].done) return;
+// one warp replaces match m by a pool entry
+__device__ __forceinline__ void lux_reset_match(const LuxBatch& b, const LuxBatch& pool, int m, uint32_t epoch, int* reset_count) {
+    const int lane = threadIdx.x & 31;
     int src = 0;
     if (lane == 0) {
         // deterministic choice (replayable trajectories): a hash of (match, epoch)
@@ -500,6 +496,48 @@ __global__ void lux_reset_done_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch,
             if (base + k * 32 + lane < total) *(uint4*)dst[k] = v[k];
     }
     if (lane < LUX_HDR_BYTES / 16) ((uint4*)(b.hdr + m))[lane] = hv;
+}
+
+__global__ void lux_reset_done_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch, int* reset_count) {
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= b.n_matches) return;
+    if (!b.hdr[m].done) return;
+    lux_reset_match(b, pool, m, epoch, reset_count);
+}
+
+// reset_done followed by gen_actions in one pass over the batch (the per-turn harness loop of the benchmarks:
+// one launch and one read of the headers instead of two)
+__global__ void __launch_bounds__(1024, 2) lux_reset_gen_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch, int* reset_count,
+                                                              uint64_t seed, uint64_t match_id_base,
+                                                              uint32_t* __restrict__ unit_actions,
+                                                              uint8_t* __restrict__ tile_actions, unsigned long long* counters) {
+    LUX_PDL_TRIGGER();
+    LUX_PDL_WAIT();
+    __shared__ unsigned cta_counters[2];
+    __shared__ unsigned cta_ticket;
+    if (counters) {
+        if (threadIdx.x < 2) cta_counters[threadIdx.x] = 0;
+        if (threadIdx.x == 2) cta_ticket = 0;
+        __syncthreads();
+    }
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m < b.n_matches) {
+        if (b.hdr[m].done) {
+            lux_reset_match(b, pool, m, epoch, reset_count);
+            __syncwarp();                   // the fresh match is read back by other lanes of this warp
+        }
+        lux_gen_actions_match(b, m, seed, match_id_base, unit_actions, tile_actions, counters ? cta_counters : nullptr);
+    }
+    if (counters && (threadIdx.x & 31) == 0) {
+        __threadfence_block();
+        if (atomicAdd(&cta_ticket, 1u) == (blockDim.x >> 5) - 1) {
+            __threadfence_block();
+            unsigned live = atomicAdd(&cta_counters[0], 0u), bytes = atomicAdd(&cta_counters[1], 0u);
+            if (live) { atomicAdd(counters, (unsigned long long)live); atomicAdd(counters + 1, (unsigned long long)bytes); }
+        }
+    }
 }
 
 // ---------------------------------------------------------------- C ABI
@@ -889,6 +927,27 @@ extern "C" int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, uint
                  *b, *pool, epoch, (int*)reset_count);
     g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_reset_done_kernel launch");
+}
+
+extern "C" int lux_b200_reset_gen(const LuxBatch* b, const LuxBatch* pool, uint32_t epoch, int32_t* reset_count, uint64_t seed,
+                                  uint64_t match_id_base, uint32_t* unit_actions, uint8_t* tile_actions, uint64_t* counters,
+                                  void* cuda_stream) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    rc = check_batch(pool);
+    if (rc) return rc;
+    if (pool->n_matches < 1 || !unit_actions || !tile_actions) return LUX_E_ARG;
+    if (pool->size != b->size || pool->u_cap != b->u_cap || pool->c_cap != b->c_cap || pool->t_cap != b->t_cap ||
+        pool->r_cap != b->r_cap)
+        return LUX_E_ARG;
+    if (b->n_matches == 0) return LUX_OK;
+    if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
+    const int wpc = g_gen_wpc;
+    lux_launch_chain(lux_reset_gen_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), 0, (cudaStream_t)cuda_stream,
+                     *b, *pool, epoch, (int*)reset_count, seed, match_id_base, unit_actions, tile_actions,
+                     (unsigned long long*)counters);
+    g_launches++;
+    return cuda_ok(cudaGetLastError(), "lux_reset_gen_kernel launch");
 }
 
 extern "C" int lux_b200_stats(const LuxBatch* b, int64_t* out16, void* cuda_stream) {

@@ -162,6 +162,34 @@ def test_done_matches_are_untouched_and_reset():
     assert (hh["done"] == 0).all() and (hh["turn"][done] == 0).all()
 
 
+def test_reset_gen_equals_reset_then_gen():
+    """The fused harness pass (lux_b200_reset_gen) against the two separate calls: same states, same action
+    tensors, same counters, turn by turn on a batch that keeps finishing matches."""
+    size, n = 12, 512
+    a, b = _game(n, size), _game(n, size)
+    pool = _game(32, size)
+    arr = mapgen.generate_batch(np.arange(3000, 3000 + n), size)
+    pool.load_arrays(mapgen.generate_batch(np.arange(7000, 7032), size))
+    for g in (a, b):
+        g.load_arrays(arr)
+    ca = torch.zeros(2, dtype=torch.int64, device="cuda")
+    cb = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ra = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rb = torch.zeros(1, dtype=torch.int32, device="cuda")
+    a.gen_actions(11, 5, counters=ca)
+    b.gen_actions(11, 5, counters=cb)
+    for turn in range(150):
+        a.step()
+        b.step()
+        a.reset_done(pool, turn, ra)
+        a.gen_actions(11, 5, counters=ca)
+        b.reset_gen(pool, turn, 11, 5, reset_count=rb, counters=cb)
+        assert torch.equal(a.unit_actions, b.unit_actions) and torch.equal(a.tile_actions, b.tile_actions), turn
+    for k in a.sections():
+        assert torch.equal(a.sections()[k], b.sections()[k]), k
+    assert torch.equal(ca, cb) and torch.equal(ra, rb) and int(ra.item()) > 0
+
+
 def test_step_host_matches_device_step():
     size = 16
     maps = [mapgen.generate(300 + i, size=size) for i in range(4)]
