@@ -207,6 +207,10 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
+        # rank 0's stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION / INFO
+        # print it to stdout) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("LUX_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     n, size = args.matches, args.size
