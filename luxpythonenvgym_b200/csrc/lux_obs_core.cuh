@@ -7,10 +7,11 @@
 //   * the per-turn node lists (agent_policy.py:197-247) are built once per match in shared memory by
 //     ballot compaction (wood / coal / uranium cells in GameMap.resources order, own city tiles in
 //     cities x cells order, own workers in dict order);
-//   * each lane owns one entity and scans the lists once per key, keeping the lexicographic
-//     (distance, index) minimum, second minimum, maximum and second maximum -- that gives both the
-//     closest and the furthest node with numpy's first-index tie-break, with and without the
-//     np.delete(closest) self-exclusion (:328-336);
+//   * the warp takes the actionable entities one at a time (a typical match has one or two) and scans
+//     each node list cooperatively, keeping the lexicographic (distance, index) minimum, second minimum,
+//     maximum and second maximum -- that gives both the closest and the furthest node with numpy's
+//     first-index tie-break, with and without the np.delete(closest) self-exclusion (:328-336); ten lanes
+//     then write the ten feature blocks of the row in parallel;
 //   * a row is ~70 % zeros: the warp first zero-fills the rows of the 32 entities in flight with
 //     coalesced 16-byte stores, then every lane drops its ~25 non-zero features into its own row.
 //     No staging tile is needed.
@@ -73,39 +74,9 @@ LUX_DEV void lux_obs_bind(LuxObsMatch& M, unsigned char* smem, const LuxObsLayou
     M.S = size; M.ncell = size * size; M.r_cap = L.r_cap;
 }
 
-// lexicographic trackers over (squared distance, list index)
-struct LuxArg { int d, i; };
-LUX_DEV void lux_arg_min2(LuxArg& a1, LuxArg& a2, int d, int i) {
-    if (d < a1.d) { a2 = a1; a1.d = d; a1.i = i; }
-    else if (d < a2.d) { a2.d = d; a2.i = i; }
-}
-LUX_DEV void lux_arg_max2(LuxArg& a1, LuxArg& a2, int d, int i) {
-    if (d > a1.d) { a2 = a1; a1.d = d; a1.i = i; }
-    else if (d > a2.d) { a2.d = d; a2.i = i; }
-}
-
-// one (closest|furthest, key) block of 7 floats (agent_policy.py:327-385), written into the (zeroed) row
-LUX_DEV void lux_obs_block(const LuxObsMatch& M, float* o, const uint32_t* nodes, int n, int px, int py,
-                           int exclude, int furthest, int key, int n_units) {
-    if (n == 0) return;                                   // key not in object_nodes
-    LuxArg mn1 = {0x7fffffff, -1}, mn2 = {0x7fffffff, -1}, mx1 = {-1, -1}, mx2 = {-1, -1};
-#pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        int xy = (int)(nodes[i] & 0xffffu);
-        int dx = (xy & 0xff) - px, dy = (xy >> 8) - py;
-        int d = dx * dx + dy * dy;
-        lux_arg_min2(mn1, mn2, d, i);
-        lux_arg_max2(mx1, mx2, d, i);
-    }
-    int pick;
-    if (exclude) {
-        if (n == 1) { o[5] = 1.0f; return; }              // nothing left after np.delete
-        if (!furthest) pick = mn2.i;
-        else pick = (mx1.i == mn1.i) ? mx2.i : mx1.i;
-    } else {
-        pick = furthest ? mx1.i : mn1.i;
-    }
-    const unsigned node = nodes[pick];
+// One (closest | furthest, key) block of 7 floats (agent_policy.py:327-385) for the chosen node, written into the
+// (zeroed) row by ONE lane.
+LUX_DEV void lux_obs_emit(const LuxObsMatch& M, float* o, unsigned node, int px, int py, int key, int n_units) {
     int tx = node & 0xff, ty = (node >> 8) & 0xff;
     // Position.direction_to (position.py:48-66): N, E, S, W, first strict improvement; slots c,n,w,s,e
     int slot = 0;
@@ -131,6 +102,35 @@ LUX_DEV void lux_obs_block(const LuxObsMatch& M, float* o, const uint32_t* nodes
         v = (double)unit_space(M.units[f]) / 100.0;
     }
     o[6] = (float)(v < 1.0 ? v : 1.0);
+}
+
+// Warp-cooperative scan of one node list for one entity: the lexicographic (squared distance, list index)
+// minimum, second minimum, maximum and second maximum -- that gives both the closest and the furthest node with
+// numpy's first-index tie-break, with and without the np.delete(closest) self-exclusion (:328-336).  Every lane
+// scans a stride of the list keeping its two smallest / largest packed keys (d << 10 | index for the minimum,
+// d << 10 | 1023 - index, + 1, for the maximum: among equal distances the FIRST index wins both ways), four
+// warp reductions merge them.  Returns list indices.
+struct LuxPick { int mn1, mn2, mx1, mx2; };
+LUX_DEV LuxPick lux_obs_scan(const uint32_t* nodes, int n, int px, int py) {
+    const int lane = lux_lane();
+    unsigned lmin1 = 0xFFFFFFFFu, lmin2 = 0xFFFFFFFFu, lmax1 = 0, lmax2 = 0;
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) {
+        int xy = (int)(nodes[i] & 0xffffu);
+        int dx = (xy & 0xff) - px, dy = (xy >> 8) - py;
+        unsigned d = (unsigned)(dx * dx + dy * dy);
+        unsigned kmin = (d << 10) | (unsigned)i, kmax = ((d << 10) | (unsigned)(1023 - i)) + 1u;
+        if (kmin < lmin1) { lmin2 = lmin1; lmin1 = kmin; } else if (kmin < lmin2) lmin2 = kmin;
+        if (kmax > lmax1) { lmax2 = lmax1; lmax1 = kmax; } else if (kmax > lmax2) lmax2 = kmax;
+    }
+    const unsigned gmin1 = lux_reduce_min_u(lmin1);
+    const unsigned gmin2 = lux_reduce_min_u(lmin1 == gmin1 ? lmin2 : lmin1);
+    const unsigned gmax1 = lux_reduce_max_u(lmax1);
+    const unsigned gmax2 = lux_reduce_max_u(lmax1 == gmax1 ? lmax2 : lmax1);
+    LuxPick P;
+    P.mn1 = (int)(gmin1 & 1023u); P.mn2 = (int)(gmin2 & 1023u);
+    P.mx1 = 1023 - (int)((gmax1 - 1u) & 1023u); P.mx2 = 1023 - (int)((gmax2 - 1u) & 1023u);
+    return P;
 }
 
 // zero-fill `count` floats starting at p: scalar head/tail, 16-byte body
@@ -243,37 +243,62 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
         // the rows of this pass are zero-filled by the whole warp (coalesced, 16-byte stores) ...
         lux_zero_floats(g_obs + (size_t)n_ent * LUX_OBS_DIM, rows_out * LUX_OBS_DIM);
         lux_sync();
-        // ... then every lane writes the non-zero features of its own row
-        if (valid && row < room) {
-            float* o = g_obs + (size_t)row * LUX_OBS_DIM;
-            o[kind] = 1.0f;
+        // ... then the warp takes the entities of this pass one at a time: a typical match has one or two
+        // actionable entities, so lanes-over-entities would leave the list scans to one or two lanes
+        unsigned todo = vm;
+#pragma unroll 1
+        while (todo) {
+            const int src = lux_ffs(todo) - 1;
+            todo &= todo - 1;
+            const int e_row = lux_shfl(row, src);
+            if (e_row >= room) continue;                              // warp-uniform
+            const int e_px = lux_shfl(px, src), e_py = lux_shfl(py, src), e_kind = lux_shfl(kind, src);
+            const int e_code = lux_shfl(code, src), e_idx = base + src;
+            float* o = g_obs + (size_t)e_row * LUX_OBS_DIM;
             int alone = 1;
-            if (kind == 0) {                       // len(cell.units) <= 1 (agent_policy.py:330)
+            if (e_kind == 0) {                       // len(cell.units) <= 1 (agent_policy.py:330)
                 int cnt = 0;
 #pragma unroll 1
-                for (int i = 0; i < n_units; i++) cnt += M.units[i].x == px && M.units[i].y == py;
+                for (int cb = 0; cb < n_units; cb += 32) {
+                    int v = cb + lane;
+                    cnt += lux_popc(lux_ballot(v < n_units && M.units[v].x == e_px && M.units[v].y == e_py));
+                }
                 alone = cnt <= 1;
             }
-            int at = 3;
 #pragma unroll 1
-            for (int furthest = 0; furthest < 2; furthest++)
-#pragma unroll 1
-                for (int key = 0; key < 5; key++, at += 7) {
-                    int exclude = (key == 3 && kind == 2) || (key == 4 && kind == 0 && alone);
-                    const uint32_t* nodes = key < 3 ? M.nodes_res + key * M.r_cap : key == 3 ? M.nodes_tile : M.nodes_work;
-                    int n = key < 3 ? n_type[key] : key == 3 ? own_tiles : own_workers;
-                    lux_obs_block(M, o + at, nodes, n, px, py, exclude, furthest, key, n_units);
+            for (int key = 0; key < 5; key++) {
+                const uint32_t* nodes = key < 3 ? M.nodes_res + key * M.r_cap : key == 3 ? M.nodes_tile : M.nodes_work;
+                const int n = key < 3 ? n_type[key] : key == 3 ? own_tiles : own_workers;
+                if (n == 0) continue;                                 // key not in object_nodes
+                const int exclude = (key == 3 && e_kind == 2) || (key == 4 && e_kind == 0 && alone);
+                const LuxPick P = lux_obs_scan(nodes, n, e_px, e_py);
+                // lane `key` writes the closest block, lane 5 + key the furthest one
+                if (lane == key || lane == 5 + key) {
+                    const int furthest = lane >= 5;
+                    float* blk = o + 3 + 35 * furthest + 7 * key;
+                    if (exclude && n == 1) {
+                        blk[5] = 1.0f;                                // nothing left after np.delete
+                    } else {
+                        int pick;
+                        if (exclude) pick = !furthest ? P.mn2 : (P.mx1 == P.mn1 ? P.mx2 : P.mx1);
+                        else pick = furthest ? P.mx1 : P.mn1;
+                        lux_obs_emit(M, blk, nodes[pick], e_px, e_py, key, n_units);
+                    }
                 }
-            if (kind != 2) o[73] = (float)((double)unit_space(M.units[e]) / 100.0);
-            o[74] = night ? 1.0f : 0.0f;
-            o[75] = f_turn;
-            o[76] = f_own_tiles; o[77] = f_opp_tiles;
-            o[78] = f_workers; o[79] = f_workers;       // agent_policy.py:214-215: the "opponent" lists hold the own units
-            o[80] = f_carts; o[81] = f_carts;
-            o[82] = f_rp;
-            o[83] = rp >= LUX_RESEARCH_COAL ? 1.0f : 0.0f;
-            o[84] = rp >= LUX_RESEARCH_URANIUM ? 1.0f : 0.0f;
-            g_ent[row] = (int16_t)code;
+            }
+            if (lane == 10) {
+                o[e_kind] = 1.0f;
+                if (e_kind != 2) o[73] = (float)((double)unit_space(M.units[e_idx]) / 100.0);
+                o[74] = night ? 1.0f : 0.0f;
+                o[75] = f_turn;
+                o[76] = f_own_tiles; o[77] = f_opp_tiles;
+                o[78] = f_workers; o[79] = f_workers;       // agent_policy.py:214-215: the "opponent" lists hold the own units
+                o[80] = f_carts; o[81] = f_carts;
+                o[82] = f_rp;
+                o[83] = rp >= LUX_RESEARCH_COAL ? 1.0f : 0.0f;
+                o[84] = rp >= LUX_RESEARCH_URANIUM ? 1.0f : 0.0f;
+                g_ent[e_row] = (int16_t)e_code;
+            }
         }
         n_ent += nv;
         lux_sync();

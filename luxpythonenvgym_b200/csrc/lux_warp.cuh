@@ -49,6 +49,8 @@ template <int G = 32> LUX_DEV unsigned lux_match_any(int key) {
     unsigned m = __match_any_sync(LUX_FULL, G == 32 ? key : (int)((unsigned)key | (lux_group_shift<G>() << 26)));
     return G == 32 ? m : (m >> lux_group_shift<G>()) & ((1u << (G & 31)) - 1u);
 }
+LUX_DEV unsigned lux_reduce_min_u(unsigned v) { return __reduce_min_sync(LUX_FULL, v); }     // whole warp
+LUX_DEV unsigned lux_reduce_max_u(unsigned v) { return __reduce_max_sync(LUX_FULL, v); }
 LUX_DEV int lux_popc(unsigned v) { return __popc(v); }
 LUX_DEV int lux_ffs(unsigned v) { return __ffs(v); }
 LUX_DEV unsigned lux_atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }

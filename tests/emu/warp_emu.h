@@ -166,6 +166,24 @@ template <int G = 32> static inline unsigned lux_match_any(int key) {
     warp_emu::barrier(6);
     return m;
 }
+static inline unsigned lux_reduce_min_u(unsigned v) {
+    warp_emu::State& s = warp_emu::st();
+    s.vals[s.cur] = (long long)v;
+    warp_emu::barrier(7);
+    long long r = s.vals[0];
+    for (int i = 1; i < 32; i++) if (s.vals[i] < r) r = s.vals[i];
+    warp_emu::barrier(7);
+    return (unsigned)r;
+}
+static inline unsigned lux_reduce_max_u(unsigned v) {
+    warp_emu::State& s = warp_emu::st();
+    s.vals[s.cur] = (long long)v;
+    warp_emu::barrier(8);
+    long long r = s.vals[0];
+    for (int i = 1; i < 32; i++) if (s.vals[i] > r) r = s.vals[i];
+    warp_emu::barrier(8);
+    return (unsigned)r;
+}
 static inline int lux_popc(unsigned v) { return __builtin_popcount(v); }
 static inline int lux_ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline unsigned lux_atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
