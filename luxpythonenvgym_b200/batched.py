@@ -97,6 +97,15 @@ class BatchedGame:
                                           _lib.LUX_STEP_PREVALIDATE if prevalidate else 0, self._stream()),
                    "lux_b200_step")
 
+    def put_actions(self, m, unit_words, tile_bytes):
+        """Host action words of ONE match (numpy uint32 [<= u_cap], uint8 [<= t_cap]) -> the action tensors."""
+        uw = np.zeros(self.caps["units"], dtype=np.uint32)
+        tb = np.zeros(self.caps["tiles"], dtype=np.uint8)
+        uw[: len(unit_words)] = unit_words
+        tb[: len(tile_bytes)] = tile_bytes
+        self.unit_actions[m].copy_(torch.from_numpy(uw.view(np.int32)))
+        self.tile_actions[m].copy_(torch.from_numpy(tb))
+
     def step_host(self, unit_actions_host, tile_actions_host, hdr_host=None, done_host=None, prevalidate=False,
                   u_used=0, t_used=0):
         """The same turn from HOST (pinned) action buffers; copies back headers/done flags."""
@@ -219,6 +228,19 @@ class BatchedGame:
                                                     offsets.data_ptr() if offsets is not None else None,
                                                     ua.data_ptr(), ta.data_ptr(), self._stream()),
                    "lux_b200_encode_actions")
+
+    def unit_word(self, m, slot, code):
+        """The packed action word AgentPolicy's unit action `code` decodes to for the unit in `slot` of match
+        `m` (lux_b200_encode_actions on a one-row entity list; used by the single-match adapters)."""
+        if getattr(self, "_one", None) is None:
+            z = lambda dt: torch.zeros((self.n, 1), dtype=dt, device=self.device)
+            self._one = (z(torch.int16), z(torch.int32), torch.zeros(self.n, dtype=torch.int32, device=self.device),
+                         torch.zeros_like(self.unit_actions), torch.zeros_like(self.tile_actions))
+        ent, codes, cnt, ua, ta = self._one
+        cnt.zero_()
+        ent[m, 0], codes[m, 0], cnt[m] = int(slot), int(code), 1
+        self.encode_actions(ent, cnt, codes, unit_actions=ua, tile_actions=ta)
+        return int(ua[m, int(slot)].item()) & 0xFFFFFFFF
 
     def reward(self, team_sel, reward_state, out=None):
         """Per-turn AgentPolicy reward (float64 [n]); reward_state is int32 [n, 4], updated in place."""

@@ -4,66 +4,28 @@
   the policy sees one observation row per actionable entity of the learning team (the rows the
   reference would produce one `LuxEnvironment.step` at a time, luxai2021/env/lux_env.py:123-161)
   and returns one action code per row.  Opponent = the reference's idle `Agent()`.
-* `LuxEnvironment` -- the reference's single-env gym-style API (`reset() -> obs`,
-  `step(action_code) -> (obs, reward, done, {})`, one DECISION per step) implemented on the same
-  device path, for code written against luxai2021.env.lux_env.LuxEnvironment.
-* `Agent`, `AgentPolicy` -- names kept from luxai2021/env/agent.py and examples/agent_policy.py.
+* `LuxEnvironment` -- the reference's single-env gym-style API (luxai2021/env/lux_env.py:73-220):
+  `LuxEnvironment(configs, learning_agent, opponent_agent, replay_validate, replay_folder, replay_prefix)`,
+  `reset() -> obs`, `step(action_code) -> (obs, reward, done, {})` (one DECISION per step), `run_no_learn()`,
+  `.game` (a `Game`), `.match_controller`.  The agents' hooks are called exactly as the reference's
+  MatchController calls them; every turn runs on the device.  When the learning agent is the stock
+  `AgentPolicy` and the opponent the idle base `Agent` (the PPO example's setup, examples/train.py:62-70) and
+  no replay option is set, the same episode is produced without the per-decision host hooks: observation,
+  action decoding, pre-validation, turn and reward all stay on the device (`fast path`).
+* `Agent`, `AgentPolicy`, ... -- re-exported from .agent (names of luxai2021/env/agent.py, examples/agent_policy.py).
 """
+import random
+
 import numpy as np
 import torch
 
 from . import mapgen
+from .agent import (Agent, AgentFromReplay, AgentFromStdInOut, AgentPolicy, AgentWithModel, OBS_DIM, N_ACTIONS,  # noqa: F401
+                    is_stock_tables, smart_transfer_to_nearby)
 from .batched import BatchedGame
-
-OBS_DIM = 85
-N_ACTIONS = 9
-
-
-class Agent:
-    """luxai2021/env/agent.py:11-86 -- the do-nothing opponent and base class for hooks."""
-
-    def __init__(self):
-        self.team = None
-        self.match_controller = None
-
-    def game_start(self, game):
-        pass
-
-    def process_turn(self, game, team):
-        return []
-
-    def pre_turn(self, game, is_first_turn=False):
-        return
-
-    def post_turn(self, game, actions):
-        return False
-
-    def turn_heurstics(self, game, is_first_turn):
-        return
-
-    def get_agent_type(self):
-        return "agent"
-
-    def set_team(self, team):
-        self.team = team
-
-    def set_controller(self, match_controller):
-        self.match_controller = match_controller
-
-
-class AgentPolicy(Agent):
-    """examples/agent_policy.py AgentPolicy: 85-float observations, 9 action codes, its reward.
-    Observation, action decoding and reward run on the device (lux_b200_observe /
-    lux_b200_encode_actions / lux_b200_reward); this object only carries the spaces."""
-
-    def __init__(self, mode="train", model=None):
-        super().__init__()
-        self.mode, self.model = mode, model
-        self.observation_shape = (OBS_DIM,)
-        self.n_actions = N_ACTIONS
-
-    def get_agent_type(self):
-        return "learning" if self.mode == "train" else "agent"
+from .constants import Constants
+from .game import Game
+from .match_controller import GameStepFailedException, MatchController
 
 
 class BatchedLuxEnvironment:
@@ -126,79 +88,146 @@ class BatchedLuxEnvironment:
 
 
 class LuxEnvironment:
-    """Single env, one decision per `step` (luxai2021/env/lux_env.py:73-183)."""
+    """Single env, one decision per `step` (luxai2021/env/lux_env.py:73-220)."""
+    metadata = {"render.modes": ["human"]}
 
     def __init__(self, configs, learning_agent=None, opponent_agent=None, replay_validate=None,
-                 replay_folder=None, replay_prefix="replay", device="cuda:0"):
+                 replay_folder=None, replay_prefix="replay", device="cuda:0", fast=None):
+        learning_agent = learning_agent if learning_agent is not None else AgentPolicy("train")
+        opponent_agent = opponent_agent if opponent_agent is not None else Agent()
         self.configs = dict(configs or {})
-        self.learning_agent = learning_agent or AgentPolicy("train")
-        self.opponent_agent = opponent_agent or Agent()
+        self.game = Game(self.configs, device=device)
+        self.match_controller = MatchController(self.game, agents=[learning_agent, opponent_agent],
+                                                replay_validate=replay_validate)
+        self.replay_prefix, self.replay_folder = replay_prefix, replay_folder
+        self.action_space = getattr(learning_agent, "action_space", [])
+        self.observation_space = getattr(learning_agent, "observation_space", {})
+        self.learning_agent, self.opponent_agent = learning_agent, opponent_agent
         self.device = device
         self.current_step = 0
-        self._rng = np.random.RandomState(self.configs.get("team_seed", 0))
-        self._env = None
+        self.match_generator = None
+        self.last_observation_object = None
+        stock = (type(learning_agent) is AgentPolicy and learning_agent.get_agent_type() == Constants.AGENT_TYPE.LEARNING
+                 and type(opponent_agent) is Agent and replay_validate is None and not replay_folder
+                 and is_stock_tables(learning_agent))
+        if fast and not stock:
+            raise ValueError("the all-device fast path needs the stock AgentPolicy('train') against the idle Agent() "
+                             "and no replay options")
+        self._fast = stock if fast is None else bool(fast)
+        self._rng = random.Random(self.configs.get("team_seed"))
 
-    def _make(self):
-        seed = self.configs.get("seed")
-        if seed is None:
-            seed = int(self._rng.randint(0, 2 ** 31 - 1))
-        state = mapgen.generate(seed, size=self.configs.get("width"))
-        if self._env is None or self._env.size != state.size:
-            self._env = BatchedGame(1, state.size, device=self.device)
-            self._e_cap = self._env.caps["units"] + self._env.caps["tiles"]
-            self._codes = torch.zeros((1, self._e_cap), dtype=torch.int32, device=self.device)
-            self._rstate = torch.zeros((1, 4), dtype=torch.int32, device=self.device)
-        self._env.load_states([state])
-        self._rstate.zero_()
+    def set_replay_path(self, replay_folder, replay_prefix):
+        self.replay_prefix, self.replay_folder = replay_prefix, replay_folder
+        if replay_folder:
+            self._fast = False
 
-    @property
-    def game(self):
-        return self._env
+    def render(self, **kwargs):
+        print(self.current_step)
+        print(self.game.map.get_map_string())
 
-    def _observe(self):
-        obs, ent, cnt = self._env.observe(self._team, self._e_cap)
+    # ------------------------------------------------------------------ the reference flow (hooks on the host)
+    def _first_team(self):
+        # the reference flips a coin per reset (match_controller.py:118-122); configs["team"] pins the learning
+        # agent's team, configs["team_seed"] seeds the coin (both are extensions for reproducible tests)
+        team = self.configs.get("team")
+        if team is None and self.configs.get("team_seed") is not None:
+            team = self._rng.randint(0, 1)
+        return team
+
+    def reset(self):
+        self.current_step = 0
+        self.last_observation_object = None
+        if self._fast:
+            return self._fast_reset()
+        self.match_controller.reset(first_team=self._first_team())
+        if self.replay_folder:
+            self.game.start_replay_logging(stateful=True, replay_folder=self.replay_folder,
+                                           replay_filename_prefix=self.replay_prefix)
+        self.match_generator = self.match_controller.run_to_next_observation()
+        unit, city_tile, team, is_new_turn = next(self.match_generator)
+        obs = self.learning_agent.get_observation(self.game, unit, city_tile, team, is_new_turn)
+        self.last_observation_object = (unit, city_tile, team, is_new_turn)
+        return obs
+
+    def step(self, action_code):
+        if self._fast:
+            return self._fast_step(action_code)
+        unit, city_tile, team, _ = self.last_observation_object
+        self.learning_agent.take_action(action_code, self.game, unit=unit, city_tile=city_tile, team=team)
+        self.current_step += 1
+        is_new_turn, is_game_over, is_game_error = True, False, False
+        try:
+            unit, city_tile, team, is_new_turn = next(self.match_generator)
+            obs = self.learning_agent.get_observation(self.game, unit, city_tile, team, is_new_turn)
+            self.last_observation_object = (unit, city_tile, team, is_new_turn)
+        except StopIteration:
+            is_game_over, obs = True, None
+        except GameStepFailedException:
+            is_game_over, is_game_error, obs = True, True, None
+        reward = self.learning_agent.get_reward(self.game, is_game_over, is_new_turn, is_game_error)
+        return obs, reward, is_game_over, {}
+
+    def run_no_learn(self):
+        """Plays a whole match between two inference agents (lux_env.py:194-220); True = the engine failed."""
+        for agent in self.match_controller.agents:
+            assert agent.get_agent_type() == Constants.AGENT_TYPE.AGENT, "Both agents must be in inference mode"
+        self.current_step = 0
+        self.last_observation_object = None
+        self.match_controller.reset(randomize_team_order=False)
+        self.match_generator = self.match_controller.run_to_next_observation()
+        is_game_error = False
+        try:
+            next(self.match_generator)
+        except StopIteration:
+            print("Episode run finished successfully!")
+        except GameStepFailedException:
+            is_game_error = True
+        return is_game_error
+
+    # ------------------------------------------------------------------ the all-device fast path
+    # Same episode as the flow above for AgentPolicy("train") vs Agent(): the learning team's actionable
+    # entities come from lux_b200_observe in MatchController's yield order, the codes are decoded by
+    # lux_b200_encode_actions, Action.is_valid is LUX_STEP_PREVALIDATE, the reward is lux_b200_reward.
+    def _fast_reset(self):
+        self.match_controller.reset(first_team=self._first_team())
+        b = self.game._batch
+        self._e_cap = b.caps["units"] + b.caps["tiles"]
+        self._codes = torch.zeros((1, self._e_cap), dtype=torch.int32, device=b.device)
+        self._rstate = torch.zeros((1, 4), dtype=torch.int32, device=b.device)
+        self._team = torch.full((1,), int(self.learning_agent.team), dtype=torch.uint8, device=b.device)
+        self._pending_reward = 0.0
+        self._done = False
+        self._fast_observe()
+        while self._n == 0 and not self._done:
+            self._fast_turn()
+        return self._rows[self._cursor] if not self._done else None
+
+    def _fast_observe(self):
+        obs, ent, cnt = self.game._batch.observe(self._team, self._e_cap)
         self._n = int(cnt.item())
         self._rows = obs[0, : self._n].cpu().numpy()
         self._cursor = 0
 
-    def reset(self):
-        self.current_step = 0
-        self._make()
-        # the reference flips a coin per reset (match_controller.py:118-122); configs["team"] pins it
-        team = int(self.configs["team"]) if self.configs.get("team") is not None else int(self._rng.randint(0, 2))
-        self.learning_agent.set_team(team)
-        self.opponent_agent.set_team(1 - team)
-        self._team = torch.full((1,), team, dtype=torch.uint8, device=self.device)
-        self._pending_reward = 0.0
-        self._done = False
-        self._advance_until_decision()
-        return self._rows[self._cursor] if not self._done else None
-
-    def _advance_until_decision(self):
-        # run turns until the learning team has an actionable entity (match_controller.py:214-324)
-        self._observe()
-        while self._n == 0 and not self._done:
-            self._play_turn()
-
-    def _play_turn(self):
-        e = self._env
-        e.encode_actions(e._ent, e._cnt, self._codes)
-        e.step(prevalidate=True)
-        self._pending_reward += float(e.reward(self._team, self._rstate).item())
-        self._done = bool(e.hdr[0, 24].item())
+    def _fast_turn(self):
+        b = self.game._batch
+        b.encode_actions(b._ent, b._cnt, self._codes)
+        b.step(prevalidate=True)
+        self.game._mark_stale()
+        self._pending_reward += float(b.reward(self._team, self._rstate).item())
+        self._done = bool(b.hdr[0, 24].item())
         self._codes.zero_()
         if not self._done:
-            self._observe()
+            self._fast_observe()
 
-    def step(self, action_code):
+    def _fast_step(self, action_code):
         self._codes[0, self._cursor] = int(action_code)
         self._cursor += 1
         self.current_step += 1
         reward = 0.0
         if self._cursor >= self._n:
-            self._play_turn()
+            self._fast_turn()
             while self._n == 0 and not self._done:
-                self._play_turn()
+                self._fast_turn()
             reward, self._pending_reward = self._pending_reward, 0.0
         obs = None if self._done else self._rows[self._cursor]
         return obs, reward, self._done, {}

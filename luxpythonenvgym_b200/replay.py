@@ -97,6 +97,17 @@ class Replay:
         if stateful:
             self.data["stateful"] = []
 
+    def clear(self):
+        """Forget the turns logged so far (Game.reset, reference replay.py:27-41)."""
+        self.data["allCommands"] = []
+        self.data["results"]["ranks"] = [{"rank": 1, "agentID": 0}, {"rank": 2, "agentID": 1}]
+        if self.stateful:
+            self.data["stateful"] = []
+
+    def add_state(self, state_after):
+        if self.stateful:
+            self.data["stateful"].append(state_object(state_after))
+
     def add_turn(self, state_before, unit_words, tile_bytes, state_after=None):
         self.data["allCommands"].append(commands_from_words(state_before, unit_words, tile_bytes))
         if self.stateful and state_after is not None:

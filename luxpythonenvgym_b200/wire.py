@@ -44,9 +44,37 @@ def state_from_updates(size, updates, turn=0, unit_id_count=0, city_id_count=0, 
     ms = S.MatchState(size, caps)
     h = ms.hdr
     h["turn"], h["unit_id_count"], h["city_id_count"], h["size"] = turn, unit_id_count, city_id_count, size
-    units = ([], [])
+    return apply_updates(ms, updates, recount_adjacency=recount_adjacency)
+
+
+def apply_updates(base, updates, recount_adjacency=False):
+    """Game.process_updates(updates, assign=True) (game.py:159-262) applied to the packed state `base`
+    (an empty map for Game.reset(updates=...) as AgentFromStdInOut uses it, agent.py:224-259); returns a new
+    MatchState.  Units, cities, tiles and resource cells of `base` stay, in their order, and the lines add to
+    them as the reference's dict / list appends do.  A line that re-declares a resource cell or a city tile
+    that already exists would leave the reference with duplicate list entries the packed form cannot hold:
+    ValueError."""
+    size = base.size
+    ms = base.copy()
+    h = ms.hdr
+    nu0, nc0, nt0, nr0 = int(h["n_units"]), int(h["n_cities"]), int(h["n_tiles"]), int(h["n_res"])
+    units = ([], [])     # per team: [id, x, y, team_type, cd_q, wood, coal, uranium]
+    for i in range(nu0):
+        u = base.units[i]
+        units[int(u["team_type"]) & 1].append([int(u["id"]), int(u["x"]), int(u["y"]), int(u["team_type"]), int(u["cd_q"]),
+                                               int(u["wood"]), int(u["coal"]), int(u["uranium"])])
     cities = {}          # id string -> [team, fuel, [cell indices]]  (dict order == Game.cities order)
-    res_order = []
+    slots = []
+    for s in range(nc0):
+        c = base.cities[s]
+        rec = [int(c["team"]), int(c["fuel"]), []]
+        cities["c_%d" % int(c["id"])] = rec
+        slots.append(rec)
+    for p in range(nt0):
+        idx = int(base.tiles[p])
+        slots[int(base.cells["city_slot"][idx])][2].append(idx)
+    res_order = [int(x) for x in base.res[:nr0]]
+    res_seen, tile_seen = set(res_order), set(int(x) for x in base.tiles[:nt0])
     for line in updates or []:
         if line == "D_DONE":
             break
@@ -57,18 +85,28 @@ def state_from_updates(size, updates, turn=0, unit_id_count=0, city_id_count=0, 
         elif op == "r":
             x, y, amt = int(p[2]), int(p[3]), int(float(p[4]))
             idx = y * size + x
+            if idx in res_seen:
+                raise ValueError("resource cell (%d, %d) declared twice" % (x, y))
+            res_seen.add(idx)
             ms.cells["amount"][idx] = amt
             ms.cells["flags"][idx] = (int(ms.cells["flags"][idx]) & ~3) | (_TYPE_CODES[p[1]] if amt > 0 else 0)
             res_order.append(idx)
         elif op == "u":
             kind, team = int(p[1]), int(p[2])
-            units[team].append((_num(p[3]), int(p[4]), int(p[5]), team | (kind << 1), _quarter(p[6]),
-                                int(p[7]), int(p[8]), int(p[9])))
+            rec = [_num(p[3]), int(p[4]), int(p[5]), team | (kind << 1), _quarter(p[6]), int(p[7]), int(p[8]), int(p[9])]
+            for k, old in enumerate(units[team]):
+                if old[0] == rec[0]:
+                    units[team][k] = rec             # same id: the dict entry is overwritten in place
+                    break
+            else:
+                units[team].append(rec)
             h["carts_built" if kind == 1 else "workers_built"][team] += 1
         elif op == "c":
-            cities[p[2]] = [int(p[1]), int(float(p[3])), []]
             if float(p[3]) != int(float(p[3])):
                 raise ValueError("fractional city fuel %r" % p[3])
+            if p[2] in cities and cities[p[2]][2]:
+                raise ValueError("city %s declared twice" % p[2])
+            cities[p[2]] = [int(p[1]), int(float(p[3])), []]
         elif op == "ct":
             team, x, y = int(p[1]), int(p[3]), int(p[4])
             idx = y * size + x
@@ -76,6 +114,9 @@ def state_from_updates(size, updates, turn=0, unit_id_count=0, city_id_count=0, 
             cd = float(p[5])
             if cd != int(cd):
                 raise ValueError("fractional city tile cooldown %r" % p[5])
+            if idx in tile_seen:
+                raise ValueError("city tile (%d, %d) declared twice" % (x, y))
+            tile_seen.add(idx)
             ms.cells["flags"][idx] = (int(ms.cells["flags"][idx]) & 3) | ((team + 1) << 2)
             ms.cells["tile_cd"][idx] = int(cd)
             city[2].append(idx)
@@ -84,6 +125,7 @@ def state_from_updates(size, updates, turn=0, unit_id_count=0, city_id_count=0, 
             ms.cells["road_q"][int(p[2]) * size + int(p[1])] = _quarter(p[3])
     # resources list: GameMap.resources order, cells with amount > 0 (oracle/flatten.py keeps the same rule)
     n = 0
+    ms.res[:] = 0
     for idx in res_order:
         if int(ms.cells["amount"][idx]) > 0:
             if n >= len(ms.res):
@@ -95,9 +137,13 @@ def state_from_updates(size, updates, turn=0, unit_id_count=0, city_id_count=0, 
     if len(cities) > len(ms.cities):
         raise ValueError("more cities than the capacity %d" % len(ms.cities))
     ntile = 0
+    ms.cities[:] = 0
+    ms.tiles[:] = 0
+    h["n_team_tiles"][:] = 0
     for slot, (cid, (team, fuel, cells)) in enumerate(cities.items()):
         c = ms.cities[slot]
-        c["id"], c["fuel"], c["team"], c["ntiles"], c["adjsum"] = _num(cid), fuel, team, len(cells), 0
+        c["id"], c["fuel"], c["team"], c["ntiles"] = _num(cid), fuel, team, len(cells)
+        adjsum = 0
         for key, idx in enumerate(cells):
             if ntile >= len(ms.tiles):
                 raise ValueError("more city tiles than the capacity %d" % len(ms.tiles))
@@ -105,6 +151,8 @@ def state_from_updates(size, updates, turn=0, unit_id_count=0, city_id_count=0, 
             ntile += 1
             ms.cells["city_slot"][idx] = slot
             ms.cells["key"][idx] = key
+            adjsum += (int(ms.cells["flags"][idx]) >> 4) & 7
+        c["adjsum"] = adjsum
         h["n_team_tiles"][team] += len(cells)
     h["n_cities"], h["n_tiles"] = len(cities), ntile
     if recount_adjacency:
@@ -127,6 +175,7 @@ def state_from_updates(size, updates, turn=0, unit_id_count=0, city_id_count=0, 
             ms.cities["adjsum"][slot] = adjsum
     # units: team A in line order, then team B
     k = 0
+    ms.units[:] = 0
     for team in (0, 1):
         h["n_team_units"][team] = len(units[team])
         for rec in units[team]:

@@ -14,6 +14,11 @@ imported through oracle/refshim.py); the packed encoding is oracle/flatten.py.
   dense.npz    replay states imported at turns 80/200/300 (process_updates, game.py:159-262)
   wire.npz     the update lines those imports consumed (input of luxpythonenvgym_b200/wire.py)
                continued for 45 turns with the canonical stream: digests + final state.
+  hostapi.npz  the reference's HOST protocol (LuxEnvironment / MatchController / agents / Game list semantics)
+               recorded with the scripted agents of tests/scripted.py: decisions, rewards, observations,
+               per-turn digests, hook call counts; the lines AgentFromStdInOut prints; messy raw action lists.
+  replay_<id>.json.gz  inputs of the reference's tests/test_replay.py flow, reduced to what the flow reads
+               (seed, per-step actions, per-step update lines).
 """
 import glob
 import json
@@ -82,10 +87,15 @@ def make_replays(ref):
         ms = flatten.flatten(g, caps=CAPS)
         store["%s/size" % rid] = np.array(ms.size)
         put(store, "%s/init" % rid, ms)
-        ua, ta, digests = [], [], []
+        ua, ta, digests, inexact = [], [], [], []
         for turn in range(len(rep["steps"]) - 1):
             cmds = [rep["steps"][turn + 1][t]["action"] for t in (0, 1)]
-            uw, tb, _ = flatten.commands_to_words(g, cmds, ms)
+            uw, tb, exact = flatten.commands_to_words(g, cmds, ms)
+            if not exact:
+                # the packed form drops something of this turn's raw command list (a second command for one
+                # entity, a command for a dead unit, ...).  The turn is still pinned: the reference's own
+                # assertion below compares the state with what the Kaggle engine produced from the RAW list.
+                inexact.append(turn)
             for s in np.nonzero(uw)[0]:
                 ua.append((turn, s, uw[s]))
             for s in np.nonzero(tb)[0]:
@@ -102,8 +112,9 @@ def make_replays(ref):
         store["%s/unit_actions" % rid] = np.array(ua, dtype=np.uint32).reshape(-1, 3)
         store["%s/tile_actions" % rid] = np.array(ta, dtype=np.uint32).reshape(-1, 3)
         store["%s/digests" % rid] = np.array(digests, dtype=np.uint64)
+        store["%s/inexact_turns" % rid] = np.array(inexact, dtype=np.int32)
         ids.append(rid)
-        print("replay", rid, ms.size, len(digests))
+        print("replay", rid, ms.size, len(digests), "turns the packed form cannot express exactly:", inexact)
     store["ids"] = np.array(ids)
     np.savez_compressed(os.path.join(OUT, "replays.npz"), **store)
 
@@ -366,17 +377,134 @@ def make_env(ref, stream_seed=90210, n=8):
     np.savez_compressed(os.path.join(OUT, "env.npz"), **store)
 
 
+SLIM_REPLAYS = ("27075871", "26688997", "26691974")
+
+
+def slim_replay(rep):
+    """What LuxEnvironment(replay_validate=rep) + AgentFromReplay(rep) read of a Kaggle episode."""
+    steps = []
+    for st in rep["steps"]:
+        steps.append([{"action": st[0].get("action"), "observation": {"updates": st[0]["observation"].get("updates")}},
+                      {"action": st[1].get("action")}])
+    return {"configuration": {"seed": rep["configuration"]["seed"]}, "steps": steps}
+
+
+def messy_commands(ref, g, ms, seed, k, turn):
+    """One turn's RAW command list [(team, text)]: the canonical stream plus what real agents get wrong --
+    repeated commands, two different commands for one entity, shuffled order (the spawn cap then binds on other
+    tiles), invalid directions, moves off the map, commands for the other team's units, dead destinations,
+    spawns off a city tile.  Never emitted: pillage / transfer FROM a missing unit and research on a non-tile
+    (they raise out of the reference's turn) and a second command for a unit that also
+    holds a move (declared outside the packed engine's domain, luxpythonenvgym_b200/game.py)."""
+    import random
+    rng = random.Random(seed * 7919 + k * 1009 + turn)
+    uw, tb = stream.gen_actions(ms, seed, k)
+    acts = flatten.words_to_actions(ref, g, uw, tb)
+    cmds = [(a.team, a.to_message(g)) for a in acts]
+    movers = set(a.unit_id for a in acts if a.action == "m")
+    extra = []
+    for a in acts:
+        r = rng.random()
+        if a.action == "m":
+            continue
+        if r < 0.12:
+            extra.append((a.team, a.to_message(g)))                                  # the same command again
+        elif r < 0.2 and a.action in ("bcity", "p", "t"):
+            extra.append((a.team, ("p %s" if a.action != "p" else "bcity %s") % (a.source_id if a.action == "t" else a.unit_id)))
+        elif r < 0.2 and a.action in ("bw", "bc", "r"):
+            extra.append((a.team, ("r %d %d" if a.action != "r" else "bw %d %d") % (a.x, a.y)))
+    size = g.map.width
+    for team in (0, 1):
+        for unit in g.state["teamStates"][team]["units"].values():
+            if unit.id in movers or any(c[1].split(" ")[1] == unit.id for c in cmds + extra if c[1][0] in "pt" or c[1].startswith("bcity")):
+                continue
+            r = rng.random()
+            if r < 0.05:
+                extra.append((team, "m %s q" % unit.id))                              # no such direction
+            elif r < 0.10:
+                extra.append((1 - team, "m %s n" % unit.id))                          # not this team's unit
+            elif r < 0.15:
+                extra.append((team, "t %s u_9999 wood 5" % unit.id))                  # destination does not exist
+            elif r < 0.18:
+                extra.append((team, "bcity %s" % unit.id))
+    if rng.random() < 0.3:
+        extra.append((rng.randint(0, 1), "bw %d %d" % (size + 3, 1)))                 # off the map
+    if rng.random() < 0.3:
+        x, y = rng.randrange(size), rng.randrange(size)
+        if not g.map.get_cell(x, y).is_city_tile():
+            extra.append((rng.randint(0, 1), "bw %d %d" % (x, y)))                    # not a city tile
+    cmds = cmds + extra
+    rng.shuffle(cmds)
+    return cmds
+
+
+def make_hostapi(ref, stream_seed=4242):
+    import gzip
+    import random
+    sys.path.insert(0, ROOT)
+    from tests import scripted
+    store = {}
+    ns = scripted.reference()
+
+    def digest(game, over):
+        return stamp_done(flatten.flatten(game, caps=CAPS), game, over).digest()
+
+    # (1) scripted LuxEnvironment episodes: custom learning agent (hooks counted, ActionSequence table entries)
+    #     against a scripted inference agent (process_turn, sequences, smart transfers)
+    specs = [(8000, 12, True), (8001, 16, False), (8002, 12, True), (8003, 16, True),
+             (8004, 24, False), (8005, 32, True), (8006, 12, False), (8007, 16, True)]
+    for k, (seed, size, sequences) in enumerate(specs):
+        rec = scripted.run_env_episode(ns, k, seed, size, sequences, stream_seed, digest,
+                                       wrap=lambda game: setattr(game, "log", lambda text: None))
+        for name, arr in rec.items():
+            store["env/%d/%s" % (k, name)] = arr
+        store["env/%d/spec" % k] = np.array([seed, size, int(sequences)])
+        print("hostapi env", k, size, "turns", len(rec["digests"]), "decisions", len(rec["decisions"]))
+    store["env/n"] = np.array(len(specs))
+    store["stream_seed"] = np.array(stream_seed)
+    # (2) slim replays + the Kaggle stdin / stdout protocol on one of them
+    for rid in SLIM_REPLAYS:
+        rep = json.load(open(os.path.join(refshim.REFERENCE_ROOT, "luxai2021/tests/replays_for_test/%s.json" % rid)))
+        raw = json.dumps(slim_replay(rep), separators=(",", ":")).encode()
+        with open(os.path.join(OUT, "replay_%s.json.gz" % rid), "wb") as f:
+            f.write(gzip.compress(raw, 9, mtime=0))
+    rep = json.load(open(os.path.join(refshim.REFERENCE_ROOT, "luxai2021/tests/replays_for_test/%s.json" % SLIM_REPLAYS[1])))
+    for team in (0, 1):
+        lines = scripted.run_stdin_episode(ns, rep, team, 80)
+        store["stdin/%d" % team] = np.array("\n".join(lines))
+        print("hostapi stdin team", team, len(lines), "lines")
+    # (3) raw action lists through Game.run_turn_with_actions
+    for k in range(6):
+        size = [12, 16, 24, 32][k % 4]
+        g = refshim.new_game(seed=8100 + k, width=size, height=size)
+        ms = flatten.flatten(g, caps=CAPS)
+        turns, digests = [], []
+        for turn in range(120):
+            cmds = messy_commands(ref, g, ms, stream_seed, k, turn)
+            turns.append(cmds)
+            acts = [g.action_from_string(text, team) for team, text in cmds]
+            over = g.run_turn_with_actions([a for a in acts if a is not None])
+            ms = stamp_done(flatten.flatten(g, caps=CAPS), g, over)
+            digests.append(ms.digest())
+            if over:
+                break
+        store["lists/%d/commands" % k] = np.array(json.dumps(turns))
+        store["lists/%d/digests" % k] = np.array(digests, dtype=np.uint64)
+        store["lists/%d/spec" % k] = np.array([8100 + k, size])
+        print("hostapi lists", k, size, "turns", len(digests), "commands", sum(len(t) for t in turns))
+    store["lists/n"] = np.array(6)
+    np.savez_compressed(os.path.join(OUT, "hostapi.npz"), **store)
+
+
 def main():
+    """python -m oracle.make_golden [maps replays random dense obs env wire hostapi]  (default: all)"""
     os.makedirs(OUT, exist_ok=True)
     os.chdir("/tmp")
     ref = refshim.load()
-    make_maps(ref)
-    make_replays(ref)
-    make_random(ref)
-    make_dense(ref)
-    make_obs(ref)
-    make_env(ref)
-    make_wire()
+    steps = {"maps": make_maps, "replays": make_replays, "random": make_random, "dense": make_dense,
+             "obs": make_obs, "env": make_env, "wire": lambda ref: make_wire(), "hostapi": make_hostapi}
+    for name in (sys.argv[1:] or list(steps)):
+        steps[name](ref)
 
 
 if __name__ == "__main__":

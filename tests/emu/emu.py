@@ -122,3 +122,15 @@ def observe(ms, team, e_cap=640):
     if rc != 0:
         raise RuntimeError("lux_emu_observe -> %d" % rc)
     return obs[: cnt[0]].copy(), ent[: cnt[0]].copy()
+
+
+def unit_word(ms, slot, code):
+    """The packed action word AgentPolicy's unit action `code` decodes to for the unit in `slot`
+    (csrc/lux_env_core.cuh: moves, smart transfers, build city, pillage)."""
+    L = lib()
+    hdr = ms.hdr.reshape(1)
+    b = LuxBatchC(1, ms.size, len(ms.units), len(ms.cities), len(ms.tiles), len(ms.res),
+                  hdr.ctypes.data, ms.cells.ctypes.data, ms.units.ctypes.data, ms.cities.ctypes.data,
+                  ms.tiles.ctypes.data, ms.res.ctypes.data)
+    L.lux_emu_unit_word.restype = ctypes.c_uint
+    return int(L.lux_emu_unit_word(ctypes.byref(b), 0, int(slot), int(code)))

@@ -152,3 +152,12 @@ extern "C" int lux_emu_observe(const LuxBatch* b, const uint8_t* team_sel, float
     free(a.smem);
     return 0;
 }
+
+// ---- AgentPolicy action decoding for one unit (csrc/lux_env_core.cuh) -----------------------
+#include "../../luxpythonenvgym_b200/csrc/lux_env_core.cuh"
+
+extern "C" unsigned lux_emu_unit_word(const LuxBatch* b, int m, int slot, int code) {
+    const LuxHeader* h = b->hdr + m;
+    if (slot < 0 || slot >= h->n_units) return 0;
+    return env_unit_word(b->units + (size_t)m * b->u_cap, h->n_units, b->size, slot, code);
+}
