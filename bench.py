@@ -32,6 +32,8 @@ POOL_MAPS = 1024
 BURN_IN_TURNS = 400          # untimed: brings the batch to a steady mix of match ages
 STREAM_SEED = 20211019
 METRIC = "match-turns/sec"
+MIN_TIMED_SECONDS = 0.25     # the K-step block is repeated until this much device time is covered
+JSON_OUT = sys.stdout
 
 
 def parse():
@@ -99,6 +101,35 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.1)
 
+    def sample_now(self):
+        """One synchronous sample (called right before / after / between the timed blocks, so that even a
+        millisecond-long region has clock evidence taken under load)."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            sm = pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(hnd, pynvml.NVML_CLOCK_SM)
+            reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
+            row = [str(sm), str(mx), "", "", "", ""]
+            for bit, col in ((pynvml.nvmlClocksThrottleReasonHwSlowdown, 2), (pynvml.nvmlClocksThrottleReasonHwThermalSlowdown, 3),
+                             (pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, 4), (pynvml.nvmlClocksThrottleReasonSwPowerCap, 5)):
+                row[col] = "Active" if reasons & bit else "Not Active"
+            self.rows.append(row)
+            return
+        except Exception:
+            pass
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout
+            parts = [p.strip() for p in out.strip().split(",")]
+            if len(parts) >= 6:
+                self.rows.append(parts)
+        except Exception:
+            pass
+
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
@@ -132,7 +163,7 @@ class CpuPort:
         def alloc(k):
             return {name: np.zeros((k, width), dtype=np.uint8) for name, width in (
                 ("hdr", 128), ("cells", size * size * 8), ("units", caps["units"] * 16),
-                ("cities", caps["cities"] * 16), ("tiles", caps["tiles"] * 2), ("res", caps["res"] * 2))}
+                ("cities", caps["cities"] * 16), ("tiles", caps["tiles"] * 2), ("res", caps["res"] * 4))}
 
         n_pool = pool_arrays["hdr"].shape[0]
         self.arr, self.parr = alloc(n_matches), {k: np.ascontiguousarray(v) for k, v in pool_arrays.items()}
@@ -190,7 +221,7 @@ def run_reference(args):
             "note": "the reference is pure Python (no compiled path) and /root/reference does not travel to the GPU "
                     "box, so this arm times the C port of the same algorithm; the unmodified Python engine measured "
                     "1-8 k match-turns/s per core in the build container (BASELINE.md section 2)"}
-    print(json.dumps(line))
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -207,10 +238,6 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
-        # rank 0's stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION / INFO
-        # print it to stdout) out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("LUX_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     n, size = args.matches, args.size
@@ -224,7 +251,6 @@ def run_b200(args):
     game.load_arrays(make_pool_arrays(size, n, seed0=1000000 * (rank + 1)))
     mapgen_s = time.perf_counter() - t_gen
     base = rank * n
-    counters = torch.zeros(2, dtype=torch.int64, device=dev)
     resets = torch.zeros(1, dtype=torch.int32, device=dev)
     epoch = [0]
 
@@ -247,34 +273,58 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- timed region: K steps, device-timed, per-step events around the step kernel
+    # ---- timed region: blocks of EXACTLY K steps, device-timed (CUDA events on the launching stream), each
+    # block bracketed by barrier + synchronize; the block is repeated R times so that at least
+    # MIN_TIMED_SECONDS of device time are covered whatever K is (a 20-step block lasts 3 ms), and the MEDIAN
+    # block is reported.  Per-step events around lux_b200_step give the step kernel's own duration.
     K = args.steps
-    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # counters: live match-turns and algorithmic bytes of the K timed turns.  The actions of the first timed turn
-    # exist already (generated by the pass that closed the last warm-up step): they are regenerated here, untimed,
-    # only to count that turn; every later turn is counted by the pass that generates its actions.
-    counters.zero_()
-    game.gen_actions(STREAM_SEED, base, counters=counters)
+
+    def timed_block(count_this, count_next):
+        ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sampler.sample_now()
+        t0.record()
+        for k in range(K):
+            ev_a[k].record()
+            game.step()
+            ev_b[k].record()
+            # the pass that closes step k counts the live matches / algorithmic bytes of the NEXT turn
+            game.reset_gen(pool, epoch[0], STREAM_SEED, base, reset_count=resets,
+                           counters=count_this if k < K - 1 else count_next)
+            epoch[0] += 1
+        t1.record()
+        barrier()
+        sampler.sample_now()
+        return t0.elapsed_time(t1), sum(x.elapsed_time(y) for x, y in zip(ev_a, ev_b)) / K
+
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    # a first block sizes R (the same on every rank: the slowest rank's block time decides)
+    R_MAX = 400
+    counters = torch.zeros((R_MAX + 2, 2), dtype=torch.int64, device=dev)
+    game.gen_actions(STREAM_SEED, base, counters=counters[0])      # untimed: counts the first timed turn
     launches0 = game.lib.lux_b200_launch_count()
-    t_start.record()
-    for k in range(K):
-        ev_a[k].record()
-        game.step()
-        ev_b[k].record()
-        game.reset_gen(pool, epoch[0], STREAM_SEED, base, reset_count=resets, counters=counters if k < K - 1 else None)
-        epoch[0] += 1
-    t_end.record()
-    launches = game.lib.lux_b200_launch_count() - launches0
-    barrier()
+    blocks = [timed_block(counters[0], counters[1])]
+    first = torch.tensor([blocks[0][0]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(first, op=dist.ReduceOp.MAX)
+    R = int(min(R_MAX, max(3, np.ceil(MIN_TIMED_SECONDS * 1e3 / max(float(first.item()), 1e-3)))))
+    for r in range(1, R):
+        blocks.append(timed_block(counters[r], counters[r + 1]))
+    launches = (game.lib.lux_b200_launch_count() - launches0) // R
     sampler.stop_flag = True
-    total_ms = t_start.elapsed_time(t_end)
-    step_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / K
-    live_turns, alg_bytes = [int(x) for x in counters.cpu().tolist()]
+    # the median block by whole-block time (max over ranks per block first)
+    block_ms = torch.tensor([bm for bm, _ in blocks], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(block_ms, op=dist.ReduceOp.MAX)
+    order = torch.argsort(block_ms)
+    mid = int(order[(R - 1) // 2].item())
+    total_ms = float(block_ms[mid].item())
+    step_ms = blocks[mid][1]
+    all_ms = sorted(block_ms.cpu().tolist())
+    live_turns, alg_bytes = [int(x) for x in counters[mid].cpu().tolist()]
 
     # ---- end to end through the host entry point: pinned host action LIST in, done flags + summary out.
     # The device path above is replayed from a snapshot: the action lists of W_e + E turns are recorded on the
@@ -358,6 +408,9 @@ def run_b200(args):
                 "config": config_dict(args, world),
                 "gpu_launches": int(launches) * world,
                 "kernel_ms": {"lux_step_kernel": step_ms, "whole_step": total_ms / K},
+                "timing": {"blocks": R, "steps_per_block": K, "reported": "median block (by whole-block device time, max over ranks)",
+                           "block_ms_min": all_ms[0], "block_ms_median": total_ms, "block_ms_max": all_ms[-1],
+                           "timed_seconds_total": sum(all_ms) * 1e-3},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "kernel": "lux_step_kernel (classify + big-class launch overlapped with the small-class launch = one step)",
                              "algorithmic_bytes_per_launch": bytes_all / world / K,
@@ -366,14 +419,22 @@ def run_b200(args):
                         "d2h_bytes_per_step": d2h * world, "steps": E, "warmup": 5,
                         "note": "lux_b200_step_host_sparse: pinned host action LIST (8 B per action) -> device, scatter, "
                                 "step, done flags + summary -> host, sync every step; counts resident matches per step "
-                                "(finished ones are reset the same step)"},
+                                "(finished ones are reset the same step).  The lists are recorded beforehand (the device "
+                                "action stream packed into entry form): building them from host Action objects is the "
+                                "caller's cost and is not in this number"},
                 "clocks": sampler.summary(),
                 "host_mapgen": {"maps": n + POOL_MAPS, "seconds": mapgen_s, "note": "untimed setup: native seeded generator"},
                 "stats": {"live": st[0], "finished_pending": st[1], "sum_units": st[7], "sum_city_tiles": st[8],
                           "status_nonzero": st[10], "resets": int(resets.item())}}
+        # `traffic` is NOT measured by this run (ncu cannot run inside a timed bench): it is the DRAM byte count of
+        # one step from the newest committed ncu capture, carried with the capture's name and source revision so
+        # that a reader can tell whether it belongs to the kernel that was timed here
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+            import glob
+            tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")))[-1]))
             line["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
+            line["roofline"]["traffic_source"] = {k: tr.get(k) for k in ("capture", "git", "kernel", "note")}
+            line["roofline"]["dram_gbs_from_traffic"] = tr.get("dram_bytes_per_launch", 0) / (step_ms * 1e-3) / 1e9
         except Exception:
             pass
         if world == 1 and not args.no_cpu_baseline:
@@ -388,13 +449,25 @@ def run_b200(args):
                                     "sample": "oracle/lux_oracle.c, %d matches x %d turns after %d burn-in turns, same maps / "
                                               "action stream / pool resets, %d host threads, step calls only (%.1f s of "
                                               "stepping per thread)" % (256 * threads, turns_sum, BURN_IN_TURNS, threads, sec_sum)}
-        print(json.dumps(line))
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def claim_stdout():
+    """Rank 0's stdout carries exactly one JSON line, printed last.  Whatever else writes to file descriptor 1
+    while the bench runs (NCCL's NCCL_DEBUG=INFO / VERSION log goes to stdout) is sent to stderr instead, so
+    the caller still sees it -- NCCL_DEBUG is left as the caller set it.  Returns the stream for the JSON line."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
     args = parse()
+    global JSON_OUT
+    JSON_OUT = claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -16,7 +16,8 @@
  *   units  [n][u_cap]          LuxUnit   (16 B) team-A units in dict order, then team B
  *   cities [n][c_cap]          LuxCity   (16 B) Game.cities dict order
  *   tiles  [n][t_cap]          uint16    cell index of each city tile, cities x city_cells order
- *   res    [n][r_cap]          uint16    cell index of each resource cell, GameMap.resources order
+ *   res    [n][r_cap]          LuxRes    (4 B) every resource cell of the map in GameMap.resources order:
+ *                                        cell index, resource type and a MIRROR of the cell's current amount
  */
 #ifndef LUX_B200_H
 #define LUX_B200_H
@@ -81,6 +82,17 @@ typedef struct LUX_ALIGNED(8) LuxCell {              /* cell.py:20-33, city.py:5
     uint16_t key;                      /* index in City.city_cells */
 } LuxCell;
 
+/* One entry of the resource list (game_map.py:53-58 `GameMap.resources`, static after reset: depleted cells stay
+ * listed with amount 0).  `amount` mirrors cells[cell].amount -- every writer of one writes the other -- so that
+ * the per-turn passes over all resource cells (depletion + wood regrowth game.py:498-510, :1081-1102; the
+ * observation's resource nodes agent_policy.py:197-247) read one contiguous list instead of one 32-byte DRAM
+ * sector per cell.  `rtype` is the type the cell was created with (it stays after depletion). */
+typedef uint32_t LuxRes;               /* [9:0] cell index, [11:10] resource type (LUX_RES_*), [31:16] amount */
+#define LUX_RES_CELL(e) ((int)((e) & 0x3FFu))
+#define LUX_RES_TYPE(e) ((int)(((e) >> 10) & 3u))
+#define LUX_RES_AMOUNT(e) ((int)((e) >> 16))
+#define LUX_RES_MAKE(cell, rtype, amount) ((LuxRes)((cell) | ((rtype) << 10) | ((uint32_t)(amount) << 16)))
+
 typedef struct LUX_ALIGNED(16) LuxUnit {              /* unit.py:15-35 */
     int32_t  id;                       /* N of "u_N" */
     uint8_t  x, y;
@@ -116,7 +128,7 @@ typedef struct LuxBatch {
     LuxUnit*   units;
     LuxCity*   cities;
     uint16_t*  tiles;
-    uint16_t*  res;
+    LuxRes*    res;
 } LuxBatch;
 
 /* Library / build identification; also reports whether a CUDA device is usable. */

@@ -32,7 +32,7 @@ class BatchedGame:
         self.units = z(self.n, c["units"] * 16)
         self.cities = z(self.n, c["cities"] * 16)
         self.tiles = z(self.n, c["tiles"] * 2)
-        self.res = z(self.n, c["res"] * 2)
+        self.res = z(self.n, c["res"] * 4)
         self.unit_actions = torch.zeros((self.n, c["units"]), dtype=torch.int32, device=self.device)
         self.tile_actions = z(self.n, c["tiles"])
         self._stats = torch.zeros(16, dtype=torch.int64, device=self.device)

@@ -180,7 +180,7 @@ bool enough(Field& f) {
 }
 
 int generate_one(int64_t seed, int size, int u_cap, int c_cap, int t_cap, int r_cap, LuxHeader* hdr, LuxCell* cells,
-                 LuxUnit* units, LuxCity* cities, uint16_t* tiles, uint16_t* res) {
+                 LuxUnit* units, LuxCity* cities, uint16_t* tiles, LuxRes* res) {
     Arc4 r("gen_" + std::to_string((long long)seed));
     static const int SIZES[4] = {12, 16, 24, 32};
     int drawn = SIZES[(int)floor(r.next() * 4)];
@@ -199,7 +199,7 @@ int generate_one(int64_t seed, int size, int u_cap, int c_cap, int t_cap, int r_
         c.amount = (uint16_t)amt;
         c.flags = (uint8_t)((c.flags & 0xFC) | kind);
         if (nres >= r_cap) return false;
-        res[nres++] = (uint16_t)(y * w + x);
+        res[nres++] = (LuxRes)(y * w + x);
         return true;
     };
     for (int y = 0; y < h; y++)
@@ -243,6 +243,11 @@ int generate_one(int64_t seed, int size, int u_cap, int c_cap, int t_cap, int r_
         if (placed == 6) break;
     }
     hdr->unit_id_count = 2; hdr->city_id_count = 2;
+    // the list entries carry the cell's type and a mirror of its final amount (include/lux_b200.h LuxRes)
+    for (int k = 0; k < nres; k++) {
+        const LuxCell& c = cells[res[k]];
+        res[k] = LUX_RES_MAKE(res[k], (uint32_t)(c.flags & 3), c.amount);
+    }
     hdr->n_units = 2; hdr->n_cities = 2; hdr->n_tiles = 2; hdr->n_res = (uint16_t)nres;
     hdr->n_team_units[0] = hdr->n_team_units[1] = 1;
     hdr->n_team_tiles[0] = hdr->n_team_tiles[1] = 1;

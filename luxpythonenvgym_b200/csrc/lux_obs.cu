@@ -36,9 +36,9 @@ __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_
     if (lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
-        mbar_expect_tx(bar, LUX_HDR_BYTES + b.r_cap * 2 + pu * 16 + pt * 2);
+        mbar_expect_tx(bar, LUX_HDR_BYTES + b.r_cap * 4 + pu * 16 + pt * 2);
         tma_g2s(M.hdr, b.hdr + m, LUX_HDR_BYTES, bar);
-        tma_g2s(M.res, b.res + (size_t)m * b.r_cap, b.r_cap * 2, bar);
+        tma_g2s(M.res, b.res + (size_t)m * b.r_cap, b.r_cap * 4, bar);
         tma_g2s(M.units, g_units, pu * 16, bar);
         tma_g2s(M.tiles, g_tiles, pt * 2, bar);
     }

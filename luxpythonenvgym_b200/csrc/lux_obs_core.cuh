@@ -42,7 +42,7 @@ LuxObsLayout lux_obs_layout(int size, int u_cap, int t_cap, int r_cap) {
     LUX_TAKE(hdr, LUX_HDR_BYTES)
     LUX_TAKE(units, u_cap * 16)
     LUX_TAKE(tiles, t_cap * 2)
-    LUX_TAKE(res, r_cap * 2)
+    LUX_TAKE(res, r_cap * 4)
     LUX_TAKE(nodes_res, 3 * r_cap * 4)  // wood, coal, uranium nodes: x | y << 8 | amount << 16, r_cap entries each
     LUX_TAKE(nodes_tile, t_cap * 4)     // own city tiles: x | y << 8 | city slot << 16
     LUX_TAKE(nodes_work, u_cap * 4)     // own workers: x | y << 8
@@ -54,7 +54,7 @@ LuxObsLayout lux_obs_layout(int size, int u_cap, int t_cap, int r_cap) {
 }
 
 struct LuxObsMatch {
-    LuxHeader* hdr; LuxUnit* units; uint16_t* tiles; uint16_t* res;
+    LuxHeader* hdr; LuxUnit* units; uint16_t* tiles; LuxRes* res;
     uint32_t* nodes_res; uint32_t* nodes_tile; uint32_t* nodes_work; uint8_t* tinfo;
     const LuxCell* cells;        // the grid stays in global memory, read once per resource cell / city tile
     const LuxCity* g_cities;     // cities stay in global memory: two lookups per entity
@@ -65,7 +65,7 @@ LUX_DEV void lux_obs_bind(LuxObsMatch& M, unsigned char* smem, const LuxObsLayou
                           const LuxCity* g_cities) {
     M.hdr = (LuxHeader*)(smem + L.hdr);
     M.units = (LuxUnit*)(smem + L.units);
-    M.tiles = (uint16_t*)(smem + L.tiles); M.res = (uint16_t*)(smem + L.res);
+    M.tiles = (uint16_t*)(smem + L.tiles); M.res = (LuxRes*)(smem + L.res);
     M.nodes_res = (uint32_t*)(smem + L.nodes_res); M.nodes_tile = (uint32_t*)(smem + L.nodes_tile);
     M.nodes_work = (uint32_t*)(smem + L.nodes_work);
     M.tinfo = smem + L.tinfo;
@@ -162,18 +162,18 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
     const int S = M.S;
     const int n_units = h->n_units, n_tiles = h->n_tiles, n_res = h->n_res;
 
-    // ---- node lists (agent_policy.py:197-247), order-preserving ballot compaction; the one pass that reads
-    // the grid: a global load per resource cell and per city tile, what later stages need rides in the entry
+    // ---- node lists (agent_policy.py:197-247), order-preserving ballot compaction; resource nodes come
+    // from the list entries (type + amount mirror), city tiles cost one grid load each; what later stages need
+    // rides in the node entry
     int n_type[3] = {0, 0, 0};
 #pragma unroll 1
     for (int base = 0; base < n_res; base += 32) {
         int r = base + lane;
-        int cell = r < n_res ? M.res[r] : 0;
-        LuxCell C;
-        C.amount = 0; C.flags = 0;
-        if (r < n_res) C = lux_ldcell(M.cells, cell);
-        const int t = C.amount > 0 ? cell_res_type(C) : 0;
-        const unsigned node = (unsigned)(cell % S) | ((unsigned)(cell / S) << 8) | ((unsigned)C.amount << 16);
+        // the list entry carries the cell's type and a mirror of its amount: no grid access
+        const LuxRes e = r < n_res ? M.res[r] : 0u;
+        const int cell = LUX_RES_CELL(e), amount = LUX_RES_AMOUNT(e);
+        const int t = amount > 0 ? LUX_RES_TYPE(e) : 0;
+        const unsigned node = (unsigned)(cell % S) | ((unsigned)(cell / S) << 8) | ((unsigned)amount << 16);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             unsigned m = lux_ballot(t == k + 1);

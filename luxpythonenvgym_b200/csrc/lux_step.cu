@@ -99,7 +99,7 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
         // trip 2: the live lists and this turn's action words, one bulk-copy batch
         if (active && lane == 0) {
             const uint32_t bu = nu * 16, bua = (nu * 4 + 15) & ~15u, bc = nc * 16, bt = (nt * 2 + 15) & ~15u,
-                           bta = (nt + 15) & ~15u, br = (nr * 2 + 15) & ~15u;
+                           bta = (nt + 15) & ~15u, br = (nr * 4 + 15) & ~15u;
             mbar_expect_tx(bar, bu + bua + bc + bt + bta + br);
             if (bu) { tma_g2s(M.units, g.units, bu, bar); tma_g2s(M.uact, g.uact, bua, bar); }
             if (bc) tma_g2s(M.cities, g.cities, bc, bar);
@@ -122,7 +122,7 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
         for (int i = lane; i < nt16; i += G) ta4[i] = make_uint4(0, 0, 0, 0);
     }
     LuxTurnOut T = lux_turn<kS, G>(M, flags & 0xFFFFu);
-    lux_finish_and_store<kS, G>(M, T, g.hdr, g.units, g.cities, g.tiles, active);
+    lux_finish_and_store<kS, G>(M, T, g.hdr, g.units, g.cities, g.tiles, g.res, active);
     // cannot happen (the classification pass routes such a match to the big class); visible if it ever does
     if (valid && result == LUX_M_SPILL && lane == 0) atomicOr((unsigned*)&g.hdr->done, (unsigned)LUX_ST_BAD_STATE << 16);   // done | winner | status | size
 }
@@ -161,7 +161,7 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
 // kPlain: compiled for flags == 0 (no pre-validation, no consumed action words): the common call, and a
 // shorter program for the instruction cache
 template <bool kTma, int kS, int kMode, int G, bool kPlain>
-__global__ void __launch_bounds__(64, (G == 32 && kMode == kSmall) ? LUX_SMALL_MIN_CTAS : 1)
+__global__ void __launch_bounds__(64, kMode == kSmall ? (G == 32 ? LUX_SMALL_MIN_CTAS : G == 16 ? 13 : 6) : 1)
 lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uint8_t* __restrict__ tile_actions,
                 int slice, unsigned flags_in, LuxSched sc) {
     const unsigned flags = kPlain ? 0u : flags_in;
@@ -195,12 +195,14 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
             const int valid = idx < count;
             lux_step_match<kTma, kS, G>(b, valid ? sc.big_list[idx] : 0, valid, unit_actions, tile_actions, smem, flags, slice, phase);
             lux_sync<G>();
+            // the slice was written with generic stores; the next match's bulk copies (async proxy) land in it
+            if (kTma && lane == 0) fence_proxy_async();
         }
         return;
     }
     const int m = blockIdx.x * gpc + grp;
     int valid = m < b.n_matches;
-    if (kMode == kSmall && valid && sc.cls[m]) valid = 0;          // the big class plays it
+    if (kMode == kSmall && valid && __ldcg(sc.cls + m)) valid = 0;          // the big class plays it
     if (lux_wany<G>(valid))
         lux_step_match<kTma, kS, G>(b, m, valid, unit_actions, tile_actions, smem, flags, slice, phase);
     // a programmatic dependent may not finish before its primary: later work on the stream waits for this grid
@@ -478,7 +480,7 @@ __device__ __forceinline__ void lux_reset_match(const LuxBatch& b, const LuxBatc
     const char* s3 = (const char*)(pool.tiles + (size_t)src * b.t_cap); char* d3 = (char*)(b.tiles + (size_t)m * b.t_cap);
     const char* s4 = (const char*)(pool.res + (size_t)src * b.r_cap); char* d4 = (char*)(b.res + (size_t)m * b.r_cap);
     // running end of each segment in the flat index space (16-byte pieces)
-    const int e0 = ncell / 2, e1 = e0 + nu, e2 = e1 + nc, e3 = e2 + (nt * 2 + 15) / 16, total = e3 + (nr * 2 + 15) / 16;
+    const int e0 = ncell / 2, e1 = e0 + nu, e2 = e1 + nc, e3 = e2 + (nt * 2 + 15) / 16, total = e3 + (nr * 4 + 15) / 16;
     for (int base = 0; base < total; base += 32 * 8) {
         uint4 v[8];
         char* dst[8];
@@ -666,6 +668,7 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     auto pick_wpc = [&](int slice, int group) {
         size_t per_warp = (size_t)slice * (32 / group);
         int w = g_warps_per_cta > 0 ? g_warps_per_cta : (per_warp >= 7 * 1024 ? 1 : 2);
+        if (w > 2) w = 2;                                          // __launch_bounds__(64, ...) of lux_step_kernel
         while (w > 1 && per_warp * w > 227 * 1024) w--;
         return w;
     };

@@ -122,7 +122,7 @@ LUX_HD LuxSmemLayout lux_smem_layout_need(int size, LuxNeed n) {
     LUX_TAKE(cities, n.c * 16)
     LUX_TAKE(tiles, n.t * 2)
     LUX_TAKE(tact, n.t)
-    LUX_TAKE(res, n.r * 2)
+    LUX_TAKE(res, n.r * 4)
     LUX_TAKE(utgt, n.u * 2)
     LUX_TAKE(ust, n.u)
     LUX_TAKE(umine, n.u)
@@ -159,7 +159,7 @@ struct LuxMatch {
     LuxUnit* units;
     LuxCity* cities;
     uint16_t* tiles;
-    uint16_t* res;
+    LuxRes* res;
     uint32_t* uact;
     uint8_t* tact;
     uint16_t* utgt;
@@ -184,7 +184,7 @@ LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayou
     M.units = (LuxUnit*)(smem + L.units);
     M.cities = (LuxCity*)(smem + L.cities);
     M.tiles = (uint16_t*)(smem + L.tiles);
-    M.res = (uint16_t*)(smem + L.res);
+    M.res = (LuxRes*)(smem + L.res);
     M.uact = (uint32_t*)(smem + L.uact);
     M.tact = (uint8_t*)(smem + L.tact);
     M.utgt = (uint16_t*)(smem + L.utgt);
@@ -230,10 +230,16 @@ LUX_DEV int cell_tile_team(const LuxCell& c) { return ((c.flags >> 2) & 3) - 1; 
 LUX_DEV int cell_res_type(const LuxCell& c) { return c.flags & 3; }
 LUX_DEV int cell_adj(const LuxCell& c) { return (c.flags >> 4) & 7; }
 
+// Grid reads go through L1 (the default .ca path): a sector holds four cell records and a unit's neighbourhood
+// and the later phases hit the lines the earlier ones fetched; bypassing L1 (ld.global.cg) was measured 18 %
+// slower on the bench batch (0.129 against 0.110 ms per step).
+#define LUX_LDG64(p) (*(const uint64_t*)(p))
+#define LUX_LDG16(p) (*(const uint16_t*)(p))
+#define LUX_LDG8(p) (*(const uint8_t*)(p))
 // one 8-byte access per cell record
 LUX_DEV LuxCell lux_ldcell(const LuxCell* cells, int i) {
     union { uint64_t w; LuxCell c; } v;
-    v.w = *(const uint64_t*)(cells + i);
+    v.w = LUX_LDG64(cells + i);
     return v.c;
 }
 LUX_DEV void lux_stcell(LuxCell* cells, int i, const LuxCell& c) {
@@ -289,7 +295,7 @@ LUX_DEV void lux_idle_header(LuxMatch& M) { lux_zero16<G>(M.hdr, LUX_HDR_BYTES);
 // ---- staging with plain loads: header first, then the lists at the sizes the header names --------------
 // Pointers into one match's sections in global memory.
 struct LuxGlobalMatch {
-    LuxHeader* hdr; LuxCell* cells; LuxUnit* units; LuxCity* cities; uint16_t* tiles; const uint16_t* res;
+    LuxHeader* hdr; LuxCell* cells; LuxUnit* units; LuxCity* cities; uint16_t* tiles; LuxRes* res;
     const uint32_t* uact; const uint8_t* tact;
 };
 enum { LUX_M_DONE = 0, LUX_M_SPILL = 1 };     // why a group is not playing: nothing to play / the turn does not fit the slice
@@ -321,7 +327,7 @@ LUX_DEV int lux_stage_plain(LuxMatch& M, unsigned char* smem, const LuxGlobalMat
         lux_copy16<G>(M.units, g.units, M.hdr->n_units * 16);
         lux_copy16<G>(M.cities, g.cities, M.hdr->n_cities * 16);
         lux_copy16<G>(M.tiles, g.tiles, M.hdr->n_tiles * 2);
-        lux_copy16<G>(M.res, g.res, M.hdr->n_res * 2);
+        lux_copy16<G>(M.res, g.res, M.hdr->n_res * 4);
         lux_copy16<G>(M.uact, g.uact, M.hdr->n_units * 4);
         lux_copy16<G>(M.tact, g.tact, M.hdr->n_tiles);
     } else {
@@ -388,7 +394,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
 #pragma unroll 1
     for (int q = lane; q < n_req; q += G) {
         int c = M.reqlist[q];
-        int left = M.cells[c].amount;                 // global; consumed after the gather below
+        int left = LUX_LDG16(&M.cells[c].amount);       // global; consumed after the gather below
         int level = 0;
         int x = c % S, y = c / S;
         // histogram of request amounts 0..20, 3 bits each (at most one request per amount and source cell)
@@ -466,7 +472,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                 }
             }
         }
-        M.p1[c] = (uint8_t)level;                     // fill level (replaces the request mark)
+        M.p1[c] = (uint8_t)(0x80u | level);           // fill level; the request mark stays for the regrowth pass
     }
     lux_sync<G>();
 
@@ -965,7 +971,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                         }
                     } else {                                          // pillage unit.py:188-192
                         int pc = U.y * S + U.x;
-                        int rq = M.cells[pc].road_q;
+                        int rq = LUX_LDG8(&M.cells[pc].road_q);
                         M.cells[pc].road_q = (uint8_t)(rq > LUX_PILLAGE_Q ? rq - LUX_PILLAGE_Q : 0);
                     }
                 }
@@ -1137,31 +1143,32 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         lux_sync<G>();
     }
 
-    // ---- depleted cells leave the list (game.py:498-510), trees regrow (:1081-1102): four resource
-    // cells per lane and round, loads first
+    // ---- depleted cells leave the list (game.py:498-510), trees regrow (:1081-1102).  The resource list
+    // carries each cell's type and a mirror of its amount, so this pass over ALL resource cells works on shared
+    // memory; only a cell somebody mined from this turn is re-read from the grid (the collection pass stored
+    // its new amount there), and only changed amounts are written to the grid.
     {
         const int n_res = h->n_res;
 #pragma unroll 1
-        for (int base = 0; base < n_res; base += 4 * G) {
-            int idx[4];
-            LuxCell c[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int r = base + G * k + lane;
-                idx[k] = r < n_res ? (int)M.res[r] : -1;
-                if (idx[k] >= 0) c[k] = lux_ldcell(M.cells, idx[k]);
+        for (int r = lane; r < n_res; r += G) {
+            const LuxRes e = M.res[r];
+            const int cell = LUX_RES_CELL(e);
+            const int before = LUX_RES_AMOUNT(e);
+            const unsigned mark = M.p1[cell];
+            int a = before;
+            if (mark) {
+                M.p1[cell] = 0;                                              // collection scratch (mark + fill level)
+                if (mark & 0x80u) a = LUX_LDG16(&M.cells[cell].amount);
             }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (idx[k] < 0) continue;
-                M.p1[idx[k]] = 0;                                          // collection scratch (fill level)
-                if (c[k].amount == 0) {
-                    if (c[k].flags & 0x03) M.cells[idx[k]].flags = (uint8_t)(c[k].flags & 0xFC);
-                } else if (cell_res_type(c[k]) == LUX_RES_WOOD && c[k].amount < LUX_MAX_WOOD) {
-                    int a = (41 * (int)c[k].amount + 39) / 40;            // == ceil(min(a*1.025, 500)), tests/test_oracle_golden.py
-                    M.cells[idx[k]].amount = (uint16_t)(a > LUX_MAX_WOOD ? LUX_MAX_WOOD : a);
-                }
+            if (a == 0) {
+                // depleted this turn: the cell loses its resource type (amount + flags share one 32-bit word)
+                if (before > 0) lux_atomic_and((unsigned*)&M.cells[cell], ~0x00030000u);
+            } else if (LUX_RES_TYPE(e) == LUX_RES_WOOD && a < LUX_MAX_WOOD) {
+                a = (41 * a + 39) / 40;                                      // == ceil(min(a*1.025, 500)), tests/test_oracle_golden.py
+                if (a > LUX_MAX_WOOD) a = LUX_MAX_WOOD;
+                M.cells[cell].amount = (uint16_t)a;
             }
+            if (a != before) M.res[r] = (e & 0xFFFFu) | ((LuxRes)a << 16);
         }
     }
     lux_sync<G>();
@@ -1176,12 +1183,14 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 // g_* are the match's sections in global memory (the grid is already up to date there).
 template <int kS, int G>
 LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g_hdr, LuxUnit* g_units,
-                                  LuxCity* g_cities, uint16_t* g_tiles, int active) {
+                                  LuxCity* g_cities, uint16_t* g_tiles, LuxRes* g_res, int active) {
     const int lane = lux_lane<G>();
     const unsigned lt = lux_lanemask_lt<G>();
     LuxHeader* h = M.hdr;
     const int S = kS > 0 ? kS : M.S;
 
+    // the resource list goes back as it stands (amount mirrors)
+    if (active) lux_copy16<G>(g_res, M.res, h->n_res * 4);
     // cities: drop the dead (ntiles == 0), keep order
     int n_alive = 0, nc0 = 0, nc1 = 0, tl0 = 0, tl1 = 0;
     const int nc_max = lux_wmax<G>(T.n_cities);
@@ -1252,7 +1261,7 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
         unsigned m0 = lux_ballot<G>(valid && team == 0), m1 = lux_ballot<G>(valid && team == 1);
         if (valid) {
             LuxUnit U = M.units[u];
-            int road = (M.uinfo[u] & UI_TILE) ? LUX_MAX_ROAD_Q : (int)M.cells[U.y * S + U.x].road_q;    // cell.py:77-85
+            int road = (M.uinfo[u] & UI_TILE) ? LUX_MAX_ROAD_Q : (int)LUX_LDG8(&M.cells[U.y * S + U.x].road_q);    // cell.py:77-85
             int cd = (int)U.cd_q - road - 4;
             U.cd_q = (uint8_t)(cd > 0 ? cd : 0);
             U.pad = 0;

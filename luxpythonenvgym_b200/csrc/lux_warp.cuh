@@ -54,6 +54,7 @@ LUX_DEV unsigned lux_reduce_max_u(unsigned v) { return __reduce_max_sync(LUX_FUL
 LUX_DEV int lux_popc(unsigned v) { return __popc(v); }
 LUX_DEV int lux_ffs(unsigned v) { return __ffs(v); }
 LUX_DEV unsigned lux_atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
+LUX_DEV void lux_atomic_and(unsigned* p, unsigned v) { atomicAnd(p, v); }
 LUX_DEV int lux_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 #endif
 

@@ -461,7 +461,7 @@ class Game:
         gmap.resources = []
         gmap.resources_by_type = {"wood": [], "coal": [], "uranium": []}
         self._res_cells = []
-        res_idx = ms.res[:n_res].tolist()
+        res_idx = S.res_cell(ms.res[:n_res]).tolist()
         for idx, amt, fl in zip(res_idx, amount[res_idx].tolist(), flags[res_idx].tolist()):
             if amt > 0:
                 cell = grid[idx // size][idx % size]

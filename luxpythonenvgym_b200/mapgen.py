@@ -272,8 +272,7 @@ def generate(seed, size=None, caps=None):
     hd["n_team_tiles"] = (1, 1)
     hd["workers_built"] = (1, 1)
     assert len(res_list) <= len(ms.res), "resource capacity too small for this map"
-    ms.res[: len(res_list)] = res_list
-    hd["n_res"] = len(res_list)
+    ms.set_res_cells(res_list)
     return ms
 
 
@@ -312,7 +311,7 @@ def generate_batch(seeds, size, caps=None, threads=0):
     n = len(seeds)
     arr = {name: np.zeros((n, width), dtype=np.uint8) for name, width in (
         ("hdr", S.HDR_BYTES), ("cells", size * size * 8), ("units", caps["units"] * 16),
-        ("cities", caps["cities"] * 16), ("tiles", caps["tiles"] * 2), ("res", caps["res"] * 2))}
+        ("cities", caps["cities"] * 16), ("tiles", caps["tiles"] * 2), ("res", caps["res"] * 4))}
     desc = LuxBatch(n, size, caps["units"], caps["cities"], caps["tiles"], caps["res"],
                     *[arr[k].ctypes.data for k in ("hdr", "cells", "units", "cities", "tiles", "res")])
     rc = lib.lux_mapgen_generate_batch(ctypes.byref(desc), seeds.ctypes.data_as(ctypes.c_void_p), int(threads))

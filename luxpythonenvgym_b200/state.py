@@ -9,8 +9,9 @@ leading match dimension (`[n_matches, ...]`, one torch uint8 tensor per section)
   cities LuxCity[C_cap]       16 B    cities in `Game.cities` dict order
   tiles  uint16[T_cap]        2 B     cell index (y*S+x) of every city tile in
                                       cities x city_cells order
-  res    uint16[R_cap]        2 B     cell index of every resource cell in
-                                      `GameMap.resources` order (static after reset)
+  res    LuxRes[R_cap]        4 B     every resource cell in `GameMap.resources` order (static after
+                                      reset): [9:0] cell index, [11:10] resource type, [31:16] a MIRROR
+                                      of the cell's amount (kept equal to cells[cell].amount by every writer)
 
 The field inventory follows the reference's state:
 luxai2021/game/game.py:85-147 (state/stats/id counters), cell.py:20-33, unit.py:15-35,
@@ -119,6 +120,24 @@ def default_caps(size):
     return dict(units=units, cities=cities, tiles=tiles, res=res)
 
 
+def res_cell(entries):
+    """Cell index of LuxRes entries (include/lux_b200.h)."""
+    return np.asarray(entries, dtype=np.uint32) & 0x3FF
+
+
+def res_type(entries):
+    return (np.asarray(entries, dtype=np.uint32) >> 10) & 3
+
+
+def res_amount(entries):
+    return np.asarray(entries, dtype=np.uint32) >> 16
+
+
+def res_make(cell, rtype, amount):
+    return (np.asarray(cell, dtype=np.uint32) | (np.asarray(rtype, dtype=np.uint32) << 10) |
+            (np.asarray(amount, dtype=np.uint32) << 16)).astype("<u4")
+
+
 def encode_move(direction):
     return UA_MOVE | (direction << 3)
 
@@ -154,7 +173,7 @@ class MatchState:
         self.units = np.zeros(caps["units"], dtype=unit_dtype)
         self.cities = np.zeros(caps["cities"], dtype=city_dtype)
         self.tiles = np.zeros(caps["tiles"], dtype="<u2")
-        self.res = np.zeros(caps["res"], dtype="<u2")
+        self.res = np.zeros(caps["res"], dtype="<u4")
         self.hdr["size"] = size
         self.hdr["winner"] = WIN_NONE
 
@@ -171,8 +190,8 @@ class MatchState:
         h["n_res"] = 0
         cells = self.cells.copy()
         cells["flags"] = np.where(cells["amount"] == 0, cells["flags"] & 0xFC, cells["flags"])
-        res = self.res[: int(self.hdr["n_res"])]
-        res = res[cells["amount"][res] > 0]
+        res = res_cell(self.res[: int(self.hdr["n_res"])])
+        res = res[cells["amount"][res] > 0].astype("<u2")      # the list as the reference holds it: cell indices
         return {
             "hdr": h,
             "cells": cells,
@@ -182,9 +201,29 @@ class MatchState:
             "res": res,
         }
 
+    def set_res_cells(self, cell_indices):
+        """Fill the resource list from cell indices in GameMap.resources order; type and amount mirror come
+        from the grid."""
+        idx = np.asarray(cell_indices, dtype=np.int64).reshape(-1)
+        if len(idx) > len(self.res):
+            raise ValueError("more resource cells than the capacity %d" % len(self.res))
+        self.res[:] = 0
+        self.res[: len(idx)] = res_make(idx, self.cells["flags"][idx] & 3, self.cells["amount"][idx])
+        self.hdr["n_res"] = len(idx)
+
+    def mirror_errors(self):
+        """Resource-list entries whose amount mirror (or, while the cell holds a resource, type) disagrees with
+        the grid -- empty for every state this package or the oracle produces."""
+        e = self.res[: int(self.hdr["n_res"])]
+        cell = res_cell(e)
+        amount = self.cells["amount"][cell]
+        bad = (res_amount(e) != amount) | ((amount > 0) & (res_type(e) != (self.cells["flags"][cell] & 3)))
+        return ["res[%d] (cell %d): mirror %d / type %d vs grid %d / type %d" % (
+            k, cell[k], res_amount(e)[k], res_type(e)[k], amount[k], self.cells["flags"][cell[k]] & 3) for k in np.nonzero(bad)[0][:4]]
+
     def diff(self, other):
         """List of human-readable differences (empty == bit-identical live state)."""
-        out = []
+        out = self.mirror_errors() + other.mirror_errors()
         a, b = self.live(), other.live()
         for name in self.SECTIONS:
             x, y = a[name], b[name]
@@ -220,17 +259,22 @@ class MatchState:
         return int.from_bytes(hh.digest(), "little")
 
     @classmethod
-    def from_arrays(cls, size, arrays):
-        """Build from a dict of raw uint8/typed arrays keyed by section name."""
+    def from_arrays(cls, size, arrays, legacy_res=False):
+        """Build from a dict of raw uint8/typed arrays keyed by section name.  `legacy_res`: the "res" array is
+        the round-1 form (uint16 cell indices, as stored in tests/golden/*.npz); it is widened to LuxRes entries
+        with type and amount taken from the grid."""
         caps = dict(units=arrays["units"].view(np.uint8).size // 16, cities=arrays["cities"].view(np.uint8).size // 16,
-                    tiles=arrays["tiles"].view(np.uint8).size // 2, res=arrays["res"].view(np.uint8).size // 2)
+                    tiles=arrays["tiles"].view(np.uint8).size // 2, res=arrays["res"].view(np.uint8).size // (2 if legacy_res else 4))
         o = cls(size, caps)
         o.hdr = np.ascontiguousarray(arrays["hdr"]).view(np.uint8).reshape(-1).copy().view(header_dtype)[0]
         o.cells = np.ascontiguousarray(arrays["cells"]).view(np.uint8).reshape(-1).copy().view(cell_dtype)
         o.units = np.ascontiguousarray(arrays["units"]).view(np.uint8).reshape(-1).copy().view(unit_dtype)
         o.cities = np.ascontiguousarray(arrays["cities"]).view(np.uint8).reshape(-1).copy().view(city_dtype)
         o.tiles = np.ascontiguousarray(arrays["tiles"]).view(np.uint8).reshape(-1).copy().view("<u2")
-        o.res = np.ascontiguousarray(arrays["res"]).view(np.uint8).reshape(-1).copy().view("<u2")
+        if legacy_res:
+            o.set_res_cells(np.ascontiguousarray(arrays["res"]).view(np.uint8).reshape(-1).copy().view("<u2")[: int(o.hdr["n_res"])])
+        else:
+            o.res = np.ascontiguousarray(arrays["res"]).view(np.uint8).reshape(-1).copy().view("<u4")
         return o
 
     def copy(self):

@@ -73,7 +73,7 @@ def apply_updates(base, updates, recount_adjacency=False):
     for p in range(nt0):
         idx = int(base.tiles[p])
         slots[int(base.cells["city_slot"][idx])][2].append(idx)
-    res_order = [int(x) for x in base.res[:nr0]]
+    res_order = [int(x) for x in S.res_cell(base.res[:nr0])]
     res_seen, tile_seen = set(res_order), set(int(x) for x in base.tiles[:nt0])
     for line in updates or []:
         if line == "D_DONE":
@@ -124,15 +124,7 @@ def apply_updates(base, updates, recount_adjacency=False):
         elif op == "ccd":
             ms.cells["road_q"][int(p[2]) * size + int(p[1])] = _quarter(p[3])
     # resources list: GameMap.resources order, cells with amount > 0 (oracle/flatten.py keeps the same rule)
-    n = 0
-    ms.res[:] = 0
-    for idx in res_order:
-        if int(ms.cells["amount"][idx]) > 0:
-            if n >= len(ms.res):
-                raise ValueError("more resource cells than the capacity %d" % len(ms.res))
-            ms.res[n] = idx
-            n += 1
-    h["n_res"] = n
+    ms.set_res_cells([idx for idx in res_order if int(ms.cells["amount"][idx]) > 0])
     # cities and tiles in dict order x city_cells order
     if len(cities) > len(ms.cities):
         raise ValueError("more cities than the capacity %d" % len(ms.cities))
@@ -213,7 +205,7 @@ def updates_from_state(ms):
     out = ["rp 0 %d" % int(h["research"][0]), "rp 1 %d" % int(h["research"][1])]
     names = S.RES_NAMES
     for r in range(int(h["n_res"])):
-        idx = int(ms.res[r])
+        idx = int(S.res_cell(ms.res[r]))
         amt = int(ms.cells["amount"][idx])
         if amt > 0:
             out.append("r %s %d %d %d" % (names[int(ms.cells["flags"][idx]) & 3], idx % size, idx // size, amt))

@@ -71,12 +71,7 @@ def flatten(game, caps=None):
             if cell.resource is not None and cell.resource.amount > 0:
                 cc["amount"] = cell.resource.amount
                 cc["flags"] |= S.RES_CODES[cell.resource.type]
-    nres = 0
-    for cell in game.map.resources:
-        if cell.resource.amount > 0:
-            ms.res[nres] = cell.pos.y * size + cell.pos.x
-            nres += 1
-    h["n_res"] = nres
+    ms.set_res_cells([cell.pos.y * size + cell.pos.x for cell in game.map.resources if cell.resource.amount > 0])
 
     # units: team A dict order, then team B
     n = 0

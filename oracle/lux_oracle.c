@@ -434,7 +434,7 @@ static void handle_resource_type(Game* g, int rtype) {
 /* ---------------------------------------------------------------- the turn (game.py:390-535) */
 
 static void oracle_turn(Game* g, const uint8_t* tile_actions, const uint16_t* tiles_in, int n_tiles_in,
-                        const uint16_t* res, int n_res) {
+                        LuxRes* res, int n_res) {
     LuxHeader* h = g->h;
     int S = g->S;
     int night = is_night(h);
@@ -605,13 +605,15 @@ static void oracle_turn(Game* g, const uint8_t* tile_actions, const uint16_t* ti
 
     /* -- depleted cells leave the resource list (:498-510), trees regrow (:1081-1102) */
     for (int k = 0; k < n_res; k++) {
-        LuxCell* c = &g->cells[res[k]];
-        if (c->amount == 0) { c->flags &= 0xFC; continue; }
-        if (res_type(c) == LUX_RES_WOOD && c->amount < MAX_WOOD) {
+        LuxCell* c = &g->cells[LUX_RES_CELL(res[k])];
+        if (c->amount == 0) c->flags &= 0xFC;
+        else if (res_type(c) == LUX_RES_WOOD && c->amount < MAX_WOOD) {
             double grown = c->amount * WOOD_GROWTH_RATE;
             if (grown > (double)MAX_WOOD) grown = (double)MAX_WOOD;
             c->amount = (uint16_t)ceil(grown);
         }
+        /* the list entry mirrors the cell's amount (include/lux_b200.h LuxRes); the grid is the oracle's truth */
+        res[k] = LUX_RES_MAKE((uint32_t)LUX_RES_CELL(res[k]), (uint32_t)LUX_RES_TYPE(res[k]), c->amount);
     }
 
     /* -- match_over (:570-592), before the turn counter moves (:515-517) */
@@ -660,7 +662,7 @@ static Scratch* scratch_get(void) {
 
 /* One turn of one match, in place.  Returns 0, or LUX_E_ARG. */
 int lux_oracle_step(LuxHeader* hdr, LuxCell* cells, LuxUnit* units, LuxCity* cities, uint16_t* tiles,
-                    const uint16_t* res, const uint32_t* unit_actions, const uint8_t* tile_actions,
+                    LuxRes* res, const uint32_t* unit_actions, const uint8_t* tile_actions,
                     int u_cap, int c_cap, int t_cap) {
     if (!hdr || !cells || !units || !cities || !tiles || !res) return LUX_E_ARG;
     if (hdr->size < 2 || hdr->size > 32 || u_cap > MAXU || c_cap > 256 || t_cap > MAXCELLS) return LUX_E_ARG;
@@ -818,7 +820,7 @@ int lux_oracle_run_batch(const LuxBatch* b, const LuxBatch* pool, uint64_t seed,
                 memcpy(b->units + (size_t)m * b->u_cap, pool->units + (size_t)src * b->u_cap, (size_t)b->u_cap * 16);
                 memcpy(b->cities + (size_t)m * b->c_cap, pool->cities + (size_t)src * b->c_cap, (size_t)b->c_cap * 16);
                 memcpy(b->tiles + (size_t)m * b->t_cap, pool->tiles + (size_t)src * b->t_cap, (size_t)b->t_cap * 2);
-                memcpy(b->res + (size_t)m * b->r_cap, pool->res + (size_t)src * b->r_cap, (size_t)b->r_cap * 2);
+                memcpy(b->res + (size_t)m * b->r_cap, pool->res + (size_t)src * b->r_cap, (size_t)b->r_cap * sizeof(LuxRes));
                 b->hdr[m] = pool->hdr[src];
             }
         }
@@ -861,7 +863,7 @@ static int obs_arg(const NodeList* l, int px, int py, int furthest) {
 }
 
 int lux_oracle_observe(const LuxHeader* h, const LuxCell* cells, const LuxUnit* units, const LuxCity* cities,
-                       const uint16_t* tiles, const uint16_t* res, int team, float* obs, int16_t* ent_slot,
+                       const uint16_t* tiles, const LuxRes* res, int team, float* obs, int16_t* ent_slot,
                        int32_t* ent_count, int e_cap) {
     if (!h || !cells || !units || !cities || !tiles || !res || !obs || !ent_slot || !ent_count) return LUX_E_ARG;
     *ent_count = 0;
@@ -870,10 +872,11 @@ int lux_oracle_observe(const LuxHeader* h, const LuxCell* cells, const LuxUnit* 
     static __thread NodeList nodes[5];      /* wood, coal, uranium, own city tiles, own workers */
     for (int k = 0; k < 5; k++) nodes[k].n = 0;
     for (int r = 0; r < h->n_res; r++) {     /* game.map.resources order; depleted cells are not in the list */
-        const LuxCell* c = &cells[res[r]];
+        const int rc = LUX_RES_CELL(res[r]);
+        const LuxCell* c = &cells[rc];
         if (c->amount == 0) continue;
         NodeList* l = &nodes[res_type(c) - 1];
-        l->x[l->n] = res[r] % S; l->y[l->n] = res[r] / S; l->n++;
+        l->x[l->n] = rc % S; l->y[l->n] = rc / S; l->n++;
     }
     int own_workers = 0, own_carts = 0, own_tiles = 0, opp_tiles = 0;
     for (int i = 0; i < h->n_units; i++) {

@@ -46,7 +46,7 @@ static void emu_lane(void* p) {
     int result;
     int active = lux_stage_plain<G>(M, smem, g, valid, b->size, b->u_cap, b->c_cap, b->t_cap, b->r_cap, a->L.total, &result);
     LuxTurnOut T = b->size == 32 ? lux_turn<32, G>(M, a->flags) : lux_turn<0, G>(M, a->flags);
-    lux_finish_and_store<0, G>(M, T, g.hdr, g.units, g.cities, g.tiles, active);
+    lux_finish_and_store<0, G>(M, T, g.hdr, g.units, g.cities, g.tiles, g.res, active);
     lux_sync<G>();
     // the engine's contract: both byte planes are clean again after the turn
     for (int i = lux_lane<G>(); i < ncell; i += G)
@@ -132,7 +132,7 @@ static void emu_obs_lane(void* p) {
     if (M.hdr->done) { if (lux_lane() == 0) a->cnt[m] = 0; return; }
     lux_copy16(M.units, b->units + (size_t)m * b->u_cap, M.hdr->n_units * 16);
     lux_copy16(M.tiles, b->tiles + (size_t)m * b->t_cap, M.hdr->n_tiles * 2);
-    lux_copy16(M.res, b->res + (size_t)m * b->r_cap, M.hdr->n_res * 2);
+    lux_copy16(M.res, b->res + (size_t)m * b->r_cap, M.hdr->n_res * 4);
     lux_sync();
     int n = lux_observe(M, a->team_sel[m], a->obs + (size_t)m * a->e_cap * LUX_OBS_DIM, a->ent + (size_t)m * a->e_cap, a->e_cap);
     if (lux_lane() == 0) a->cnt[m] = n < a->e_cap ? n : a->e_cap;

@@ -187,4 +187,5 @@ static inline unsigned lux_reduce_max_u(unsigned v) {
 static inline int lux_popc(unsigned v) { return __builtin_popcount(v); }
 static inline int lux_ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline unsigned lux_atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+static inline void lux_atomic_and(unsigned* p, unsigned v) { *p &= v; }
 static inline int lux_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }

@@ -17,7 +17,9 @@ def npz(name):
 
 def get_state(z, prefix):
     size = int(z[prefix.split("/")[0] + "/size"])
-    return S.MatchState.from_arrays(size, {k: z["%s/%s" % (prefix, k)] for k in S.MatchState.SECTIONS})
+    # the fixtures hold the resource list as uint16 cell indices (round-1 layout); digests are defined over that
+    # view (MatchState.live), so they stay valid for the LuxRes layout
+    return S.MatchState.from_arrays(size, {k: z["%s/%s" % (prefix, k)] for k in S.MatchState.SECTIONS}, legacy_res=True)
 
 
 def replay_ids():

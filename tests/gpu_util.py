@@ -34,7 +34,8 @@ def diff_batches(host, game):
     bad = np.zeros(host.n, dtype=bool)
     bad |= (host.arr["hdr"] != dev["hdr"]).any(axis=1)
     bad |= (host.arr["cells"] != dev["cells"]).any(axis=1)
-    for name, rec, count in (("units", 16, hh["n_units"]), ("cities", 16, hh["n_cities"]), ("tiles", 2, hh["n_tiles"])):
+    for name, rec, count in (("units", 16, hh["n_units"]), ("cities", 16, hh["n_cities"]), ("tiles", 2, hh["n_tiles"]),
+                             ("res", 4, hh["n_res"])):
         cap = host.arr[name].shape[1] // rec
         live = (np.arange(cap)[None, :] < count[:, None]).repeat(rec, axis=1)
         bad |= ((host.arr[name] != dev[name]) & live).any(axis=1)

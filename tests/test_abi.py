@@ -59,7 +59,7 @@ def test_no_device_is_an_error_not_a_fallback():
     assert lib.lux_b200_device_count() == 0
     n, size, caps = 2, 12, S.default_caps(12)
     bufs = [np.zeros(n * w + 16, dtype=np.uint8) for w in (128, 144 * 8, caps["units"] * 16, caps["cities"] * 16,
-                                                           caps["tiles"] * 2, caps["res"] * 2)]
+                                                           caps["tiles"] * 2, caps["res"] * 4)]
     ptrs = [(b.ctypes.data + 15) & ~15 for b in bufs]
     desc = _lib.LuxBatch(n, size, caps["units"], caps["cities"], caps["tiles"], caps["res"], *ptrs)
     ua = np.zeros(n * caps["units"] + 4, dtype=np.uint32)
