@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = as many as --steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the dense and config-4 legs (N = 1 only)")
     return ap.parse_args()
 
 
@@ -225,6 +226,114 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def dense_leg(dev, n, peak, steps=20, min_seconds=0.15):
+    """Extra leg (N = 1): the same step on a DENSE late-game batch -- n resident 32x32 matches started from the
+    replay states of tests/golden/dense.npz (Kaggle episodes imported at turn 80 / 200 / 300 by the reference's
+    process_updates), canonical action stream, finished matches reset from the same pool.  Same timing rules as
+    the main leg (blocks of `steps` steps, median block)."""
+    import torch
+    from luxpythonenvgym_b200 import state as S
+    from luxpythonenvgym_b200.batched import BatchedGame
+    from tests import golden_util as G
+    z = G.npz("dense")
+    caps = S.default_caps(32)
+    states = []
+    for name in G.dense_names():
+        if int(z[name + "/size"]) != 32:
+            continue
+        ms = G.get_state(z, name + "/init")
+        o = S.MatchState(32, caps)
+        o.hdr, o.cells = ms.hdr.copy(), ms.cells.copy()
+        for sec in ("units", "cities", "tiles", "res"):
+            dst, src = getattr(o, sec), getattr(ms, sec)
+            k = min(len(dst), len(src))
+            dst[:k] = src[:k]
+        states.append(o)
+    game, pool = BatchedGame(n, 32, device=dev), BatchedGame(len(states), 32, device=dev)
+    pool.load_states(states)
+    game.load_states([states[i % len(states)] for i in range(n)])
+    resets = torch.zeros(1, dtype=torch.int32, device=dev)
+    seed, epoch = 31337, 0
+    game.gen_actions(seed, 0)
+    for _ in range(30):
+        game.step()
+        game.reset_gen(pool, epoch, seed, 0, reset_count=resets)
+        epoch += 1
+    torch.cuda.synchronize()
+    blocks, spent = [], 0.0
+    counters = torch.zeros((402, 2), dtype=torch.int64, device=dev)
+    game.gen_actions(seed, 0, counters=counters[0])
+    while len(blocks) < 400 and (spent < min_seconds or len(blocks) < 3):
+        r = len(blocks)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0.record()
+        for k in range(steps):
+            ev[k][0].record()
+            game.step()
+            ev[k][1].record()
+            game.reset_gen(pool, epoch, seed, 0, reset_count=resets, counters=counters[r] if k < steps - 1 else counters[r + 1])
+            epoch += 1
+        t1.record()
+        torch.cuda.synchronize()
+        blocks.append((t0.elapsed_time(t1), sum(a.elapsed_time(b) for a, b in ev) / steps, r))
+        spent += blocks[-1][0] * 1e-3
+    blocks.sort()
+    total_ms, step_ms, r = blocks[(len(blocks) - 1) // 2]
+    live, alg = [int(x) for x in counters[r].cpu().tolist()]
+    st = game.stats().cpu().tolist()
+    achieved = alg / steps / (step_ms * 1e-3) / 1e9
+    return {"workload": "%d resident 32x32 matches from the dense replay-state pool (tests/golden/dense.npz, %d states), "
+                        "canonical action stream, pool resets" % (n, len(states)),
+            "value": live / (total_ms * 1e-3), "unit": "match-turns/s", "ms_per_step": total_ms / steps,
+            "kernel_ms": {"lux_step_kernel": step_ms, "whole_step": total_ms / steps}, "blocks": len(blocks),
+            "steps_per_block": steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_launch": alg / steps},
+            "mean_units_per_match": st[7] / max(st[0], 1), "mean_city_tiles_per_match": st[8] / max(st[0], 1),
+            "live": st[0], "status_nonzero": st[10]}
+
+
+def config4_leg(dev, n_envs, steps=60):
+    """Extra leg (N = 1): BASELINE.json config 4, the LuxEnvironment-shaped rollout loop on the device --
+    packed per-entity observation rows -> torch MLP 85-64-64-9 (tanh; the SB3 MlpPolicy shape) sampling one
+    code per actionable entity -> lux_b200_encode_actions -> lux_b200_step(prevalidate) -> lux_b200_reward ->
+    masked resets and team draws.  One host synchronisation per turn (the packed row count)."""
+    import torch
+    from luxpythonenvgym_b200.env import BatchedLuxEnvironment
+    torch.manual_seed(0)
+    env = BatchedLuxEnvironment(n_envs, size=32, seed=9000, pool_maps=256, device=dev, packed=True)
+    net = torch.nn.Sequential(torch.nn.Linear(85, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(),
+                              torch.nn.Linear(64, 9)).to(dev)
+
+    @torch.no_grad()
+    def act(obs):
+        return torch.multinomial(torch.softmax(net(obs), dim=-1), 1).squeeze(1).to(torch.int32)
+
+    obs, ent, cnt, offsets = env.reset()
+    for _ in range(100):
+        (obs, ent, cnt, offsets), reward, done = env.step(act(obs))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    decisions = torch.zeros((), dtype=torch.int64, device=dev)
+    rows = 0
+    e0.record()
+    for _ in range(steps):
+        rows += int(obs.shape[0])
+        decisions += cnt.sum()
+        (obs, ent, cnt, offsets), reward, done = env.step(act(obs))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    decisions = int(decisions.item())
+    return {"workload": "%d envs (32x32), learning team drawn per reset, idle opponent, torch MLP policy 85-64-64-9" % n_envs,
+            "ms_per_turn": ms / steps, "env_turns_per_s": n_envs * steps / (ms * 1e-3),
+            "entity_decisions_per_s": decisions / (ms * 1e-3), "decisions_per_turn": decisions / steps,
+            "policy_rows_per_turn": rows / steps, "steps": steps,
+            "obs_bytes_per_turn": 340 * decisions / steps}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -437,6 +546,12 @@ def run_b200(args):
             line["roofline"]["dram_gbs_from_traffic"] = tr.get("dram_bytes_per_launch", 0) / (step_ms * 1e-3) / 1e9
         except Exception:
             pass
+        if world == 1 and not args.no_extra_legs:
+            # free the main leg's snapshots first
+            del snap, ent_h, views
+            torch.cuda.empty_cache()
+            line["dense"] = dense_leg(dev, n, peak)
+            line["config4"] = config4_leg(dev, n)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             port = CpuPort(size, 256 * threads, threads, pool_arrays)

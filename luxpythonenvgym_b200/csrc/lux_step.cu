@@ -397,7 +397,7 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
     }
 }
 
-__global__ void __launch_bounds__(1024, 2) lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match_id_base,
+__global__ void __launch_bounds__(256, 6) lux_gen_actions_kernel(LuxBatch b, uint64_t seed, uint64_t match_id_base,
                                        uint32_t* __restrict__ unit_actions, uint8_t* __restrict__ tile_actions,
                                        unsigned long long* counters) {
     LUX_PDL_TRIGGER();
@@ -452,7 +452,9 @@ __global__ void lux_stats_kernel(LuxBatch b, unsigned long long* out) {
 }
 
 // ---------------------------------------------------------------- reset finished matches from a pool
-// one warp replaces match m by a pool entry
+// one warp replaces match m by a pool entry; K = 16-byte loads in flight per lane (the fused reset + action-stream
+// kernel takes the rare reset path with fewer, so that the common path keeps its registers)
+template <int K>
 __device__ __forceinline__ void lux_reset_match(const LuxBatch& b, const LuxBatch& pool, int m, uint32_t epoch, int* reset_count) {
     const int lane = threadIdx.x & 31;
     int src = 0;
@@ -481,11 +483,11 @@ __device__ __forceinline__ void lux_reset_match(const LuxBatch& b, const LuxBatc
     const char* s4 = (const char*)(pool.res + (size_t)src * b.r_cap); char* d4 = (char*)(b.res + (size_t)m * b.r_cap);
     // running end of each segment in the flat index space (16-byte pieces)
     const int e0 = ncell / 2, e1 = e0 + nu, e2 = e1 + nc, e3 = e2 + (nt * 2 + 15) / 16, total = e3 + (nr * 4 + 15) / 16;
-    for (int base = 0; base < total; base += 32 * 8) {
-        uint4 v[8];
-        char* dst[8];
+    for (int base = 0; base < total; base += 32 * K) {
+        uint4 v[K];
+        char* dst[K];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < K; k++) {
             const int f = base + k * 32 + lane;
             const char* sb = f < e0 ? s0 : f < e1 ? s1 : f < e2 ? s2 : f < e3 ? s3 : s4;
             char* db = f < e0 ? d0 : f < e1 ? d1 : f < e2 ? d2 : f < e3 ? d3 : d4;
@@ -494,7 +496,7 @@ __device__ __forceinline__ void lux_reset_match(const LuxBatch& b, const LuxBatc
             if (f < total) v[k] = *(const uint4*)(sb + (size_t)o * 16);
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++)
+        for (int k = 0; k < K; k++)
             if (base + k * 32 + lane < total) *(uint4*)dst[k] = v[k];
     }
     if (lane < LUX_HDR_BYTES / 16) ((uint4*)(b.hdr + m))[lane] = hv;
@@ -506,12 +508,12 @@ __global__ void lux_reset_done_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch,
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= b.n_matches) return;
     if (!b.hdr[m].done) return;
-    lux_reset_match(b, pool, m, epoch, reset_count);
+    lux_reset_match<8>(b, pool, m, epoch, reset_count);
 }
 
 // reset_done followed by gen_actions in one pass over the batch (the per-turn harness loop of the benchmarks:
 // one launch and one read of the headers instead of two)
-__global__ void __launch_bounds__(1024, 2) lux_reset_gen_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch, int* reset_count,
+__global__ void __launch_bounds__(256, 6) lux_reset_gen_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch, int* reset_count,
                                                               uint64_t seed, uint64_t match_id_base,
                                                               uint32_t* __restrict__ unit_actions,
                                                               uint8_t* __restrict__ tile_actions, unsigned long long* counters) {
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(1024, 2) lux_reset_gen_kernel(LuxBatch b, LuxB
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m < b.n_matches) {
         if (b.hdr[m].done) {
-            lux_reset_match(b, pool, m, epoch, reset_count);
+            lux_reset_match<2>(b, pool, m, epoch, reset_count);
             __syncwarp();                   // the fresh match is read back by other lanes of this warp
         }
         lux_gen_actions_match(b, m, seed, match_id_base, unit_actions, tile_actions, counters ? cta_counters : nullptr);
@@ -586,7 +588,7 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "tma")) { g_use_tma = value != 0; return LUX_OK; }
     if (!strcmp(name, "warps_per_cta")) { g_warps_per_cta = value; return LUX_OK; }
     if (!strcmp(name, "two_class")) { g_two_class = value; return LUX_OK; }
-    if (!strcmp(name, "gen_wpc")) { g_gen_wpc = value < 1 ? 1 : value > 32 ? 32 : value; return LUX_OK; }
+    if (!strcmp(name, "gen_wpc")) { g_gen_wpc = value < 1 ? 1 : value > 8 ? 8 : value; return LUX_OK; }
     if (!strcmp(name, "list_grid")) { g_list_grid = value; return LUX_OK; }
     if (!strcmp(name, "overlap")) { g_overlap = value != 0; return LUX_OK; }
     if (!strcmp(name, "group")) { g_group = value; return LUX_OK; }

@@ -47,7 +47,7 @@ def config3(n_per_size=16384, steps=100):
             states = []
             for nm in names:
                 if int(z[nm + "/size"]) == size:
-                    ms = S.MatchState.from_arrays(size, {k: z["%s/init/%s" % (nm, k)] for k in S.MatchState.SECTIONS})
+                    ms = S.MatchState.from_arrays(size, {k: z["%s/init/%s" % (nm, k)] for k in S.MatchState.SECTIONS}, legacy_res=True)
                     states.append(recap(ms, caps))
         g = BatchedGame(n_per_size, size)
         pool = BatchedGame(len(states), size)

@@ -26,7 +26,21 @@ if os.environ.get("LUX_SWEEP_DENSE"):
     from tests import golden_util as G
     z = G.npz("dense")
     states = [G.get_state(z, name + "/init") for name in G.dense_names()]
-    states = [s for s in states if s.size == SIZE]
+    from luxpythonenvgym_b200 import state as S
+    caps = S.default_caps(SIZE)
+
+    def recap(ms):
+        o = S.MatchState(ms.size, caps)
+        o.hdr, o.cells = ms.hdr.copy(), ms.cells.copy()
+        for name in ("units", "cities", "tiles", "res"):
+            dst, src = getattr(o, name), getattr(ms, name)
+            k = min(len(dst), len(src))
+            dst[:k] = src[:k]
+        return o
+
+    states = [recap(s) for s in states if s.size == SIZE]
+    pool = BatchedGame(len(states), SIZE)
+    pool.load_states(states)
     game.load_states([states[i % len(states)] for i in range(N)])
     burn = 20
 else:
