@@ -165,6 +165,7 @@ struct LuxMatch {
     uint16_t* utgt;
     uint8_t* ust;
     uint8_t* umine;
+    uint8_t* unext;
     uint32_t* uinfo;
     uint16_t* umin;
     uint32_t* tmask;
@@ -190,6 +191,7 @@ LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayou
     M.utgt = (uint16_t*)(smem + L.utgt);
     M.ust = (uint8_t*)(smem + L.ust);
     M.umine = (uint8_t*)(smem + L.umine);
+    M.unext = (uint8_t*)(smem + L.utgt);   // next unit (index + 1) on the same non-city cell; shares utgt[], which is done with after the moves
     M.uinfo = (uint32_t*)(smem + L.uinfo);
     M.umin = (uint16_t*)(smem + L.umin);
     M.tmask = (uint32_t*)(smem + L.tmask);
@@ -343,7 +345,7 @@ LUX_DEV int lux_stage_plain(LuxMatch& M, unsigned char* smem, const LuxGlobalMat
 // Works on shared memory only, except for the amount of each requested cell (one global load and one
 // store per cell): which neighbours a worker can mine was cached in umin[] by the unit pass.
 template <int kS, int G>
-LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researched0, int researched1) {
+LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researched0, int researched1, int stacked) {
     const int lane = lux_lane<G>();
     const int S = kS > 0 ? kS : M.S;
     LuxHeader* h = M.hdr;
@@ -404,6 +406,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
         int n = 0, sum = 0;
         // the occupants of the five source cells, one byte each (most are empty)
         uint64_t occ5 = 0;
+        int crowded = 0;
 #pragma unroll
         for (int j = 0; j < 5; j++) {
             int p = lux_cell5(S, x, y, j);
@@ -427,6 +430,12 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
                 }
             } else {
                 int a = M.umine[o - 1];
+                if (stacked) {
+                    // further units stacked on the same non-city cell (left behind by a fallen city) follow in
+                    // a chain; the histogram counts up to seven equal requests
+                    if (a != 0xFF && ((hist >> (3 * a)) & 7) == 7) crowded = 1;
+                    occ5 |= (uint64_t)M.unext[o - 1] << (8 * j);
+                }
                 if (a != 0xFF) { hist += (uint64_t)1 << (3 * a); present |= 1u << a; n++; sum += a; }
             }
         }
@@ -473,6 +482,7 @@ LUX_DEV void lux_collect_type(LuxMatch& M, int rtype, int n_units, int researche
             }
         }
         M.p1[c] = (uint8_t)(0x80u | level);           // fill level; the request mark stays for the regrowth pass
+        if (crowded) h->status |= LUX_ST_BAD_STATE;
     }
     lux_sync<G>();
 
@@ -988,6 +998,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     // :257-269), and the per-unit caches the rest of the turn works from -- what the unit stands on
     // (uinfo), which of its five cells it can mine (umin, 2 bits of resource type per direction) and the
     // occupant mark of its cell.  This is the one place a unit reads the grid: five independent loads.
+    int stacked = 0;                       // some non-city cell holds several units (rare; see below)
     {
         int rb0 = 0, rb1 = 0, bad = 0;
 #pragma unroll 1
@@ -1020,7 +1031,8 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                     M.cells[ucell].road_q = (uint8_t)(r > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : r);
                     if (unit_team(U)) rb1 += LUX_ROAD_DEV_Q; else rb0 += LUX_ROAD_DEV_Q;
                 }
-                // a non-city cell holds one unit in play; a stack (left behind by a destroyed city) is flagged
+                // a non-city cell holds one unit in play; a stack (left behind by a destroyed city) is rare and
+                // gets its occupant chain rebuilt below
                 if (lux_atomic_or_byte(M.occ, ucell, (unsigned)(u + 1))) bad = 1;
             }
             unsigned mm = 0;
@@ -1037,9 +1049,27 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             int packed = lux_reduce_add<G>(rb0 | (rb1 << 12) | (bad << 24));
             rb0 = packed & 0xFFF; rb1 = (packed >> 12) & 0xFFF; bad = packed >> 24;
         }
-        if (lane == 0) {
-            h->roads_built_q[0] += rb0; h->roads_built_q[1] += rb1;
-            if (bad) h->status |= LUX_ST_BAD_STATE;
+        if (lane == 0) h->roads_built_q[0] += rb0, h->roads_built_q[1] += rb1;
+        stacked = bad;
+        if (lux_wany<G>(bad)) {
+            // several units share a non-city cell (game.py:1173: a city fell under them and they survived the
+            // night): the OR-ed occupant bytes of those cells are meaningless; lane 0 rebuilds them as chains
+            // occ[cell] -> unit -> unext -> ... in unit order
+            lux_sync<G>();
+            if (bad && lane == 0) {
+#pragma unroll 1
+                for (int u = 0; u < n_units; u++) {
+                    M.unext[u] = 0;
+                    if (!(M.uinfo[u] & UI_TILE)) M.occ[M.units[u].y * S + M.units[u].x] = 0;
+                }
+#pragma unroll 1
+                for (int u = n_units - 1; u >= 0; u--) {
+                    if (M.uinfo[u] & UI_TILE) continue;
+                    const int cell = M.units[u].y * S + M.units[u].x;
+                    M.unext[u] = M.occ[cell];
+                    M.occ[cell] = (uint8_t)(u + 1);
+                }
+            }
         }
     }
     lux_sync<G>();
@@ -1051,7 +1081,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         for (int rtype = LUX_RES_URANIUM; rtype >= LUX_RES_WOOD; rtype--) {
             int need = rtype == LUX_RES_WOOD ? 0 : rtype == LUX_RES_COAL ? LUX_RESEARCH_COAL : LUX_RESEARCH_URANIUM;
                     if (!lux_wany<G>(rp0 >= need || rp1 >= need)) continue;   // nobody in the warp may mine this type yet
-            lux_collect_type<kS, G>(M, rtype, n_units, rp0 >= need, rp1 >= need);
+            lux_collect_type<kS, G>(M, rtype, n_units, rp0 >= need, rp1 >= need, stacked);
         }
     }
 
