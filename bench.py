@@ -295,7 +295,7 @@ def dense_leg(dev, n, peak, steps=20, min_seconds=0.15):
             "live": st[0], "status_nonzero": st[10]}
 
 
-def config4_leg(dev, n_envs, steps=60):
+def config4_leg(dev, n_envs, steps=200):
     """Extra leg (N = 1): BASELINE.json config 4, the LuxEnvironment-shaped rollout loop on the device --
     packed per-entity observation rows -> torch MLP 85-64-64-9 (tanh; the SB3 MlpPolicy shape) sampling one
     code per actionable entity -> lux_b200_encode_actions -> lux_b200_step(prevalidate) -> lux_b200_reward ->
@@ -311,26 +311,47 @@ def config4_leg(dev, n_envs, steps=60):
     def act(obs):
         return torch.multinomial(torch.softmax(net(obs), dim=-1), 1).squeeze(1).to(torch.int32)
 
-    obs, ent, cnt, offsets = env.reset()
-    for _ in range(100):
-        (obs, ent, cnt, offsets), reward, done = env.step(act(obs))
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    decisions = torch.zeros((), dtype=torch.int64, device=dev)
-    rows = 0
-    e0.record()
-    for _ in range(steps):
-        rows += int(obs.shape[0])
-        decisions += cnt.sum()
-        (obs, ent, cnt, offsets), reward, done = env.step(act(obs))
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    decisions = int(decisions.item())
+    env.reset()
+    mode = "one CUDA graph per turn (policy, encode, step, reward, resets, observe); no host synchronisation"
+    try:
+        roll = env.graphed(act, row_cap=3 * n_envs)
+        for _ in range(100):
+            roll.turn()
+        torch.cuda.synchronize()
+        d0 = int(roll.decisions.item())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            roll.turn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        decisions = int(roll.decisions.item()) - d0
+        rows = roll.row_cap * steps
+        if int(env.game.row_overflow.item()):
+            mode += "; %d rows cut by the row capacity" % int(env.game.row_overflow.item())
+    except Exception as exc:                                    # capture refused: the eager loop, one sync per turn
+        mode = "eager loop, one host synchronisation per turn (graph capture failed: %s)" % (str(exc)[:120],)
+        obs, ent, cnt, offsets = env.reset()
+        for _ in range(100):
+            (obs, ent, cnt, offsets), reward, done = env.step(act(obs))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        decisions = torch.zeros((), dtype=torch.int64, device=dev)
+        rows = 0
+        e0.record()
+        for _ in range(steps):
+            rows += int(obs.shape[0])
+            decisions += cnt.sum()
+            (obs, ent, cnt, offsets), reward, done = env.step(act(obs))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        decisions = int(decisions.item())
     return {"workload": "%d envs (32x32), learning team drawn per reset, idle opponent, torch MLP policy 85-64-64-9" % n_envs,
             "ms_per_turn": ms / steps, "env_turns_per_s": n_envs * steps / (ms * 1e-3),
             "entity_decisions_per_s": decisions / (ms * 1e-3), "decisions_per_turn": decisions / steps,
-            "policy_rows_per_turn": rows / steps, "steps": steps,
+            "policy_rows_per_turn": rows / steps, "steps": steps, "mode": mode,
             "obs_bytes_per_turn": 340 * decisions / steps}
 
 

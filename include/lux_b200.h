@@ -254,6 +254,11 @@ int lux_b200_reward(const LuxBatch* b, const uint8_t* team_sel, int32_t* reward_
  */
 int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, uint32_t epoch,
                         int32_t* reset_count, void* cuda_stream);
+/* The same with the epoch read from DEVICE memory (*epoch_dev) when the kernel runs: a caller that replays one
+ * captured CUDA graph per turn advances the counter on the device. */
+int lux_b200_reset_done_dev(const LuxBatch* b, const LuxBatch* pool, const uint32_t* epoch_dev,
+                            int32_t* reset_count, void* cuda_stream);
+
 
 /*
  * lux_b200_reset_done followed by lux_b200_gen_actions in one pass over the batch (the per-turn harness loop
@@ -272,6 +277,25 @@ int lux_b200_reset_gen(const LuxBatch* b, const LuxBatch* pool, uint32_t epoch, 
  * This is the vector NCCL all-reduces across GPUs.
  */
 int lux_b200_stats(const LuxBatch* b, int64_t* out16, void* cuda_stream);
+
+/*
+ * Row offsets of the packed observation layout, computed on the device: offsets[m] = min(row_cap, sum over the
+ * matches before m of (units + city tiles of the match's selected team)), offsets[n] = min(row_cap, total).
+ * offsets: int64[n+1]; overflow (optional, int64*): the rows cut by row_cap are added to it.  Nothing is read back
+ * to the host, so observe / encode of a turn can be captured in a CUDA graph with fixed-capacity row buffers.
+ */
+int lux_b200_observe_offsets(const LuxBatch* b, const uint8_t* team_sel, int64_t row_cap, int64_t* offsets,
+                             int64_t* overflow, void* cuda_stream);
+
+/*
+ * End of an environment turn in one pass (LuxEnvironment.step's tail, luxai2021/env/lux_env.py:123-161, for every
+ * env): reward as lux_b200_reward, done[m] = hdr.done, and for a finished match the reset from `pool` (entry chosen
+ * like lux_b200_reset_done with epoch = *turn_dev), a cleared reward state, and the learning team of the new match
+ * (MatchController.reset's coin flip, match_controller.py:118-122, as a counter-based hash of (match, *turn_dev)).
+ * team_sel is updated in place.  reward: double[n], done: uint8[n], turn_dev: device uint32.
+ */
+int lux_b200_env_finish(const LuxBatch* b, const LuxBatch* pool, uint8_t* team_sel, int32_t* reward_state,
+                        double* reward, uint8_t* done, const uint32_t* turn_dev, int32_t* reset_count, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ _ERR = {LUX_E_ARG: "bad argument", LUX_E_CAPACITY: "capacity out of range",
 EXPORTS = ("lux_b200_version", "lux_b200_device_count", "lux_b200_set_option", "lux_b200_step_smem_bytes",
            "lux_b200_step", "lux_b200_step_host", "lux_b200_gen_actions", "lux_b200_observe",
            "lux_b200_reset_done", "lux_b200_stats", "lux_b200_encode_actions", "lux_b200_reward", "lux_b200_launch_count", "lux_b200_step_host_sparse",
-           "lux_b200_reset_gen")
+           "lux_b200_reset_gen", "lux_b200_reset_done_dev", "lux_b200_observe_offsets", "lux_b200_env_finish")
 
 
 class LuxError(RuntimeError):
@@ -61,6 +61,9 @@ def load():
     lib.lux_b200_gen_actions.argtypes = [bp, u64, u64, vp, vp, vp, vp]
     lib.lux_b200_observe.argtypes = [bp, vp, vp, vp, vp, i32, vp, vp]
     lib.lux_b200_reset_done.argtypes = [bp, bp, ctypes.c_uint32, vp, vp]
+    lib.lux_b200_reset_done_dev.argtypes = [bp, bp, vp, vp, vp]
+    lib.lux_b200_observe_offsets.argtypes = [bp, vp, ctypes.c_int64, vp, vp, vp]
+    lib.lux_b200_env_finish.argtypes = [bp, bp, vp, vp, vp, vp, vp, vp, vp]
     lib.lux_b200_reset_gen.argtypes = [bp, bp, ctypes.c_uint32, vp, u64, u64, vp, vp, vp, vp]
     lib.lux_b200_stats.argtypes = [bp, vp, vp]
     lib.lux_b200_encode_actions.argtypes = [bp, vp, vp, vp, i32, vp, vp, vp, vp]

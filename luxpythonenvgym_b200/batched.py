@@ -160,6 +160,12 @@ class BatchedGame:
                                                 reset_count.data_ptr() if reset_count is not None else None,
                                                 self._stream()), "lux_b200_reset_done")
 
+    def reset_done_dev(self, pool, epoch_dev, reset_count=None):
+        """reset_done with the epoch in a device uint32 / int32 tensor (read when the kernel runs)."""
+        _lib.check(self.lib.lux_b200_reset_done_dev(ctypes.byref(self._desc), ctypes.byref(pool._desc), epoch_dev.data_ptr(),
+                                                    reset_count.data_ptr() if reset_count is not None else None,
+                                                    self._stream()), "lux_b200_reset_done_dev")
+
     def reset_gen(self, pool, epoch, seed, match_id_base=0, reset_count=None, counters=None, unit_actions=None,
                   tile_actions=None):
         """reset_done(pool, epoch) followed by gen_actions(seed, match_id_base) in one kernel (harness loops)."""
@@ -192,12 +198,31 @@ class BatchedGame:
                    "lux_b200_observe")
         return self._obs, self._ent, self._cnt
 
-    def observe_packed(self, team_sel):
+    def observe_packed(self, team_sel, row_cap=None):
         """Observation rows without padding: returns (obs [R, 85], ent [R] int16 (-1 = unused row),
         count [n] int32, offsets [n+1] int64).  Match m owns rows offsets[m] .. offsets[m+1]: an upper
-        bound of its team's units + tiles (from the headers), of which the first count[m] are entities."""
+        bound of its team's units + tiles (from the headers), of which the first count[m] are entities.
+        With `row_cap` the buffers have exactly that many rows and nothing is read back to the host (the call
+        can be captured in a CUDA graph): offsets are clamped to row_cap, so matches that would not fit get
+        no rows that turn -- `self.row_overflow` (device int64) counts the rows that were cut."""
         if not torch.is_tensor(team_sel):
             team_sel = torch.full((self.n,), int(team_sel), dtype=torch.uint8, device=self.device)
+        if row_cap is not None:
+            row_cap = int(row_cap)
+            if getattr(self, "_fixed_rows", 0) != row_cap:
+                self._fobs = torch.zeros((row_cap, 85), dtype=torch.float32, device=self.device)
+                self._fent = torch.full((row_cap,), -1, dtype=torch.int16, device=self.device)
+                self._fcnt = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+                self._foff = torch.zeros(self.n + 1, dtype=torch.int64, device=self.device)
+                self.row_overflow = torch.zeros((), dtype=torch.int64, device=self.device)
+                self._fixed_rows = row_cap
+            _lib.check(self.lib.lux_b200_observe_offsets(ctypes.byref(self._desc), team_sel.data_ptr(), row_cap,
+                                                         self._foff.data_ptr(), self.row_overflow.data_ptr(), self._stream()),
+                       "lux_b200_observe_offsets")
+            _lib.check(self.lib.lux_b200_observe(ctypes.byref(self._desc), team_sel.data_ptr(), self._fobs.data_ptr(),
+                                                 self._fent.data_ptr(), self._fcnt.data_ptr(), 0, self._foff.data_ptr(),
+                                                 self._stream()), "lux_b200_observe")
+            return self._fobs, self._fent, self._fcnt, self._foff
         h16 = self.hdr.view(torch.int16)
         sel = team_sel.to(torch.int64)
         tu = torch.gather(h16[:, 10:12].to(torch.int64) & 0xFFFF, 1, sel[:, None])[:, 0]      # n_team_units
@@ -241,6 +266,15 @@ class BatchedGame:
         ent[m, 0], codes[m, 0], cnt[m] = int(slot), int(code), 1
         self.encode_actions(ent, cnt, codes, unit_actions=ua, tile_actions=ta)
         return int(ua[m, int(slot)].item()) & 0xFFFFFFFF
+
+    def env_finish(self, pool, team_sel, reward_state, reward, done, turn_dev, reset_count=None):
+        """End of an environment turn in one kernel (lux_b200_env_finish): reward [n] float64 and done [n] uint8 of
+        the turn just played; finished matches are reset from `pool`, their reward state cleared and their
+        learning team drawn (team_sel updated in place).  turn_dev: device int32 / uint32 counter."""
+        _lib.check(self.lib.lux_b200_env_finish(ctypes.byref(self._desc), ctypes.byref(pool._desc), team_sel.data_ptr(),
+                                                reward_state.data_ptr(), reward.data_ptr(), done.data_ptr(),
+                                                turn_dev.data_ptr(), reset_count.data_ptr() if reset_count is not None else None,
+                                                self._stream()), "lux_b200_env_finish")
 
     def reward(self, team_sel, reward_state, out=None):
         """Per-turn AgentPolicy reward (float64 [n]); reward_state is int32 [n, 4], updated in place."""

@@ -502,12 +502,13 @@ __device__ __forceinline__ void lux_reset_match(const LuxBatch& b, const LuxBatc
     if (lane < LUX_HDR_BYTES / 16) ((uint4*)(b.hdr + m))[lane] = hv;
 }
 
-__global__ void lux_reset_done_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch, int* reset_count) {
+__global__ void lux_reset_done_kernel(LuxBatch b, LuxBatch pool, uint32_t epoch, const uint32_t* epoch_dev, int* reset_count) {
     LUX_PDL_TRIGGER();
     LUX_PDL_WAIT();
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= b.n_matches) return;
     if (!b.hdr[m].done) return;
+    if (epoch_dev) epoch += *epoch_dev;          // an epoch counter kept on the device (CUDA-graph replays)
     lux_reset_match<8>(b, pool, m, epoch, reset_count);
 }
 
@@ -915,8 +916,22 @@ extern "C" int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t m
     return cuda_ok(cudaGetLastError(), "lux_gen_actions_kernel launch");
 }
 
+static int reset_done_impl(const LuxBatch* b, const LuxBatch* pool, uint32_t epoch, const uint32_t* epoch_dev,
+                           int32_t* reset_count, void* cuda_stream);
+
 extern "C" int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, uint32_t epoch,
                                    int32_t* reset_count, void* cuda_stream) {
+    return reset_done_impl(b, pool, epoch, nullptr, reset_count, cuda_stream);
+}
+
+extern "C" int lux_b200_reset_done_dev(const LuxBatch* b, const LuxBatch* pool, const uint32_t* epoch_dev,
+                                       int32_t* reset_count, void* cuda_stream) {
+    if (!epoch_dev) return LUX_E_ARG;
+    return reset_done_impl(b, pool, 0, epoch_dev, reset_count, cuda_stream);
+}
+
+static int reset_done_impl(const LuxBatch* b, const LuxBatch* pool, uint32_t epoch, const uint32_t* epoch_dev,
+                           int32_t* reset_count, void* cuda_stream) {
     int rc = check_batch(b);
     if (rc) return rc;
     rc = check_batch(pool);
@@ -929,7 +944,7 @@ extern "C" int lux_b200_reset_done(const LuxBatch* b, const LuxBatch* pool, uint
     if (lux_b200_device_count() <= 0) return LUX_E_NO_DEVICE;
     const int wpc = 4;
     lux_launch_chain(lux_reset_done_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), 0, (cudaStream_t)cuda_stream,
-                 *b, *pool, epoch, (int*)reset_count);
+                 *b, *pool, epoch, epoch_dev, (int*)reset_count);
     g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_reset_done_kernel launch");
 }

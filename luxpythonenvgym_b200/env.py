@@ -43,6 +43,10 @@ class BatchedLuxEnvironment:
         self._gen = torch.Generator(device=self.device).manual_seed(team_seed)
         self._epoch = 0
 
+    def graphed(self, policy, row_cap=None):
+        """The whole turn (policy included) as one replayable CUDA graph; see GraphedRollout.  Call after reset()."""
+        return GraphedRollout(self, policy, row_cap=row_cap)
+
     def _draw_teams(self, mask=None):
         # learning team = coin flip per reset (MatchController.reset, match_controller.py:118-122); drawn on the
         # device so that a step never waits for the host
@@ -85,6 +89,56 @@ class BatchedLuxEnvironment:
         self._draw_teams(done)
         self._epoch += 1
         return self._observe(), reward, done
+
+
+class GraphedRollout:
+    """One environment turn of a `BatchedLuxEnvironment` as ONE CUDA graph: policy on the current observation
+    rows -> lux_b200_encode_actions -> lux_b200_step(prevalidate) -> lux_b200_reward -> masked resets and team
+    draws -> lux_b200_observe for the next turn.  Nothing returns to the host inside a turn; the kernels of the
+    chain are programmatic dependents of one another inside the graph as they are on a stream.
+
+    `policy(obs_rows[row_cap, 85] float32) -> codes[row_cap] int32` must be capturable (static shapes, no host
+    synchronisation); it sees every row of the fixed-capacity buffer, rows without an entity are ignored.
+    After `turn()`: `.reward` [n] float64 and `.done` [n] bool of the turn just played, `.obs / .ent / .count /
+    .offsets` for the next one, `.decisions` (device int64, running total of entity decisions).
+    The tail of the turn is lux_b200_env_finish: team draws are a counter-based hash of (env, turn) instead of the
+    eager path's torch generator, and the pool entry of a reset is chosen from the device-side turn counter."""
+
+    def __init__(self, env, policy, row_cap=None, warmup=3):
+        g = env.game
+        self.env, self.policy = env, policy
+        self.row_cap = int(row_cap or 4 * env.n)
+        dev = env.device
+        self.turns = torch.zeros((), dtype=torch.int32, device=dev)
+        self.decisions = torch.zeros((), dtype=torch.int64, device=dev)
+        self.reward = torch.zeros(env.n, dtype=torch.float64, device=dev)
+        self._done8 = torch.zeros(env.n, dtype=torch.uint8, device=dev)
+        self.done = self._done8.view(torch.bool)
+        self.obs, self.ent, self.count, self.offsets = g.observe_packed(env.team, row_cap=self.row_cap)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):      # first-call allocations (library scratch, torch workspaces) happen here
+                self._turn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._turn()
+
+    def _turn(self):
+        env, g = self.env, self.env.game
+        codes = self.policy(self.obs)
+        self.decisions += self.count.sum()
+        g.encode_actions(self.ent, self.count, codes, offsets=self.offsets)
+        g.step(prevalidate=True)
+        g.env_finish(env.pool, env.team, env.reward_state, self.reward, self._done8, self.turns, env.resets)
+        self.turns += 1
+        g.observe_packed(env.team, row_cap=self.row_cap)      # writes obs / ent / count / offsets in place
+
+    def turn(self):
+        self.graph.replay()
+        return self.reward, self.done
 
 
 class LuxEnvironment:

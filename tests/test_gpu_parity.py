@@ -439,6 +439,97 @@ def test_packed_observations_equal_padded():
     assert (env.game.headers()["status"] == 0).all()
 
 
+def test_env_finish_and_device_offsets_equal_the_separate_calls():
+    """lux_b200_env_finish == lux_b200_reward + done flags + lux_b200_reset_done(epoch = turn) + cleared reward state
+    (+ the documented team draw), and lux_b200_observe_offsets == the host-side cumulative sum of the packed
+    layout, clamped to the row capacity."""
+    from luxpythonenvgym_b200.batched import BatchedGame
+    n, size = 700, 16                     # not a multiple of the scan block: two blocks, the second partial
+    arrays = mapgen.generate_batch(np.arange(600, 600 + 64), size)
+    pool = BatchedGame(64, size)
+    pool.load_arrays(arrays)
+    a, b = BatchedGame(n, size), BatchedGame(n, size)
+    for g in (a, b):
+        g.load_arrays({k: v[np.arange(n) % 64] for k, v in arrays.items()})
+    team_a = (torch.arange(n, device="cuda") % 2).to(torch.uint8)
+    team_b = team_a.clone()
+    rs_a = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+    rs_b = rs_a.clone()
+    reward_b = torch.zeros(n, dtype=torch.float64, device="cuda")
+    done_b = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    turn = torch.zeros((), dtype=torch.int32, device="cuda")
+    resets_a = torch.zeros(1, dtype=torch.int32, device="cuda")
+    resets_b = resets_a.clone()
+    for t in range(70):
+        a.gen_actions(99, 0)
+        b.unit_actions.copy_(a.unit_actions)
+        b.tile_actions.copy_(a.tile_actions)
+        a.step()
+        b.step()
+        if t % 9 == 4:                    # finish a few matches early so that resets happen
+            for g in (a, b):
+                g.hdr[t::37, 24] = 1
+        reward_a = a.reward(team_a, rs_a)
+        done_a = a.hdr[:, 24] != 0
+        a.reset_done(pool, t, resets_a)
+        rs_a.masked_fill_(done_a[:, None], 0)
+        idx = torch.arange(n, dtype=torch.int64, device="cuda")
+        hsh = ((idx * 0x9E3779B1 + t * 0x85EBCA6B) & 0xFFFFFFFF) * 0x2C1B3C6D & 0xFFFFFFFF
+        team_a = torch.where(done_a, ((hsh >> 17) & 1).to(torch.uint8), team_a)
+        turn.fill_(t)
+        b.env_finish(pool, team_b, rs_b, reward_b, done_b, turn, resets_b)
+        assert torch.equal(reward_a, reward_b) and torch.equal(done_a, done_b.bool()), t
+        assert torch.equal(team_a, team_b) and torch.equal(rs_a, rs_b), t
+        for k in a.sections():
+            assert torch.equal(a.sections()[k], b.sections()[k]), (t, k)
+        # offsets on the device vs on the host
+        want = a.observe_packed(team_a)[3].clone()
+        for cap in (100000, int(want[-1]) // 2):
+            got = b.observe_packed(team_b, row_cap=cap)[3]
+            assert torch.equal(got, want.clamp(max=cap)), (t, cap)
+    assert int(resets_a) == int(resets_b) > 0
+    assert int(b.row_overflow) > 0
+
+
+def test_graphed_rollout_turns():
+    """BatchedLuxEnvironment.graphed(policy): the whole turn replayed as one CUDA graph.  The observation rows it
+    leaves for the next turn equal a fresh eager observation of the same state, finished matches are reset, no
+    match raises a status flag, and a second graph with the same seeds reproduces the rewards."""
+    from luxpythonenvgym_b200.env import BatchedLuxEnvironment
+
+    def run(turns):
+        torch.manual_seed(5)
+        env = BatchedLuxEnvironment(512, size=16, seed=300, pool_maps=32, packed=True)
+        env.reset()
+        net = torch.nn.Sequential(torch.nn.Linear(85, 32), torch.nn.Tanh(), torch.nn.Linear(32, 9)).cuda()
+
+        @torch.no_grad()
+        def policy(obs):
+            return net(obs).argmax(dim=-1).to(torch.int32)
+
+        roll = env.graphed(policy, row_cap=8 * 512)
+        total, finished = torch.zeros(512, dtype=torch.float64, device="cuda"), 0
+        for t in range(turns):
+            reward, done = roll.turn()
+            total += reward
+            finished += int(done.sum())
+        return env, roll, total, finished
+
+    env, roll, total, finished = run(80)
+    g = env.game
+    assert finished > 0 and int(roll.decisions) > 80 * 512 // 2 and int(g.row_overflow) == 0
+    assert (g.headers()["status"] == 0).all() and (g.headers()["done"] == 0).all()
+    want_obs, want_ent, want_cnt = [t.clone() for t in g.observe(env.team)]
+    off = roll.offsets.cpu().numpy()
+    cnt = roll.count.cpu().numpy()
+    assert np.array_equal(cnt, want_cnt.cpu().numpy())
+    for m in range(0, 512, 5):
+        c, o = int(cnt[m]), int(off[m])
+        assert torch.equal(roll.obs[o:o + c], want_obs[m, :c]) and torch.equal(roll.ent[o:o + c], want_ent[m, :c])
+    _, _, total2, finished2 = run(80)
+    assert finished2 == finished and torch.equal(total, total2)
+
+
 def test_spill_list_and_scheduling_paths_under_load():
     """Force the rarely taken launch paths on a real batch: a tiny small-class slice (3200 B) so that a large
     share of a dense batch goes to the big class every turn, with and without overlapping the two classes,
