@@ -19,6 +19,9 @@
 
 namespace {
 
+struct Pow2Neg { double v[160]; Pow2Neg() { for (int k = 0; k < 160; k++) v[k] = ldexp(1.0, -k); } };
+const Pow2Neg POW2_NEG;
+
 struct Arc4 {
     uint8_t s[256];
     int i = 0, j = 0;
@@ -34,21 +37,31 @@ struct Arc4 {
         take(256);
     }
     uint64_t take(int n) {
+        // i, j live in registers for the run (the byte stores into s[] may alias the members otherwise)
         uint64_t acc = 0;
+        unsigned a = (unsigned)i, b = (unsigned)j;
         for (int k = 0; k < n; k++) {
-            i = (i + 1) & 255;
-            j = (j + s[i]) & 255;
-            uint8_t t = s[i]; s[i] = s[j]; s[j] = t;
-            acc = (acc << 8) | s[(s[i] + s[j]) & 255];
+            a = (a + 1) & 255;
+            const unsigned sa = s[a];
+            b = (b + sa) & 255;
+            const unsigned sb = s[b];
+            s[a] = (uint8_t)sb; s[b] = (uint8_t)sa;
+            acc = (acc << 8) | s[(sa + sb) & 255];
         }
+        i = (int)a; j = (int)b;
         return acc;
     }
+    // seedrandom's random(): 48 bits, topped up byte-wise to >= 52 significant bits, halved below 2^53, divided by
+    // the matching power of 256.  Every intermediate of the original's double arithmetic is an exactly
+    // representable integer (num < 2^53 before each "* 256", and a multiple of the bits shifted out while it is
+    // halved), so the same value comes out of integer shifts and one exact scaling by a power of two.
     double next() {
-        double num = (double)take(6), den = 281474976710656.0;
+        uint64_t num = take(6);
+        int den_bits = 48;
         uint32_t extra = 0;
-        while (num < 4503599627370496.0) { num = (num + extra) * 256.0; den *= 256.0; extra = (uint32_t)take(1); }
-        while (num >= 9007199254740992.0) { num /= 2.0; den /= 2.0; extra >>= 1; }
-        return (num + extra) / den;
+        while (num < (1ull << 52)) { num = (num + extra) << 8; den_bits += 8; extra = (uint32_t)take(1); }
+        while (num >= (1ull << 53)) { num >>= 1; den_bits -= 1; extra >>= 1; }
+        return (double)(num + extra) * POW2_NEG.v[den_bits];            // exact: a power of two
     }
 };
 
@@ -60,8 +73,10 @@ inline int sgn(double v) { return v > 0 ? 1 : (v < 0 ? -1 : 0); }
 struct Field {
     int w, h;
     std::vector<int> at;          // index into pool, -1 empty
+    std::vector<int> scratch;     // the drift step's output grid (swapped with `at`)
+    std::vector<uint8_t> bits;    // automaton layer / per-cell resource kind of the drift step
     std::vector<Res> pool;        // deposits are moved by reference in the original; indices play that role
-    Field(int w_, int h_) : w(w_), h(h_), at((size_t)w_ * h_, -1) {}
+    Field(int w_, int h_) : w(w_), h(h_), at((size_t)w_ * h_, -1) { pool.reserve(256); }
     int& cell(int x, int y) { return at[(size_t)y * w + x]; }
 };
 
@@ -70,55 +85,90 @@ int coal_amt(Arc4& r) { return 350 + (int)floor(r.next() * 75); }
 int uranium_amt(Arc4& r) { return 300 + (int)floor(r.next() * 50); }
 int amount_of(int kind, Arc4& r) { return kind == LUX_RES_WOOD ? wood_amt(r) : kind == LUX_RES_COAL ? coal_amt(r) : uranium_amt(r); }
 
-void automaton_layer(Arc4& r, double density, double spread, int w, int h, int death, int birth, std::vector<int>& g) {
+void automaton_layer(Arc4& r, double density, double spread, int w, int h, int death, int birth, std::vector<uint8_t>& g) {
     double p = density - spread / 2 + spread * r.next();
     g.assign((size_t)w * h, 0);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) g[(size_t)y * w + x] = r.next() < p ? 1 : 0;
+    // two sweeps of the life-like rule, IN PLACE (a cell sees the already updated cells before it, as the
+    // original's single grid does)
     for (int round = 0; round < 2; round++)
-        for (int i = 1; i < h - 1; i++)
+        for (int i = 1; i < h - 1; i++) {
+            uint8_t* up = &g[(size_t)(i - 1) * w];
+            uint8_t* me = up + w;
+            uint8_t* dn = me + w;
             for (int j = 1; j < w - 1; j++) {
-                int alive = 0;
-                for (auto& d : DELTA) alive += g[(size_t)(i + d[1]) * w + (j + d[0])] == 1;
-                int& c = g[(size_t)i * w + j];
-                if (c == 1) c = alive < death ? 0 : 1;
-                else c = alive > birth ? 1 : 0;
+                const int alive = up[j - 1] + up[j] + up[j + 1] + me[j - 1] + me[j + 1] + dn[j - 1] + dn[j] + dn[j + 1];
+                me[j] = me[j] ? (alive < death ? 0 : 1) : (alive > birth ? 1 : 0);
             }
+        }
 }
 
+// Force contributions of a neighbour at offset (dx, dy) = (x - xx, y - yy), dx, dy in [-4, 5]:
+// pow(dx / md, 2) * sgn(dx) and the same for dy, evaluated once with the very expressions of the original loop
+// (so that the sums below add the same doubles in the same order).
+struct DriftTable {
+    double fx[10][10], fy[10][10];
+    DriftTable() {
+        for (int dy = -4; dy <= 5; dy++)
+            for (int dx = -4; dx <= 5; dx++) {
+                const int md = abs(dx) + abs(dy);
+                fx[dy + 4][dx + 4] = dx ? pow((double)dx / md, 2) * sgn(dx) : 0.0;
+                fy[dy + 4][dx + 4] = dy ? pow((double)dy / md, 2) * sgn(dy) : 0.0;
+            }
+    }
+};
+const DriftTable DRIFT;
+const double SIGN[2] = {1.0, -1.0};
+
+// One gravity step (game_map.py:330-380): every deposit is pushed away from deposits of other kinds and pulled
+// towards its own kind inside a 10 x 10 window, then moves one cell along the sign of the force.  Occupied cells
+// are found through one 32-bit occupancy mask per row; the neighbours of a window are visited row by row with
+// ascending x, i.e. in the order of the original double loop, which fixes the floating-point sums.
 void drift(Field& f) {
     const int w = f.w, h = f.h;
-    for (int y = 0; y < h; y++)
+    uint32_t rows[32];
+    std::vector<uint8_t>& kinds = f.bits;
+    kinds.assign((size_t)w * h, 0);
+    for (int y = 0; y < h; y++) {
+        uint32_t m = 0;
         for (int x = 0; x < w; x++) {
-            int id = f.cell(x, y);
-            if (id < 0) continue;
-            Res& r = f.pool[id];
+            const int id = f.cell(x, y);
+            if (id >= 0) { m |= 1u << x; kinds[(size_t)y * w + x] = (uint8_t)f.pool[id].kind; }
+        }
+        rows[y] = m;
+    }
+    for (int y = 0; y < h; y++)
+        for (uint32_t own = rows[y]; own; own &= own - 1) {
+            const int x = __builtin_ctz(own);
+            Res& r = f.pool[f.cell(x, y)];
+            const int kind = r.kind;
             double fx = 0, fy = 0;
-            for (int yy = y - 5; yy < y + 5; yy++) {
-                if (yy < 0 || yy >= h) continue;
-                for (int xx = x - 5; xx < x + 5; xx++) {
-                    if (xx < 0 || xx >= w) continue;
-                    int od = f.cell(xx, yy);
-                    if (od < 0) continue;
-                    const Res& o = f.pool[od];
-                    int dx = x - xx, dy = y - yy;
-                    int md = abs(dx) + abs(dy);
-                    if (o.kind != r.kind) {
-                        if (dx) fx += pow((double)dx / md, 2) * sgn(dx);
-                        if (dy) fy += pow((double)dy / md, 2) * sgn(dy);
-                    } else {
-                        if (dx) fx -= pow((double)dx / md, 2) * sgn(dx);
-                        if (dy) fy -= pow((double)dy / md, 2) * sgn(dy);
-                    }
+            const int x0 = x - 5 < 0 ? 0 : x - 5, x1 = x + 5 > w ? w : x + 5;          // [x0, x1)
+            const uint32_t window = (x1 >= 32 ? 0xffffffffu : ((1u << x1) - 1u)) & ~((1u << x0) - 1u);
+            const int y0 = y - 5 < 0 ? 0 : y - 5, y1 = y + 5 > h ? h : y + 5;
+            for (int yy = y0; yy < y1; yy++) {
+                const uint8_t* krow = &kinds[(size_t)yy * w];
+                const double* tx = DRIFT.fx[y - yy + 4] + (x + 4);                   // tx[-xx] = fx[dy + 4][x - xx + 4]
+                const double* ty = DRIFT.fy[y - yy + 4] + (x + 4);
+                for (uint32_t bits = rows[yy] & window; bits; bits &= bits - 1) {
+                    const int xx = __builtin_ctz(bits);
+                    // other kinds push (+), the same kind pulls (-); a zero component adds +-0.0, which leaves
+                    // the sum's value (and its sign test) as the original's skipped addition does
+                    // (the sign comes from a two-entry table: x * -1.0 == -x exactly, and no branch to mispredict)
+                    const double sg = SIGN[krow[xx] == kind];
+                    fx += tx[-xx] * sg;
+                    fy += ty[-xx] * sg;
                 }
             }
             r.fx = fx; r.fy = fy;
         }
-    std::vector<int> out((size_t)w * h, -1);
+    std::vector<int>& out = f.scratch;
+    out.assign((size_t)w * h, -1);
     for (int y = 0; y < h; y++)
-        for (int x = 0; x < w; x++) {
-            int id = f.cell(x, y);
-            if (id < 0) continue;
+        for (uint32_t own = rows[y]; own; own &= own - 1) {
+            const int x = __builtin_ctz(own);
+            const int id = f.cell(x, y);
             const Res& r = f.pool[id];
             int nx = x + sgn(r.fx), ny = y + sgn(r.fy);
             nx = nx < 0 ? 0 : (nx > w - 1 ? w - 1 : nx);
@@ -133,7 +183,7 @@ Field layout(Arc4& r, int symmetry_vertical, int w, int h, int hw, int hh) {
     Field f(w, h);
     const struct { int kind; double density, spread; int death, birth; } layers[3] = {
         {LUX_RES_WOOD, 0.21, 0.01, 2, 4}, {LUX_RES_COAL, 0.11, 0.02, 2, 4}, {LUX_RES_URANIUM, 0.055, 0.04, 1, 6}};
-    std::vector<int> g;
+    std::vector<uint8_t>& g = f.bits;
     for (auto& L : layers) {
         automaton_layer(r, L.density, L.spread, hw, hh, L.death, L.birth, g);
         for (int y = 0; y < hh; y++)
