@@ -185,8 +185,8 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
             mbar_init((uint64_t*)(smem + L0.mbar), 1);
             fence_mbar_init();
         }
-        lux_zero16<G>(smem + L0.p1, (size * size + 15) & ~15);
-        lux_zero16<G>(smem + L0.occ, (size * size + 15) & ~15);
+        if (kS > 0) lux_zero_fixed<G, 2 * ((kS * kS + 15) & ~15)>(smem + L0.p1);      // the two planes are adjacent
+        else lux_zero16<G>(smem + L0.p1, 2 * ((size * size + 15) & ~15));
     }
     lux_sync<G>();
     if (kMode == kList) {

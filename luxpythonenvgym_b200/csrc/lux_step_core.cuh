@@ -107,33 +107,31 @@ LUX_HD LuxNeed lux_need_header(const LuxHeader* h, int u_cap, int c_cap, int t_c
 }
 
 // The byte planes, the barrier and the header sit at fixed offsets (they are needed before the match's
-// sizes are known); the lists follow.
+// sizes are known); the lists follow in four blocks whose inner offsets are fixed multiples of the (rounded)
+// counts -- per-unit arrays, per-tile arrays, resource and request lists, per-city arrays -- so that a warp
+// derives the whole layout with a dozen multiply-adds (the first version aligned nineteen fields one by one:
+// 9 % of the executed instructions of a turn).  Every bulk-copy destination is 16-byte aligned.
 LUX_HD LuxSmemLayout lux_smem_layout_need(int size, LuxNeed n) {
     LuxSmemLayout L;
-    int ncell = size * size;
-    int o = 0;
-#define LUX_TAKE(field, bytes) L.field = o; o += (((bytes) + 15) & ~15);
-    LUX_TAKE(p1, ncell)                 // per-cell flag plane (movement flags, then collection mark / fill level)
-    LUX_TAKE(occ, ncell)                // per-cell occupant plane (unit index + 1 during collection)
-    LUX_TAKE(mbar, 16)
-    LUX_TAKE(hdr, LUX_HDR_BYTES)
-    LUX_TAKE(units, n.u * 16)
-    LUX_TAKE(uact, n.u * 4)
-    LUX_TAKE(cities, n.c * 16)
-    LUX_TAKE(tiles, n.t * 2)
-    LUX_TAKE(tact, n.t)
-    LUX_TAKE(res, n.r * 4)
-    LUX_TAKE(utgt, n.u * 2)
-    LUX_TAKE(ust, n.u)
-    LUX_TAKE(umine, n.u)
-    LUX_TAKE(uinfo, n.u * 4)
-    LUX_TAKE(umin, n.u * 2)
-    LUX_TAKE(tmask, n.t * 4)
-    LUX_TAKE(cprefix, (n.c + 1) * 2)
-    LUX_TAKE(cremap, n.c)
-    LUX_TAKE(reqlist, n.q * 2 + 16)     // cells requested this collection pass (+ counter)
-#undef LUX_TAKE
-    L.total = o;
+    const int plane = (size * size + 15) & ~15;
+    const int ur = (n.u + 7) & ~7, cr = (n.c + 7) & ~7, tr = (n.t + 15) & ~15, rr = (n.r + 7) & ~7, qr = (n.q + 7) & ~7;
+    L.p1 = 0;                           // per-cell flag plane (movement flags, then collection mark / fill level)
+    L.occ = plane;                      // per-cell occupant plane (unit index + 1 during collection)
+    L.mbar = 2 * plane;
+    L.hdr = 2 * plane + 16;
+    int o = 2 * plane + 16 + LUX_HDR_BYTES;
+    L.units = o; L.uact = o + 16 * ur; L.uinfo = o + 20 * ur; L.utgt = o + 24 * ur; L.umin = o + 26 * ur;
+    L.ust = o + 28 * ur; L.umine = o + 29 * ur;
+    o += 30 * ur;
+    L.tiles = o; L.tact = o + 2 * tr; L.tmask = o + 3 * tr;
+    o += 7 * tr;
+    L.res = o;
+    o += 4 * rr;
+    L.reqlist = o;                      // cells requested this collection pass (counter first)
+    o += 16 + 2 * qr;
+    L.cities = o; L.cprefix = o + 16 * cr; L.cremap = o + 18 * cr + 16;
+    o += 19 * cr + 16;
+    L.total = (o + 15) & ~15;
     return L;
 }
 
@@ -272,6 +270,18 @@ LUX_DEV void lux_zero16(void* p, int bytes) {   // bytes multiple of 16, p 16-by
     uint64_t* q = (uint64_t*)p;
 #pragma unroll 1
     for (int i = lane; i < bytes / 16; i += G) { q[2 * i] = 0; q[2 * i + 1] = 0; }
+}
+
+// compile-time size: straight 16-byte stores, no loop
+template <int G, int BYTES>
+LUX_DEV void lux_zero_fixed(void* p) {
+    const int lane = lux_lane<G>();
+    struct alignas(16) Q { uint64_t a, b; };
+    Q* q = (Q*)p;
+    Q z; z.a = 0; z.b = 0;
+#pragma unroll
+    for (int i = 0; i < (BYTES / 16 + G - 1) / G; i++)
+        if (i * G + lane < BYTES / 16) q[i * G + lane] = z;
 }
 
 // umin[] holds 2 bits of resource type for each of a worker's five cells; bit 2j of the result is set where
@@ -999,8 +1009,10 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     // (uinfo), which of its five cells it can mine (umin, 2 bits of resource type per direction) and the
     // occupant mark of its cell.  This is the one place a unit reads the grid: five independent loads.
     int stacked = 0;                       // some non-city cell holds several units (rare; see below)
+    unsigned minable = 0;                  // bit t: some worker of the match has a cell of resource type t in reach
     {
         int rb0 = 0, rb1 = 0, bad = 0;
+        unsigned has_t1 = 0, has_t2 = 0, has_t3 = 0;
 #pragma unroll 1
         for (int u = lane; u < n_units; u += G) {
             LuxUnit& U = M.units[u];
@@ -1044,7 +1056,13 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             M.uinfo[u] = info;
             M.umin[u] = (uint16_t)mm;
             M.ust[u] = 0;
+            {   // which resource types occur among the five fields (type = hi:lo of a field)
+                const unsigned lo = mm & 0x155u, hi = (mm >> 1) & 0x155u;
+                has_t1 |= lo & ~hi; has_t2 |= hi & ~lo; has_t3 |= lo & hi;
+            }
         }
+        minable = (lux_any<G>(has_t1 != 0) ? 1u << LUX_RES_WOOD : 0u) | (lux_any<G>(has_t2 != 0) ? 1u << LUX_RES_COAL : 0u) |
+                  (lux_any<G>(has_t3 != 0) ? 1u << LUX_RES_URANIUM : 0u);
         {   // one reduction: road steps are < 2^12 per team (3 per cart), stacks < 2^8
             int packed = lux_reduce_add<G>(rb0 | (rb1 << 12) | (bad << 24));
             rb0 = packed & 0xFFF; rb1 = (packed >> 12) & 0xFFF; bad = packed >> 24;
@@ -1080,7 +1098,9 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 #pragma unroll 1
         for (int rtype = LUX_RES_URANIUM; rtype >= LUX_RES_WOOD; rtype--) {
             int need = rtype == LUX_RES_WOOD ? 0 : rtype == LUX_RES_COAL ? LUX_RESEARCH_COAL : LUX_RESEARCH_URANIUM;
-                    if (!lux_wany<G>(rp0 >= need || rp1 >= need)) continue;   // nobody in the warp may mine this type yet
+            // nobody in the warp may mine this type yet, or no worker stands next to a cell of it: the pass would
+            // find no request (every umine = none, nothing marked, nothing gained)
+            if (!lux_wany<G>((rp0 >= need || rp1 >= need) && ((minable >> rtype) & 1u))) continue;
             lux_collect_type<kS, G>(M, rtype, n_units, rp0 >= need, rp1 >= need, stacked);
         }
     }

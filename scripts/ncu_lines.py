@@ -6,7 +6,8 @@ def I(x):
     except ValueError: return 0
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 fn_filter = sys.argv[3] if len(sys.argv) > 3 else None   # substring of the kernel name to keep
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
+import os
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"] + os.environ.get("NCU_SELECT", "").split(), capture_output=True, text=True).stdout
 lines = list(csv.reader(io.StringIO(out)))
 cur_file = None; cols = None
 agg = collections.defaultdict(lambda: [0, 0, 0.0, ""])   # (file,line) -> inst, samples, thread_inst, text

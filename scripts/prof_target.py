@@ -10,8 +10,14 @@ import torch
 from luxpythonenvgym_b200 import mapgen
 from luxpythonenvgym_b200.batched import BatchedGame
 
+import os
+from luxpythonenvgym_b200 import _lib
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-N, SIZE = 16384, 32
+N, SIZE = 16384, int(os.environ.get("LUX_SIZE", "32"))
+for opt in os.environ.get("LUX_OPTS", "").split(","):       # e.g. LUX_OPTS=group=16,carveout=100
+    if "=" in opt:
+        k, v = opt.split("=")
+        assert _lib.load().lux_b200_set_option(k.encode(), int(v)) == 0, opt
 game = BatchedGame(N, SIZE)
 pool = BatchedGame(1024, SIZE)
 pool.load_arrays(mapgen.generate_batch(np.arange(424242, 424242 + 1024), SIZE))
