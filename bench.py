@@ -496,11 +496,13 @@ def run_b200(args):
         if k == W_e:
             barrier()
             w0 = time.perf_counter()
-        # H2D: this turn's action list (8 bytes per action); step; D2H: done flags + summary; sync
-        game.step_host_sparse(views[k], ent_k[k], done_h, summ_h)
+        # H2D: this turn's action list (8 bytes per action); step; the pool resets of the matches that just finished
+        # are queued behind it BEFORE the host blocks; D2H: done flags + summary; the host waits for them every step
+        game.step_host_sparse_submit(views[k], ent_k[k])
+        game.reset_done(pool, epoch[0], resets)
+        game.step_host_wait(done_h, summ_h)
         if k >= W_e:
             h2d_total += 8 * ent_k[k]
-        game.reset_done(pool, epoch[0], resets)
         epoch[0] += 1
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
@@ -547,8 +549,9 @@ def run_b200(args):
                              "live_match_turns_per_launch": live_all / world / K},
                 "e2e": {"value": e2e_turns / e2e_s, "unit": "match-turns/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "steps": E, "warmup": 5,
-                        "note": "lux_b200_step_host_sparse: pinned host action LIST (8 B per action) -> device, scatter, "
-                                "step, done flags + summary -> host, sync every step; counts resident matches per step "
+                        "note": "lux_b200_step_host_sparse_submit + lux_b200_step_host_wait: pinned host action LIST (8 B per action) -> device, scatter, "
+                                "step, done flags + summary -> host (mapped pinned memory), the host blocks on them every step (the pool "
+                                "reset of finished matches is queued before it blocks); counts resident matches per step "
                                 "(finished ones are reset the same step).  The lists are recorded beforehand (the device "
                                 "action stream packed into entry form): building them from host Action objects is the "
                                 "caller's cost and is not in this number"},

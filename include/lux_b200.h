@@ -198,6 +198,19 @@ int lux_b200_step_host_sparse(const LuxBatch* b, const void* entries_host, int k
                               uint32_t flags, void* cuda_stream);
 
 /*
+ * The same turn in two halves, for a caller that has more work to queue behind the step before it blocks
+ * (pool resets, the observation pass): _submit uploads the list and queues scatter, step and the done-flag /
+ * summary pass without waiting; _wait blocks until that pass has published its results (it polls the sequence
+ * number the pass writes behind them in mapped host memory, and falls back to synchronising the stream), then
+ * fills the host buffers exactly as lux_b200_step_host_sparse does.  Work queued on the stream after _submit may
+ * still be running when _wait returns.  lux_b200_step_host_sparse == _submit + _wait + a stream synchronisation.
+ * _wait without a preceding _submit for the batch returns LUX_E_ARG.
+ */
+int lux_b200_step_host_sparse_submit(const LuxBatch* b, const void* entries_host, int k, uint32_t* unit_actions_dev,
+                                     uint8_t* tile_actions_dev, uint32_t flags, void* cuda_stream);
+int lux_b200_step_host_wait(const LuxBatch* b, uint8_t* done_host, int32_t* summary_host, void* cuda_stream);
+
+/*
  * Canonical seeded action stream, written as packed action
  * tensors for every live match: action = f(hash64(seed, match_id_base+m, turn, kind, key)).
  * Harness utility (benchmarks, parity tests); a policy normally fills the tensors itself.

@@ -17,7 +17,7 @@ _ERR = {LUX_E_ARG: "bad argument", LUX_E_CAPACITY: "capacity out of range",
 # every symbol include/lux_b200.h declares
 EXPORTS = ("lux_b200_version", "lux_b200_device_count", "lux_b200_set_option", "lux_b200_step_smem_bytes",
            "lux_b200_step", "lux_b200_step_host", "lux_b200_gen_actions", "lux_b200_observe",
-           "lux_b200_reset_done", "lux_b200_stats", "lux_b200_encode_actions", "lux_b200_reward", "lux_b200_launch_count", "lux_b200_step_host_sparse",
+           "lux_b200_reset_done", "lux_b200_stats", "lux_b200_encode_actions", "lux_b200_reward", "lux_b200_launch_count", "lux_b200_step_host_sparse", "lux_b200_step_host_sparse_submit", "lux_b200_step_host_wait",
            "lux_b200_reset_gen", "lux_b200_reset_done_dev", "lux_b200_observe_offsets", "lux_b200_env_finish")
 
 
@@ -58,6 +58,8 @@ def load():
     lib.lux_b200_step.argtypes = [bp, vp, vp, ctypes.c_uint32, vp]
     lib.lux_b200_step_host.argtypes = [bp, vp, vp, vp, vp, vp, vp, i32, i32, ctypes.c_uint32, vp]
     lib.lux_b200_step_host_sparse.argtypes = [bp, vp, i32, vp, vp, vp, vp, ctypes.c_uint32, vp]
+    lib.lux_b200_step_host_sparse_submit.argtypes = [bp, vp, i32, vp, vp, ctypes.c_uint32, vp]
+    lib.lux_b200_step_host_wait.argtypes = [bp, vp, vp, vp]
     lib.lux_b200_gen_actions.argtypes = [bp, u64, u64, vp, vp, vp, vp]
     lib.lux_b200_observe.argtypes = [bp, vp, vp, vp, vp, i32, vp, vp]
     lib.lux_b200_reset_done.argtypes = [bp, bp, ctypes.c_uint32, vp, vp]

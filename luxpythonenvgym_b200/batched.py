@@ -125,6 +125,20 @@ class BatchedGame:
             summary_host.data_ptr() if summary_host is not None else None,
             _lib.LUX_STEP_PREVALIDATE if prevalidate else 0, self._stream()), "lux_b200_step_host_sparse")
 
+    def step_host_sparse_submit(self, entries_host, k, prevalidate=False):
+        """First half of `step_host_sparse`: upload the list and queue scatter + step + done-flag pass; returns
+        without waiting, so the caller can queue more work (pool resets, observations) behind it."""
+        _lib.check(self.lib.lux_b200_step_host_sparse_submit(
+            ctypes.byref(self._desc), entries_host.data_ptr(), int(k), self.unit_actions.data_ptr(),
+            self.tile_actions.data_ptr(), _lib.LUX_STEP_PREVALIDATE if prevalidate else 0, self._stream()),
+            "lux_b200_step_host_sparse_submit")
+
+    def step_host_wait(self, done_host=None, summary_host=None):
+        """Second half: block until the submitted turn's done flags and summary are in host memory."""
+        _lib.check(self.lib.lux_b200_step_host_wait(
+            ctypes.byref(self._desc), done_host.data_ptr() if done_host is not None else None,
+            summary_host.data_ptr() if summary_host is not None else None, self._stream()), "lux_b200_step_host_wait")
+
     def pack_entries(self, unit_actions=None, tile_actions=None):
         """Device helper: the non-zero live entries of dense action tensors as an int32 [k, 2] entry list
         (the format step_host_sparse uploads).  Rows beyond the live prefixes are ignored."""

@@ -158,13 +158,14 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
     }
 }
 
-// kPlain: compiled for flags == 0 (no pre-validation, no consumed action words): the common call, and a
-// shorter program for the instruction cache
-template <bool kTma, int kS, int kMode, int G, bool kPlain>
+// kSpec: 1 = compiled for flags == 0 (no pre-validation, no consumed action words): the common device call;
+// 2 = compiled for the host list path without pre-validation (action words consumed); 0 = any flags.  The
+// specialised programs are shorter, which is what the instruction cache wants.
+template <bool kTma, int kS, int kMode, int G, int kSpec>
 __global__ void __launch_bounds__(64, kMode == kSmall ? (G == 32 ? LUX_SMALL_MIN_CTAS : G == 16 ? 13 : 6) : 1)
 lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uint8_t* __restrict__ tile_actions,
                 int slice, unsigned flags_in, LuxSched sc) {
-    const unsigned flags = kPlain ? 0u : flags_in;
+    const unsigned flags = kSpec == 1 ? 0u : kSpec == 2 ? LUX_STEP_CONSUME : flags_in;
     extern __shared__ __align__(128) unsigned char lux_smem[];
     // the big class needs the classification pass complete; after that the small class may start while this
     // class is still running (the two touch disjoint matches).  The small class itself only lets its successor
@@ -220,21 +221,21 @@ static int g_carveout = -1;       // preferred shared-memory carve-out in percen
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
 
 // `gpc` = matches (lane groups) per CTA; the CTA has gpc * G threads and gpc slices of `slice` bytes
-template <bool kTma, int kS, int kMode, int G, bool kPlain>
+template <bool kTma, int kS, int kMode, int G, int kSpec>
 static int launch_step_plain(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, int slice, unsigned flags, const LuxSched& sc,
                        int n_groups, int wpc, cudaStream_t st) {
     const int gpc = wpc * (32 / G);
     size_t smem = (size_t)slice * gpc;
-    cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G, kPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G, kSpec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return LUX_E_CUDA;
     // Carve-out: the grid is read in place through L1, so part of the SM's 256 KB stays cache; and the big and
     // the small class only share an SM when both ask for the same split (measured: 72 % = 164 KB, 0.119 -> 0.110 ms)
     const int carve = g_carveout >= 0 ? g_carveout : (kMode != kAll ? 72 : -1);
     if (carve >= 0) {
-        e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G, kPlain>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        e = cudaFuncSetAttribute(lux_step_kernel<kTma, kS, kMode, G, kSpec>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return LUX_E_CUDA;
     }
-    e = lux_launch_chain(lux_step_kernel<kTma, kS, kMode, G, kPlain>, dim3((n_groups + gpc - 1) / gpc), dim3(32 * wpc), smem, st,
+    e = lux_launch_chain(lux_step_kernel<kTma, kS, kMode, G, kSpec>, dim3((n_groups + gpc - 1) / gpc), dim3(32 * wpc), smem, st,
                      *b, ua, ta, slice, flags, sc);
     if (e != cudaSuccess) return LUX_E_CUDA;
     g_launches++;
@@ -245,9 +246,10 @@ template <bool kTma, int kS, int kMode, int G>
 static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, int slice, unsigned flags, const LuxSched& sc,
                        int n_groups, int wpc, cudaStream_t st) {
     if constexpr (kTma && G == 32) {
-        if (flags == 0) return launch_step_plain<kTma, kS, kMode, G, true>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
+        if (flags == 0) return launch_step_plain<kTma, kS, kMode, G, 1>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
+        if (flags == LUX_STEP_CONSUME) return launch_step_plain<kTma, kS, kMode, G, 2>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
     }
-    return launch_step_plain<kTma, kS, kMode, G, false>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
+    return launch_step_plain<kTma, kS, kMode, G, 0>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
 }
 
 template <bool kTma, int kMode, int G>
@@ -611,6 +613,7 @@ struct StepScratch {
     uint8_t* done_pinned;        // mapped pinned: compact done flags for the host path, followed by
     int* summary_pinned;         // [0] max n_units, [1] max n_tiles, [2] live matches, [3] finished
     int* summary_acc;            // device accumulators of the summary kernel (+ its CTA ticket)
+    int seq;                     // sequence number of the last submitted host call (published behind its results)
     unsigned step;
 };
 static StepScratch g_scratch[8];
@@ -811,7 +814,8 @@ __global__ void lux_apply_entries_kernel(LuxBatch b, const uint2* __restrict__ e
 // done flags and the 4-int summary straight into mapped pinned host memory: every thread packs the flags of
 // four matches into one word (coalesced 128-byte rows over the bus), CTAs accumulate into device scratch and
 // the last one to finish publishes the summary and clears the scratch for the next call.
-__global__ void lux_summary_kernel(LuxBatch b, uint32_t* __restrict__ done4, int* __restrict__ summary, int* __restrict__ acc) {
+__global__ void lux_summary_kernel(LuxBatch b, uint32_t* __restrict__ done4, int* __restrict__ summary, int* __restrict__ acc,
+                                   int seq) {
     LUX_PDL_TRIGGER();
     LUX_PDL_WAIT();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;      // matches 4q .. 4q+3
@@ -840,14 +844,20 @@ __global__ void lux_summary_kernel(LuxBatch b, uint32_t* __restrict__ done4, int
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        __threadfence_system();          // this CTA's flag words (mapped host memory) before its ticket
         last = atomicAdd(acc + 4, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x < 5) {
-        __threadfence();
-        if (threadIdx.x < 4) summary[threadIdx.x] = atomicExch(acc + threadIdx.x, 0);
-        else acc[4] = 0;
+    if (last) {
+        if (threadIdx.x < 5) {
+            __threadfence();
+            if (threadIdx.x < 4) summary[threadIdx.x] = atomicExch(acc + threadIdx.x, 0);
+            else acc[4] = 0;
+        }
+        __syncthreads();
+        // the call's sequence number goes out last: a host that polls it (lux_b200_step_host_wait) then finds
+        // every flag word and the summary in place
+        if (threadIdx.x == 0) { __threadfence_system(); *(volatile int*)(summary + 4) = seq; }
     }
 }
 
@@ -856,9 +866,8 @@ __global__ void lux_summary_kernel(LuxBatch b, uint32_t* __restrict__ done4, int
 // not written by anything else: the step consumes the words it plays), the step runs, and done flags
 // (n bytes) + a 4-int summary come back through mapped pinned memory.  Per step this moves 8*k bytes up
 // and n + 16 bytes down instead of dense action tensors and full headers: four launches and one copy.
-extern "C" int lux_b200_step_host_sparse(const LuxBatch* b, const void* entries_host, int k, uint32_t* unit_actions_dev,
-                                         uint8_t* tile_actions_dev, uint8_t* done_host, int32_t* summary_host,
-                                         uint32_t flags, void* cuda_stream) {
+extern "C" int lux_b200_step_host_sparse_submit(const LuxBatch* b, const void* entries_host, int k, uint32_t* unit_actions_dev,
+                                                uint8_t* tile_actions_dev, uint32_t flags, void* cuda_stream) {
     int rc = check_batch(b);
     if (rc) return rc;
     if (k < 0 || (k > 0 && !entries_host) || !unit_actions_dev || !tile_actions_dev) return LUX_E_ARG;
@@ -870,6 +879,8 @@ extern "C" int lux_b200_step_host_sparse(const LuxBatch* b, const void* entries_
     if (!S->done_pinned) {
         if (cudaHostAlloc(&S->done_pinned, (size_t)b->n_matches + 64, cudaHostAllocMapped) != cudaSuccess) return LUX_E_CUDA;
         S->summary_pinned = (int*)(S->done_pinned + (((size_t)b->n_matches + 15) & ~(size_t)15));
+        S->summary_pinned[4] = 0;
+        S->seq = 0;
         if (cudaMalloc(&S->summary_acc, 8 * sizeof(int)) != cudaSuccess) return LUX_E_CUDA;
         if (cudaMemsetAsync(S->summary_acc, 0, 8 * sizeof(int), st) != cudaSuccess) return LUX_E_CUDA;
     }
@@ -891,14 +902,49 @@ extern "C" int lux_b200_step_host_sparse(const LuxBatch* b, const void* entries_
     }
     rc = lux_step_impl(b, unit_actions_dev, tile_actions_dev, (flags & 0xFFFFu) | LUX_STEP_CONSUME, cuda_stream);
     if (rc) return rc;
+    S->seq = S->seq == 0x7fffffff ? 1 : S->seq + 1;
     lux_launch_chain(lux_summary_kernel, dim3((b->n_matches + 1023) / 1024), dim3(256), 0, st, *b, (uint32_t*)S->done_pinned,
-                     S->summary_pinned, S->summary_acc);
+                     S->summary_pinned, S->summary_acc, S->seq);
     g_launches++;
-    rc = cuda_ok(cudaStreamSynchronize(st), "step sync");
+    return cuda_ok(cudaGetLastError(), "lux_summary_kernel launch");
+}
+
+extern "C" int lux_b200_step_host_wait(const LuxBatch* b, uint8_t* done_host, int32_t* summary_host, void* cuda_stream) {
+    int rc = check_batch(b);
     if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    StepScratch* S = scratch_get(b, st);
+    if (!S) return LUX_E_CUDA;
+    if (!S->done_pinned || S->seq == 0) return LUX_E_ARG;          // nothing was submitted for this batch
+    // The summary kernel publishes the call's sequence number behind its results in mapped host memory: spin on
+    // it (a few microseconds sooner than the stream's completion reaches a blocked host thread), and fall back to
+    // the stream when it does not show up (a fault in the chain surfaces there).
+    const volatile int* seq = (const volatile int*)(S->summary_pinned + 4);
+    bool seen = false;
+    for (long spin = 0; spin < 4000000L; spin++) {
+        if (__atomic_load_n(seq, __ATOMIC_ACQUIRE) == S->seq) { seen = true; break; }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (!seen) {
+        rc = cuda_ok(cudaStreamSynchronize(st), "step sync");
+        if (rc) return rc;
+    }
     if (done_host) memcpy(done_host, S->done_pinned, (size_t)b->n_matches);
     if (summary_host) memcpy(summary_host, S->summary_pinned, 4 * sizeof(int));
     return LUX_OK;
+}
+
+extern "C" int lux_b200_step_host_sparse(const LuxBatch* b, const void* entries_host, int k, uint32_t* unit_actions_dev,
+                                         uint8_t* tile_actions_dev, uint8_t* done_host, int32_t* summary_host,
+                                         uint32_t flags, void* cuda_stream) {
+    int rc = lux_b200_step_host_sparse_submit(b, entries_host, k, unit_actions_dev, tile_actions_dev, flags, cuda_stream);
+    if (rc) return rc;
+    rc = lux_b200_step_host_wait(b, done_host, summary_host, cuda_stream);
+    if (rc) return rc;
+    // this form promises a quiet stream on return
+    return cuda_ok(cudaStreamSynchronize((cudaStream_t)cuda_stream), "step sync");
 }
 
 extern "C" int lux_b200_gen_actions(const LuxBatch* b, uint64_t seed, uint64_t match_id_base,

@@ -250,6 +250,49 @@ def test_step_host_sparse_matches_device_step():
         assert torch.equal(a.sections()[k], b.sections()[k]), k
 
 
+def test_step_host_submit_wait_with_work_queued_behind():
+    """The two-call form of the host list path: submit, queue pool resets behind it, wait -- flags and summary
+    describe the state right after the step (before the resets), and the batch ends equal to the device path's
+    step + reset.  32x32 without pre-validation: the consume-only specialisation of the small / big classes."""
+    size, n = 32, 512
+    a, b = _game(n, size), _game(n, size)
+    arr = mapgen.generate_batch(np.arange(5000, 5000 + n), size)
+    pool = _game(16, size)
+    pool.load_arrays(mapgen.generate_batch(np.arange(77, 93), size))
+    for g in (a, b):
+        g.load_arrays(arr)
+        g.hdr[::3, 0:4] = torch.tensor([94, 1, 0, 0], dtype=torch.uint8, device=g.device)   # turn 350: these end within ten turns
+    lib = _lib.load()
+    import ctypes
+    assert lib.lux_b200_step_host_wait(ctypes.byref(b._desc), None, None, None) == _lib.LUX_E_ARG     # nothing submitted
+    ent_h = torch.zeros((n * 64 + 8, 2), dtype=torch.int32).pin_memory()
+    done_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    summ_h = torch.zeros(4, dtype=torch.int32).pin_memory()
+    ra = torch.zeros(1, dtype=torch.int32, device=a.device)
+    rb = torch.zeros(1, dtype=torch.int32, device=a.device)
+    for turn in range(120):
+        a.unit_actions.zero_()
+        a.tile_actions.zero_()
+        a.gen_actions(23, 0)
+        ent = a.pack_entries()
+        k = ent.shape[0]
+        ent_h[:k].copy_(ent)
+        a.step()
+        hh = a.headers()
+        b.step_host_sparse_submit(ent_h, k)
+        b.reset_done(pool, turn, rb)                 # queued behind the step, before the host blocks
+        b.step_host_wait(done_h, summ_h)
+        assert np.array_equal(done_h.numpy(), hh["done"]), turn
+        assert summ_h.tolist() == [int(hh["n_units"].max()), int(hh["n_tiles"].max()), int((hh["done"] == 0).sum()),
+                                   int((hh["done"] != 0).sum())], turn
+        a.reset_done(pool, turn, ra)
+        torch.cuda.synchronize()
+        assert torch.equal(b.hdr, a.hdr), turn
+    assert int(ra.item()) == int(rb.item()) and int(ra.item()) > 0
+    for k in a.sections():
+        assert torch.equal(a.sections()[k], b.sections()[k]), k
+
+
 def test_bad_arguments_are_rejected():
     import ctypes
     lib = _lib.load()
