@@ -143,6 +143,14 @@ int lux_b200_device_count(void);
  * Returns LUX_E_ARG for an unknown name. */
 int lux_b200_set_option(const char* name, int value);
 
+/*
+ * Measurement aid (not part of the reference's interface): after lux_b200_set_option("trace", 1) every launch of
+ * a two-class step stamps its first start and last end (%globaltimer, ns) into a device buffer; this call
+ * synchronises the device and copies the eight stamps out: [0,1] big-class launch, [4,5] small-class launch,
+ * [6,7] classification pass (~0 / 0 where a launch did not run).  scripts/trace_step.py prints the timeline.
+ */
+int lux_b200_debug_trace(unsigned long long* out8);
+
 /* Number of kernels the step / gen_actions / reset_done / stats entry points have launched so far. */
 unsigned long long lux_b200_launch_count(void);
 

@@ -18,7 +18,7 @@ _ERR = {LUX_E_ARG: "bad argument", LUX_E_CAPACITY: "capacity out of range",
 EXPORTS = ("lux_b200_version", "lux_b200_device_count", "lux_b200_set_option", "lux_b200_step_smem_bytes",
            "lux_b200_step", "lux_b200_step_host", "lux_b200_gen_actions", "lux_b200_observe",
            "lux_b200_reset_done", "lux_b200_stats", "lux_b200_encode_actions", "lux_b200_reward", "lux_b200_launch_count", "lux_b200_step_host_sparse", "lux_b200_step_host_sparse_submit", "lux_b200_step_host_wait",
-           "lux_b200_reset_gen", "lux_b200_reset_done_dev", "lux_b200_observe_offsets", "lux_b200_env_finish")
+           "lux_b200_debug_trace", "lux_b200_reset_gen", "lux_b200_reset_done_dev", "lux_b200_observe_offsets", "lux_b200_env_finish")
 
 
 class LuxError(RuntimeError):

@@ -127,6 +127,17 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
     if (valid && result == LUX_M_SPILL && lane == 0) atomicOr((unsigned*)&g.hdr->done, (unsigned)LUX_ST_BAD_STATE << 16);   // done | winner | status | size
 }
 
+// Measurement aid: with set_option("trace", 1) every launch of a step stamps its first start and last end
+// (%globaltimer) into a small device buffer, read back with lux_b200_debug_trace; scripts/trace_step.py prints the
+// timeline of a step (which class is the long pole, how far the two overlap).
+__device__ __forceinline__ unsigned long long lux_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define LUX_TRACE_BEGIN(tr, slot) do { if ((tr) && (threadIdx.x & 31) == 0) atomicMin((tr) + 2 * (slot), lux_globaltimer()); } while (0)
+#define LUX_TRACE_END(tr, slot) do { if ((tr) && (threadIdx.x & 31) == 0) atomicMax((tr) + 2 * (slot) + 1, lux_globaltimer()); } while (0)
+
 // Classification of one step (device pointers, owned by the library, see StepScratch below).
 #define LUX_N_CAND 4     // candidate slice sizes the classification pass keeps statistics for
 struct LuxSched {
@@ -135,11 +146,13 @@ struct LuxSched {
     int* zero;                        // the previous step's counters: trailed to the host, then cleared for reuse
     int* seen_host;                   // pinned, mapped host words
     int cand[LUX_N_CAND];             // big_cnt[1 + i] += matches whose need exceeds cand[i]
+    unsigned long long* trace;        // measurement aid (option "trace"): first start / last end (globaltimer, ns) per launch kind
 };
 
 __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
     LUX_PDL_TRIGGER();
     LUX_PDL_WAIT();
+    LUX_TRACE_BEGIN(sc.trace, 3);
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     // the previous step's statistics go to the host (stale values only delay its choice of slice), then clear
     if (m <= LUX_N_CAND) { sc.seen_host[m] = sc.zero[m]; sc.zero[m] = 0; }
@@ -156,6 +169,7 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
         unsigned over = __ballot_sync(0xffffffffu, total > sc.cand[i]);
         if ((threadIdx.x & 31) == 0 && over) atomicAdd(sc.big_cnt + 1 + i, __popc(over));
     }
+    LUX_TRACE_END(sc.trace, 3);
 }
 
 // kSpec: 1 = compiled for flags == 0 (no pre-validation, no consumed action words): the common device call;
@@ -192,6 +206,7 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
     lux_sync<G>();
     if (kMode == kList) {
         const int count = *sc.big_cnt;
+        LUX_TRACE_BEGIN(sc.trace, 0);
         for (int idx = blockIdx.x * gpc + grp; lux_wany<G>(idx < count); idx += gridDim.x * gpc) {
             const int valid = idx < count;
             lux_step_match<kTma, kS, G>(b, valid ? sc.big_list[idx] : 0, valid, unit_actions, tile_actions, smem, flags, slice, phase);
@@ -199,13 +214,16 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
             // the slice was written with generic stores; the next match's bulk copies (async proxy) land in it
             if (kTma && lane == 0) fence_proxy_async();
         }
+        LUX_TRACE_END(sc.trace, 0);
         return;
     }
     const int m = blockIdx.x * gpc + grp;
     int valid = m < b.n_matches;
     if (kMode == kSmall && valid && __ldcg(sc.cls + m)) valid = 0;          // the big class plays it
+    LUX_TRACE_BEGIN(sc.trace, 2);
     if (lux_wany<G>(valid))
         lux_step_match<kTma, kS, G>(b, m, valid, unit_actions, tile_actions, smem, flags, slice, phase);
+    LUX_TRACE_END(sc.trace, 2);
     // a programmatic dependent may not finish before its primary: later work on the stream waits for this grid
     if (kMode == kSmall) LUX_PDL_WAIT();
 }
@@ -217,6 +235,8 @@ static int g_gen_wpc = 8;         // warps (matches) per CTA of the action-strea
 static int g_list_grid = 0;       // CTAs of the big-class launch (0 = automatic)
 static int g_overlap = 1;         // 1 = programmatic dependent launches: the two step classes overlap, launch gaps hide
 extern "C" int lux_b200_overlap_enabled(void) { return g_overlap; }
+static unsigned long long* g_trace = nullptr;   // device buffer of 8 timestamps (option "trace" allocates it)
+static int g_only_class = 0;      // measurement aid: 1 = launch only the big class, 2 = only the small class (results are then incomplete)
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
 
@@ -597,6 +617,12 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "group")) { g_group = value; return LUX_OK; }
     if (!strcmp(name, "carveout")) { g_carveout = value > 100 ? 100 : value; return LUX_OK; }
     if (!strcmp(name, "slice")) { g_slice = value; return LUX_OK; }
+    if (!strcmp(name, "only_class")) { g_only_class = value; return LUX_OK; }
+    if (!strcmp(name, "trace")) {
+        if (value && !g_trace && cudaMalloc(&g_trace, 8 * sizeof(unsigned long long)) != cudaSuccess) return LUX_E_CUDA;
+        if (!value && g_trace) { cudaFree(g_trace); g_trace = nullptr; }
+        return LUX_OK;
+    }
     return LUX_E_ARG;
 }
 
@@ -736,6 +762,11 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     sc.cls = S->cls;
     sc.zero = S->counts + ((t + 2) % 3) * (1 + LUX_N_CAND);
     sc.seen_host = S->seen;
+    sc.trace = g_trace;
+    if (g_trace) {
+        static const unsigned long long init[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+        cudaMemcpyAsync(g_trace, init, sizeof init, cudaMemcpyHostToDevice, st);
+    }
     for (int i = 0; i < LUX_N_CAND; i++) sc.cand[i] = cand[i];
     lux_launch_chain(lux_classify_kernel, dim3((b->n_matches + 255) / 256), dim3(256), 0, st, *b, small, sc);
     g_launches++;
@@ -745,8 +776,9 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     int grid_l = b->n_matches / 4 > 148 * 4 ? b->n_matches / 4 : 148 * 4;
     if (g_list_grid > 0) grid_l = g_list_grid;
     if (grid_l > b->n_matches) grid_l = b->n_matches;
-    rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, full, flags, sc, grid_l, 1, st);
+    if (g_only_class != 2) rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, full, flags, sc, grid_l, 1, st);
     if (rc) return rc;
+    if (g_only_class == 1) return LUX_OK;
     rc = cuda_ok(cudaGetLastError(), "lux_step_kernel (big class) launch");
     if (rc) return rc;
     int group = pick_group(small);
@@ -1028,4 +1060,13 @@ extern "C" int lux_b200_stats(const LuxBatch* b, int64_t* out16, void* cuda_stre
     lux_launch_chain(lux_stats_kernel, dim3((b->n_matches + 127) / 128), dim3(128), 0, st, *b, (unsigned long long*)out16);
     g_launches++;
     return cuda_ok(cudaGetLastError(), "lux_stats_kernel launch");
+}
+
+// measurement aid: {first start, last end} in ns (%globaltimer) of the last two-class step's big-class launch [0,1],
+// small-class launch [4,5] and classification pass [6,7] (~0 / 0 where a launch did not run); needs
+// set_option("trace", 1); synchronises the device
+extern "C" int lux_b200_debug_trace(unsigned long long* out8) {
+    if (!out8 || !g_trace) return LUX_E_ARG;
+    if (cudaDeviceSynchronize() != cudaSuccess) return LUX_E_CUDA;
+    return cudaMemcpy(out8, g_trace, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? LUX_OK : LUX_E_CUDA;
 }

@@ -634,7 +634,7 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
 // and hdr.done == 0.  On exit the grid holds the post-turn cells, shared memory the post-turn
 // header / cities (uncompacted) / units (uncompacted, ust says who died); lux_finish_and_store
 // compacts while writing.
-struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; int alive0; int alive1; };
+struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; int alive0; int alive1; int tt0; int tt1; };
 
 // utgt[u]: [9:0] target cell of the unit's validated move (own cell otherwise), bit 14 = the target is a city tile
 #define UTGT_TILE 0x4000u
@@ -1094,13 +1094,18 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
 
     // ---- resource collection: uranium, coal, wood (distribute_all_resources game.py:868-880)
     {
-        int rp0 = h->research[0], rp1 = h->research[1];
+        const int rp0 = h->research[0], rp1 = h->research[1];
+        // the passes worth running: a team has researched the type AND some worker stands next to a cell of it
+        // (otherwise the pass finds no request: every umine = none, nothing marked, nothing gained)
+        unsigned run = minable & ((1u << LUX_RES_WOOD) | ((rp0 >= LUX_RESEARCH_COAL || rp1 >= LUX_RESEARCH_COAL) ? 1u << LUX_RES_COAL : 0u) |
+                                  ((rp0 >= LUX_RESEARCH_URANIUM || rp1 >= LUX_RESEARCH_URANIUM) ? 1u << LUX_RES_URANIUM : 0u));
+        if (G != 32)     // the groups of a warp walk through the union of their passes
+            run = (lux_any_warp(run & 2u) ? 2u : 0u) | (lux_any_warp(run & 4u) ? 4u : 0u) | (lux_any_warp(run & 8u) ? 8u : 0u);
 #pragma unroll 1
-        for (int rtype = LUX_RES_URANIUM; rtype >= LUX_RES_WOOD; rtype--) {
-            int need = rtype == LUX_RES_WOOD ? 0 : rtype == LUX_RES_COAL ? LUX_RESEARCH_COAL : LUX_RESEARCH_URANIUM;
-            // nobody in the warp may mine this type yet, or no worker stands next to a cell of it: the pass would
-            // find no request (every umine = none, nothing marked, nothing gained)
-            if (!lux_wany<G>((rp0 >= need || rp1 >= need) && ((minable >> rtype) & 1u))) continue;
+        while (run) {
+            const int rtype = (run & 8u) ? LUX_RES_URANIUM : (run & 4u) ? LUX_RES_COAL : LUX_RES_WOOD;
+            run &= ~(1u << rtype);
+            const int need = rtype == LUX_RES_WOOD ? 0 : rtype == LUX_RES_COAL ? LUX_RESEARCH_COAL : LUX_RESEARCH_URANIUM;
             lux_collect_type<kS, G>(M, rtype, n_units, rp0 >= need, rp1 >= need, stacked);
         }
     }
@@ -1226,6 +1231,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     LuxTurnOut out;
     out.n_units = n_units; out.n_cities = n_cities; out.n_tiles = n_tiles; out.tiles_dirty = tiles_dirty;
     out.alive0 = tu0 + born0 - died0; out.alive1 = tu1 + born1 - died1;
+    out.tt0 = tt0; out.tt1 = tt1;
     return out;
 }
 
@@ -1241,8 +1247,14 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
 
     // the resource list goes back as it stands (amount mirrors)
     if (active) lux_copy16<G>(g_res, M.res, h->n_res * 4);
-    // cities: drop the dead (ntiles == 0), keep order
-    int n_alive = 0, nc0 = 0, nc1 = 0, tl0 = 0, tl1 = 0;
+    // Cities.  The common turn neither founds, merges nor loses a city tile (tiles_dirty == 0: the tile list did not
+    // grow and no city fell): the cities go back as they stand and the per-team tile counts are the turn's opening
+    // ones.  Otherwise: drop the dead (ntiles == 0), keep order, rebuild the canonical tile list.
+    int n_alive = T.n_cities, tl0 = T.tt0, tl1 = T.tt1;
+    if (!lux_wany<G>(T.tiles_dirty)) {
+        if (active) lux_copy16<G>(g_cities, M.cities, T.n_cities * 16);
+    } else {
+    n_alive = 0; tl0 = 0; tl1 = 0;
     const int nc_max = lux_wmax<G>(T.n_cities);
 #pragma unroll 1
     for (int base = 0; base < nc_max; base += G) {
@@ -1251,13 +1263,11 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
         unsigned m = lux_ballot<G>(alive);
         if (s < T.n_cities) M.cremap[s] = (uint8_t)(alive ? n_alive + lux_popc(m & lt) : 0xFF);
         n_alive += lux_popc(m);
-        int team = alive ? M.cities[s].team : 0;
-        nc0 += alive && team == 0; nc1 += alive && team == 1;
-        if (alive) { if (team) tl1 += M.cities[s].ntiles; else tl0 += M.cities[s].ntiles; }
+        if (alive) { if (M.cities[s].team) tl1 += M.cities[s].ntiles; else tl0 += M.cities[s].ntiles; }
     }
-    {   // two reductions instead of four (cities <= 255, tiles <= 1024 per team)
-        unsigned pc = (unsigned)lux_reduce_add<G>(nc0 | (nc1 << 16)), pt = (unsigned)lux_reduce_add<G>(tl0 | (tl1 << 16));
-        nc0 = (int)(pc & 0xFFFFu); nc1 = (int)(pc >> 16); tl0 = (int)(pt & 0xFFFFu); tl1 = (int)(pt >> 16);
+    {   // one reduction (tiles <= 1024 per team)
+        unsigned pt = (unsigned)lux_reduce_add<G>(tl0 | (tl1 << 16));
+        tl0 = (int)(pt & 0xFFFFu); tl1 = (int)(pt >> 16);
     }
     lux_sync<G>();
     const int cities_moved = n_alive != T.n_cities;
@@ -1269,7 +1279,6 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
     }
     // canonical tile list: position = prefix[new slot] + key; surviving tiles of moved cities get their
     // new slot written into the grid in the same pass
-    int n_tiles_live = tl0 + tl1;
     const int relist = T.tiles_dirty || cities_moved;
     if (lux_wany<G>(relist)) {
         const int nt_r = relist ? T.n_tiles : 0;
@@ -1295,10 +1304,13 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
             }
         }
     }
+    }
+    const int n_tiles_live = tl0 + tl1;
 
     // match_over (game.py:570-592) is evaluated before the turn counter moves (:515-517)
     const int alive0 = T.alive0, alive1 = T.alive1;    // start-of-turn counts + spawns - night deaths
-    int over = h->turn >= LUX_MAX_DAYS - 1 || (alive0 + nc0 == 0) || (alive1 + nc1 == 0);
+    // (a team holds a city exactly when it holds a city tile)
+    int over = h->turn >= LUX_MAX_DAYS - 1 || (alive0 + tl0 == 0) || (alive1 + tl1 == 0);
 
     // run_cooldowns (game.py:560-568) and the stable partition team A | team B while storing
     int run0 = 0, run1 = 0;

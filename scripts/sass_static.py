@@ -2,7 +2,7 @@
   python scripts/sass_static.py [kernel-substring]       default: the 32x32 small-class plain kernel
 Extracts the cubins of luxpythonenvgym_b200/_lux_b200.so and reads nvdisasm -g line annotations."""
 import collections, os, re, subprocess, sys, tempfile
-kern = sys.argv[1] if len(sys.argv) > 1 else "lux_step_kernelILb1ELi32ELi1ELi32ELb1E"
+kern = sys.argv[1] if len(sys.argv) > 1 else "lux_step_kernelILb1ELi32ELi1ELi32ELi1E"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "luxpythonenvgym_b200", "_lux_b200.so")], cwd=tmp, capture_output=True)
