@@ -146,8 +146,9 @@ int lux_b200_set_option(const char* name, int value);
 /*
  * Measurement aid (not part of the reference's interface): after lux_b200_set_option("trace", 1) every launch of
  * a two-class step stamps its first start and last end (%globaltimer, ns) into a device buffer; this call
- * synchronises the device and copies the eight stamps out: [0,1] big-class launch, [4,5] small-class launch,
- * [6,7] classification pass (~0 / 0 where a launch did not run).  scripts/trace_step.py prints the timeline.
+ * synchronises the device and copies 40 words out: stamps [0,1] big-class launch, [4,5] small-class launch, [6,7]
+ * classification pass (~0 / 0 where a launch did not run), then two histograms in 8 us bins from the start of the
+ * classification pass: [8..23] small-class warps starting, [24..39] big-class warps ending.  scripts/trace_step.py prints the timeline.
  */
 int lux_b200_debug_trace(unsigned long long* out8);
 

@@ -25,10 +25,15 @@
 //   classify : one thread per match reads the header, marks the matches whose turn does not fit the small
 //              slice (cls[m] = 1) and appends them to the big list;
 //   kList    : the big list, slices sized for the full capacities, grid-stride over the list;
-//   kSmall   : every other match, `slice` bytes each (default 4.5 KB: 32 resident matches leave room for the
-//              L1 cache the in-place grid accesses run through).  Launched as a programmatic dependent of
-//              kList (griddepcontrol), so the two run CONCURRENTLY: a dense match is a long single-warp job
-//              (30-45 us) and as a separate serialized launch it added that much to every step.
+//   kSmall   : every other match, `slice` bytes each (default 5 KB: ~30 resident matches leave room for the
+//              L1 cache the in-place grid accesses run through).
+// A dense match is a long single-warp job (30-45 us alone, up to ~80 us beside a full machine), so the two classes
+// must run CONCURRENTLY, and HOW matters (scripts/trace_step.py): with the small class launched as a
+// programmatic dependent of the big class (round 1) the hardware started one wave of small CTAs and then hardly any
+// until the big grid had completed -- the small class took 96 us instead of the 68 us it needs alone.  Now the big
+// class runs as an independent grid on a high-priority side stream (event fork behind the classification pass, event
+// join behind the small class): the small class's CTAs flow continuously, the big matches take the slots they need as
+// soon as the first wave retires (step 0.099 -> 0.084 ms).  Option "fork" = 0 selects the dependent-launch form.
 // kAll is the single full-capacity launch (small maps, dense batches, the non-TMA path).
 enum { kAll = 0, kSmall = 1, kList = 2 };
 // internal step flag (upper half of `flags`; the public half is masked at the ABI): the kernel zeroes the
@@ -137,6 +142,11 @@ __device__ __forceinline__ unsigned long long lux_globaltimer() {
 }
 #define LUX_TRACE_BEGIN(tr, slot) do { if ((tr) && (threadIdx.x & 31) == 0) atomicMin((tr) + 2 * (slot), lux_globaltimer()); } while (0)
 #define LUX_TRACE_END(tr, slot) do { if ((tr) && (threadIdx.x & 31) == 0) atomicMax((tr) + 2 * (slot) + 1, lux_globaltimer()); } while (0)
+// histograms in 8 us bins relative to the classification pass's start: [8..23] warps of the small class STARTING,
+// [24..39] warps of the big class ENDING
+#define LUX_TRACE_BIN(tr, base) do { if ((tr) && (threadIdx.x & 31) == 0) { \
+    unsigned long long t0 = *(volatile unsigned long long*)((tr) + 6), t = lux_globaltimer(); \
+    unsigned long long k = t > t0 ? (t - t0) / 8000ull : 0ull; if (k > 15) k = 15; atomicAdd((tr) + (base) + k, 1ull); } } while (0)
 
 // Classification of one step (device pointers, owned by the library, see StepScratch below).
 #define LUX_N_CAND 4     // candidate slice sizes the classification pass keeps statistics for
@@ -146,6 +156,7 @@ struct LuxSched {
     int* zero;                        // the previous step's counters: trailed to the host, then cleared for reuse
     int* seen_host;                   // pinned, mapped host words
     int cand[LUX_N_CAND];             // big_cnt[1 + i] += matches whose need exceeds cand[i]
+    int wait_first;                   // small class launched right behind the classification pass (big class on a side stream): wait at the START
     unsigned long long* trace;        // measurement aid (option "trace"): first start / last end (globaltimer, ns) per launch kind
 };
 
@@ -184,7 +195,7 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
     // the big class needs the classification pass complete; after that the small class may start while this
     // class is still running (the two touch disjoint matches).  The small class itself only lets its successor
     // in early and waits for the big class at its END.
-    if (kMode == kList) LUX_PDL_WAIT();
+    if (kMode == kList || (kMode == kSmall && sc.wait_first)) LUX_PDL_WAIT();
     if (kMode != kAll) LUX_PDL_TRIGGER();
     if (kMode == kAll) { LUX_PDL_TRIGGER(); LUX_PDL_WAIT(); }
     // a group of G lanes plays one match; 32 / G matches share a warp
@@ -215,17 +226,19 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
             if (kTma && lane == 0) fence_proxy_async();
         }
         LUX_TRACE_END(sc.trace, 0);
+        LUX_TRACE_BIN(sc.trace, 24);
         return;
     }
     const int m = blockIdx.x * gpc + grp;
     int valid = m < b.n_matches;
     if (kMode == kSmall && valid && __ldcg(sc.cls + m)) valid = 0;          // the big class plays it
     LUX_TRACE_BEGIN(sc.trace, 2);
+    LUX_TRACE_BIN(sc.trace, 8);
     if (lux_wany<G>(valid))
         lux_step_match<kTma, kS, G>(b, m, valid, unit_actions, tile_actions, smem, flags, slice, phase);
     LUX_TRACE_END(sc.trace, 2);
     // a programmatic dependent may not finish before its primary: later work on the stream waits for this grid
-    if (kMode == kSmall) LUX_PDL_WAIT();
+    if (kMode == kSmall && !sc.wait_first) LUX_PDL_WAIT();
 }
 
 // kernels this library has launched (all entry points of this translation unit); bench.py reports the
@@ -236,6 +249,7 @@ static int g_list_grid = 0;       // CTAs of the big-class launch (0 = automatic
 static int g_overlap = 1;         // 1 = programmatic dependent launches: the two step classes overlap, launch gaps hide
 extern "C" int lux_b200_overlap_enabled(void) { return g_overlap; }
 static unsigned long long* g_trace = nullptr;   // device buffer of 8 timestamps (option "trace" allocates it)
+static int g_fork = 1;            // 1: the big class runs on a high-priority side stream as an independent grid (event fork / join); 0: as the small class's programmatic primary
 static int g_only_class = 0;      // measurement aid: 1 = launch only the big class, 2 = only the small class (results are then incomplete)
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
@@ -618,8 +632,9 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "carveout")) { g_carveout = value > 100 ? 100 : value; return LUX_OK; }
     if (!strcmp(name, "slice")) { g_slice = value; return LUX_OK; }
     if (!strcmp(name, "only_class")) { g_only_class = value; return LUX_OK; }
+    if (!strcmp(name, "fork")) { g_fork = value != 0; return LUX_OK; }
     if (!strcmp(name, "trace")) {
-        if (value && !g_trace && cudaMalloc(&g_trace, 8 * sizeof(unsigned long long)) != cudaSuccess) return LUX_E_CUDA;
+        if (value && !g_trace && cudaMalloc(&g_trace, 40 * sizeof(unsigned long long)) != cudaSuccess) return LUX_E_CUDA;
         if (!value && g_trace) { cudaFree(g_trace); g_trace = nullptr; }
         return LUX_OK;
     }
@@ -641,6 +656,8 @@ struct StepScratch {
     int* summary_acc;            // device accumulators of the summary kernel (+ its CTA ticket)
     int seq;                     // sequence number of the last submitted host call (published behind its results)
     unsigned step;
+    cudaStream_t side;           // the big class's stream when the two classes run as independent grids ("fork")
+    cudaEvent_t ev_fork, ev_join;
 };
 static StepScratch g_scratch[8];
 static unsigned g_scratch_clock = 0;
@@ -653,6 +670,7 @@ static void scratch_free(StepScratch& s) {
     if (s.entries) cudaFree(s.entries);
     if (s.done_pinned) cudaFreeHost(s.done_pinned);
     if (s.summary_acc) cudaFree(s.summary_acc);
+    if (s.side) { cudaStreamDestroy(s.side); cudaEventDestroy(s.ev_fork); cudaEventDestroy(s.ev_join); }
     memset(&s, 0, sizeof s);
 }
 
@@ -719,10 +737,10 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
 
     // The small class: every match whose turn fits `small` bytes (the empty-match floor is planes + header).
     // Automatic choice: the smallest candidate slice that at most 1/12 of the batch exceeded a step or two ago
-    // (sparse batches: 4.5 KB; dense late-game batches: 8-12 KB), the single full-capacity launch when even the
+    // (sparse batches: 5 KB; dense late-game batches: 8-12 KB), the single full-capacity launch when even the
     // largest candidate leaves most of the batch to the big class.
     const int floor_bytes = lux_smem_layout_need(b->size, lux_need_none(b->u_cap, b->c_cap, b->t_cap, b->r_cap)).total;
-    const int cand[LUX_N_CAND] = {4608, 6144, 8192, 12288};
+    const int cand[LUX_N_CAND] = {5120, 6144, 8192, 12288};
     bool two = g_two_class != 0 && (g_two_class == 1 || cand[0] * 2 <= full);
     StepScratch* S = two ? scratch_get(b, st) : nullptr;
     if (two && !S) return LUX_E_CUDA;
@@ -764,7 +782,7 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     sc.seen_host = S->seen;
     sc.trace = g_trace;
     if (g_trace) {
-        static const unsigned long long init[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+        static const unsigned long long init[40] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
         cudaMemcpyAsync(g_trace, init, sizeof init, cudaMemcpyHostToDevice, st);
     }
     for (int i = 0; i < LUX_N_CAND; i++) sc.cand[i] = cand[i];
@@ -776,6 +794,27 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     int grid_l = b->n_matches / 4 > 148 * 4 ? b->n_matches / 4 : 148 * 4;
     if (g_list_grid > 0) grid_l = g_list_grid;
     if (grid_l > b->n_matches) grid_l = b->n_matches;
+    if (g_fork && g_only_class == 0) {
+        if (!S->side) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);           // hi = the numerically lowest = greatest priority
+            if (cudaStreamCreateWithPriority(&S->side, cudaStreamNonBlocking, hi) != cudaSuccess) return LUX_E_CUDA;
+            cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming);
+        }
+        cudaEventRecord(S->ev_fork, st);                      // behind the classification pass
+        cudaStreamWaitEvent(S->side, S->ev_fork, 0);
+        rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, full, flags, sc, grid_l, 1, S->side);
+        if (rc) return rc;
+        LuxSched ss = sc;
+        ss.wait_first = 1;
+        int group = pick_group(small);
+        rc = launch_step_group<true, kSmall>(group, b, unit_actions, tile_actions, small, flags, ss, b->n_matches, pick_wpc(small, group), st);
+        if (rc) return rc;
+        cudaEventRecord(S->ev_join, S->side);
+        cudaStreamWaitEvent(st, S->ev_join, 0);
+        return cuda_ok(cudaGetLastError(), "lux_step_kernel (forked classes) launch");
+    }
     if (g_only_class != 2) rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, full, flags, sc, grid_l, 1, st);
     if (rc) return rc;
     if (g_only_class == 1) return LUX_OK;
@@ -1065,8 +1104,8 @@ extern "C" int lux_b200_stats(const LuxBatch* b, int64_t* out16, void* cuda_stre
 // measurement aid: {first start, last end} in ns (%globaltimer) of the last two-class step's big-class launch [0,1],
 // small-class launch [4,5] and classification pass [6,7] (~0 / 0 where a launch did not run); needs
 // set_option("trace", 1); synchronises the device
-extern "C" int lux_b200_debug_trace(unsigned long long* out8) {
+extern "C" int lux_b200_debug_trace(unsigned long long* out8) {      // 40 words: 8 stamps + two 16-bin histograms
     if (!out8 || !g_trace) return LUX_E_ARG;
     if (cudaDeviceSynchronize() != cudaSuccess) return LUX_E_CUDA;
-    return cudaMemcpy(out8, g_trace, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? LUX_OK : LUX_E_CUDA;
+    return cudaMemcpy(out8, g_trace, 40 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? LUX_OK : LUX_E_CUDA;
 }

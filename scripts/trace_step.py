@@ -16,7 +16,7 @@ for t in range(400):
     game.step(); game.reset_gen(pool, t, 20211019, 0, reset_count=resets)
 torch.cuda.synchronize()
 lib.lux_b200_set_option(b"trace", 1)
-out = (ctypes.c_ulonglong * 8)()
+out = (ctypes.c_ulonglong * 40)()
 t = 400
 for spec in sys.argv[1:] or ["only_class=0"]:
     for kv in spec.split(","):
@@ -26,8 +26,10 @@ for spec in sys.argv[1:] or ["only_class=0"]:
         game.step()
         lib.lux_b200_debug_trace(out)
         v = list(out)
+        hist = v[8:40]
         game.reset_gen(pool, t, 20211019, 0, reset_count=resets); t += 1
         t0 = v[6]
         rows.append([(v[2 * i] - t0) / 1e3 if v[2 * i + 1] else float("nan") for i in (3, 0, 1, 2)] + [(v[2 * i + 1] - t0) / 1e3 if v[2 * i + 1] else float("nan") for i in (3, 0, 1, 2)])
     r = np.nanmedian(np.array(rows[2:]), axis=0)
+    print("   small-class warps starting per 8 us bin:", hist[:16], " big-class warps ending per bin:", hist[16:])
     print("%-40s classify %.1f-%.1f  big class %.1f-%.1f  small class %.1f-%.1f us" % (spec, r[0], r[4], r[1], r[5], r[3], r[7]))
