@@ -17,7 +17,7 @@ The field inventory follows the reference's state:
 luxai2021/game/game.py:85-147 (state/stats/id counters), cell.py:20-33, unit.py:15-35,
 city.py:15-66, game_map.py:53-58.  Cooldowns and road levels are multiples of 0.25 in
 the reference and are stored as integer quarter units.  `include/lux_b200.h` declares the
-same structs for C/CUDA; tests/test_layout.py checks the two agree.
+same structs for C/CUDA; tests/test_abi.py checks the two agree.
 """
 import numpy as np
 
