@@ -32,17 +32,20 @@ def _recap(ms, caps):
     return o
 
 
-@pytest.mark.parametrize("tma,two_class,overlap,group", [(1, -1, 1, 0), (1, 1, 0, 16), (1, 0, 1, 32), (1, 0, 0, 8),
-                                                          (1, 1, 1, 32), (1, 1, 1, 8), (0, -1, 1, 0)])
-def test_replays_bit_exact(tma, two_class, overlap, group):
+@pytest.mark.parametrize("tma,two_class,overlap,group,fork", [(1, -1, 1, 0, 1), (1, 1, 0, 16, 0), (1, 0, 1, 32, 1), (1, 0, 0, 8, 0),
+                                                               (1, 1, 1, 32, 1), (1, 1, 1, 32, 0), (1, 1, 1, 8, 0), (1, 1, 0, 32, 1),
+                                                               (0, -1, 1, 0, 1)])
+def test_replays_bit_exact(tma, two_class, overlap, group, fork):
     """The 7 Kaggle episodes of the reference's test_replay.py, 360 turns each, through every launch
-    path: TMA staging with the automatic / forced / disabled two-class launch, 8 / 16 / 32 lanes per match,
+    path: TMA staging with the automatic / forced / disabled two-class launch (the big class as an independent
+    grid on the side stream, fork = 1, or as the small class's programmatic primary), 8 / 16 / 32 lanes per match,
     and plain loads."""
     lib = _lib.load()
     lib.lux_b200_set_option(b"group", group)
     lib.lux_b200_set_option(b"tma", tma)
     lib.lux_b200_set_option(b"two_class", two_class)
     lib.lux_b200_set_option(b"overlap", overlap)
+    lib.lux_b200_set_option(b"fork", fork)
     try:
         z = G.npz("replays")
         for rid in G.replay_ids():
@@ -64,6 +67,7 @@ def test_replays_bit_exact(tma, two_class, overlap, group):
         lib.lux_b200_set_option(b"tma", 1)
         lib.lux_b200_set_option(b"two_class", -1)
         lib.lux_b200_set_option(b"overlap", 1)
+        lib.lux_b200_set_option(b"fork", 1)
 
 
 def test_random_and_dense_fixtures():
@@ -584,11 +588,13 @@ def test_spill_list_and_scheduling_paths_under_load():
     inits = [_recap(G.get_state(z, nm + "/init"), caps) for nm in names]
     sparse = mapgen.generate_batch(np.arange(4000, 4096), 32)
     try:
-        for heavy in (0, 1):          # overlap of the two classes off / on
-            for k, v in ((b"slice", 3200), (b"two_class", 1), (b"overlap", heavy),
-                         (b"group", 16 if heavy else 8)):
+        # heavy 0: serialized launches; 1: round 1's dependent-launch overlap; 2: the big class forked to the side
+        # stream (the default); 3: the same on a batch smaller than the machine (every CTA resident at once)
+        for heavy in (0, 1, 2, 3):
+            for k, v in ((b"slice", 3200), (b"two_class", 1), (b"overlap", int(heavy > 0)), (b"fork", int(heavy >= 2)),
+                         (b"group", (8, 16, 32, 32)[heavy])):
                 assert lib.lux_b200_set_option(k, v) == 0
-            n = 384
+            n = 384 if heavy < 3 else 120
             g = _game(n, 32)
             g.load_states([inits[i % len(inits)] for i in range(n - 96)])       # dense: spill
             g.load_arrays(sparse, first=n - 96)                                   # fresh maps: fit
@@ -615,6 +621,6 @@ def test_spill_list_and_scheduling_paths_under_load():
         for i, gm in enumerate(games):
             assert len(gpu_util.diff_batches(hosts[i], gm)) == 0, i
     finally:
-        for k, v in ((b"slice", 0), (b"two_class", -1), (b"overlap", 1),
+        for k, v in ((b"slice", 0), (b"two_class", -1), (b"overlap", 1), (b"fork", 1),
                      (b"group", 0)):
             lib.lux_b200_set_option(k, v)
