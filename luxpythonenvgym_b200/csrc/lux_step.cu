@@ -7,9 +7,12 @@
 // (lux_step_core.cuh), and the compacted unit / city / tile lists and the header are written back with
 // plain vector stores.  No CPU fallback exists: without a device the entry points return LUX_E_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+
+#include <mutex>
 
 #include "lux_step_core.cuh"
 #include "lux_tma.cuh"
@@ -44,9 +47,18 @@ enum { kAll = 0, kSmall = 1, kList = 2 };
 #define LUX_SMALL_MIN_CTAS 16      // 2-warp CTAs per SM the small-class kernel is compiled for: 64 registers (48 / 40 measured slower)
 #endif
 
+// A header the engine cannot play safely: live counts beyond the batch capacities (they size the bulk copies) or
+// per-team unit counts that do not add up (they place the compacted unit list).  Such a match is left untouched and
+// flagged LUX_ST_BAD_STATE; the classification pass checks it for the two-class step, lux_step_match for the single
+// launch.
+__device__ __forceinline__ bool lux_header_unplayable(const LuxHeader* h, int u_cap, int c_cap, int t_cap, int r_cap) {
+    return h->n_units > u_cap || h->n_cities > c_cap || h->n_tiles > t_cap || h->n_res > r_cap ||
+           (int)h->n_team_units[0] + (int)h->n_team_units[1] != (int)h->n_units;
+}
+
 // One lane group plays match `m` (or, with valid == 0, walks along on an empty match: the groups of a
 // warp run in lockstep and every collective needs all 32 lanes).
-template <bool kTma, int kS, int G>
+template <bool kTma, int kS, int G, bool kCheck = false>
 __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int valid, const uint32_t* __restrict__ unit_actions,
                                                const uint8_t* __restrict__ tile_actions, unsigned char* smem, unsigned flags,
                                                int slice, uint32_t& phase) {
@@ -80,6 +92,10 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
         lux_sync<G>();
         if (active) { mbar_wait(bar, phase); phase ^= 1; }
         if (active && sh->done) active = 0;
+        if (kCheck && active && lux_header_unplayable(sh, b.u_cap, b.c_cap, b.t_cap, b.r_cap)) {
+            active = 0;
+            if (lane == 0) atomicOr((unsigned*)&g.hdr->done, (unsigned)LUX_ST_BAD_STATE << 16);   // done | winner | status | size
+        }
         LuxNeed need = none;
         uint32_t nu = 0, nc = 0, nt = 0, nr = 0;
         if (active) {
@@ -129,7 +145,7 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
     LuxTurnOut T = lux_turn<kS, G>(M, flags & 0xFFFFu);
     lux_finish_and_store<kS, G>(M, T, g.hdr, g.units, g.cities, g.tiles, g.res, active);
     // cannot happen (the classification pass routes such a match to the big class); visible if it ever does
-    if (valid && result == LUX_M_SPILL && lane == 0) atomicOr((unsigned*)&g.hdr->done, (unsigned)LUX_ST_BAD_STATE << 16);   // done | winner | status | size
+    if (valid && (result == LUX_M_SPILL || result == LUX_M_BAD) && lane == 0) atomicOr((unsigned*)&g.hdr->done, (unsigned)LUX_ST_BAD_STATE << 16);   // done | winner | status | size
 }
 
 // Measurement aid: with set_option("trace", 1) every launch of a step stamps its first start and last end
@@ -169,10 +185,12 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
     if (m <= LUX_N_CAND) { sc.seen_host[m] = sc.zero[m]; sc.zero[m] = 0; }
     int total = 0;
     if (m < b.n_matches) {
-        const LuxHeader* h = b.hdr + m;
-        if (!h->done) total = lux_smem_layout_need(b.size, lux_need_header(h, b.u_cap, b.c_cap, b.t_cap, b.r_cap)).total;
+        LuxHeader* h = b.hdr + m;
+        const bool bad = !h->done && lux_header_unplayable(h, b.u_cap, b.c_cap, b.t_cap, b.r_cap);
+        if (bad) atomicOr((unsigned*)&h->done, (unsigned)LUX_ST_BAD_STATE << 16);           // done | winner | status | size
+        else if (!h->done) total = lux_smem_layout_need(b.size, lux_need_header(h, b.u_cap, b.c_cap, b.t_cap, b.r_cap)).total;
         const int big = total > slice;
-        sc.cls[m] = (uint8_t)big;
+        sc.cls[m] = (uint8_t)(bad ? 2 : big);       // 2: neither class plays it
         if (big) sc.big_list[atomicAdd(sc.big_cnt, 1)] = m;
     }
 #pragma unroll
@@ -235,7 +253,7 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
     LUX_TRACE_BEGIN(sc.trace, 2);
     LUX_TRACE_BIN(sc.trace, 8);
     if (lux_wany<G>(valid))
-        lux_step_match<kTma, kS, G>(b, m, valid, unit_actions, tile_actions, smem, flags, slice, phase);
+        lux_step_match<kTma, kS, G, kMode == kAll>(b, m, valid, unit_actions, tile_actions, smem, flags, slice, phase);
     LUX_TRACE_END(sc.trace, 2);
     // a programmatic dependent may not finish before its primary: later work on the stream waits for this grid
     if (kMode == kSmall && !sc.wait_first) LUX_PDL_WAIT();
@@ -674,7 +692,12 @@ static void scratch_free(StepScratch& s) {
     memset(&s, 0, sizeof s);
 }
 
+// The scratch table is process-global: one lock serialises look-up / creation / eviction (a host thread per GPU is
+// the expected multi-threaded use; the entries themselves are only touched by the thread that drives their batch).
+static std::mutex g_scratch_mutex;
+
 static StepScratch* scratch_get(const LuxBatch* b, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     StepScratch* slot = nullptr;
@@ -684,11 +707,16 @@ static StepScratch* scratch_get(const LuxBatch* b, cudaStream_t st) {
         if (!s.key) { slot = &s; break; }
     if (!slot) { slot = &g_scratch[g_scratch_clock++ % 8]; cudaStreamSynchronize(st); scratch_free(*slot); }
     size_t n = (size_t)b->n_matches;
-    if (cudaMalloc(&slot->counts, 3 * (1 + LUX_N_CAND) * sizeof(int)) != cudaSuccess) return nullptr;
-    if (cudaMalloc(&slot->list, n * sizeof(int)) != cudaSuccess) return nullptr;
-    if (cudaMalloc(&slot->cls, n) != cudaSuccess) return nullptr;
-    if (cudaHostAlloc(&slot->seen, (1 + LUX_N_CAND) * sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
-    if (cudaMemsetAsync(slot->counts, 0, 3 * (1 + LUX_N_CAND) * sizeof(int), st) != cudaSuccess) return nullptr;
+    // a partial failure frees what was allocated and leaves the slot empty (no key: the next call starts over)
+    if (cudaMalloc(&slot->counts, 3 * (1 + LUX_N_CAND) * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&slot->list, n * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&slot->cls, n) != cudaSuccess ||
+        cudaHostAlloc(&slot->seen, (1 + LUX_N_CAND) * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaMemsetAsync(slot->counts, 0, 3 * (1 + LUX_N_CAND) * sizeof(int), st) != cudaSuccess) {
+        cudaGetLastError();
+        scratch_free(*slot);
+        return nullptr;
+    }
     for (int i = 0; i <= LUX_N_CAND; i++) slot->seen[i] = 0;
     slot->key = b->hdr; slot->n = b->n_matches; slot->dev = dev; slot->step = 0;
     return slot;
@@ -854,6 +882,12 @@ extern "C" int lux_b200_step_host(const LuxBatch* b, const uint32_t* unit_action
     if (rc) return rc;
     if (hdr_host) {
         rc = cuda_ok(cudaMemcpyAsync(hdr_host, b->hdr, n * LUX_HDR_BYTES, cudaMemcpyDeviceToHost, st), "d2h headers");
+        if (rc) return rc;
+    }
+    if (done_host && !hdr_host) {
+        // only the flags are wanted: one byte per match, strided out of the headers
+        rc = cuda_ok(cudaMemcpy2DAsync(done_host, 1, (const uint8_t*)b->hdr + offsetof(LuxHeader, done), LUX_HDR_BYTES, 1, n,
+                                       cudaMemcpyDeviceToHost, st), "d2h done flags");
         if (rc) return rc;
     }
     rc = cuda_ok(cudaStreamSynchronize(st), "step sync");

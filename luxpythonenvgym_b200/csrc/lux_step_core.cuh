@@ -310,7 +310,7 @@ struct LuxGlobalMatch {
     LuxHeader* hdr; LuxCell* cells; LuxUnit* units; LuxCity* cities; uint16_t* tiles; LuxRes* res;
     const uint32_t* uact; const uint8_t* tact;
 };
-enum { LUX_M_DONE = 0, LUX_M_SPILL = 1 };     // why a group is not playing: nothing to play / the turn does not fit the slice
+enum { LUX_M_DONE = 0, LUX_M_SPILL = 1, LUX_M_BAD = 2 };     // why a group is not playing: nothing to play / the turn does not fit the slice / unplayable header
 
 // Returns the group's `active` flag (0: nothing to play -- invalid, finished, or the turn's footprint does not
 // fit `slice` bytes, in which case *result says which) with M bound and, when active, staged.  An inactive
@@ -325,6 +325,11 @@ LUX_DEV int lux_stage_plain(LuxMatch& M, unsigned char* smem, const LuxGlobalMat
     if (active) lux_copy16<G>(sh, g.hdr, LUX_HDR_BYTES);
     lux_sync<G>();
     if (active && sh->done) active = 0;
+    // live counts beyond the capacities, or per-team unit counts that do not add up: not playable (the caller flags it)
+    if (active && (sh->n_units > u_cap || sh->n_cities > c_cap || sh->n_tiles > t_cap || sh->n_res > r_cap ||
+                   (int)sh->n_team_units[0] + (int)sh->n_team_units[1] != (int)sh->n_units)) {
+        active = 0; *result = LUX_M_BAD;
+    }
     LuxNeed need = lux_need_none(u_cap, c_cap, t_cap, r_cap);
     if (active) need = lux_need_header(sh, u_cap, c_cap, t_cap, r_cap);
     LuxSmemLayout L = lux_smem_layout_need(size, need);

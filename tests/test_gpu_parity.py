@@ -215,6 +215,16 @@ def test_step_host_matches_device_step():
         assert torch.equal(hdr_h, a.hdr.cpu())
     for k in a.sections():
         assert torch.equal(a.sections()[k], b.sections()[k]), k
+    # the done flags alone (no header buffer): some matches made to finish on this turn
+    for g in (a, b):
+        g.hdr[::5, 0:4] = torch.tensor([103, 1, 0, 0], dtype=torch.uint8, device=g.device)      # turn 359
+    a.gen_actions(3, 0)
+    ua_h.copy_(a.unit_actions)
+    ta_h.copy_(a.tile_actions)
+    a.step()
+    done_h.zero_()
+    b.step_host(ua_h, ta_h, None, done_h)
+    assert np.array_equal(done_h.numpy(), a.headers()["done"]) and int(done_h.sum()) >= 7
 
 
 def test_step_host_sparse_matches_device_step():

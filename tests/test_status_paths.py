@@ -197,6 +197,48 @@ def test_overflow_and_stack_states_on_the_gpu(two_class, group):
         lib.lux_b200_set_option(b"group", 0)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("two_class,tma", [(-1, 1), (0, 1), (0, 0)])
+def test_unplayable_headers_are_flagged_and_left_alone(two_class, tma):
+    """A caller-built state whose header cannot be played safely -- per-team unit counts that do not add up, a live
+    count beyond the batch capacity -- is left untouched with LUX_ST_BAD_STATE set; its neighbours play on, equal
+    to the oracle.  Two-class step (the classification pass checks), single launch, plain staging."""
+    import torch
+    from luxpythonenvgym_b200 import _lib
+    from luxpythonenvgym_b200.batched import BatchedGame
+    lib = _lib.load()
+    states = normal_states(16)
+    bad_a, bad_b = 3, 10
+    states[bad_a].hdr["n_team_units"][0] += 1                      # 2 + 1 != n_units
+    states[bad_b].hdr["n_tiles"] = CAPS["tiles"] + 16              # beyond t_cap
+    good = [m for m in range(16) if m not in (bad_a, bad_b)]
+    traj, acts = oracle_play([states[m] for m in good], [None] * len(good), [None] * len(good), 5)
+    try:
+        lib.lux_b200_set_option(b"two_class", two_class)
+        lib.lux_b200_set_option(b"tma", tma)
+        game = BatchedGame(16, SIZE, caps=CAPS)
+        game.load_states(states)
+        before = game.export_states()
+        for t in range(5):
+            ua = np.zeros((16, CAPS["units"]), dtype=np.uint32)
+            ta = np.zeros((16, CAPS["tiles"]), dtype=np.uint8)
+            for j, m in enumerate(good):
+                ua[m], ta[m] = acts[t][0][j], acts[t][1][j]
+            game.unit_actions.copy_(torch.from_numpy(ua.view(np.int32)))
+            game.tile_actions.copy_(torch.from_numpy(ta))
+            game.step()
+            got = game.export_states()
+            for j, m in enumerate(good):
+                assert traj[t][j].diff(got[m]) == [], (t, m)
+            for m in (bad_a, bad_b):
+                assert int(got[m].hdr["status"]) & S.ST_BAD_STATE, (t, m)
+                assert int(got[m].hdr["turn"]) == int(before[m].hdr["turn"]) and int(got[m].hdr["done"]) == 0
+                assert np.array_equal(got[m].cells, before[m].cells) and np.array_equal(got[m].units, before[m].units)
+    finally:
+        lib.lux_b200_set_option(b"two_class", -1)
+        lib.lux_b200_set_option(b"tma", 1)
+
+
 @pytest.mark.reference
 def test_oracle_equals_reference_on_stacked_units():
     """The unmodified reference plays the stacked state (imported with its own process_updates) for 25 turns of
