@@ -16,6 +16,7 @@
 
 struct LuxObsLayoutDev { LuxObsLayout L; int mbar; int total; };
 
+template <int kS>
 __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_sel, float* __restrict__ obs,
                                    int16_t* __restrict__ ent_slot, int32_t* __restrict__ ent_count, int e_cap,
                                    const int64_t* __restrict__ row_offsets, LuxObsLayoutDev D) {
@@ -64,7 +65,7 @@ __global__ void lux_observe_kernel(LuxBatch b, const uint8_t* __restrict__ team_
         __syncwarp();
         mbar_wait(bar, 1);
     }
-    int n = lux_observe(M, team_sel[m] & 1, obs + row0 * LUX_OBS_DIM, ent_slot + row0, room);
+    int n = lux_observe<kS>(M, team_sel[m] & 1, obs + row0 * LUX_OBS_DIM, ent_slot + row0, room);
     if (n > room) n = room;
     if (lane == 0) ent_count[m] = n;
     if (row_offsets) for (int i = n + lane; i < room; i += 32) ent_slot[row0 + i] = -1;      // gap rows
@@ -89,10 +90,20 @@ extern "C" int lux_b200_observe(const LuxBatch* b, const uint8_t* team_sel, floa
     int wpc = D.total >= 8 * 1024 ? 1 : 2;
     size_t smem = (size_t)D.total * wpc;
     if (smem > 227 * 1024) return LUX_E_CAPACITY;
-    cudaError_t e = cudaFuncSetAttribute(lux_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { fprintf(stderr, "lux_b200: observe smem attr: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
-    e = lux_launch_chain(lux_observe_kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), smem, (cudaStream_t)cuda_stream,
-                         *b, team_sel, obs, ent_slot, ent_count, e_cap, row_offsets, D);
+    cudaError_t e = cudaSuccess;
+    auto launch = [&](auto kernel) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return;
+        e = lux_launch_chain(kernel, dim3((b->n_matches + wpc - 1) / wpc), dim3(32 * wpc), smem, (cudaStream_t)cuda_stream,
+                             *b, team_sel, obs, ent_slot, ent_count, e_cap, row_offsets, D);
+    };
+    switch (b->size) {           // the standard map sides get their own instantiation
+        case 12: launch(lux_observe_kernel<12>); break;
+        case 16: launch(lux_observe_kernel<16>); break;
+        case 24: launch(lux_observe_kernel<24>); break;
+        case 32: launch(lux_observe_kernel<32>); break;
+        default: launch(lux_observe_kernel<0>); break;
+    }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { fprintf(stderr, "lux_b200: lux_observe_kernel launch: %s\n", cudaGetErrorString(e)); return LUX_E_CUDA; }
     return LUX_OK;

@@ -74,6 +74,18 @@ LUX_DEV void lux_obs_bind(LuxObsMatch& M, unsigned char* smem, const LuxObsLayou
     M.S = size; M.ncell = size * size; M.r_cap = L.r_cap;
 }
 
+// float32(a / c) for a small integer a (|a| < 2^16) and an integer constant c <= 500, as the Python expression
+// computes it (a double division, rounded once more when the row is stored as float32) -- without the division:
+// a * RN64(1 / c) is within 2^-52 of a / c, and a / c is never closer than 2^-25 / c >= 2^-34 (relative) to a
+// float32 rounding boundary (a . 2^(24-e) - (2m+1) c is a non-zero integer: a / c cannot carry a 25-bit odd
+// significand unless a >= 2^15 c), so both round to the same float32.  A double division costs ~30 instructions on
+// the FP64 pipe; the rows need seven of them per entity.  min(v, 1) is applied in float32: RN32 is monotone.
+LUX_DEV float lux_ratio32(int a, double inv_c) { return (float)((double)a * inv_c); }
+LUX_DEV float lux_ratio32_cap1(int a, double inv_c) {
+    const float v = lux_ratio32(a, inv_c);
+    return v < 1.0f ? v : 1.0f;
+}
+
 // One (closest | furthest, key) block of 7 floats (agent_policy.py:327-385) for the chosen node, written into the
 // (zeroed) row by ONE lane.
 LUX_DEV void lux_obs_emit(const LuxObsMatch& M, float* o, unsigned node, int px, int py, int key, int n_units) {
@@ -83,15 +95,16 @@ LUX_DEV void lux_obs_emit(const LuxObsMatch& M, float* o, unsigned node, int px,
     if (ty < py) slot = 1; else if (tx > px) slot = 4; else if (ty > py) slot = 3; else if (tx < px) slot = 2;
     o[slot] = 1.0f;
     int man = (tx > px ? tx - px : px - tx) + (ty > py ? ty - py : py - ty);
-    double dist = (double)man / 20.0;
-    o[5] = (float)(dist < 1.0 ? dist : 1.0);
+    o[5] = lux_ratio32_cap1(man, 1.0 / 20.0);
+    if (key < 3) {
+        o[6] = lux_ratio32_cap1((int)(node >> 16), 1.0 / 500.0);
+        return;
+    }
     double v;
     if (key == 3) {
         const LuxCity city = M.g_cities[node >> 16];
         double upkeep = (double)((int)city.ntiles * LUX_UPKEEP_CITY - (int)city.adjsum * LUX_ADJ_BONUS);
         v = (double)city.fuel / (upkeep * 200.0);
-    } else if (key < 3) {
-        v = (double)(node >> 16) / 500.0;
     } else {
         // first unit in that cell's dict (:380-381): every unit standing on a cell gives the same value in
         // reachable states; the first in slot order is taken
@@ -99,7 +112,8 @@ LUX_DEV void lux_obs_emit(const LuxObsMatch& M, float* o, unsigned node, int px,
 #pragma unroll 1
         for (int i = 0; i < n_units; i++)
             if (M.units[i].x == tx && M.units[i].y == ty) { f = i; break; }
-        v = (double)unit_space(M.units[f]) / 100.0;
+        o[6] = lux_ratio32_cap1(unit_space(M.units[f]), 1.0 / 100.0);
+        return;
     }
     o[6] = (float)(v < 1.0 ? v : 1.0);
 }
@@ -155,11 +169,13 @@ LUX_DEV void lux_zero_floats(float* p, int count) {
 
 // Shared memory holds the match's lists (hdr, units, tiles, res); the grid is read in place.  Writes obs rows, entity codes and
 // returns the number of entities (rows beyond `room` are dropped).
+// kS: the map side when known at compile time (cell % S and cell / S are then shifts / multiplies), 0 otherwise.
+template <int kS = 0>
 LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, int room) {
     const int lane = lux_lane();
     const unsigned lt = lux_lanemask_lt();
     const LuxHeader* h = M.hdr;
-    const int S = M.S;
+    const int S = kS > 0 ? kS : M.S;
     const int n_units = h->n_units, n_tiles = h->n_tiles, n_res = h->n_res;
 
     // ---- node lists (agent_policy.py:197-247), order-preserving ballot compaction; resource nodes come
@@ -210,11 +226,11 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
     lux_sync();
 
     const int night = (h->turn % LUX_CYCLE_LENGTH) >= LUX_DAY_LENGTH;
-    const float f_turn = (float)((double)h->turn / 360.0);
-    const float f_own_tiles = (float)((double)own_tiles / 30.0), f_opp_tiles = (float)((double)opp_tiles / 30.0);
-    const float f_workers = (float)((double)own_workers / 30.0), f_carts = (float)((double)own_carts / 30.0);
+    const float f_turn = lux_ratio32(h->turn, 1.0 / 360.0);
+    const float f_own_tiles = lux_ratio32(own_tiles, 1.0 / 30.0), f_opp_tiles = lux_ratio32(opp_tiles, 1.0 / 30.0);
+    const float f_workers = lux_ratio32(own_workers, 1.0 / 30.0), f_carts = lux_ratio32(own_carts, 1.0 / 30.0);
     const int rp = h->research[team];
-    const float f_rp = (float)((double)rp / 200.0);
+    const float f_rp = lux_ratio32(rp, 1.0 / 200.0);
 
     // ---- entities: the team's units with can_act, then its tiles with can_act, 32 per pass
     int n_ent = 0;
@@ -288,7 +304,7 @@ LUX_DEV int lux_observe(LuxObsMatch& M, int team, float* g_obs, int16_t* g_ent, 
             }
             if (lane == 10) {
                 o[e_kind] = 1.0f;
-                if (e_kind != 2) o[73] = (float)((double)unit_space(M.units[e_idx]) / 100.0);
+                if (e_kind != 2) o[73] = lux_ratio32(unit_space(M.units[e_idx]), 1.0 / 100.0);
                 o[74] = night ? 1.0f : 0.0f;
                 o[75] = f_turn;
                 o[76] = f_own_tiles; o[77] = f_opp_tiles;

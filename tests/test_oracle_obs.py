@@ -22,3 +22,15 @@ def test_observation_oracle(name):
         assert got.shape == want.shape
         assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), np.argwhere(want != got)[:5]
         assert np.array_equal(z["%s/obs64_%d" % (name, team)].astype(np.float32), want)
+
+
+def test_ratio_features_need_no_division():
+    """The CUDA observation kernel computes float32(a / c) as float32(a * (1 / c)) (lux_obs_core.cuh lux_ratio32:
+    the FP64 division is the expensive part of a row).  Exhaustive over the numerators a row can hold and the six
+    divisors of agent_policy.py:188-424 -- with and without the min(v, 1) cap."""
+    a = np.arange(-70000, 70000, dtype=np.int64).astype(np.float64)
+    for c in (20.0, 500.0, 100.0, 360.0, 30.0, 200.0):
+        ref = (a / c).astype(np.float32)
+        alt = (a * (1.0 / c)).astype(np.float32)
+        assert np.array_equal(ref.view(np.uint32), alt.view(np.uint32)), c
+        assert np.array_equal(np.minimum(a / c, 1.0).astype(np.float32), np.minimum(alt, np.float32(1.0))), c
