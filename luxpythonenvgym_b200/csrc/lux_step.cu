@@ -165,7 +165,7 @@ __device__ __forceinline__ unsigned long long lux_globaltimer() {
     unsigned long long k = t > t0 ? (t - t0) / 8000ull : 0ull; if (k > 15) k = 15; atomicAdd((tr) + (base) + k, 1ull); } } while (0)
 
 // Classification of one step (device pointers, owned by the library, see StepScratch below).
-#define LUX_N_CAND 4     // candidate slice sizes the classification pass keeps statistics for
+#define LUX_N_CAND 5     // candidate slice sizes the classification pass keeps statistics for
 struct LuxSched {
     int* big_cnt; int* big_list;      // matches of the big class (written by classify, read by kList)
     uint8_t* cls;                     // [n] 1 = big class (kSmall skips it)
@@ -268,6 +268,7 @@ static int g_overlap = 1;         // 1 = programmatic dependent launches: the tw
 extern "C" int lux_b200_overlap_enabled(void) { return g_overlap; }
 static unsigned long long* g_trace = nullptr;   // device buffer of 8 timestamps (option "trace" allocates it)
 static int g_fork = 1;            // 1: the big class runs on a high-priority side stream as an independent grid (event fork / join); 0: as the small class's programmatic primary
+static int g_big_share = 12;      // the small slice is the smallest candidate that at most 1 / g_big_share of the batch exceeded
 static int g_only_class = 0;      // measurement aid: 1 = launch only the big class, 2 = only the small class (results are then incomplete)
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
@@ -650,6 +651,7 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "carveout")) { g_carveout = value > 100 ? 100 : value; return LUX_OK; }
     if (!strcmp(name, "slice")) { g_slice = value; return LUX_OK; }
     if (!strcmp(name, "only_class")) { g_only_class = value; return LUX_OK; }
+    if (!strcmp(name, "big_share")) { g_big_share = value < 1 ? 1 : value; return LUX_OK; }
     if (!strcmp(name, "fork")) { g_fork = value != 0; return LUX_OK; }
     if (!strcmp(name, "trace")) {
         if (value && !g_trace && cudaMalloc(&g_trace, 40 * sizeof(unsigned long long)) != cudaSuccess) return LUX_E_CUDA;
@@ -768,7 +770,7 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     // (sparse batches: 5 KB; dense late-game batches: 8-12 KB), the single full-capacity launch when even the
     // largest candidate leaves most of the batch to the big class.
     const int floor_bytes = lux_smem_layout_need(b->size, lux_need_none(b->u_cap, b->c_cap, b->t_cap, b->r_cap)).total;
-    const int cand[LUX_N_CAND] = {5120, 6144, 8192, 12288};
+    const int cand[LUX_N_CAND] = {5120, 6144, 7168, 8192, 12288};
     bool two = g_two_class != 0 && (g_two_class == 1 || cand[0] * 2 <= full);
     StepScratch* S = two ? scratch_get(b, st) : nullptr;
     if (two && !S) return LUX_E_CUDA;
@@ -776,7 +778,7 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     if (two && g_slice <= 0) {
         int pick = LUX_N_CAND - 1;
         for (int i = LUX_N_CAND - 1; i >= 0; i--)
-            if (S->seen[1 + i] * 12 <= b->n_matches) pick = i;
+            if ((long long)S->seen[1 + i] * g_big_share <= b->n_matches) pick = i;
         small = cand[pick];
         if (g_two_class < 0 && (S->seen[1 + pick] * 2 > b->n_matches || small * 4 > full * 3)) two = false;
     }
