@@ -25,6 +25,13 @@ from luxpythonenvgym_b200.batched import BatchedGame  # noqa: E402
 from luxpythonenvgym_b200.env import BatchedLuxEnvironment  # noqa: E402
 
 
+for _opt in os.environ.get("LUX_OPTS", "").split(","):        # e.g. LUX_OPTS=fork=0,big_share=12 (tuning probes)
+    if "=" in _opt:
+        from luxpythonenvgym_b200 import _lib as _l
+        _k, _v = _opt.split("=")
+        assert _l.load().lux_b200_set_option(_k.encode(), int(_v)) == 0, _opt
+
+
 def recap(ms, caps):
     o = S.MatchState(ms.size, caps)
     o.hdr, o.cells = ms.hdr.copy(), ms.cells.copy()
@@ -56,23 +63,35 @@ def config3(n_per_size=16384, steps=100):
         games.append((size, g, pool))
     counters = torch.zeros(2, dtype=torch.int64, device="cuda")
 
+    # one stream per batch: the four batches are independent, so the tail of one size's step overlaps with the
+    # next size's (LUX_C3_STREAMS=0: everything on one stream, as in round 1)
+    multi = os.environ.get("LUX_C3_STREAMS", "1") != "0"
+    streams = [torch.cuda.Stream() for _ in games]
+    counts = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in games]
+
     def step_all(epoch, count):
-        for size, g, pool in games:
-            g.gen_actions(31337, 0, counters=count)
-            g.step()
-            g.reset_done(pool, epoch)
+        for i, (size, g, pool) in enumerate(games):
+            with torch.cuda.stream(streams[i] if multi else torch.cuda.current_stream()):
+                g.gen_actions(31337, 0, counters=counts[i] if count is not None else None)
+                g.step()
+                g.reset_done(pool, epoch)
 
     for w in range(30):
         step_all(w, None)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main = torch.cuda.current_stream()
     e0.record()
+    for st in streams:
+        st.wait_stream(main)            # the timed region opens on every stream
     for k in range(steps):
         step_all(100 + k, counters)
+    for st in streams:
+        main.wait_stream(st)            # ... and closes when all of them are done
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    live, alg = [int(x) for x in counters.cpu().tolist()]
+    live, alg = [int(x) for x in sum(c.cpu() for c in counts).tolist()]
     pops = {size: {"units_per_match": float(g.stats().cpu()[7]) / g.n, "tiles_per_match": float(g.stats().cpu()[8]) / g.n,
                    "status_nonzero": int(g.stats().cpu()[10])} for size, g, pool in games}
     return {"matches": 4 * n_per_size, "steps": steps, "ms_per_step_all_sizes": ms / steps,
