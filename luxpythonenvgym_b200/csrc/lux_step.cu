@@ -156,6 +156,7 @@ __device__ __forceinline__ unsigned long long lux_globaltimer() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+__device__ unsigned long long* g_trace_dev = nullptr;      // set with the "trace" option (the harness kernel stamps slot 1)
 #define LUX_TRACE_BEGIN(tr, slot) do { if ((tr) && (threadIdx.x & 31) == 0) atomicMin((tr) + 2 * (slot), lux_globaltimer()); } while (0)
 #define LUX_TRACE_END(tr, slot) do { if ((tr) && (threadIdx.x & 31) == 0) atomicMax((tr) + 2 * (slot) + 1, lux_globaltimer()); } while (0)
 // histograms in 8 us bins relative to the classification pass's start: [8..23] warps of the small class STARTING,
@@ -584,6 +585,7 @@ __global__ void __launch_bounds__(256, 6) lux_reset_gen_kernel(LuxBatch b, LuxBa
         __syncthreads();
     }
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    LUX_TRACE_BEGIN(g_trace_dev, 1);
     if (m < b.n_matches) {
         if (b.hdr[m].done) {
             lux_reset_match<2>(b, pool, m, epoch, reset_count);
@@ -591,6 +593,7 @@ __global__ void __launch_bounds__(256, 6) lux_reset_gen_kernel(LuxBatch b, LuxBa
         }
         lux_gen_actions_match(b, m, seed, match_id_base, unit_actions, tile_actions, counters ? cta_counters : nullptr);
     }
+    LUX_TRACE_END(g_trace_dev, 1);
     if (counters && (threadIdx.x & 31) == 0) {
         __threadfence_block();
         if (atomicAdd(&cta_ticket, 1u) == (blockDim.x >> 5) - 1) {
@@ -657,6 +660,7 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "trace")) {
         if (value && !g_trace && cudaMalloc(&g_trace, 40 * sizeof(unsigned long long)) != cudaSuccess) return LUX_E_CUDA;
         if (!value && g_trace) { cudaFree(g_trace); g_trace = nullptr; }
+        cudaMemcpyToSymbol(g_trace_dev, &g_trace, sizeof g_trace);
         return LUX_OK;
     }
     return LUX_E_ARG;

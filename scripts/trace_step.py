@@ -24,12 +24,12 @@ for spec in sys.argv[1:] or ["only_class=0"]:
     rows = []
     for rep in range(12):
         game.step()
+        game.reset_gen(pool, t, 20211019, 0, reset_count=resets); t += 1
         lib.lux_b200_debug_trace(out)
         v = list(out)
         hist = v[8:40]
-        game.reset_gen(pool, t, 20211019, 0, reset_count=resets); t += 1
         t0 = v[6]
-        rows.append([(v[2 * i] - t0) / 1e3 if v[2 * i + 1] else float("nan") for i in (3, 0, 1, 2)] + [(v[2 * i + 1] - t0) / 1e3 if v[2 * i + 1] else float("nan") for i in (3, 0, 1, 2)])
+        rows.append([(v[2 * i] - t0) / 1e3 if v[2 * i + 1] else float("nan") for i in (3, 0, 1, 2)] + [(v[2 * i + 1] - t0) / 1e3 if v[2 * i + 1] else float("nan") for i in (3, 0, 1, 2)])   # columns: classify, big, harness (reset + action stream), small
     r = np.nanmedian(np.array(rows[2:]), axis=0)
     print("   small-class warps starting per 8 us bin:", hist[:16], " big-class warps ending per bin:", hist[16:])
-    print("%-40s classify %.1f-%.1f  big class %.1f-%.1f  small class %.1f-%.1f us" % (spec, r[0], r[4], r[1], r[5], r[3], r[7]))
+    print("%-40s classify %.1f-%.1f  big class %.1f-%.1f  small class %.1f-%.1f  reset + action stream %.1f-%.1f us" % (spec, r[0], r[4], r[1], r[5], r[3], r[7], r[2], r[6]))
