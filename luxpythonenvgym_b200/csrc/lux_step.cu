@@ -211,9 +211,11 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
                 int slice, unsigned flags_in, LuxSched sc) {
     const unsigned flags = kSpec == 1 ? 0u : kSpec == 2 ? LUX_STEP_CONSUME : flags_in;
     extern __shared__ __align__(128) unsigned char lux_smem[];
-    // the big class needs the classification pass complete; after that the small class may start while this
-    // class is still running (the two touch disjoint matches).  The small class itself only lets its successor
-    // in early and waits for the big class at its END.
+    // Both classes need the classification pass complete.  Default ("fork"): the big class is an ordinary launch on
+    // the side stream behind an event, the small class a programmatic dependent of the classification pass that
+    // waits at its START (wait_first).  Round 1's form ("fork" = 0): the small class is a programmatic dependent of the
+    // big class, which has waited for the classification; it only lets its successor in early and waits for the big
+    // class at its END (the two classes touch disjoint matches).
     if (kMode == kList || (kMode == kSmall && sc.wait_first)) LUX_PDL_WAIT();
     if (kMode != kAll) LUX_PDL_TRIGGER();
     if (kMode == kAll) { LUX_PDL_TRIGGER(); LUX_PDL_WAIT(); }
