@@ -744,6 +744,17 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         M.ust[u] = (uint8_t)st;
         M.utgt[u] = (uint16_t)tgt;
         any_move |= (st & 7) == LUX_UA_MOVE;
+        if (!(flags & LUX_STEP_PREVALIDATE)) {
+            // the movement flags of this unit (see the collision stage below) go out in the same pass; with
+            // pre-validation they depend on which moves survive it and are set after that stage
+            const int moving = (st & 7) == LUX_UA_MOVE;
+            unsigned old = lux_atomic_or_byte(M.p1, ucell, P1_HAS1 | (moving ? 0u : P1_STILL));
+            if (old & P1_HAS1) lux_atomic_or_byte(M.p1, ucell, P1_HAS2);
+            if (moving && !(tgt & UTGT_TILE)) {
+                unsigned o2 = lux_atomic_or_byte(M.p1, tgt & UTGT_CELL, P1_IN1);
+                if (o2 & P1_IN1) lux_atomic_or_byte(M.p1, tgt & UTGT_CELL, P1_IN2);
+            }
+        }
     }
     lux_sync<G>();
     // no validated move anywhere in the warp: the whole collision stage is a no-op (a group without moves
@@ -781,6 +792,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     // ---- collision pruning (handle_movement_actions game.py:1104-1195); shared memory only.
     // Flags are set on every cell (city tiles too) but only ever read on non-city target cells.
     if (any_move_w) {
+    if (flags & LUX_STEP_PREVALIDATE) {
 #pragma unroll 1
     for (int u = lane; u < n_units0; u += G) {
         const LuxUnit& U = M.units[u];
@@ -799,6 +811,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         }
     }
     lux_sync<G>();
+    }
     // seeds: >= 2 moves into a non-city cell, or one move into a non-city cell whose single
     // occupant is not moving (:1164-1179)
 #pragma unroll 1
@@ -835,15 +848,8 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         lux_sync<G>();
         if (!lux_any_warp(changed)) break;
     }
-    // the movement flags have served: clear the byte of every cell a unit stands on or aimed at
-#pragma unroll 1
-    for (int u = lane; u < n_units0; u += G) {
-        const LuxUnit& U = M.units[u];
-        M.p1[U.y * S + U.x] = 0;
-        M.p1[M.utgt[u] & UTGT_CELL] = 0;
-    }
-    lux_sync<G>();
     }   // any_move_w
+    // (the movement flags are cleared by the moves pass below: the byte of every cell a unit stands on or aimed at)
 
     // ---- city tiles: spawn validation (game.py:696-718) + CityTile.turn (city.py:96-120)
     int n_units = n_units0;
@@ -925,11 +931,14 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     // moves are conflict-free after pruning: lane-parallel
 #pragma unroll 1
     for (int u = lane; u < n_units0; u += G) {
+        LuxUnit& U = M.units[u];
+        // the movement flags have served (set above, or -- with pre-validation -- only when a move was left)
+        M.p1[U.y * S + U.x] = 0;
+        M.p1[M.utgt[u] & UTGT_CELL] = 0;
         unsigned st = M.ust[u];
         if ((st & 7) != LUX_UA_MOVE) continue;
         int dir = (st >> 3) & 7;
         if ((st & UST_REVERTED) || dir == LUX_DIR_CENTER) { M.ust[u] = 0; continue; }   // game.py:462-465
-        LuxUnit& U = M.units[u];
         U.x = (uint8_t)(U.x + lux_dx(dir));
         U.y = (uint8_t)(U.y + lux_dy(dir));
     }
