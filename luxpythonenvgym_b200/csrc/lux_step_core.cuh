@@ -812,23 +812,11 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     }
     lux_sync<G>();
     }
-    // seeds: >= 2 moves into a non-city cell, or one move into a non-city cell whose single
-    // occupant is not moving (:1164-1179)
-#pragma unroll 1
-    for (int u = lane; u < n_units0; u += G) {
-        unsigned st = M.ust[u];
-        if ((st & 7) != LUX_UA_MOVE) continue;
-        unsigned tg = M.utgt[u];
-        if (tg & UTGT_TILE) continue;
-        unsigned f = M.p1[tg & UTGT_CELL];
-        if ((f & P1_IN2) || ((f & P1_HAS1) && !(f & P1_HAS2) && (f & P1_STILL))) {
-            M.ust[u] = (uint8_t)(st | UST_REVERTED);
-            const LuxUnit& U = M.units[u];
-            lux_atomic_or_byte(M.p1, U.y * S + U.x, P1_BLOCKED);
-        }
-    }
-    lux_sync<G>();
-    // cascade (revert_action :1138-1156): a reverted mover blocks its own non-city cell
+    // One monotone closure, iterated to its fixpoint: a move is reverted when >= 2 moves aim at its (non-city)
+    // target cell, or the cell's single occupant is not moving (the seeds, :1164-1179), or a reverted mover stays
+    // there (the cascade, revert_action :1138-1156: a reverted mover blocks its own non-city cell).  Whatever order
+    // the lanes see each other's BLOCKED flags in, the fixpoint is the set the reference's recursion computes; a
+    // turn without collisions (the common one) costs a single pass.
 #pragma unroll 1
     for (;;) {
         int changed = 0;
@@ -838,7 +826,8 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             if ((st & 7) != LUX_UA_MOVE || (st & UST_REVERTED)) continue;
             unsigned tg = M.utgt[u];
             if (tg & UTGT_TILE) continue;
-            if (M.p1[tg & UTGT_CELL] & P1_BLOCKED) {
+            const unsigned f = M.p1[tg & UTGT_CELL];
+            if ((f & (P1_BLOCKED | P1_IN2)) || ((f & P1_HAS1) && !(f & P1_HAS2) && (f & P1_STILL))) {
                 M.ust[u] = (uint8_t)(st | UST_REVERTED);
                 const LuxUnit& U = M.units[u];
                 lux_atomic_or_byte(M.p1, U.y * S + U.x, P1_BLOCKED);
@@ -849,7 +838,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         if (!lux_any_warp(changed)) break;
     }
     }   // any_move_w
-    // (the movement flags are cleared by the moves pass below: the byte of every cell a unit stands on or aimed at)
+    // (the movement flags are cleared at the head of the unit pass: the byte of every cell a unit stands on or aimed at)
 
     // ---- city tiles: spawn validation (game.py:696-718) + CityTile.turn (city.py:96-120)
     int n_units = n_units0;
@@ -928,21 +917,9 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     lux_sync<G>();
 
     // ---- unit turns (Worker.turn unit.py:162-197, Cart.turn :234-269)
-    // moves are conflict-free after pruning: lane-parallel
-#pragma unroll 1
-    for (int u = lane; u < n_units0; u += G) {
-        LuxUnit& U = M.units[u];
-        // the movement flags have served (set above, or -- with pre-validation -- only when a move was left)
-        M.p1[U.y * S + U.x] = 0;
-        M.p1[M.utgt[u] & UTGT_CELL] = 0;
-        unsigned st = M.ust[u];
-        if ((st & 7) != LUX_UA_MOVE) continue;
-        int dir = (st >> 3) & 7;
-        if ((st & UST_REVERTED) || dir == LUX_DIR_CENTER) { M.ust[u] = 0; continue; }   // game.py:462-465
-        U.x = (uint8_t)(U.x + lux_dx(dir));
-        U.y = (uint8_t)(U.y + lux_dy(dir));
-    }
-    lux_sync<G>();
+    // Moves are conflict-free after pruning and nothing reads another unit's position before the unit pass (a unit
+    // holds ONE action: the ordered actions below -- transfer by id, build / pillage on the own cell -- belong to units
+    // that do not move), so the moves are applied at the head of the unit pass instead of in a pass of their own.
     // transfer / build city / pillage depend on unit order (team A then B == slot order): one pending
     // action per group and round, the groups of the warp in lockstep
     const int nu_max = lux_wmax<G>(n_units);
@@ -1032,6 +1009,17 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             LuxUnit& U = M.units[u];
             const int isold = u < n_units0;
             unsigned st = isold ? M.ust[u] : 0u;
+            if (isold) {
+                // the movement flags have served (set in the validation pass, or -- with pre-validation -- only when a
+                // move was left): clear the byte of the cell the unit stood on and of the cell it aimed at
+                M.p1[U.y * S + U.x] = 0;
+                M.p1[M.utgt[u] & UTGT_CELL] = 0;
+                if ((st & 7) == LUX_UA_MOVE) {
+                    const int dir = (st >> 3) & 7;
+                    if ((st & UST_REVERTED) || dir == LUX_DIR_CENTER) st = 0;                      // game.py:462-465
+                    else { U.x = (uint8_t)(U.x + lux_dx(dir)); U.y = (uint8_t)(U.y + lux_dy(dir)); }
+                }
+            }
             const int cart = unit_is_cart(U);
             const int ucell = U.y * S + U.x;
             int pos[5];
