@@ -116,7 +116,7 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
             need = none;
             L = lux_smem_layout_need(size, none);
         }
-        lux_match_bind(M, smem, L, g.cells, size, need);
+        lux_match_bind(M, smem, L, g.cells, g.res, size, need);
         // trip 2: the live lists and this turn's action words, one bulk-copy batch
         if (active && lane == 0) {
             const uint32_t bu = nu * 16, bua = (nu * 4 + 15) & ~15u, bc = nc * 16, bt = (nt * 2 + 15) & ~15u,

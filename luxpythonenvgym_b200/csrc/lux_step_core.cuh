@@ -158,6 +158,7 @@ struct LuxMatch {
     LuxCity* cities;
     uint16_t* tiles;
     LuxRes* res;
+    LuxRes* g_res;       // the resource list in global memory: the regrowth pass writes the entries it changes straight there
     uint32_t* uact;
     uint8_t* tact;
     uint16_t* utgt;
@@ -176,10 +177,11 @@ struct LuxMatch {
     int S, ncell, u_cap, c_cap, t_cap, r_cap;
 };
 
-LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayout& L, LuxCell* g_cells, int size,
+LUX_DEV void lux_match_bind(LuxMatch& M, unsigned char* smem, const LuxSmemLayout& L, LuxCell* g_cells, LuxRes* g_res, int size,
                             const LuxNeed& need) {
     M.hdr = (LuxHeader*)(smem + L.hdr);
     M.cells = g_cells;
+    M.g_res = g_res;
     M.units = (LuxUnit*)(smem + L.units);
     M.cities = (LuxCity*)(smem + L.cities);
     M.tiles = (uint16_t*)(smem + L.tiles);
@@ -338,7 +340,7 @@ LUX_DEV int lux_stage_plain(LuxMatch& M, unsigned char* smem, const LuxGlobalMat
         need = lux_need_none(u_cap, c_cap, t_cap, r_cap);
         L = lux_smem_layout_need(size, need);
     }
-    lux_match_bind(M, smem, L, g.cells, size, need);
+    lux_match_bind(M, smem, L, g.cells, g.res, size, need);
     lux_sync<G>();                            // every lane has read the header before an idle group clears it
     if (active) {
         lux_copy16<G>(M.units, g.units, M.hdr->n_units * 16);
@@ -1225,7 +1227,9 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 if (a > LUX_MAX_WOOD) a = LUX_MAX_WOOD;
                 M.cells[cell].amount = (uint16_t)a;
             }
-            if (a != before) M.res[r] = (e & 0xFFFFu) | ((LuxRes)a << 16);
+            // nothing reads the staged list after this pass: a changed entry goes straight to the list in global memory
+            // (the unchanged ones -- coal, uranium, full or unmined wood -- are not written at all)
+            if (a != before) M.g_res[r] = (e & 0xFFFFu) | ((LuxRes)a << 16);
         }
     }
     lux_sync<G>();
@@ -1247,8 +1251,8 @@ LUX_DEV void lux_finish_and_store(LuxMatch& M, const LuxTurnOut& T, LuxHeader* g
     LuxHeader* h = M.hdr;
     const int S = kS > 0 ? kS : M.S;
 
-    // the resource list goes back as it stands (amount mirrors)
-    if (active) lux_copy16<G>(g_res, M.res, h->n_res * 4);
+    // (the resource list: the regrowth pass has written its changed entries in place)
+    (void)g_res;
     // Cities.  The common turn neither founds, merges nor loses a city tile (tiles_dirty == 0: the tile list did not
     // grow and no city fell): the cities go back as they stand and the per-team tile counts are the turn's opening
     // ones.  Otherwise: drop the dead (ntiles == 0), keep order, rebuild the canonical tile list.
