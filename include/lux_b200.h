@@ -136,10 +136,16 @@ int lux_b200_version(void);
 int lux_b200_device_count(void);
 
 /* Tuning knobs: "tma" (1 = cp.async.bulk staging, 0 = plain vector loads/stores),
- * "warps_per_cta" (0 = automatic), "two_class" (-1 automatic, 0 off, 1 always), "overlap" (1 = big and small class run concurrently),
+ * "warps_per_cta" (0 = automatic), "two_class" (-1 automatic, 0 off, 1 always), "fork" (1 = the big class runs as an
+ * independent grid on a high-priority side stream, default; 0 = as the small class's programmatic primary),
+ * "overlap" (1 = programmatic dependent launches along the chain), "big_share" (the small slice is the smallest
+ * candidate that at most 1 / big_share of the batch exceeded; default 3),
  * "slice" (shared-memory bytes per match of the small class, 0 = default), "group" (lanes per match: 0 automatic,
  * 8 / 16 / 32), "carveout" (preferred shared-memory carve-out in percent, -1 = automatic), "list_grid" (CTAs of
- * the big-class launch, 0 = automatic), "gen_wpc" (matches per CTA of the action-stream kernel).
+ * the big-class launch, 0 = automatic), "gen_wpc" (matches per CTA of the action-stream kernel); measurement aids:
+ * "trace" (see lux_b200_debug_trace), "only_class" (1 / 2: launch only the big / small class -- results incomplete).
+ * The options are process-global and not synchronised: set them before the first step and from one thread
+ * (the per-batch scratch the library caches is behind a lock; one host thread per GPU is the supported use).
  * Returns LUX_E_ARG for an unknown name. */
 int lux_b200_set_option(const char* name, int value);
 
