@@ -307,6 +307,47 @@ def test_step_host_submit_wait_with_work_queued_behind():
         assert torch.equal(a.sections()[k], b.sections()[k]), k
 
 
+def test_step_is_deterministic_across_launch_forms():
+    """The same trajectory from one snapshot, twice per launch form (races between the classes or between a step
+    and the pass queued behind it would show as run-to-run differences) and across forms: big class forked to the
+    side stream / as the small class's programmatic primary / one full-capacity launch -- byte-equal batches."""
+    lib = _lib.load()
+    n, size = 4096, 32
+    g = _game(n, size)
+    pool = _game(64, size)
+    pool.load_arrays(mapgen.generate_batch(np.arange(31000, 31064), size))
+    g.load_arrays(mapgen.generate_batch(np.arange(32000, 32000 + n), size))
+    resets = torch.zeros(1, dtype=torch.int32, device=g.device)
+    g.gen_actions(99, 0)
+    for t in range(150):
+        g.step()
+        g.reset_gen(pool, t, 99, 0, reset_count=resets)
+    torch.cuda.synchronize()
+    snap = {k: v.clone() for k, v in g.sections().items()}
+    ua, ta = g.unit_actions.clone(), g.tile_actions.clone()
+    want = None
+    try:
+        for fork, two, rep in ((1, -1, 0), (1, -1, 1), (0, -1, 0), (0, -1, 1), (1, 0, 0)):
+            lib.lux_b200_set_option(b"fork", fork)
+            lib.lux_b200_set_option(b"two_class", two)
+            for k, v in g.sections().items():
+                v.copy_(snap[k])
+            g.unit_actions.copy_(ua)
+            g.tile_actions.copy_(ta)
+            for t in range(60):
+                g.step()
+                g.reset_gen(pool, 150 + t, 99, 0, reset_count=resets)
+            torch.cuda.synchronize()
+            got = {k: v.clone() for k, v in g.sections().items()}
+            if want is None:
+                want = got
+            for k in want:
+                assert torch.equal(want[k], got[k]), (fork, two, rep, k)
+    finally:
+        lib.lux_b200_set_option(b"fork", 1)
+        lib.lux_b200_set_option(b"two_class", -1)
+
+
 def test_bad_arguments_are_rejected():
     import ctypes
     lib = _lib.load()
