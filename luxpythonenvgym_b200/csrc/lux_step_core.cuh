@@ -1042,10 +1042,15 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 info = (unsigned)(M.cprefix[C.city_slot] + C.key) | ((unsigned)C.city_slot << 16) | UI_TILE |
                        (cell_tile_team(C) == unit_team(U) ? UI_OWN : 0u);
             } else {
-                if (cart && !(st & UST_FAILED) && C.road_q < LUX_MAX_ROAD_Q) {
-                    int r = C.road_q + LUX_ROAD_DEV_Q;
-                    M.cells[ucell].road_q = (uint8_t)(r > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : r);
-                    if (unit_team(U)) rb1 += LUX_ROAD_DEV_Q; else rb0 += LUX_ROAD_DEV_Q;
+                if (cart) {
+                    // the road level this cart found (and whether its turn was cut short): should the cell turn out
+                    // to hold several carts, lane 0 redoes their road steps one after the other (below)
+                    M.umine[u] = (uint8_t)(C.road_q | ((st & UST_FAILED) ? 0x80u : 0u));
+                    if (!(st & UST_FAILED) && C.road_q < LUX_MAX_ROAD_Q) {
+                        int r = C.road_q + LUX_ROAD_DEV_Q;
+                        M.cells[ucell].road_q = (uint8_t)(r > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : r);
+                        if (unit_team(U)) rb1 += LUX_ROAD_DEV_Q; else rb0 += LUX_ROAD_DEV_Q;
+                    }
                 }
                 // a non-city cell holds one unit in play; a stack (left behind by a destroyed city) is rare and
                 // gets its occupant chain rebuilt below
@@ -1090,6 +1095,38 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                     const int cell = M.units[u].y * S + M.units[u].x;
                     M.unext[u] = M.occ[cell];
                     M.occ[cell] = (uint8_t)(u + 1);
+                }
+                // Carts of one stack each add their road step IN TURN (unit.py:257-269: cart after cart, each only
+                // while the road is below the maximum).  The lanes above all started from the level they loaded; for
+                // a cell with two or more carts the steps are redone here in unit order from the level the first of
+                // them found (the smallest recorded one), and the statistics corrected by the difference.
+#pragma unroll 1
+                for (int u = 0; u < n_units; u++) {
+                    if ((M.uinfo[u] & UI_TILE) || !M.unext[u]) continue;
+                    const int cell = M.units[u].y * S + M.units[u].x;
+                    if (M.occ[cell] != u + 1) continue;                      // not the head of its chain
+                    int ncart = 0, c0 = 255, par0 = 0, par1 = 0;
+#pragma unroll 1
+                    for (int v = u + 1; v; v = M.unext[v - 1]) {
+                        const LuxUnit& V = M.units[v - 1];
+                        if (!unit_is_cart(V)) continue;
+                        const int seen = M.umine[v - 1] & 0x7F, failed = M.umine[v - 1] & 0x80;
+                        ncart++;
+                        if (seen < c0) c0 = seen;
+                        if (!failed && seen < LUX_MAX_ROAD_Q) { if (unit_team(V)) par1 += LUX_ROAD_DEV_Q; else par0 += LUX_ROAD_DEV_Q; }
+                    }
+                    if (ncart < 2) continue;
+                    int road = c0, seq0 = 0, seq1 = 0;
+#pragma unroll 1
+                    for (int v = u + 1; v; v = M.unext[v - 1]) {
+                        const LuxUnit& V = M.units[v - 1];
+                        if (!unit_is_cart(V) || (M.umine[v - 1] & 0x80) || road >= LUX_MAX_ROAD_Q) continue;
+                        road = road + LUX_ROAD_DEV_Q > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : road + LUX_ROAD_DEV_Q;
+                        if (unit_team(V)) seq1 += LUX_ROAD_DEV_Q; else seq0 += LUX_ROAD_DEV_Q;
+                    }
+                    M.cells[cell].road_q = (uint8_t)road;
+                    h->roads_built_q[0] += seq0 - par0;
+                    h->roads_built_q[1] += seq1 - par1;
                 }
             }
         }

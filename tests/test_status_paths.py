@@ -92,6 +92,15 @@ def stacked_lines():
             "c 0 c_1 400 23", "ct 0 c_1 3 4 0", "c 1 c_2 400 23", "ct 1 c_2 28 28 0", "ccd 10 11 2.5"]
 
 
+def stacked_carts_lines(road):
+    """Two team-0 carts and a team-1 cart on ONE open cell (a stack), road level `road` under them; bystanders."""
+    return ["rp 0 0", "rp 1 0", "r wood 20 20 400",
+            "u 1 0 u_1 10 11 0 0 0 0", "u 1 0 u_2 10 11 0 0 0 0", "u 1 1 u_3 10 11 0 0 0 0",
+            "u 0 0 u_4 5 5 0 0 0 0", "u 0 1 u_5 6 6 0 0 0 0", "u 1 1 u_6 15 15 0 0 0 0",
+            "c 0 c_1 400 23", "ct 0 c_1 3 4 0", "c 1 c_2 400 23", "ct 1 c_2 28 28 0"] + \
+           (["ccd 10 11 %s" % road] if road else [])
+
+
 def normal_states(k):
     z = G.npz("dense")
     names = [n for n in G.dense_names() if int(z[n + "/size"]) == SIZE]
@@ -237,6 +246,65 @@ def test_unplayable_headers_are_flagged_and_left_alone(two_class, tma):
     finally:
         lib.lux_b200_set_option(b"two_class", -1)
         lib.lux_b200_set_option(b"tma", 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("road", [0, 4.5, 5.25])
+def test_stacked_carts_build_their_road_in_turn_on_the_gpu(road):
+    """Several carts of a stack each add their road step in turn (unit.py:257-269), the later ones only while the road
+    is below the maximum -- which also decides whose statistics the step goes to.  The lanes of the unit pass all
+    start from the level they load, so the stack path redoes the steps in unit order; idle turns (the carts just
+    stand there), from an empty road and from levels where the maximum cuts the sequence short."""
+    import torch
+    from luxpythonenvgym_b200.batched import BatchedGame
+    ms = build(stacked_carts_lines(road), uid=8, cid=2)
+    others = normal_states(3)
+    states = [others[0], ms, others[1], ms.copy(), others[2]]
+    traj = [s.copy() for s in states]
+    game = BatchedGame(len(states), SIZE, caps=CAPS)
+    game.load_states(states)
+    zu, zt = np.zeros(CAPS["units"], dtype=np.uint32), np.zeros(CAPS["tiles"], dtype=np.uint8)
+    cell = 11 * SIZE + 10
+    for t in range(6):
+        for m in traj:
+            coracle.step(m, zu, zt)
+        game.unit_actions.zero_()
+        game.tile_actions.zero_()
+        game.step()
+        got = game.export_states()
+        for m in range(len(states)):
+            assert traj[m].diff(got[m]) == [], (t, m)
+    assert int(traj[1].cells[cell]["road_q"]) == 24 and int(traj[1].hdr["status"]) == 0
+
+
+@pytest.mark.reference
+def test_oracle_equals_reference_on_stacked_carts():
+    """The unmodified reference on the stacked-carts state: cart after cart adds its road step; the C oracle
+    reproduces every turn (idle turns)."""
+    import os
+    from oracle import flatten, refshim
+    ref = refshim.load()
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    try:
+        for road in (0, 4.5, 5.25):
+            cfg = dict(ref.LuxMatchConfigs_Default)
+            cfg.update(seed=None, mapType="empty", width=SIZE, height=SIZE)
+            game = ref.Game(cfg)
+            game.log = lambda text: None
+            game.reset(updates=stacked_carts_lines(road) + ["D_DONE"])
+            game.global_unit_id_count, game.global_city_id_count = 8, 2
+            game.state["turn"] = 3
+            mine = flatten.flatten(game, caps=CAPS)
+            assert len(game.map.get_cell(10, 11).units) == 3
+            zu, zt = np.zeros(CAPS["units"], dtype=np.uint32), np.zeros(CAPS["tiles"], dtype=np.uint8)
+            for turn in range(6):
+                game.run_turn_with_actions([])
+                coracle.step(mine, zu, zt)
+                assert flatten.flatten(game, caps=CAPS).diff(mine) == [], (road, turn)
+            assert game.map.get_cell(10, 11).get_road() == 6.0
+    finally:
+        os.chdir(cwd)
 
 
 @pytest.mark.reference
