@@ -563,9 +563,50 @@ LUX_DEV void lux_city_prefix(LuxMatch& M, int n_cities) {
     lux_sync<G>();
 }
 
+// utgt[u]: [9:0] target cell of the unit's validated move (own cell otherwise), bit 14 = the target is a city tile
+#define UTGT_TILE 0x4000u
+#define UTGT_CELL 0x03FFu
+
+// Units that precede unit `u` in unit order and share its cell (a stack; movers count where they arrive) have had
+// their turn on the open cell before `u` founds a city there: a cart among them has added its road step, which the
+// unit pass -- it finds a city tile -- will not do.  Replayed in unit order (pillages of the cell included: the first
+// pillager recorded the level the turn opened with); returns the cell's road level.  Lane 0 only.
+template <int kS>
+LUX_DEV int lux_road_before_city(LuxMatch& M, int u, int idx, int road_now) {
+    LuxHeader* h = M.hdr;
+    const int S = kS > 0 ? kS : M.S;
+    int opened = -1, carts = 0;
+#pragma unroll 1
+    for (int v = 0; v < u; v++) {
+        const unsigned sv = M.ust[v];
+        const LuxUnit& V = M.units[v];
+        const int at = (sv & UST_REVERTED) ? V.y * S + V.x : (int)(M.utgt[v] & UTGT_CELL);
+        if (at != idx) continue;
+        if (unit_is_cart(V)) carts++;
+        else if ((sv & 7) == LUX_UA_PILLAGE && opened < 0) opened = M.umine[v];
+    }
+    if (!carts) return road_now;
+    int road = opened >= 0 ? opened : road_now;
+#pragma unroll 1
+    for (int v = 0; v < u; v++) {
+        const unsigned sv = M.ust[v];
+        const LuxUnit& V = M.units[v];
+        const int at = (sv & UST_REVERTED) ? V.y * S + V.x : (int)(M.utgt[v] & UTGT_CELL);
+        if (at != idx) continue;
+        if (unit_is_cart(V)) {
+            if ((sv & UST_FAILED) || road >= LUX_MAX_ROAD_Q) continue;
+            road = road + LUX_ROAD_DEV_Q > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : road + LUX_ROAD_DEV_Q;
+            h->roads_built_q[unit_team(V)] += LUX_ROAD_DEV_Q;
+        } else if ((sv & 7) == LUX_UA_PILLAGE) {
+            road = road > LUX_PILLAGE_Q ? road - LUX_PILLAGE_Q : 0;
+        }
+    }
+    return road;
+}
+
 // ---- build a city tile under unit `u` (spawn_city_tile game.py:798-854); lane 0 only ---------
 template <int kS, int G>
-LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tiles) {
+LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tiles, int prevalidate) {
     LuxHeader* h = M.hdr;
     LuxUnit& U = M.units[u];
     const int S = kS > 0 ? kS : M.S;
@@ -592,9 +633,17 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
             if (!seen) found[nfound++] = P.city_slot;
         }
     }
+    // A second unit of a stack founding a city on the cell an earlier one has just turned into a tile: the reference
+    // builds a second CityTile object over the first and leaves the cell in two cities' lists (spawn_city_tile does not
+    // look at the cell itself, game.py:798-854) -- not a state the packed form can hold.  Flagged, nothing built.
+    if (cell_is_tile(C)) { h->status |= LUX_ST_BAD_STATE; return; }
     if (n_tiles >= M.t_cap) { h->status |= LUX_ST_TILE_OVERFLOW; return; }
+    if (nsame == 0 && n_cities >= M.c_cap) { h->status |= LUX_ST_CITY_OVERFLOW; return; }
+    // the cell turns into a city tile NOW, in this unit's turn: what earlier units of a stack did on the open cell first.
+    // The movement flags of the cell are still up (second occupant / a validated move aiming at it); with
+    // pre-validation they are only set when some unit of the warp moves, so that mode always looks.
+    if (u > 0 && (prevalidate || (M.p1[idx] & (P1_HAS2 | P1_IN1)))) C.road_q = (uint8_t)lux_road_before_city<kS>(M, u, idx, C.road_q);
     if (nsame == 0) {
-        if (n_cities >= M.c_cap) { h->status |= LUX_ST_CITY_OVERFLOW; return; }
         LuxCity& city = M.cities[n_cities];
         city.id = ++h->city_id_count;
         city.fuel = 0; city.ntiles = 1; city.adjsum = 0; city.team = (uint8_t)team;
@@ -635,6 +684,69 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
     }
 }
 
+// Several units share a non-city cell (game.py:1173: a city fell under them and they survived the night): the OR-ed
+// occupant bytes of those cells are meaningless; the occupants are rebuilt as chains occ[cell] -> unit -> unext -> ...
+// in unit order, and the road work of each such cell is replayed in unit order.  Lane 0 only; rare.
+template <int kS>
+LUX_DEV void lux_stack_paths(LuxMatch& M, int n_units) {
+    LuxHeader* h = M.hdr;
+    const int S = kS > 0 ? kS : M.S;
+#pragma unroll 1
+    for (int u = 0; u < n_units; u++) {
+        M.unext[u] = 0;
+        if (!(M.uinfo[u] & UI_TILE)) M.occ[M.units[u].y * S + M.units[u].x] = 0;
+    }
+#pragma unroll 1
+    for (int u = n_units - 1; u >= 0; u--) {
+        if (M.uinfo[u] & UI_TILE) continue;
+        const int cell = M.units[u].y * S + M.units[u].x;
+        M.unext[u] = M.occ[cell];
+        M.occ[cell] = (uint8_t)(u + 1);
+    }
+    // The road of a stack's cell is worked on IN TURN (Worker.turn / Cart.turn, unit.py:188-192, :257-269):
+    // unit after unit, a pillaging worker takes its step off, a cart adds its own while the road is below
+    // the maximum.  The engine has applied the pillages first (ordered section) and then let every cart's
+    // lane add a step to the level it loaded; for a cell that holds two or more such units the sequence
+    // is replayed here in unit order from the level the first of them found, and the statistics
+    // corrected by the difference.
+#pragma unroll 1
+    for (int u = 0; u < n_units; u++) {
+        if ((M.uinfo[u] & UI_TILE) || !M.unext[u]) continue;
+        const int cell = M.units[u].y * S + M.units[u].x;
+        if (M.occ[cell] != u + 1) continue;                      // not the head of its chain
+        int nact = 0, r0 = -1, c0 = 255, par0 = 0, par1 = 0;
+#pragma unroll 1
+        for (int v = u + 1; v; v = M.unext[v - 1]) {
+            const LuxUnit& V = M.units[v - 1];
+            if (unit_is_cart(V)) {
+                const int seen = M.umine[v - 1] & 0x7F, failed = M.umine[v - 1] & 0x80;
+                nact++;
+                if (seen < c0) c0 = seen;
+                if (!failed && seen < LUX_MAX_ROAD_Q) { if (unit_team(V)) par1 += LUX_ROAD_DEV_Q; else par0 += LUX_ROAD_DEV_Q; }
+            } else if ((M.ust[v - 1] & 7) == LUX_UA_PILLAGE) {
+                nact++;
+                if (r0 < 0) r0 = M.umine[v - 1];                 // the first pillager saw the turn's opening level
+            }
+        }
+        if (nact < 2) continue;                                  // a single step was applied as it should be
+        int road = r0 >= 0 ? r0 : c0, seq0 = 0, seq1 = 0;
+#pragma unroll 1
+        for (int v = u + 1; v; v = M.unext[v - 1]) {
+            const LuxUnit& V = M.units[v - 1];
+            if (unit_is_cart(V)) {
+                if ((M.umine[v - 1] & 0x80) || road >= LUX_MAX_ROAD_Q) continue;
+                road = road + LUX_ROAD_DEV_Q > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : road + LUX_ROAD_DEV_Q;
+                if (unit_team(V)) seq1 += LUX_ROAD_DEV_Q; else seq0 += LUX_ROAD_DEV_Q;
+            } else if ((M.ust[v - 1] & 7) == LUX_UA_PILLAGE) {
+                road = road > LUX_PILLAGE_Q ? road - LUX_PILLAGE_Q : 0;
+            }
+        }
+        M.cells[cell].road_q = (uint8_t)road;
+        h->roads_built_q[0] += seq0 - par0;
+        h->roads_built_q[1] += seq1 - par1;
+    }
+}
+
 // ---- the turn ------------------------------------------------------------------------------
 // On entry the match's lists are staged in shared memory (M.hdr, units[0..n_units), cities, tiles,
 // res, uact, tact), the two byte planes are all-zero, M.cells points at the grid in global memory
@@ -643,9 +755,6 @@ LUX_DEV void lux_build_city_lane0(LuxMatch& M, int u, int& n_cities, int& n_tile
 // compacts while writing.
 struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; int alive0; int alive1; int tt0; int tt1; };
 
-// utgt[u]: [9:0] target cell of the unit's validated move (own cell otherwise), bit 14 = the target is a city tile
-#define UTGT_TILE 0x4000u
-#define UTGT_CELL 0x03FFu
 
 template <int kS, int G>
 LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
@@ -973,7 +1082,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                 LuxUnit& U = M.units[su];
                 if (!unit_is_cart(U)) {
                     if (kind == LUX_UA_BCITY) {
-                        lux_build_city_lane0<kS, G>(M, su, n_cities, n_tiles);
+                        lux_build_city_lane0<kS, G>(M, su, n_cities, n_tiles, (flags & LUX_STEP_PREVALIDATE) != 0);
                         int spent = 0;                                // expend_resources_for_city unit.py:146-160
                         uint16_t* cg[3] = {&U.wood, &U.coal, &U.uranium};
 #pragma unroll 1
@@ -986,6 +1095,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
                         int pc = U.y * S + U.x;
                         int rq = LUX_LDG8(&M.cells[pc].road_q);
                         M.cells[pc].road_q = (uint8_t)(rq > LUX_PILLAGE_Q ? rq - LUX_PILLAGE_Q : 0);
+                        M.umine[su] = (uint8_t)rq;            // the level it found (read back by the stack path only)
                     }
                 }
             }
@@ -1064,7 +1174,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             }
             M.uinfo[u] = info;
             M.umin[u] = (uint16_t)mm;
-            M.ust[u] = 0;
+            M.ust[u] = (uint8_t)(st & 7);          // flags off (the night marks the dead with UST_FAILED); the kind stays for the stack path
             {   // which resource types occur among the five fields (type = hi:lo of a field)
                 const unsigned lo = mm & 0x155u, hi = (mm >> 1) & 0x155u;
                 has_t1 |= lo & ~hi; has_t2 |= hi & ~lo; has_t3 |= lo & hi;
@@ -1083,52 +1193,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
             // night): the OR-ed occupant bytes of those cells are meaningless; lane 0 rebuilds them as chains
             // occ[cell] -> unit -> unext -> ... in unit order
             lux_sync<G>();
-            if (bad && lane == 0) {
-#pragma unroll 1
-                for (int u = 0; u < n_units; u++) {
-                    M.unext[u] = 0;
-                    if (!(M.uinfo[u] & UI_TILE)) M.occ[M.units[u].y * S + M.units[u].x] = 0;
-                }
-#pragma unroll 1
-                for (int u = n_units - 1; u >= 0; u--) {
-                    if (M.uinfo[u] & UI_TILE) continue;
-                    const int cell = M.units[u].y * S + M.units[u].x;
-                    M.unext[u] = M.occ[cell];
-                    M.occ[cell] = (uint8_t)(u + 1);
-                }
-                // Carts of one stack each add their road step IN TURN (unit.py:257-269: cart after cart, each only
-                // while the road is below the maximum).  The lanes above all started from the level they loaded; for
-                // a cell with two or more carts the steps are redone here in unit order from the level the first of
-                // them found (the smallest recorded one), and the statistics corrected by the difference.
-#pragma unroll 1
-                for (int u = 0; u < n_units; u++) {
-                    if ((M.uinfo[u] & UI_TILE) || !M.unext[u]) continue;
-                    const int cell = M.units[u].y * S + M.units[u].x;
-                    if (M.occ[cell] != u + 1) continue;                      // not the head of its chain
-                    int ncart = 0, c0 = 255, par0 = 0, par1 = 0;
-#pragma unroll 1
-                    for (int v = u + 1; v; v = M.unext[v - 1]) {
-                        const LuxUnit& V = M.units[v - 1];
-                        if (!unit_is_cart(V)) continue;
-                        const int seen = M.umine[v - 1] & 0x7F, failed = M.umine[v - 1] & 0x80;
-                        ncart++;
-                        if (seen < c0) c0 = seen;
-                        if (!failed && seen < LUX_MAX_ROAD_Q) { if (unit_team(V)) par1 += LUX_ROAD_DEV_Q; else par0 += LUX_ROAD_DEV_Q; }
-                    }
-                    if (ncart < 2) continue;
-                    int road = c0, seq0 = 0, seq1 = 0;
-#pragma unroll 1
-                    for (int v = u + 1; v; v = M.unext[v - 1]) {
-                        const LuxUnit& V = M.units[v - 1];
-                        if (!unit_is_cart(V) || (M.umine[v - 1] & 0x80) || road >= LUX_MAX_ROAD_Q) continue;
-                        road = road + LUX_ROAD_DEV_Q > LUX_MAX_ROAD_Q ? LUX_MAX_ROAD_Q : road + LUX_ROAD_DEV_Q;
-                        if (unit_team(V)) seq1 += LUX_ROAD_DEV_Q; else seq0 += LUX_ROAD_DEV_Q;
-                    }
-                    M.cells[cell].road_q = (uint8_t)road;
-                    h->roads_built_q[0] += seq0 - par0;
-                    h->roads_built_q[1] += seq1 - par1;
-                }
-            }
+            if (bad && lane == 0) lux_stack_paths<kS>(M, n_units);
         }
     }
     lux_sync<G>();

@@ -277,6 +277,25 @@ def test_stacked_carts_build_their_road_in_turn_on_the_gpu(road):
     assert int(traj[1].cells[cell]["road_q"]) == 24 and int(traj[1].hdr["status"]) == 0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 5])
+def test_random_stacks_soak_on_the_gpu(seed):
+    """scripts/stack_soak.py as a test: random hand-built states with stacks of both teams' workers and carts on open
+    cells next to resources and on roads, 25 turns of the canonical action stream, GPU against the C oracle on every
+    turn.  This is where the orders of a stack's road work (pillage / cart steps / a city founded under earlier
+    units) were found to matter; a match in which a second unit founds a city on a cell an earlier one has just built
+    on is flagged LUX_ST_BAD_STATE and left alone (a handful per few hundred states)."""
+    import subprocess, sys, os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "stack_soak.py"), "160", "25", str(seed)],
+                         capture_output=True, text=True, cwd=root, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    m = re.search(r"mismatching match-turns: (\d+), matches flagged LUX_ST_BAD_STATE \(left alone\): (\d+)", out.stdout)
+    assert m, out.stdout[-2000:]
+    assert int(m.group(1)) == 0, out.stdout[-3000:]
+    assert int(m.group(2)) <= 8
+
+
 @pytest.mark.reference
 def test_oracle_equals_reference_on_stacked_carts():
     """The unmodified reference on the stacked-carts state: cart after cart adds its road step; the C oracle
