@@ -296,6 +296,22 @@ def test_random_stacks_soak_on_the_gpu(seed):
     assert int(m.group(2)) <= 8
 
 
+@pytest.mark.gpu
+def test_nightfall_chaos_soak_on_the_gpu():
+    """scripts/chaos_soak.py as a test: random hand-built states at nightfall -- multi-tile cities of both teams with
+    little fuel and several units on their tiles, cargo that does or does not last the night, resources and roads
+    around -- 45 turns of the canonical action stream, GPU against the C oracle on every turn (city falls under
+    units, starvation, merges of cities built next to each other)."""
+    import subprocess, sys, os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "chaos_soak.py"), "160", "45", "7"],
+                         capture_output=True, text=True, cwd=root, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    m = re.search(r"mismatching match-turns: (\d+), flagged LUX_ST_BAD_STATE: (\d+)", out.stdout)
+    assert m, out.stdout[-2000:]
+    assert int(m.group(1)) == 0 and int(m.group(2)) == 0, out.stdout[-3000:]
+
+
 @pytest.mark.reference
 def test_oracle_equals_reference_on_stacked_carts():
     """The unmodified reference on the stacked-carts state: cart after cart adds its road step; the C oracle
