@@ -139,7 +139,10 @@ int lux_b200_device_count(void);
  * "warps_per_cta" (0 = automatic), "two_class" (-1 automatic, 0 off, 1 always), "fork" (1 = the big class runs as an
  * independent grid on a high-priority side stream, default; 0 = as the small class's programmatic primary),
  * "overlap" (1 = programmatic dependent launches along the chain), "big_share" (the small slice is the smallest
- * candidate that at most 1 / big_share of the batch exceeded; default 3),
+ * candidate that at most 1 / big_share of the batch exceeded; default 3), "mid_slice" (shared-memory bytes per match
+ * of the big class: 0 = automatic, 12 KB, with the rare match beyond it played by a launch of its own with
+ * full-capacity slices; -1 = full capacity for the whole big class), "over_own" (that launch on a stream of its own:
+ * -1 = when the statistics have seen such matches, otherwise it follows the big class on its stream; 0 never; 1 always),
  * "slice" (shared-memory bytes per match of the small class, 0 = default), "group" (lanes per match: 0 automatic,
  * 8 / 16 / 32), "carveout" (preferred shared-memory carve-out in percent, -1 = automatic), "list_grid" (CTAs of
  * the big-class launch, 0 = automatic), "gen_wpc" (matches per CTA of the action-stream kernel); measurement aids:

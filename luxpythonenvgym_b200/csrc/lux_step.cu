@@ -167,8 +167,11 @@ __device__ unsigned long long* g_trace_dev = nullptr;      // set with the "trac
 
 // Classification of one step (device pointers, owned by the library, see StepScratch below).
 #define LUX_N_CAND 5     // candidate slice sizes the classification pass keeps statistics for
+#define LUX_CNT_SET (2 + LUX_N_CAND)     // one set of counters: [0] big-class count, [1..N_CAND] statistics, [1 + N_CAND] oversize count
 struct LuxSched {
     int* big_cnt; int* big_list;      // matches of the big class (written by classify, read by kList)
+    int* over_cnt; int* over_list;    // big matches whose need exceeds `mid` (the big class's slice): played with full-capacity slices
+    int mid;                          // by a launch of their own (kList with big_cnt / big_list pointing here)
     uint8_t* cls;                     // [n] 1 = big class (kSmall skips it)
     int* zero;                        // the previous step's counters: trailed to the host, then cleared for reuse
     int* seen_host;                   // pinned, mapped host words
@@ -184,6 +187,7 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     // the previous step's statistics go to the host (stale values only delay its choice of slice), then clear
     if (m <= LUX_N_CAND) { sc.seen_host[m] = sc.zero[m]; sc.zero[m] = 0; }
+    if (m == LUX_N_CAND + 1) sc.zero[m] = 0;
     int total = 0;
     if (m < b.n_matches) {
         LuxHeader* h = b.hdr + m;
@@ -192,7 +196,10 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
         else if (!h->done) total = lux_smem_layout_need(b.size, lux_need_header(h, b.u_cap, b.c_cap, b.t_cap, b.r_cap)).total;
         const int big = total > slice;
         sc.cls[m] = (uint8_t)(bad ? 2 : big);       // 2: neither class plays it
-        if (big) sc.big_list[atomicAdd(sc.big_cnt, 1)] = m;
+        if (big) {
+            if (total > sc.mid) sc.over_list[atomicAdd(sc.over_cnt, 1)] = m;
+            else sc.big_list[atomicAdd(sc.big_cnt, 1)] = m;
+        }
     }
 #pragma unroll
     for (int i = 0; i < LUX_N_CAND; i++) {
@@ -268,11 +275,14 @@ static unsigned long long g_launches = 0;
 static int g_gen_wpc = 8;         // warps (matches) per CTA of the action-stream kernel
 static int g_list_grid = 0;       // CTAs of the big-class launch (0 = automatic)
 static int g_overlap = 1;         // 1 = programmatic dependent launches: the two step classes overlap, launch gaps hide
-extern "C" int lux_b200_overlap_enabled(void) { return g_overlap; }
+static thread_local int t_plain_launch = 0;     // the next launches of this thread are ordinary ones (no programmatic dependence)
+extern "C" int lux_b200_overlap_enabled(void) { return g_overlap && !t_plain_launch; }
 static unsigned long long* g_trace = nullptr;   // device buffer of 8 timestamps (option "trace" allocates it)
 static int g_fork = 1;            // 1: the big class runs on a high-priority side stream as an independent grid (event fork / join); 0: as the small class's programmatic primary
 static int g_big_share = 3;       // the small slice is the smallest candidate that at most 1 / g_big_share of the batch exceeded (12 before the
                                   // classes ran as independent grids; a dense batch now plays 13 % faster with a third of it in the big class)
+static int g_mid_slice = 0;       // slice of the big class: 0 = automatic (12 KB), -1 = full capacity (no oversize launch)
+static int g_over_own = -1;       // oversize launch on a stream of its own: -1 = when the statistics have seen oversize matches, 0 never, 1 always
 static int g_only_class = 0;      // measurement aid: 1 = launch only the big class, 2 = only the small class (results are then incomplete)
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
@@ -659,6 +669,8 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "only_class")) { g_only_class = value; return LUX_OK; }
     if (!strcmp(name, "big_share")) { g_big_share = value < 1 ? 1 : value; return LUX_OK; }
     if (!strcmp(name, "fork")) { g_fork = value != 0; return LUX_OK; }
+    if (!strcmp(name, "mid_slice")) { g_mid_slice = value; return LUX_OK; }
+    if (!strcmp(name, "over_own")) { g_over_own = value; return LUX_OK; }
     if (!strcmp(name, "trace")) {
         if (value && !g_trace && cudaMalloc(&g_trace, 40 * sizeof(unsigned long long)) != cudaSuccess) return LUX_E_CUDA;
         if (!value && g_trace) { cudaFree(g_trace); g_trace = nullptr; }
@@ -672,7 +684,7 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
 // mixed map sizes, a pool -- each keep their own lists).
 struct StepScratch {
     const void* key; int n; int dev;
-    int* counts;                 // 3 x (1 + LUX_N_CAND): big-class count + statistics (rotation: this step, next, being cleared)
+    int* counts;                 // 3 x LUX_CNT_SET: big-class count + statistics + oversize count (rotation: this step, next, being cleared)
     int* list;                   // [n] big-class matches of this step
     unsigned char* cls;          // [n] 1 = big class
     int* seen;                   // pinned host copy of a recent step's counters (may be stale)
@@ -685,6 +697,8 @@ struct StepScratch {
     unsigned step;
     cudaStream_t side;           // the big class's stream when the two classes run as independent grids ("fork")
     cudaEvent_t ev_fork, ev_join;
+    cudaStream_t side2;          // the oversize launch's stream (big matches beyond the big class's slice)
+    cudaEvent_t ev_join2;
 };
 static StepScratch g_scratch[8];
 static unsigned g_scratch_clock = 0;
@@ -698,6 +712,7 @@ static void scratch_free(StepScratch& s) {
     if (s.done_pinned) cudaFreeHost(s.done_pinned);
     if (s.summary_acc) cudaFree(s.summary_acc);
     if (s.side) { cudaStreamDestroy(s.side); cudaEventDestroy(s.ev_fork); cudaEventDestroy(s.ev_join); }
+    if (s.side2) { cudaStreamDestroy(s.side2); cudaEventDestroy(s.ev_join2); }
     memset(&s, 0, sizeof s);
 }
 
@@ -717,11 +732,11 @@ static StepScratch* scratch_get(const LuxBatch* b, cudaStream_t st) {
     if (!slot) { slot = &g_scratch[g_scratch_clock++ % 8]; cudaStreamSynchronize(st); scratch_free(*slot); }
     size_t n = (size_t)b->n_matches;
     // a partial failure frees what was allocated and leaves the slot empty (no key: the next call starts over)
-    if (cudaMalloc(&slot->counts, 3 * (1 + LUX_N_CAND) * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&slot->list, n * sizeof(int)) != cudaSuccess ||
+    if (cudaMalloc(&slot->counts, 3 * LUX_CNT_SET * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&slot->list, 2 * n * sizeof(int)) != cudaSuccess ||                  // big list, oversize list
         cudaMalloc(&slot->cls, n) != cudaSuccess ||
         cudaHostAlloc(&slot->seen, (1 + LUX_N_CAND) * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
-        cudaMemsetAsync(slot->counts, 0, 3 * (1 + LUX_N_CAND) * sizeof(int), st) != cudaSuccess) {
+        cudaMemsetAsync(slot->counts, 0, 3 * LUX_CNT_SET * sizeof(int), st) != cudaSuccess) {
         cudaGetLastError();
         scratch_free(*slot);
         return nullptr;
@@ -797,10 +812,11 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
         // the host would never see the batch thin out again: classify runs with the current choice.
         if (S) {
             const unsigned t = S->step++;
-            sc.big_cnt = S->counts + (t % 3) * (1 + LUX_N_CAND);
+            sc.big_cnt = S->counts + (t % 3) * LUX_CNT_SET;
             sc.big_list = S->list;
+            sc.over_cnt = sc.big_cnt + 1 + LUX_N_CAND; sc.over_list = S->list + b->n_matches; sc.mid = 0x7fffffff;
             sc.cls = S->cls;
-            sc.zero = S->counts + ((t + 2) % 3) * (1 + LUX_N_CAND);
+            sc.zero = S->counts + ((t + 2) % 3) * LUX_CNT_SET;
             sc.seen_host = S->seen;
             for (int i = 0; i < LUX_N_CAND; i++) sc.cand[i] = cand[i];
             lux_launch_chain(lux_classify_kernel, dim3((b->n_matches + 255) / 256), dim3(256), 0, st, *b, full, sc);
@@ -812,10 +828,18 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
         return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
     }
     const unsigned t = S->step++;
-    sc.big_cnt = S->counts + (t % 3) * (1 + LUX_N_CAND);
+    sc.big_cnt = S->counts + (t % 3) * LUX_CNT_SET;
     sc.big_list = S->list;
+    // The big class plays with slices of `mid` bytes (12 KB: more of its long single-warp jobs fit beside the small
+    // class than with full-capacity slices, step 0.082 -> 0.080 ms); the rare match beyond that goes to a launch of
+    // its own with full-capacity slices.  Only with independent grids ("fork"): a chain of programmatic dependents
+    // would make one of the two launches wait for the other.
+    int mid = g_mid_slice > 0 ? g_mid_slice : 12288;
+    if (g_mid_slice < 0 || !(g_fork && g_only_class == 0) || mid <= small || mid >= full) mid = full;
+    mid = (mid + 127) & ~127;
+    sc.over_cnt = sc.big_cnt + 1 + LUX_N_CAND; sc.over_list = S->list + b->n_matches; sc.mid = mid;
     sc.cls = S->cls;
-    sc.zero = S->counts + ((t + 2) % 3) * (1 + LUX_N_CAND);
+    sc.zero = S->counts + ((t + 2) % 3) * LUX_CNT_SET;
     sc.seen_host = S->seen;
     sc.trace = g_trace;
     if (g_trace) {
@@ -839,17 +863,44 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
             cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming);
         }
+        // Oversize matches seen a step or two ago (statistics of the 12 KB candidate): their launch -- the longest jobs
+        // of the step -- gets a stream of its own, so that neither big-class launch waits for the other.  None seen (the
+        // usual sparse batch): the almost certainly empty oversize launch follows the big class on its stream as an
+        // ORDINARY launch (a programmatic dependent would sit on the SMs with full-capacity slices while it waits).
+        const bool over_own = mid < full && (g_over_own >= 0 ? g_over_own != 0 : !(mid == cand[LUX_N_CAND - 1] && S->seen[LUX_N_CAND] == 0));
+        if (over_own && !S->side2) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (cudaStreamCreateWithPriority(&S->side2, cudaStreamNonBlocking, hi) != cudaSuccess) return LUX_E_CUDA;
+            cudaEventCreateWithFlags(&S->ev_join2, cudaEventDisableTiming);
+        }
         cudaEventRecord(S->ev_fork, st);                      // behind the classification pass
         cudaStreamWaitEvent(S->side, S->ev_fork, 0);
-        rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, full, flags, sc, grid_l, 1, S->side);
+        LuxSched so = sc;
+        so.big_cnt = sc.over_cnt; so.big_list = sc.over_list;
+        const int grid_o = grid_l < 148 * 2 ? grid_l : 148 * 2;
+        if (over_own) {
+            cudaStreamWaitEvent(S->side2, S->ev_fork, 0);
+            rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, full, flags, so, grid_o, 1, S->side2);
+            if (rc) return rc;
+            cudaEventRecord(S->ev_join2, S->side2);
+        }
+        rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, mid, flags, sc, grid_l, 1, S->side);
         if (rc) return rc;
         LuxSched ss = sc;
         ss.wait_first = 1;
         int group = pick_group(small);
         rc = launch_step_group<true, kSmall>(group, b, unit_actions, tile_actions, small, flags, ss, b->n_matches, pick_wpc(small, group), st);
         if (rc) return rc;
+        if (mid < full && !over_own) {
+            t_plain_launch = 1;
+            rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, full, flags, so, grid_o, 1, S->side);
+            t_plain_launch = 0;
+            if (rc) return rc;
+        }
         cudaEventRecord(S->ev_join, S->side);
         cudaStreamWaitEvent(st, S->ev_join, 0);
+        if (over_own) cudaStreamWaitEvent(st, S->ev_join2, 0);
         return cuda_ok(cudaGetLastError(), "lux_step_kernel (forked classes) launch");
     }
     if (g_only_class != 2) rc = launch_step_group<true, kList>(32, b, unit_actions, tile_actions, full, flags, sc, grid_l, 1, st);
