@@ -29,7 +29,7 @@ def build_mapgen(force=False):
     hdr = os.path.join(HERE, "..", "include", "lux_b200.h")
     if not force and os.path.exists(MAPGEN_OUT) and os.path.getmtime(MAPGEN_OUT) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
         return MAPGEN_OUT
-    cmd = ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", MAPGEN_OUT, src]
+    cmd = ["g++", "-O3", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", MAPGEN_OUT, src]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

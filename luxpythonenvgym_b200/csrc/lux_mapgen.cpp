@@ -6,6 +6,7 @@
 // (BASELINE.json north_star); this is what makes 10^5..10^6 distinct seeded matches practical
 // (the Python statement needs ~20 ms per map).  Output: the packed initial state of include/lux_b200.h.
 // tests/test_mapgen_native.py pins it against the reference's 100 golden maps and against mapgen.py.
+#include <emmintrin.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -25,20 +26,35 @@ const Pow2Neg POW2_NEG;
 struct Arc4 {
     uint8_t s[256];
     int i = 0, j = 0;
+    // the first `len` bytes of the keystream (behind seedrandom's 256 discarded ones) may have been produced ahead
+    // of time (Arc4x4 below); take() serves them from `buf` and carries on from the state they left behind
+    const uint8_t* buf = nullptr;
+    int pos = 0, len = 0;
+    Arc4() {}
     explicit Arc4(const std::string& key) {
+        schedule(key);
+        take(256);
+    }
+    void schedule(const std::string& key) {
         for (int k = 0; k < 256; k++) s[k] = (uint8_t)k;
         int jj = 0;
-        const int len = key.empty() ? 1 : (int)key.size();
+        const int klen = key.empty() ? 1 : (int)key.size();
         for (int k = 0; k < 256; k++) {
-            int kc = key.empty() ? 0 : (uint8_t)key[k % len];
+            int kc = key.empty() ? 0 : (uint8_t)key[k % klen];
             jj = (jj + s[k] + kc) & 255;
             uint8_t t = s[k]; s[k] = s[jj]; s[jj] = t;
         }
-        take(256);
     }
     uint64_t take(int n) {
-        // i, j live in registers for the run (the byte stores into s[] may alias the members otherwise)
         uint64_t acc = 0;
+        if (pos + n <= len) {
+            const uint8_t* q = buf + pos;
+            pos += n;
+            for (int k = 0; k < n; k++) acc = (acc << 8) | q[k];
+            return acc;
+        }
+        while (pos < len && n > 0) { acc = (acc << 8) | buf[pos++]; n--; }
+        // i, j live in registers for the run (the byte stores into s[] may alias the members otherwise)
         unsigned a = (unsigned)i, b = (unsigned)j;
         for (int k = 0; k < n; k++) {
             a = (a + 1) & 255;
@@ -62,6 +78,45 @@ struct Arc4 {
         while (num < (1ull << 52)) { num = (num + extra) << 8; den_bits += 8; extra = (uint32_t)take(1); }
         while (num >= (1ull << 53)) { num >>= 1; den_bits -= 1; extra >>= 1; }
         return (double)(num + extra) * POW2_NEG.v[den_bits];            // exact: a power of two
+    }
+};
+
+// Four keystreams side by side.  One RC4 byte is a chain of dependent loads and stores through the 256-byte state
+// (3.5 ns here); four independent states in one loop fill the pipeline instead (1.2 ns per byte and stream).  A map
+// needs 13.2 KB of keystream on average (32 x 32; 95 % below 13.7 KB): PREFIX bytes per map are produced this way,
+// the rare map that needs more (a layout that failed the resource minimum and is drawn again) continues alone.
+struct Arc4x4 {
+    enum { PREFIX = 14 * 1024 };
+    Arc4 r[4];
+    std::vector<uint8_t> stream;      // 4 x (256 + PREFIX)
+    Arc4x4() : stream(4 * (256 + PREFIX)) {}
+    void start(const std::string key[4], int prefix) {
+        if (prefix > PREFIX) prefix = PREFIX;
+        for (int q = 0; q < 4; q++) r[q].schedule(key[q]);
+        // the four states side by side in one local block (the compiler can then tell the streams apart)
+        uint8_t st[4][256];
+        for (int q = 0; q < 4; q++) memcpy(st[q], r[q].s, 256);
+        uint8_t* out[4];
+        for (int q = 0; q < 4; q++) out[q] = &stream[(size_t)q * (256 + PREFIX)];
+        unsigned a = 0, bs[4] = {0, 0, 0, 0};
+        const int total = 256 + prefix;
+        for (int k = 0; k < total; k++) {
+            a = (a + 1) & 255;
+#pragma GCC unroll 4
+            for (int q = 0; q < 4; q++) {
+                const unsigned x = st[q][a];
+                bs[q] = (bs[q] + x) & 255;
+                const unsigned y = st[q][bs[q]];
+                st[q][a] = (uint8_t)y; st[q][bs[q]] = (uint8_t)x;
+                out[q][k] = st[q][(x + y) & 255];
+            }
+        }
+        for (int q = 0; q < 4; q++) memcpy(r[q].s, st[q], 256);
+        for (int q = 0; q < 4; q++) {
+            r[q].i = (int)a; r[q].j = (int)bs[q];
+            r[q].buf = &stream[(size_t)q * (256 + PREFIX) + 256];      // seedrandom discards the first 256 bytes
+            r[q].pos = 0; r[q].len = prefix;
+        }
     }
 };
 
@@ -106,63 +161,92 @@ void automaton_layer(Arc4& r, double density, double spread, int w, int h, int d
 
 // Force contributions of a neighbour at offset (dx, dy) = (x - xx, y - yy), dx, dy in [-4, 5]:
 // pow(dx / md, 2) * sgn(dx) and the same for dy, evaluated once with the very expressions of the original loop
-// (so that the sums below add the same doubles in the same order).
+// (so that the sums below add the same doubles in the same order).  Flat: entry (dy + 4) * 10 + (dx + 4).
+// f[sign][index] = (x component, y component); sign 1 = the negated pair (x * -1.0 == -x exactly, so the table
+// entry is what the original's multiplication by -1 produces, zeros included).
 struct DriftTable {
-    double fx[10][10], fy[10][10];
+    __m128d f[2][100];
     DriftTable() {
         for (int dy = -4; dy <= 5; dy++)
             for (int dx = -4; dx <= 5; dx++) {
                 const int md = abs(dx) + abs(dy);
-                fx[dy + 4][dx + 4] = dx ? pow((double)dx / md, 2) * sgn(dx) : 0.0;
-                fy[dy + 4][dx + 4] = dy ? pow((double)dy / md, 2) * sgn(dy) : 0.0;
+                const double fx = dx ? pow((double)dx / md, 2) * sgn(dx) : 0.0;
+                const double fy = dy ? pow((double)dy / md, 2) * sgn(dy) : 0.0;
+                f[0][(dy + 4) * 10 + dx + 4] = _mm_set_pd(fy, fx);
+                f[1][(dy + 4) * 10 + dx + 4] = _mm_set_pd(fy * -1.0, fx * -1.0);
             }
     }
 };
 const DriftTable DRIFT;
-const double SIGN[2] = {1.0, -1.0};
 
 // One gravity step (game_map.py:330-380): every deposit is pushed away from deposits of other kinds and pulled
-// towards its own kind inside a 10 x 10 window, then moves one cell along the sign of the force.  Occupied cells
-// are found through one 32-bit occupancy mask per row; the neighbours of a window are visited row by row with
-// ascending x, i.e. in the order of the original double loop, which fixes the floating-point sums.
+// towards its own kind inside a 10 x 10 window, then moves one cell along the sign of the force.  Occupancy is kept
+// as one 32-bit mask per row and kind; the window of a deposit -- at most 10 rows of 10 cells -- is cut out of them
+// into a 100-bit word (bit r * 10 + c = row y0 + r, column x0 + c), whose set bits are visited in ascending
+// order, i.e. row by row with ascending x: the order of the original double loop, which fixes the floating-point
+// sums.  One loop per deposit instead of one per window row: a single hard-to-predict loop exit, and the table
+// index of bit k is simply `base - k`.
 void drift(Field& f) {
     const int w = f.w, h = f.h;
-    uint32_t rows[32];
-    std::vector<uint8_t>& kinds = f.bits;
-    kinds.assign((size_t)w * h, 0);
+    uint32_t rows[32], rows_kind[4][32];
     for (int y = 0; y < h; y++) {
-        uint32_t m = 0;
+        uint32_t m = 0, mk[4] = {0, 0, 0, 0};
         for (int x = 0; x < w; x++) {
             const int id = f.cell(x, y);
-            if (id >= 0) { m |= 1u << x; kinds[(size_t)y * w + x] = (uint8_t)f.pool[id].kind; }
+            if (id >= 0) { m |= 1u << x; mk[f.pool[id].kind & 3] |= 1u << x; }
         }
         rows[y] = m;
+        for (int k = 0; k < 4; k++) rows_kind[k][y] = mk[k];
     }
+    // pass 1: the window words of every deposit (integer work only)
+    struct Win { uint64_t all[2], same[2]; int base; Res* res; };
+    static thread_local std::vector<Win> wins;
+    wins.clear();
     for (int y = 0; y < h; y++)
         for (uint32_t own = rows[y]; own; own &= own - 1) {
             const int x = __builtin_ctz(own);
-            Res& r = f.pool[f.cell(x, y)];
-            const int kind = r.kind;
-            double fx = 0, fy = 0;
-            const int x0 = x - 5 < 0 ? 0 : x - 5, x1 = x + 5 > w ? w : x + 5;          // [x0, x1)
-            const uint32_t window = (x1 >= 32 ? 0xffffffffu : ((1u << x1) - 1u)) & ~((1u << x0) - 1u);
+            Win wn;
+            wn.res = &f.pool[f.cell(x, y)];
+            const uint32_t* same_rows = rows_kind[wn.res->kind & 3];
+            const int x0 = x - 5 < 0 ? 0 : x - 5;                                       // columns [x0, x0 + 10) cut to the map
             const int y0 = y - 5 < 0 ? 0 : y - 5, y1 = y + 5 > h ? h : y + 5;
+            const uint32_t cut = (x + 5 >= 32 ? 0xffffffffu : ((1u << (x + 5)) - 1u)) >> x0;     // window columns, shifted down; <= 10 bits
+            // bits 0..59: window rows 0..5, bits 60..99: rows 6..9 (second word)
+            wn.all[0] = wn.all[1] = wn.same[0] = wn.same[1] = 0;
             for (int yy = y0; yy < y1; yy++) {
-                const uint8_t* krow = &kinds[(size_t)yy * w];
-                const double* tx = DRIFT.fx[y - yy + 4] + (x + 4);                   // tx[-xx] = fx[dy + 4][x - xx + 4]
-                const double* ty = DRIFT.fy[y - yy + 4] + (x + 4);
-                for (uint32_t bits = rows[yy] & window; bits; bits &= bits - 1) {
-                    const int xx = __builtin_ctz(bits);
-                    // other kinds push (+), the same kind pulls (-); a zero component adds +-0.0, which leaves
-                    // the sum's value (and its sign test) as the original's skipped addition does
-                    // (the sign comes from a two-entry table: x * -1.0 == -x exactly, and no branch to mispredict)
-                    const double sg = SIGN[krow[xx] == kind];
-                    fx += tx[-xx] * sg;
-                    fy += ty[-xx] * sg;
-                }
+                const int rr = yy - y0, word = rr >= 6, sh = (word ? rr - 6 : rr) * 10;
+                wn.all[word] |= (uint64_t)((rows[yy] >> x0) & cut) << sh;
+                wn.same[word] |= (uint64_t)((same_rows[yy] >> x0) & cut) << sh;
             }
-            r.fx = fx; r.fy = fy;
+            // dx = x - x0 - c, dy = y - y0 - r  ->  table index (dy + 4) * 10 + dx + 4 = base - (r * 10 + c)
+            wn.base = (y - y0 + 4) * 10 + (x - x0 + 4);
+            wins.push_back(wn);
         }
+    // pass 2: the sums, two deposits side by side (each sum is a chain of dependent additions in a fixed order; two
+    // independent chains keep the adder busy).  Other kinds push (+), the same kind pulls (-): the pair (x, y) of a
+    // contribution comes out of the table with its sign and is added with one two-lane addition (each lane is the
+    // original's scalar sum; a zero component adds +-0.0, which leaves the sum's value -- and its sign test -- as
+    // the original's skipped addition does).
+#define LUX_DRIFT_STEP(bits, sm, tab, acc) do { const int k_ = __builtin_ctzll(bits); bits &= bits - 1; \
+        acc = _mm_add_pd(acc, tab[(int)((sm >> k_) & 1) * 100 - k_]); } while (0)
+    const size_t nw = wins.size();
+    for (size_t i = 0; i < nw; i += 2) {
+        const Win& A = wins[i];
+        const Win& B = wins[i + 1 < nw ? i + 1 : i];
+        __m128d af = _mm_setzero_pd(), bf = _mm_setzero_pd();
+        for (int word = 0; word < 2; word++) {
+            const __m128d* at = DRIFT.f[0] + A.base - 60 * word;
+            const __m128d* bt = DRIFT.f[0] + B.base - 60 * word;
+            uint64_t ab = A.all[word], bb = B.all[word];
+            const uint64_t as = A.same[word], bs = B.same[word];
+            while (ab && bb) { LUX_DRIFT_STEP(ab, as, at, af); LUX_DRIFT_STEP(bb, bs, bt, bf); }
+            while (ab) LUX_DRIFT_STEP(ab, as, at, af);
+            while (bb) LUX_DRIFT_STEP(bb, bs, bt, bf);
+        }
+        A.res->fx = _mm_cvtsd_f64(af); A.res->fy = _mm_cvtsd_f64(_mm_unpackhi_pd(af, af));
+        if (i + 1 < nw) { B.res->fx = _mm_cvtsd_f64(bf); B.res->fy = _mm_cvtsd_f64(_mm_unpackhi_pd(bf, bf)); }
+    }
+#undef LUX_DRIFT_STEP
     std::vector<int>& out = f.scratch;
     out.assign((size_t)w * h, -1);
     for (int y = 0; y < h; y++)
@@ -229,9 +313,8 @@ bool enough(Field& f) {
     return tot[LUX_RES_WOOD] >= 2000 && tot[LUX_RES_COAL] >= 1500 && tot[LUX_RES_URANIUM] >= 300;
 }
 
-int generate_one(int64_t seed, int size, int u_cap, int c_cap, int t_cap, int r_cap, LuxHeader* hdr, LuxCell* cells,
+int generate_one(Arc4& r, int size, int u_cap, int c_cap, int t_cap, int r_cap, LuxHeader* hdr, LuxCell* cells,
                  LuxUnit* units, LuxCity* cities, uint16_t* tiles, LuxRes* res) {
-    Arc4 r("gen_" + std::to_string((long long)seed));
     static const int SIZES[4] = {12, 16, 24, 32};
     int drawn = SIZES[(int)floor(r.next() * 4)];
     int w = size > 0 ? size : drawn, h = w;
@@ -327,15 +410,26 @@ extern "C" int lux_mapgen_generate_batch(const LuxBatch* out, const int64_t* see
     if (threads < 1) threads = 1;
     if (threads > n) threads = n > 0 ? n : 1;
     std::atomic<int> next(0), status(LUX_OK);
+    // keystream produced ahead per map: what a map of this side needs (measured mean + 4 %: 32 x 32 13.7 KB)
+    const int prefix = size >= 32 ? 14 * 1024 : size >= 24 ? 8 * 1024 : size >= 16 ? 4 * 1024 : 2560;
     auto work = [&]() {
+        Arc4x4 quad;
         for (;;) {
-            int m = next.fetch_add(1);
-            if (m >= n) break;
-            int rc = generate_one(seeds[m], size, out->u_cap, out->c_cap, out->t_cap, out->r_cap, out->hdr + m,
-                                  out->cells + (size_t)m * size * size, out->units + (size_t)m * out->u_cap,
-                                  out->cities + (size_t)m * out->c_cap, out->tiles + (size_t)m * out->t_cap,
-                                  out->res + (size_t)m * out->r_cap);
-            if (rc != LUX_OK) status.store(rc);
+            // four maps at a time: their keystreams are produced side by side, then each map is laid out from its own
+            const int m0 = next.fetch_add(4);
+            if (m0 >= n) break;
+            const int cnt = n - m0 < 4 ? n - m0 : 4;
+            std::string key[4];
+            for (int q = 0; q < 4; q++) key[q] = "gen_" + std::to_string((long long)seeds[m0 + (q < cnt ? q : 0)]);
+            quad.start(key, prefix);
+            for (int q = 0; q < cnt; q++) {
+                const int m = m0 + q;
+                int rc = generate_one(quad.r[q], size, out->u_cap, out->c_cap, out->t_cap, out->r_cap, out->hdr + m,
+                                      out->cells + (size_t)m * size * size, out->units + (size_t)m * out->u_cap,
+                                      out->cities + (size_t)m * out->c_cap, out->tiles + (size_t)m * out->t_cap,
+                                      out->res + (size_t)m * out->r_cap);
+                if (rc != LUX_OK) status.store(rc);
+            }
         }
     };
     std::vector<std::thread> pool;
