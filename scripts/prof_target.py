@@ -1,6 +1,6 @@
 """Profiling target: the bench workload (32x32, 16384 matches, 400 burn-in turns) followed by a few steps.
-  python scripts/prof_target.py [steps]      -- run under ncu with  -k regex:lux_step_kernel -s 806 -c 2
-(400 burn-in + 3 warm-up steps = 806 lux_step_kernel launches: big class, small class per step)."""
+  python scripts/prof_target.py [steps]      -- run under ncu with  -k regex:lux_step_kernel -s 1209 -c 3
+(400 burn-in + 3 warm-up steps = 1209 lux_step_kernel launches: big class, small class, oversize launch per step)."""
 import sys
 
 sys.path.insert(0, ".")
