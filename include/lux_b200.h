@@ -143,6 +143,9 @@ int lux_b200_device_count(void);
  * of the big class: 0 = automatic, 12 KB, with the rare match beyond it played by a launch of its own with
  * full-capacity slices; -1 = full capacity for the whole big class), "over_own" (that launch on a stream of its own:
  * -1 = when the statistics have seen such matches, otherwise it follows the big class on its stream; 0 never; 1 always),
+ * "cta_sync" (warps per CTA of the small class with a CTA-wide rendezvous at some phase boundaries of the turn, so that
+ * the warps fetch a phase's code together: -1 = automatic, 8 on dense batches and none on sparse ones; 0 = never; n = always n;
+ * 32 x 32 maps, flags 0 only), "sync_mask" (which of the nine rendezvous points are armed, default 0x54),
  * "slice" (shared-memory bytes per match of the small class, 0 = default), "group" (lanes per match: 0 automatic,
  * 8 / 16 / 32), "carveout" (preferred shared-memory carve-out in percent, -1 = automatic), "list_grid" (CTAs of
  * the big-class launch, 0 = automatic), "gen_wpc" (matches per CTA of the action-stream kernel); measurement aids:

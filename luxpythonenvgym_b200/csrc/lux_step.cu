@@ -104,11 +104,11 @@ __device__ __forceinline__ void lux_step_match(const LuxBatch& b, int m, int val
         }
         // one group per warp: a group with nothing to play has nobody to keep in step with and leaves at once
         // (finished matches of a draining batch then cost a header load, not a walk through an empty turn)
-        if (G == 32 && !active) return;
+        if (G == 32 && !active && !(flags & LUX_TURN_CTA_SYNC)) return;
         LuxSmemLayout L = lux_smem_layout_need(size, need);
         if (active && L.total > slice) {
             active = 0; result = LUX_M_SPILL;
-            if (G == 32) {
+            if (G == 32 && !(flags & LUX_TURN_CTA_SYNC)) {
                 // cannot happen (the classification pass routes such a match to the big class); visible if it ever does
                 if (lane == 0) atomicOr((unsigned*)&g.hdr->done, (unsigned)LUX_ST_BAD_STATE << 16);   // done | winner | status | size
                 return;
@@ -213,10 +213,10 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
 // 2 = compiled for the host list path without pre-validation (action words consumed); 0 = any flags.  The
 // specialised programs are shorter, which is what the instruction cache wants.
 template <bool kTma, int kS, int kMode, int G, int kSpec>
-__global__ void __launch_bounds__(64, kMode == kSmall ? (G == 32 ? LUX_SMALL_MIN_CTAS : G == 16 ? 13 : 6) : 1)
+__global__ void __launch_bounds__(kSpec == 3 ? 1024 : 64, kSpec == 3 ? 1 : kMode == kSmall ? (G == 32 ? LUX_SMALL_MIN_CTAS : G == 16 ? 13 : 6) : 1)
 lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uint8_t* __restrict__ tile_actions,
                 int slice, unsigned flags_in, LuxSched sc) {
-    const unsigned flags = kSpec == 1 ? 0u : kSpec == 2 ? LUX_STEP_CONSUME : flags_in;
+    const unsigned flags = kSpec == 1 ? 0u : kSpec == 2 ? LUX_STEP_CONSUME : kSpec == 3 ? LUX_TURN_CTA_SYNC : flags_in;
     extern __shared__ __align__(128) unsigned char lux_smem[];
     // Both classes need the classification pass complete.  Default ("fork"): the big class is an ordinary launch on
     // the side stream behind an event, the small class a programmatic dependent of the classification pass that
@@ -262,7 +262,7 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
     if (kMode == kSmall && valid && __ldcg(sc.cls + m)) valid = 0;          // the big class plays it
     LUX_TRACE_BEGIN(sc.trace, 2);
     LUX_TRACE_BIN(sc.trace, 8);
-    if (lux_wany<G>(valid))
+    if (kSpec == 3 || lux_wany<G>(valid))
         lux_step_match<kTma, kS, G, kMode == kAll>(b, m, valid, unit_actions, tile_actions, smem, flags, slice, phase);
     LUX_TRACE_END(sc.trace, 2);
     // a programmatic dependent may not finish before its primary: later work on the stream waits for this grid
@@ -283,6 +283,9 @@ static int g_big_share = 3;       // the small slice is the smallest candidate t
                                   // classes ran as independent grids; a dense batch now plays 13 % faster with a third of it in the big class)
 static int g_mid_slice = 0;       // slice of the big class: 0 = automatic (12 KB), -1 = full capacity (no oversize launch)
 static int g_over_own = -1;       // oversize launch on a stream of its own: -1 = when the statistics have seen oversize matches, 0 never, 1 always
+static int g_cta_sync = -1;       // warps per CTA of the small class with a CTA-wide rendezvous between phases: -1 = automatic (8 on dense
+                                  // batches, i.e. when the small slice is 6 KB or more; none on sparse ones), 0 = never, n = always n
+static thread_local int t_sync_w = 0;     // the choice for the launch being issued (lux_step_impl -> launch_step)
 static int g_only_class = 0;      // measurement aid: 1 = launch only the big class, 2 = only the small class (results are then incomplete)
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
@@ -312,6 +315,9 @@ static int launch_step_plain(const LuxBatch* b, const uint32_t* ua, const uint8_
 template <bool kTma, int kS, int kMode, int G>
 static int launch_step(const LuxBatch* b, const uint32_t* ua, const uint8_t* ta, int slice, unsigned flags, const LuxSched& sc,
                        int n_groups, int wpc, cudaStream_t st) {
+    if constexpr (kTma && G == 32 && kS == 32 && kMode == kSmall) {
+        if (flags == 0 && t_sync_w > 0) return launch_step_plain<kTma, kS, kMode, G, 3>(b, ua, ta, slice, flags, sc, n_groups, t_sync_w, st);
+    }
     if constexpr (kTma && G == 32) {
         if (flags == 0) return launch_step_plain<kTma, kS, kMode, G, 1>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
         if (flags == LUX_STEP_CONSUME) return launch_step_plain<kTma, kS, kMode, G, 2>(b, ua, ta, slice, flags, sc, n_groups, wpc, st);
@@ -671,6 +677,8 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "fork")) { g_fork = value != 0; return LUX_OK; }
     if (!strcmp(name, "mid_slice")) { g_mid_slice = value; return LUX_OK; }
     if (!strcmp(name, "over_own")) { g_over_own = value; return LUX_OK; }
+    if (!strcmp(name, "sync_mask")) { unsigned v = (unsigned)value; return cudaMemcpyToSymbol(lux_phase_sync_mask, &v, sizeof v) == cudaSuccess ? LUX_OK : LUX_E_CUDA; }
+    if (!strcmp(name, "cta_sync")) { g_cta_sync = value < 0 ? -1 : value > 32 ? 32 : value; return LUX_OK; }
     if (!strcmp(name, "trace")) {
         if (value && !g_trace && cudaMalloc(&g_trace, 40 * sizeof(unsigned long long)) != cudaSuccess) return LUX_E_CUDA;
         if (!value && g_trace) { cudaFree(g_trace); g_trace = nullptr; }
@@ -890,7 +898,14 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
         LuxSched ss = sc;
         ss.wait_first = 1;
         int group = pick_group(small);
+        // Dense batches (small slice of 6 KB or more): 8 warps per CTA that meet at three points of the turn, so that
+        // they fetch a phase's code together -- the dense small class spends 42 % of its stall samples waiting for
+        // instructions (profiles/r02f_dense_*); 0.199 -> 0.182 ms per step.  Sparse batches gain nothing (stragglers
+        // cost what the fetches save) and keep 2-warp CTAs without rendezvous.
+        t_sync_w = group == 32 ? (g_cta_sync >= 0 ? g_cta_sync : (small >= 6144 ? 8 : 0)) : 0;
+        while (t_sync_w > 1 && (size_t)t_sync_w * small > 160 * 1024) t_sync_w--;
         rc = launch_step_group<true, kSmall>(group, b, unit_actions, tile_actions, small, flags, ss, b->n_matches, pick_wpc(small, group), st);
+        t_sync_w = 0;
         if (rc) return rc;
         if (mid < full && !over_own) {
             t_plain_launch = 1;

@@ -19,6 +19,11 @@
 //   * dead units / cities are compacted and the canonical orders (team A then B units,
 //     cities x city_cells tiles) rebuilt while storing.
 #pragma once
+#ifndef LUX_EMULATE
+__constant__ unsigned lux_phase_sync_mask = 0x54u;       // which of the nine rendezvous points of lux_turn are armed (option "sync_mask";
+                                                         // default: before the city-tile turns, the unit pass and the deposit)
+#endif
+#define LUX_TURN_CTA_SYNC 0x8000u      // internal turn flag: CTA-wide rendezvous between phases (launcher experiment "cta_sync")
 #include "../../include/lux_b200.h"
 #include "lux_warp.cuh"
 
@@ -758,6 +763,15 @@ struct LuxTurnOut { int n_units; int n_cities; int n_tiles; int tiles_dirty; int
 
 template <int kS, int G>
 LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
+    // Phase rendezvous of the CTA's warps (LUX_TURN_CTA_SYNC, set by the launcher for dense batches): warps that enter
+    // a phase together fetch its code together (the turn is a once-through program larger than the SM's 32 KB
+    // instruction cache).  Every warp of the CTA walks through lux_turn (idle ones on an empty match), so every warp
+    // executes the same barriers.
+#ifdef LUX_EMULATE
+#define LUX_PHASE_SYNC(i) do { } while (0)
+#else
+#define LUX_PHASE_SYNC(i) do { if ((flags & LUX_TURN_CTA_SYNC) && ((lux_phase_sync_mask >> (i)) & 1u)) asm volatile("bar.sync 1, %0;" :: "r"(blockDim.x) : "memory"); } while (0)
+#endif
     const int lane = lux_lane<G>();
     const unsigned lt = lux_lanemask_lt<G>();
     LuxHeader* h = M.hdr;
@@ -794,6 +808,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     const int tu0 = h->n_team_units[0], tu1 = h->n_team_units[1];
 
     int any_move = 0;
+    LUX_PHASE_SYNC(0);
     // ---- unit action validation (validate_command game.py:646-695), lanes over units; at most one
     // global cell load per unit (its own cell for a build, the target cell for a move)
 #pragma unroll 1
@@ -900,6 +915,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         }
     }
 
+    LUX_PHASE_SYNC(1);
     // ---- collision pruning (handle_movement_actions game.py:1104-1195); shared memory only.
     // Flags are set on every cell (city tiles too) but only ever read on non-city target cells.
     if (any_move_w) {
@@ -951,6 +967,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     }   // any_move_w
     // (the movement flags are cleared at the head of the unit pass: the byte of every cell a unit stands on or aimed at)
 
+    LUX_PHASE_SYNC(2);
     // ---- city tiles: spawn validation (game.py:696-718) + CityTile.turn (city.py:96-120)
     int n_units = n_units0;
     int born0 = 0, born1 = 0, died0 = 0, died1 = 0;      // per-team population changes of this turn
@@ -1027,6 +1044,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     }
     lux_sync<G>();
 
+    LUX_PHASE_SYNC(3);
     // ---- unit turns (Worker.turn unit.py:162-197, Cart.turn :234-269)
     // Moves are conflict-free after pruning and nothing reads another unit's position before the unit pass (a unit
     // holds ONE action: the ordered actions below -- transfer by id, build / pillage on the own cell -- belong to units
@@ -1107,6 +1125,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     if (n_tiles != n_tiles0) tiles_dirty = 1;
     lux_city_prefix<G>(M, n_cities);     // also syncs
 
+    LUX_PHASE_SYNC(4);
     // ---- the unit pass: cooldowns of the acting units, the carts' automatic roads (unit.py:196-197,
     // :257-269), and the per-unit caches the rest of the turn works from -- what the unit stands on
     // (uinfo), which of its five cells it can mine (umin, 2 bits of resource type per direction) and the
@@ -1198,6 +1217,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     }
     lux_sync<G>();
 
+    LUX_PHASE_SYNC(5);
     // ---- resource collection: uranium, coal, wood (distribute_all_resources game.py:868-880)
     {
         const int rp0 = h->research[0], rp1 = h->research[1];
@@ -1216,6 +1236,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         }
     }
 
+    LUX_PHASE_SYNC(6);
     // ---- deposit (handle_resource_deposit game.py:1003-1023)
     {
         int fg0 = 0, fg1 = 0;
@@ -1237,6 +1258,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
     }
     lux_sync<G>();
 
+    LUX_PHASE_SYNC(7);
     // ---- night (handle_night game.py:537-558); matches of one warp differ in their turn counters, so
     // the phase runs when any of them has night and the others walk through it with empty lists
     if (lux_wany<G>(night)) {
@@ -1304,6 +1326,7 @@ LUX_DEV LuxTurnOut lux_turn(LuxMatch& M, unsigned flags) {
         lux_sync<G>();
     }
 
+    LUX_PHASE_SYNC(8);
     // ---- depleted cells leave the list (game.py:498-510), trees regrow (:1081-1102).  The resource list
     // carries each cell's type and a mirror of its amount, so this pass over ALL resource cells works on shared
     // memory; only a cell somebody mined from this turn is re-read from the grid (the collection pass stored

@@ -329,9 +329,11 @@ def test_step_is_deterministic_across_launch_forms():
     try:
         # mid: the big class's slice (0 = 12 KB + oversize launch, -1 = full capacity, 5632: most big matches oversize)
         for fork, two, mid, rep in ((1, -1, 0, 0), (1, -1, 0, 1), (0, -1, 0, 0), (0, -1, 0, 1), (1, 0, 0, 0), (1, -1, -1, 0),
-                                    (1, -1, 5632, 0), (1, -1, 5632, 1), (1, -1, 5633, 0), (1, -1, 5633, 1)):
+                                    (1, -1, 5632, 0), (1, -1, 5632, 1), (1, -1, 5633, 0), (1, -1, 5633, 1),
+                                    (1, -1, 0, 8), (1, -1, 0, 9), (1, 1, 0, 4), (1, 1, 0, 5)):
             lib.lux_b200_set_option(b"fork", fork)
             lib.lux_b200_set_option(b"two_class", two)
+            lib.lux_b200_set_option(b"cta_sync", (rep // 2) * 2 if rep >= 4 else 0)      # rep >= 4: rendezvous CTAs of 4 / 8 warps
             lib.lux_b200_set_option(b"mid_slice", mid & ~1)
             lib.lux_b200_set_option(b"over_own", -1 if mid <= 0 else mid & 1)      # odd: oversize launch on its own stream
             for k, v in g.sections().items():
@@ -352,6 +354,7 @@ def test_step_is_deterministic_across_launch_forms():
         lib.lux_b200_set_option(b"two_class", -1)
         lib.lux_b200_set_option(b"mid_slice", 0)
         lib.lux_b200_set_option(b"over_own", -1)
+        lib.lux_b200_set_option(b"cta_sync", -1)
 
 
 def test_bad_arguments_are_rejected():
@@ -648,11 +651,14 @@ def test_spill_list_and_scheduling_paths_under_load():
         # heavy 0: serialized launches; 1: round 1's dependent-launch overlap; 2: the big class forked to the side
         # stream (the default); 3: the same on a batch smaller than the machine (every CTA resident at once);
         # 4: forked, with a big-class slice so small that most dense matches go to the oversize launch (on its own
-        # stream); 5: the same with the oversize launch behind the big class on its stream
-        for heavy in (0, 1, 2, 3, 4, 5):
+        # stream); 5: the same with the oversize launch behind the big class on its stream; 6: the small class in
+        # 8-warp CTAs with a rendezvous at all nine phase boundaries (CTAs with idle warps: big-class matches, the
+        # batch's ragged end); 7: the same, 5 warps, default rendezvous points
+        for heavy in (0, 1, 2, 3, 4, 5, 6, 7):
             for k, v in ((b"slice", 3200), (b"two_class", 1), (b"overlap", int(heavy > 0)), (b"fork", int(heavy >= 2)),
-                         (b"group", (8, 16, 32, 32, 32, 32)[heavy]), (b"mid_slice", 6144 if heavy >= 4 else 0),
-                         (b"over_own", (-1, -1, -1, -1, 1, 0)[heavy])):
+                         (b"group", (8, 16, 32, 32, 32, 32, 32, 32)[heavy]), (b"mid_slice", 6144 if heavy in (4, 5) else 0),
+                         (b"over_own", (-1, -1, -1, -1, 1, 0, -1, -1)[heavy]), (b"cta_sync", (0, 0, 0, 0, 0, 0, 8, 5)[heavy]),
+                         (b"sync_mask", 0x1FF if heavy == 6 else 0x54)):
                 assert lib.lux_b200_set_option(k, v) == 0
             n = 384 if heavy < 3 else 120
             g = _game(n, 32)
@@ -682,5 +688,5 @@ def test_spill_list_and_scheduling_paths_under_load():
             assert len(gpu_util.diff_batches(hosts[i], gm)) == 0, i
     finally:
         for k, v in ((b"slice", 0), (b"two_class", -1), (b"overlap", 1), (b"fork", 1),
-                     (b"group", 0), (b"mid_slice", 0), (b"over_own", -1)):
+                     (b"group", 0), (b"mid_slice", 0), (b"over_own", -1), (b"cta_sync", -1), (b"sync_mask", 0x54)):
             lib.lux_b200_set_option(k, v)
