@@ -166,6 +166,43 @@ def test_done_matches_are_untouched_and_reset():
     assert (hh["done"] == 0).all() and (hh["turn"][done] == 0).all()
 
 
+def test_bench_trajectory_at_full_size_equals_the_cpu_arm():
+    """BASELINE.json config 5's per-GPU shape at FULL size -- 16384 resident 32x32 matches, seeded action stream,
+    finished matches replaced from a map pool -- played for 150 turns exactly as bench.py plays it (step, then the
+    fused reset + action-stream pass), against the loop bench.py's CPU arm times (lux_oracle_run_batch: stream,
+    step, pool reset; 16 host threads over disjoint blocks of matches): every live byte of every match equal, and
+    the same number of resets.  Pins the full-size run to the oracle AND the two bench arms to the same work."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import coracle
+    n, size, n_pool, turns, seed = 16384, 32, 256, 150, 20211019
+    pool_arr = mapgen.generate_batch(np.arange(770000, 770000 + n_pool), size)
+    g = _game(n, size)
+    pool = _game(n_pool, size)
+    pool.load_arrays(pool_arr)
+    g.load_arrays({k: np.ascontiguousarray(v[np.arange(n) % n_pool]) for k, v in pool_arr.items()})
+    host = gpu_util.HostBatch(g)
+    parr = {k: np.ascontiguousarray(v) for k, v in pool_arr.items()}
+    pdesc = coracle.batch_desc(size, g.caps, parr, n_pool)
+    resets = torch.zeros(1, dtype=torch.int32, device="cuda")
+    g.gen_actions(seed, 0)
+    for t in range(turns):
+        g.step()
+        g.reset_gen(pool, t, seed, 0, reset_count=resets)
+    torch.cuda.synchronize()
+    threads = 16
+    chunks = [(k * n // threads, (k + 1) * n // threads) for k in range(threads)]
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(lambda c: coracle.run_batch(host.desc, pdesc, seed, 0, host.ua, host.ta, c[0], c[1] - c[0], turns, 0), chunks))
+    bad = gpu_util.diff_batches(host, g)
+    assert len(bad) == 0, "%d matches differ, first %d: %s" % (len(bad), bad[0], gpu_util.explain(host, g, int(bad[0])))
+    hh = host.hdr()
+    assert (hh["status"] == 0).all() and (hh["done"] == 0).all()
+    assert int(resets.item()) > n // 8                   # the pool-reset path carried real traffic
+    st = g.stats().cpu().numpy()
+    assert int(st[0]) == n and int(st[7]) == int(hh["n_units"].sum()) and int(st[8]) == int(hh["n_tiles"].sum())
+    assert sum(r[1] for r in res) > n * turns * 0.95     # live match-turns the CPU arm counted
+
+
 def test_reset_gen_equals_reset_then_gen():
     """The fused harness pass (lux_b200_reset_gen) against the two separate calls: same states, same action
     tensors, same counters, turn by turn on a batch that keeps finishing matches."""
