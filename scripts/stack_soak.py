@@ -11,6 +11,13 @@ from luxpythonenvgym_b200.batched import BatchedGame
 n_states = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 turns = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 rng = np.random.default_rng(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+# launcher options for the run, e.g. LUX_OPTS=cta_sync=8,sync_mask=511,slice=3200,two_class=1,mid_slice=6144
+import os
+if os.environ.get("LUX_OPTS"):
+    from luxpythonenvgym_b200 import _lib as _opt_lib
+    for _kv in os.environ["LUX_OPTS"].split(","):
+        _k, _v = _kv.split("=")
+        assert _opt_lib.load().lux_b200_set_option(_k.encode(), int(_v)) == 0, _kv
 states = []
 for k in range(n_states):
     used = set()
