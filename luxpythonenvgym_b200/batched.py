@@ -14,6 +14,9 @@ import torch
 from . import _lib
 from . import state as S
 
+# torch's current stream as a raw handle (an int ctypes passes as void*); the public accessor builds a Stream object
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
 
 class BatchedGame:
     def __init__(self, n_matches, size, caps=None, device="cuda:0"):
@@ -24,6 +27,7 @@ class BatchedGame:
         self.size = int(size)
         self.caps = dict(S.default_caps(size), **(caps or {}))
         self.device = torch.device(device)
+        self._dev_index = self.device.index if self.device.index is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
         c = self.caps
         ncell = size * size
         z = lambda *shape: torch.zeros(shape, dtype=torch.uint8, device=self.device)
@@ -48,6 +52,9 @@ class BatchedGame:
                              self.cities.data_ptr(), self.tiles.data_ptr(), self.res.data_ptr())
 
     def _stream(self):
+        # the raw handle of torch's current stream (no Stream object per call: this sits on the per-turn host path)
+        if _RAW_STREAM is not None:
+            return _RAW_STREAM(self._dev_index)
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def sections(self):

@@ -376,7 +376,7 @@ __device__ __forceinline__ unsigned lux_mod64(uint64_t r, unsigned m) {
 // one warp per match, state read in place from global memory (harness kernel, not the hot path)
 __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, uint64_t seed, uint64_t match_id_base,
                                                       uint32_t* __restrict__ unit_actions,
-                                                      uint8_t* __restrict__ tile_actions, unsigned* counters) {
+                                                      uint8_t* __restrict__ tile_actions, unsigned* counters, uint2* skeys) {
     const int lane = threadIdx.x & 31;
     const int ncell = b.size * b.size, S = b.size;
     const LuxHeader* h = b.hdr + m;
@@ -399,6 +399,20 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
     // units and city tiles share one pass (entity e < nu_w: unit slot e, else tile position e - nu_w): the
     // 64-bit hash is most of the work and a typical match has fewer than 32 entities of both kinds together
     const int total = nu_w + nt_w;
+    // the hash of an entity is lux_hash(seed, match, turn, kind, key): its first two rounds are the same for the whole match
+    const uint64_t HG = 0x9E3779B97F4A7C15ULL;
+    const uint64_t hash2 = lux_mix64(lux_mix64(seed + HG * (mid + 1)) + HG * ((uint64_t)turn + 1));
+    // Transfer targets ("the lowest-id teammate on the unit's cell or next to it") are looked up through packed
+    // positions team << 12 | y << 6 | x: for a difference d of two of them, d * d is 0, 1 or 4096 exactly when the
+    // teams are equal and the cells are the same or adjacent (|dx|, |dy| <= 31 < 64).  A match with more than 32
+    // units keeps the (position, id) pairs of all of them in the warp's shared-memory strip.
+    if (!done && nu > 32) {
+        for (int j = lane; j < nu; j += 32) {
+            const LuxUnit V = units[j];
+            skeys[j] = make_uint2(((unsigned)(V.team_type & 1) << 12) | ((unsigned)V.y << 6) | V.x, (unsigned)V.id);
+        }
+        __syncwarp();
+    }
     for (int base = 0; base < total; base += 32) {          // warp-uniform trip count (shuffles inside)
         const int e = base + lane;
         const int in_range = e < total;
@@ -412,7 +426,7 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
         if (live) {
             if (is_unit) { U = units[i]; cell = U.y * S + U.x; }
             else cell = tiles[i];
-            r = lux_hash(seed, mid, (uint64_t)turn, is_unit ? 0 : 1, is_unit ? (uint64_t)U.id : (uint64_t)cell);
+            r = lux_mix64(lux_mix64(hash2 + HG * (is_unit ? 1 : 2)) + HG * ((is_unit ? (uint64_t)U.id : (uint64_t)cell) + 1));   // == lux_hash(...)
         }
         uint32_t w = 0;
         uint8_t code = 0;
@@ -443,21 +457,20 @@ __device__ __forceinline__ void lux_gen_actions_match(const LuxBatch& b, int m, 
         }
         if (__any_sync(0xffffffffu, want_target)) {
             int best_id = 0x7fffffff;
+            const int mine = ((int)(U.team_type & 1) << 12) | ((int)U.y << 6) | (int)U.x;
             if (base == 0 && nu <= 32) {
                 // every unit of the match sits in a lane of this pass: broadcast them one by one
-                const int mine = (int)U.x | ((int)U.y << 8) | ((int)(U.team_type & 1) << 16);
                 for (int j = 0; j < nu; j++) {
-                    const int other = __shfl_sync(0xffffffffu, mine, j), oid = __shfl_sync(0xffffffffu, U.id, j);
-                    if (j == i || ((other ^ mine) >> 16)) continue;
-                    int d = abs((other & 0xff) - (int)U.x) + abs(((other >> 8) & 0xff) - (int)U.y);
-                    if (d <= 1 && oid < best_id) best_id = oid;
+                    const int d = __shfl_sync(0xffffffffu, mine, j) - mine, oid = __shfl_sync(0xffffffffu, U.id, j);
+                    const unsigned sq = (unsigned)(d * d);
+                    if ((sq <= 1u || sq == 4096u) && j != i && oid < best_id) best_id = oid;
                 }
             } else if (want_target) {
                 for (int j = 0; j < nu; j++) {
-                    const LuxUnit V = units[j];
-                    if (j == i || ((V.team_type ^ U.team_type) & 1)) continue;
-                    int d = abs((int)V.x - (int)U.x) + abs((int)V.y - (int)U.y);
-                    if (d <= 1 && V.id < best_id) best_id = V.id;
+                    const uint2 kv = skeys[j];
+                    const int d = (int)kv.x - mine;
+                    const unsigned sq = (unsigned)(d * d);
+                    if ((sq <= 1u || sq == 4096u) && j != i && (int)kv.y < best_id) best_id = (int)kv.y;
                 }
             }
             if (want_target && best_id != 0x7fffffff) {
@@ -487,7 +500,9 @@ __global__ void __launch_bounds__(256, 6) lux_gen_actions_kernel(LuxBatch b, uin
         __syncthreads();
     }
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (m < b.n_matches) lux_gen_actions_match(b, m, seed, match_id_base, unit_actions, tile_actions, counters ? cta_counters : nullptr);
+    __shared__ uint2 gen_keys[8][256];          // per warp: (packed position, id) of the units of a match with more than 32
+    if (m < b.n_matches) lux_gen_actions_match(b, m, seed, match_id_base, unit_actions, tile_actions, counters ? cta_counters : nullptr,
+                                               gen_keys[threadIdx.x >> 5]);
     if (counters && (threadIdx.x & 31) == 0) {
         __threadfence_block();
         if (atomicAdd(&cta_ticket, 1u) == (blockDim.x >> 5) - 1) {
@@ -602,6 +617,7 @@ __global__ void __launch_bounds__(256, 6) lux_reset_gen_kernel(LuxBatch b, LuxBa
         if (threadIdx.x == 2) cta_ticket = 0;
         __syncthreads();
     }
+    __shared__ uint2 gen_keys[8][256];          // see lux_gen_actions_kernel
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     LUX_TRACE_BEGIN(g_trace_dev, 1);
     if (m < b.n_matches) {
@@ -609,7 +625,8 @@ __global__ void __launch_bounds__(256, 6) lux_reset_gen_kernel(LuxBatch b, LuxBa
             lux_reset_match<2>(b, pool, m, epoch, reset_count);
             __syncwarp();                   // the fresh match is read back by other lanes of this warp
         }
-        lux_gen_actions_match(b, m, seed, match_id_base, unit_actions, tile_actions, counters ? cta_counters : nullptr);
+        lux_gen_actions_match(b, m, seed, match_id_base, unit_actions, tile_actions, counters ? cta_counters : nullptr,
+                              gen_keys[threadIdx.x >> 5]);
     }
     LUX_TRACE_END(g_trace_dev, 1);
     if (counters && (threadIdx.x & 31) == 0) {
