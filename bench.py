@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--matches", type=int, default=MATCHES_PER_GPU)
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = as many as --steps")
+    ap.add_argument("--e2e-halves", action="store_true", help="end-to-end leg ALSO with the batch driven as two pipelined half-batches "
+                                                              "(reported as e2e.two_halves_value; measured +2.4 %: the leg is device-bound)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the dense and config-4 legs (N = 1 only)")
     return ap.parse_args()
@@ -355,6 +357,78 @@ def config4_leg(dev, n_envs, steps=200):
             "obs_bytes_per_turn": 340 * decisions / steps}
 
 
+def e2e_two_halves(game, pool, snap, base, epoch0, resets, W_e, E, barrier):
+    """The end-to-end leg with the resident batch driven as TWO half-batches, each through its own
+    submit / wait pair on its own stream: while the host blocks on one half's done flags and uploads that half's next
+    action list, the device plays the other half.  Per half and per turn nothing changes: the turn's host action list
+    is uploaded from pinned memory, the host waits for THAT turn's done flags + summary before it submits the half's
+    next turn.  Returns (seconds for E turns of both halves, h2d bytes per turn, d2h bytes per turn); the final
+    headers of the host path are checked against the device path of the same half-batches."""
+    import torch
+    from luxpythonenvgym_b200.batched import BatchedGame
+    dev, n, size = game.device, game.n, game.size
+    h = n // 2
+    halves, fin, ents, ent_ks = [], [], [], []
+    for i in range(2):
+        g = BatchedGame(h, size, caps=game.caps, device=dev)
+        for k, t in g.sections().items():
+            t.copy_(snap[k][i * h:(i + 1) * h])
+        # recording pass (untimed): the device action stream of this half, turn by turn, packed into entry lists
+        ent_dev, ent_k = [], []
+        for k in range(W_e + E):
+            g.unit_actions.zero_()
+            g.tile_actions.zero_()
+            g.gen_actions(STREAM_SEED, base + i * h)
+            ent = g.pack_entries()
+            ent_dev.append(ent)
+            ent_k.append(int(ent.shape[0]))
+            g.step()
+            g.reset_done(pool, epoch0 + k, resets)
+        torch.cuda.synchronize()
+        fin.append(g.hdr.clone())
+        off = np.concatenate([[0], np.cumsum(ent_k)]).astype(np.int64)
+        ent_h = torch.empty((max(int(off[-1]), 1), 2), dtype=torch.int32).pin_memory()
+        for k, ent in enumerate(ent_dev):
+            ent_h[off[k]: off[k + 1]].copy_(ent)
+        del ent_dev
+        for k, t in g.sections().items():     # rewind
+            t.copy_(snap[k][i * h:(i + 1) * h])
+        g.unit_actions.zero_()
+        g.tile_actions.zero_()
+        halves.append(g)
+        ents.append([ent_h[off[k]: off[k + 1]] for k in range(W_e + E)])
+        ent_ks.append(ent_k)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    done_h = [torch.empty(h, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    summ_h = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def submit(i, k):
+        with torch.cuda.stream(streams[i]):
+            halves[i].step_host_sparse_submit(ents[i][k], ent_ks[i][k])
+            halves[i].reset_done(pool, epoch0 + k, resets)       # queued before the host blocks on this half
+
+    def wait(i):
+        with torch.cuda.stream(streams[i]):
+            halves[i].step_host_wait(done_h[i], summ_h[i])
+
+    for k in range(W_e):                     # untimed: first-call allocations, pinned-page faults
+        submit(0, k); submit(1, k); wait(0); wait(1)
+    barrier()
+    w0 = time.perf_counter()
+    submit(0, W_e); submit(1, W_e)
+    for k in range(W_e + 1, W_e + E):
+        wait(0); submit(0, k)
+        wait(1); submit(1, k)
+    wait(0); wait(1)
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - w0
+    for i in range(2):
+        assert torch.equal(halves[i].hdr, fin[i]), "host-buffer path (two halves) diverged from the device path"
+    h2d = sum(8 * ent_ks[i][k] for i in range(2) for k in range(W_e, W_e + E)) // max(E, 1)
+    return secs, h2d, 2 * (h + 16)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -510,16 +584,23 @@ def run_b200(args):
     # live match-turns of those E steps = the same trajectory the device path ran
     h2d = h2d_total // max(E, 1)
     d2h = n + 16
+    # the same leg with the batch driven as two pipelined half-batches (each with its own submit / wait)
+    e2e_halves_s = 0.0
+    if n >= 2048 and n % 2 == 0 and args.e2e_halves:
+        for k, t in game.sections().items():     # rewind (the halves start from the same snapshot)
+            t.copy_(snap[k])
+        pipe_s, pipe_h2d, pipe_d2h = e2e_two_halves(game, pool, snap, base, epoch0, resets, W_e, E, barrier)
+        e2e_halves_s = pipe_s
 
     # ---- reduce over ranks: time = max, work = sum; stats vector all-reduced with NCCL
     stats = game.stats().clone()
-    red = torch.tensor([total_ms, step_ms, e2e_s], dtype=torch.float64, device=dev)
+    red = torch.tensor([total_ms, step_ms, e2e_s, e2e_halves_s], dtype=torch.float64, device=dev)
     work = torch.tensor([live_turns, alg_bytes, n * E], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-    total_ms, step_ms, e2e_s = red.cpu().tolist()
+    total_ms, step_ms, e2e_s, e2e_halves_s = red.cpu().tolist()
     live_all, bytes_all, e2e_turns = work.cpu().tolist()
     st = stats.cpu().tolist()
 
@@ -549,12 +630,15 @@ def run_b200(args):
                              "live_match_turns_per_launch": live_all / world / K},
                 "e2e": {"value": e2e_turns / e2e_s, "unit": "match-turns/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "steps": E, "warmup": 5,
+                        "two_halves_value": (e2e_turns / e2e_halves_s) if e2e_halves_s > 0 else None,
                         "note": "lux_b200_step_host_sparse_submit + lux_b200_step_host_wait: pinned host action LIST (8 B per action) -> device, scatter, "
                                 "step, done flags + summary -> host (mapped pinned memory), the host blocks on them every step (the pool "
                                 "reset of finished matches is queued before it blocks); counts resident matches per step "
                                 "(finished ones are reset the same step).  The lists are recorded beforehand (the device "
                                 "action stream packed into entry form): building them from host Action objects is the "
-                                "caller's cost and is not in this number"},
+                                "caller's cost and is not in this number.  `two_halves_value` (--e2e-halves): the resident batch driven as "
+                                "TWO half-batches, each through its own submit / wait pair on its own stream, so that the device plays "
+                                "one half while the host turns the other around"},
                 "clocks": sampler.summary(),
                 "host_mapgen": {"maps": n + POOL_MAPS, "seconds": mapgen_s, "note": "untimed setup: native seeded generator"},
                 "stats": {"live": st[0], "finished_pending": st[1], "sum_units": st[7], "sum_city_tiles": st[8],
