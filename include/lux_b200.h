@@ -146,6 +146,9 @@ int lux_b200_device_count(void);
  * "cta_sync" (warps per CTA of the small class with a CTA-wide rendezvous at some phase boundaries of the turn, so that
  * the warps fetch a phase's code together: -1 = automatic, 8 on dense batches and none on sparse ones; 0 = never; n = always n;
  * 32 x 32 maps, flags 0 only), "sync_mask" (which of the nine rendezvous points are armed, default 0x54),
+ * "order" (1 = the small class plays its heavy matches first, through order lists the classification pass builds, so that
+ * the grid ends on light ones; default), "n_ord" / "ord_step" (tuning probes: force the number of need classes, 0 =
+ * automatic, and their spacing in percent of the slice),
  * "slice" (shared-memory bytes per match of the small class, 0 = default), "group" (lanes per match: 0 automatic,
  * 8 / 16 / 32), "carveout" (preferred shared-memory carve-out in percent, -1 = automatic), "list_grid" (CTAs of
  * the big-class launch, 0 = automatic), "gen_wpc" (matches per CTA of the action-stream kernel); measurement aids:

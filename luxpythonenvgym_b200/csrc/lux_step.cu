@@ -167,11 +167,15 @@ __device__ unsigned long long* g_trace_dev = nullptr;      // set with the "trac
 
 // Classification of one step (device pointers, owned by the library, see StepScratch below).
 #define LUX_N_CAND 5     // candidate slice sizes the classification pass keeps statistics for
-#define LUX_CNT_SET (2 + LUX_N_CAND)     // one set of counters: [0] big-class count, [1..N_CAND] statistics, [1 + N_CAND] oversize count
+#define LUX_N_ORD 8      // need classes of the small class's play order (heaviest first)
+#define LUX_CNT_SET (2 + LUX_N_CAND + LUX_N_ORD)     // one set of counters: [0] big-class count, [1..N_CAND] statistics, [1 + N_CAND] oversize count, then the order-list counts
 struct LuxSched {
     int* big_cnt; int* big_list;      // matches of the big class (written by classify, read by kList)
     int* over_cnt; int* over_list;    // big matches whose need exceeds `mid` (the big class's slice): played with full-capacity slices
     int mid;                          // by a launch of their own (kList with big_cnt / big_list pointing here)
+    // play order of the small class: LUX_N_ORD lists of capacity `ord_cap`, heaviest need class first, so that the
+    // matches that start last -- the tail of the grid -- are the lightest (null: index order, see cls)
+    int* ord_cnt; int* ord_list; int ord_cap; int n_ord; int ord_lim[LUX_N_ORD - 1];
     uint8_t* cls;                     // [n] 1 = big class (kSmall skips it)
     int* zero;                        // the previous step's counters: trailed to the host, then cleared for reuse
     int* seen_host;                   // pinned, mapped host words
@@ -186,8 +190,7 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
     LUX_TRACE_BEGIN(sc.trace, 3);
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     // the previous step's statistics go to the host (stale values only delay its choice of slice), then clear
-    if (m <= LUX_N_CAND) { sc.seen_host[m] = sc.zero[m]; sc.zero[m] = 0; }
-    if (m == LUX_N_CAND + 1) sc.zero[m] = 0;
+    if (m < LUX_CNT_SET) { sc.seen_host[m] = sc.zero[m]; sc.zero[m] = 0; }
     int total = 0;
     if (m < b.n_matches) {
         LuxHeader* h = b.hdr + m;
@@ -199,6 +202,28 @@ __global__ void lux_classify_kernel(LuxBatch b, int slice, LuxSched sc) {
         if (big) {
             if (total > sc.mid) sc.over_list[atomicAdd(sc.over_cnt, 1)] = m;
             else sc.big_list[atomicAdd(sc.big_cnt, 1)] = m;
+        }
+    }
+    if (sc.ord_list) {
+        // live matches of the small class, appended to the list of their need class (one atomic per warp and class)
+        const int lane = threadIdx.x & 31;
+        int cls_ord = -1;
+        if (total > 0 && total <= slice) {
+            cls_ord = sc.n_ord - 1;
+#pragma unroll
+            for (int i = LUX_N_ORD - 2; i >= 0; i--)
+                if (i < sc.n_ord - 1 && total > sc.ord_lim[i]) cls_ord = i;
+        }
+#pragma unroll
+        for (int i = 0; i < LUX_N_ORD; i++) {
+            if (i >= sc.n_ord) break;
+            const unsigned mk = __ballot_sync(0xffffffffu, cls_ord == i);
+            if (mk) {
+                int pos0 = 0;
+                if (lane == __ffs(mk) - 1) pos0 = atomicAdd(sc.ord_cnt + i, __popc(mk));
+                pos0 = __shfl_sync(0xffffffffu, pos0, __ffs(mk) - 1);
+                if (cls_ord == i) sc.ord_list[(size_t)i * sc.ord_cap + pos0 + __popc(mk & ((1u << lane) - 1u))] = m;
+            }
         }
     }
 #pragma unroll
@@ -257,9 +282,21 @@ lux_step_kernel(LuxBatch b, const uint32_t* __restrict__ unit_actions, const uin
         LUX_TRACE_BIN(sc.trace, 24);
         return;
     }
-    const int m = blockIdx.x * gpc + grp;
+    int m = blockIdx.x * gpc + grp;
     int valid = m < b.n_matches;
-    if (kMode == kSmall && valid && __ldcg(sc.cls + m)) valid = 0;          // the big class plays it
+    if (kMode == kSmall && sc.ord_list) {
+        // slot -> match through the order lists (heaviest need class first); slots past the last list have nothing to play
+        int slot = m, at = -1;
+#pragma unroll
+        for (int i = 0; i < LUX_N_ORD; i++) {
+            if (i >= sc.n_ord) break;
+            const int c = __ldcg(sc.ord_cnt + i);
+            if (at < 0 && slot < c) at = i * sc.ord_cap + slot;
+            if (at < 0) slot -= c;
+        }
+        valid = at >= 0;
+        m = valid ? __ldcg(sc.ord_list + at) : 0;
+    } else if (kMode == kSmall && valid && __ldcg(sc.cls + m)) valid = 0;          // the big class plays it
     LUX_TRACE_BEGIN(sc.trace, 2);
     LUX_TRACE_BIN(sc.trace, 8);
     if (kSpec == 3 || lux_wany<G>(valid))
@@ -286,6 +323,8 @@ static int g_over_own = -1;       // oversize launch on a stream of its own: -1 
 static int g_cta_sync = -1;       // warps per CTA of the small class with a CTA-wide rendezvous between phases: -1 = automatic (8 on dense
                                   // batches, i.e. when the small slice is 6 KB or more; none on sparse ones), 0 = never, n = always n
 static thread_local int t_sync_w = 0;     // the choice for the launch being issued (lux_step_impl -> launch_step)
+static int g_n_ord = 0, g_ord_step = 10;       // tuning probes: force the number of need classes (0 = automatic) and their spacing in percent of the slice
+static int g_order = 1;           // 1: the small class plays its matches heaviest need class first (order lists built by the classification pass)
 static int g_only_class = 0;      // measurement aid: 1 = launch only the big class, 2 = only the small class (results are then incomplete)
 static int g_carveout = -1;       // preferred shared-memory carve-out in percent (-1 = driver default)
 extern "C" unsigned long long lux_b200_launch_count(void) { return g_launches; }
@@ -693,6 +732,9 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
     if (!strcmp(name, "big_share")) { g_big_share = value < 1 ? 1 : value; return LUX_OK; }
     if (!strcmp(name, "fork")) { g_fork = value != 0; return LUX_OK; }
     if (!strcmp(name, "mid_slice")) { g_mid_slice = value; return LUX_OK; }
+    if (!strcmp(name, "n_ord")) { g_n_ord = value; return LUX_OK; }
+    if (!strcmp(name, "ord_step")) { g_ord_step = value; return LUX_OK; }
+    if (!strcmp(name, "order")) { g_order = value != 0; return LUX_OK; }
     if (!strcmp(name, "over_own")) { g_over_own = value; return LUX_OK; }
     if (!strcmp(name, "sync_mask")) { unsigned v = (unsigned)value; return cudaMemcpyToSymbol(lux_phase_sync_mask, &v, sizeof v) == cudaSuccess ? LUX_OK : LUX_E_CUDA; }
     if (!strcmp(name, "cta_sync")) { g_cta_sync = value < 0 ? -1 : value > 32 ? 32 : value; return LUX_OK; }
@@ -709,6 +751,8 @@ extern "C" int lux_b200_set_option(const char* name, int value) {
 // mixed map sizes, a pool -- each keep their own lists).
 struct StepScratch {
     const void* key; int n; int dev;
+    int graphed;                 // a step of this batch was captured into a CUDA graph: see counters_for_step
+    int* order;                  // LUX_N_ORD x n: play order of the small class (lists per need class)
     int* counts;                 // 3 x LUX_CNT_SET: big-class count + statistics + oversize count (rotation: this step, next, being cleared)
     int* list;                   // [n] big-class matches of this step
     unsigned char* cls;          // [n] 1 = big class
@@ -731,6 +775,7 @@ static unsigned g_scratch_clock = 0;
 static void scratch_free(StepScratch& s) {
     if (s.counts) cudaFree(s.counts);
     if (s.list) cudaFree(s.list);
+    if (s.order) cudaFree(s.order);
     if (s.cls) cudaFree(s.cls);
     if (s.seen) cudaFreeHost(s.seen);
     if (s.entries) cudaFree(s.entries);
@@ -759,14 +804,16 @@ static StepScratch* scratch_get(const LuxBatch* b, cudaStream_t st) {
     // a partial failure frees what was allocated and leaves the slot empty (no key: the next call starts over)
     if (cudaMalloc(&slot->counts, 3 * LUX_CNT_SET * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&slot->list, 2 * n * sizeof(int)) != cudaSuccess ||                  // big list, oversize list
+        cudaMalloc(&slot->order, LUX_N_ORD * n * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&slot->cls, n) != cudaSuccess ||
-        cudaHostAlloc(&slot->seen, (1 + LUX_N_CAND) * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc(&slot->seen, LUX_CNT_SET * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaMemsetAsync(slot->counts, 0, 3 * LUX_CNT_SET * sizeof(int), st) != cudaSuccess) {
         cudaGetLastError();
         scratch_free(*slot);
         return nullptr;
     }
-    for (int i = 0; i <= LUX_N_CAND; i++) slot->seen[i] = 0;
+    for (int i = 0; i < LUX_CNT_SET; i++) slot->seen[i] = 0;
+    slot->graphed = 0;
     slot->key = b->hdr; slot->n = b->n_matches; slot->dev = dev; slot->step = 0;
     return slot;
 }
@@ -777,6 +824,22 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
 extern "C" int lux_b200_step(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions,
                              uint32_t flags, void* cuda_stream) {
     return lux_step_impl(b, unit_actions, tile_actions, flags & 0xFFFFu, cuda_stream);
+}
+
+// The classification counters of a step: set t % 3 is used, set (t + 2) % 3 -- the previous step's -- is trailed to the
+// host and cleared by the classification pass, so a set is clean again two steps after its use without a memset on
+// the step's path.  That rotation is HOST state: a step captured into a CUDA graph replays with the set it was
+// captured with, which nobody clears between replays -- so a captured step (and every later step of a batch that
+// has been captured once, whose sets the replays may have left dirty) clears its set explicitly in front of the
+// classification pass (a memset node in the graph).
+static void counters_for_step(StepScratch* S, cudaStream_t st, LuxSched& sc) {
+    const unsigned t = S->step++;
+    sc.big_cnt = S->counts + (t % 3) * LUX_CNT_SET;
+    sc.zero = S->counts + ((t + 2) % 3) * LUX_CNT_SET;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+    if (cs != cudaStreamCaptureStatusNone) S->graphed = 1;
+    if (S->graphed) cudaMemsetAsync(sc.big_cnt, 0, LUX_CNT_SET * sizeof(int), st);
 }
 
 static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const uint8_t* tile_actions, uint32_t flags,
@@ -836,12 +899,10 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
         // single full-capacity launch (small maps, very dense batches).  The statistics still have to move, or
         // the host would never see the batch thin out again: classify runs with the current choice.
         if (S) {
-            const unsigned t = S->step++;
-            sc.big_cnt = S->counts + (t % 3) * LUX_CNT_SET;
+            counters_for_step(S, st, sc);
             sc.big_list = S->list;
             sc.over_cnt = sc.big_cnt + 1 + LUX_N_CAND; sc.over_list = S->list + b->n_matches; sc.mid = 0x7fffffff;
             sc.cls = S->cls;
-            sc.zero = S->counts + ((t + 2) % 3) * LUX_CNT_SET;
             sc.seen_host = S->seen;
             for (int i = 0; i < LUX_N_CAND; i++) sc.cand[i] = cand[i];
             lux_launch_chain(lux_classify_kernel, dim3((b->n_matches + 255) / 256), dim3(256), 0, st, *b, full, sc);
@@ -852,8 +913,7 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
         if (rc) return rc;
         return cuda_ok(cudaGetLastError(), "lux_step_kernel launch");
     }
-    const unsigned t = S->step++;
-    sc.big_cnt = S->counts + (t % 3) * LUX_CNT_SET;
+    counters_for_step(S, st, sc);
     sc.big_list = S->list;
     // The big class plays with slices of `mid` bytes (12 KB: more of its long single-warp jobs fit beside the small
     // class than with full-capacity slices, step 0.082 -> 0.080 ms); the rare match beyond that goes to a launch of
@@ -863,8 +923,28 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     if (g_mid_slice < 0 || !(g_fork && g_only_class == 0) || mid <= small || mid >= full) mid = full;
     mid = (mid + 127) & ~127;
     sc.over_cnt = sc.big_cnt + 1 + LUX_N_CAND; sc.over_list = S->list + b->n_matches; sc.mid = mid;
+    if (g_order && g_fork && g_only_class == 0) {
+        // Play order of the small class: the heavy matches first, so that the grid ends on light ones (the last
+        // wave's matches are the kernel's tail: sparse step 0.082 -> 0.078 ms, dense 0.182 -> 0.163 ms).
+        // Dense batches (small slice of 6 KB or more): four need classes, above 90 / 80 / 70 % of the slice and the rest.
+        // Sparse batches: two classes, need above 70 % of the slice first -- more lists scatter the play order over
+        // the batch and cost more than the shorter tail returns (four classes: no gain, eight: 8 % slower), and so does
+        // a first class that holds half of the batch (threshold 60 %: 5 % slower; 65-75 %: 0.078 ms; 80 %: no gain).
+        // A threshold steered by the class's share of the batch was built and found to walk out of that window
+        // (needs are quantised, the share is a step function of the threshold), so it is fixed.
+        sc.ord_cnt = sc.big_cnt + 2 + LUX_N_CAND; sc.ord_list = S->order; sc.ord_cap = b->n_matches;
+        if (g_n_ord > 0) {                        // forced (tuning probes)
+            sc.n_ord = g_n_ord < 2 ? 2 : g_n_ord > LUX_N_ORD ? LUX_N_ORD : g_n_ord;
+            for (int i = 0; i < LUX_N_ORD - 1; i++) sc.ord_lim[i] = small * (100 - (i + 1) * g_ord_step) / 100;
+        } else if (small >= 6144) {
+            sc.n_ord = 4;
+            for (int i = 0; i < LUX_N_ORD - 1; i++) sc.ord_lim[i] = small * (9 - i) / 10;
+        } else {
+            sc.n_ord = 2;
+            for (int i = 0; i < LUX_N_ORD - 1; i++) sc.ord_lim[i] = small * 7 / 10;
+        }
+    }
     sc.cls = S->cls;
-    sc.zero = S->counts + ((t + 2) % 3) * LUX_CNT_SET;
     sc.seen_host = S->seen;
     sc.trace = g_trace;
     if (g_trace) {

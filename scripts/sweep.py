@@ -15,7 +15,7 @@ from luxpythonenvgym_b200.batched import BatchedGame
 N = int(os.environ.get("LUX_SWEEP_N", "16384"))
 STEPS = int(os.environ.get("LUX_SWEEP_STEPS", "60"))
 SIZE = int(os.environ.get("LUX_SWEEP_SIZE", "32"))
-DEFAULTS = {"only_class": 0, "big_share": 3, "tma": 1, "warps_per_cta": 0, "two_class": -1, "list_grid": 0, "overlap": 1, "group": 0, "carveout": -1, "slice": 0, "fork": 1, "mid_slice": 0, "over_own": -1, "cta_sync": -1, "sync_mask": 84}
+DEFAULTS = {"only_class": 0, "big_share": 3, "tma": 1, "warps_per_cta": 0, "two_class": -1, "list_grid": 0, "overlap": 1, "group": 0, "carveout": -1, "slice": 0, "fork": 1, "mid_slice": 0, "over_own": -1, "cta_sync": -1, "sync_mask": 84, "order": 1, "n_ord": 0, "ord_step": 10}
 
 lib = _lib.load()
 pool_arrays = mapgen.generate_batch(np.arange(424242, 424242 + 1024), SIZE)

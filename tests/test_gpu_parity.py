@@ -386,7 +386,30 @@ def test_step_is_deterministic_across_launch_forms():
                 want = got
             for k in want:
                 assert torch.equal(want[k], got[k]), (fork, two, mid, rep, k)
+        # play order of the small class (heavy matches first through the classification pass's order lists): off,
+        # automatic (the default above), eight / three / two forced need classes
+        lib.lux_b200_set_option(b"fork", 1)
+        lib.lux_b200_set_option(b"two_class", -1)
+        lib.lux_b200_set_option(b"mid_slice", 0)
+        lib.lux_b200_set_option(b"over_own", -1)
+        lib.lux_b200_set_option(b"cta_sync", -1)
+        for order, n_ord, step in ((0, 0, 10), (1, 8, 5), (1, 3, 15), (1, 2, 40), (1, 0, 10)):
+            for name, v in ((b"order", order), (b"n_ord", n_ord), (b"ord_step", step)):
+                assert lib.lux_b200_set_option(name, v) == 0
+            for k, v in g.sections().items():
+                v.copy_(snap[k])
+            g.unit_actions.copy_(ua)
+            g.tile_actions.copy_(ta)
+            for t in range(60):
+                g.step()
+                g.reset_gen(pool, 150 + t, 99, 0, reset_count=resets)
+            torch.cuda.synchronize()
+            for k, v in g.sections().items():
+                assert torch.equal(want[k], v), (order, n_ord, step, k)
     finally:
+        lib.lux_b200_set_option(b"order", 1)
+        lib.lux_b200_set_option(b"n_ord", 0)
+        lib.lux_b200_set_option(b"ord_step", 10)
         lib.lux_b200_set_option(b"fork", 1)
         lib.lux_b200_set_option(b"two_class", -1)
         lib.lux_b200_set_option(b"mid_slice", 0)
@@ -672,6 +695,66 @@ def test_graphed_rollout_turns():
         assert torch.equal(roll.obs[o:o + c], want_obs[m, :c]) and torch.equal(roll.ent[o:o + c], want_ent[m, :c])
     _, _, total2, finished2 = run(80)
     assert finished2 == finished and torch.equal(total, total2)
+
+
+def test_step_in_a_cuda_graph_equals_the_eager_steps():
+    """One turn (step + fused reset / action-stream pass) captured into a CUDA graph and replayed 60 times against
+    the same 60 turns issued eagerly from the same snapshot: byte-equal batches.  The classification pass's counters
+    rotate through HOST state, which a replay does not advance -- a captured step has to clear its counters itself,
+    or its big list and play-order lists grow from replay to replay (matches played twice).  Sparse matches with a
+    dense tail so that all three launches of a step carry work; then eager steps again on the batch that was graphed."""
+    n, size = 2048, 32
+    z = G.npz("dense")
+    caps = S.default_caps(size)
+    dense = [_recap(G.get_state(z, nm + "/init"), caps) for nm in G.dense_names() if int(z[nm + "/size"]) == size]
+    g = _game(n, size)
+    pool = _game(64, size)
+    pool.load_arrays(mapgen.generate_batch(np.arange(41000, 41064), size))
+    g.load_arrays(mapgen.generate_batch(np.arange(42000, 42000 + n), size))
+    g.load_states([dense[i % len(dense)] for i in range(192)], first=n - 192)
+    resets = torch.zeros(1, dtype=torch.int32, device=g.device)
+    g.gen_actions(77, 0)
+    for t in range(30):
+        g.step()
+        g.reset_gen(pool, 5, 77, 0, reset_count=resets)
+    torch.cuda.synchronize()
+    snap = {k: v.clone() for k, v in g.sections().items()}
+    ua, ta = g.unit_actions.clone(), g.tile_actions.clone()
+
+    def rewind():
+        for k, v in g.sections().items():
+            v.copy_(snap[k])
+        g.unit_actions.copy_(ua)
+        g.tile_actions.copy_(ta)
+
+    for t in range(60):                      # eager
+        g.step()
+        g.reset_gen(pool, 5, 77, 0, reset_count=resets)
+    torch.cuda.synchronize()
+    want = {k: v.clone() for k, v in g.sections().items()}
+    rewind()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            g.step()
+            g.reset_gen(pool, 5, 77, 0, reset_count=resets)
+    torch.cuda.current_stream().wait_stream(side)
+    rewind()                                 # (capture does not execute; start from the snapshot anyway)
+    for t in range(60):
+        graph.replay()
+    torch.cuda.synchronize()
+    for k, v in g.sections().items():
+        assert torch.equal(want[k], v), "graph replays differ from the eager steps in " + k
+    assert (g.headers()["status"] == 0).all()
+    rewind()
+    for t in range(60):                      # eager again, on a batch whose counters the replays have used
+        g.step()
+        g.reset_gen(pool, 5, 77, 0, reset_count=resets)
+    torch.cuda.synchronize()
+    for k, v in g.sections().items():
+        assert torch.equal(want[k], v), "eager steps after a capture differ in " + k
 
 
 def test_spill_list_and_scheduling_paths_under_load():
