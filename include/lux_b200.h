@@ -148,7 +148,7 @@ int lux_b200_device_count(void);
  * 32 x 32 maps, flags 0 only), "sync_mask" (which of the nine rendezvous points are armed, default 0x54),
  * "order" (1 = the small class plays its heavy matches first, through order lists the classification pass builds, so that
  * the grid ends on light ones; default), "n_ord" / "ord_step" (tuning probes: force the number of need classes, 0 =
- * automatic, and their spacing in percent of the slice),
+ * automatic = two on sparse batches, four on dense ones, and their spacing in percent of the slice),
  * "slice" (shared-memory bytes per match of the small class, 0 = default), "group" (lanes per match: 0 automatic,
  * 8 / 16 / 32), "carveout" (preferred shared-memory carve-out in percent, -1 = automatic), "list_grid" (CTAs of
  * the big-class launch, 0 = automatic), "gen_wpc" (matches per CTA of the action-stream kernel); measurement aids:
