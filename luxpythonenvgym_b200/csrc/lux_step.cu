@@ -923,7 +923,7 @@ static int lux_step_impl(const LuxBatch* b, const uint32_t* unit_actions, const 
     if (g_mid_slice < 0 || !(g_fork && g_only_class == 0) || mid <= small || mid >= full) mid = full;
     mid = (mid + 127) & ~127;
     sc.over_cnt = sc.big_cnt + 1 + LUX_N_CAND; sc.over_list = S->list + b->n_matches; sc.mid = mid;
-    if (g_order && g_fork && g_only_class == 0) {
+    if (g_order && g_fork && g_only_class == 0 && g_group != 8 && g_group != 16) {      // (full-warp matches only: the narrow lane groups are tuning forms)
         // Play order of the small class: the heavy matches first, so that the grid ends on light ones (the last
         // wave's matches are the kernel's tail: sparse step 0.082 -> 0.078 ms, dense 0.182 -> 0.163 ms).
         // Dense batches (small slice of 6 KB or more): four need classes, above 90 / 80 / 70 % of the slice and the rest.
